@@ -1,0 +1,32 @@
+# Builds the sm_100a CUDA library (the product) and the CPU oracle (test infrastructure).
+#   make            -> zk-paillier_b200/libzkp_b200.so + oracle/liboracle.so
+#   make lib        -> CUDA library only
+#   make oracle     -> oracle only
+NVCC      ?= nvcc
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS   := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall -Xptxas -v
+CSRC      := zk-paillier_b200/csrc
+BUILD     := build
+CU        := $(wildcard $(CSRC)/*.cu)
+OBJ       := $(patsubst $(CSRC)/%.cu,$(BUILD)/%.o,$(CU))
+LIB       := zk-paillier_b200/libzkp_b200.so
+
+all: lib oracle
+
+lib: $(LIB)
+
+$(BUILD)/%.o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.h) $(wildcard $(CSRC)/*.cuh) include/zkp_b200.h
+	@mkdir -p $(BUILD)
+	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(BUILD)/$*.ptxas.log || (cat $(BUILD)/$*.ptxas.log; false)
+
+$(LIB): $(OBJ)
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJ) -lcudart
+
+oracle:
+	$(MAKE) -C oracle
+
+clean:
+	rm -rf $(BUILD) $(LIB)
+	$(MAKE) -C oracle clean
+
+.PHONY: all lib oracle clean

@@ -1,0 +1,180 @@
+/*
+ * zkp_b200.h - C ABI of the B200-native batched Paillier zero-knowledge engine.
+ *
+ * This is the drop-in boundary for the hot path of ZenGo-X/zk-paillier: the
+ * security-parameter loops of big-integer modular exponentiation inside
+ * zkproofs::RangeProofNi::{prove,verify} and NiCorrectKeyProof::verify (plus
+ * the modexps of ZeroProof / CiphertextProof / MulProof / VerlinProof).  The
+ * reference has no FFI of its own: its seam is the Rust call surface between the
+ * proof protocols (src/zkproofs/*.rs) and curv-kzen / kzen-paillier (GMP).  Each
+ * entry point below names the reference code it replaces; the Rust `extern "C"`
+ * block a maintainer would add is in INTEGRATION.md and rust/src/ffi.rs.
+ *
+ * Conventions
+ *  - Integers cross as little-endian arrays of uint32_t limbs, fixed width per
+ *    call, zero padded; batches are dense row-major.  (On little-endian hosts the
+ *    same bytes are little-endian uint64_t limbs when the limb count is even.)
+ *    Every limb count passed in must be a multiple of 4 (16-byte rows: rows are
+ *    staged with 1-D TMA bulk copies).
+ *  - All buffers are HOST memory owned by the caller; nothing is retained after
+ *    the call returns.  Device memory lives in the opaque zkp_ctx (one per GPU).
+ *    The *_stage / *_run / *_fetch triples split one call into host->device
+ *    copy, kernels only, device->host copy (for measurement and pipelining).
+ *  - Every function returns 0 on success, a negative ZKP_E_* code otherwise;
+ *    zkp_last_error() gives text.  Nothing throws across the boundary.  There is
+ *    NO CPU fallback: without a CUDA device zkp_ctx_create fails.
+ *  - Soundness failures are reported per item in accept[] (1 = Ok(()), 0 =
+ *    Err(IncorrectProof)).  Inputs on which the reference would PANIC instead
+ *    (response/bit-vector shorter than error_factor, non-invertible value in
+ *    MulProof) set fault[] = 1 so the shim can re-raise.
+ *  - Randomness is always an input; the library never samples.
+ *  - A context is single-threaded; use one context per thread / per GPU.
+ */
+#ifndef ZKP_B200_H
+#define ZKP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ZKP_OK 0
+#define ZKP_E_ARG (-1)     /* bad argument (width, null, range) */
+#define ZKP_E_CUDA (-2)    /* CUDA runtime error, see zkp_last_error */
+#define ZKP_E_STATE (-3)   /* call order (no key set, nothing staged) */
+#define ZKP_E_NOMEM (-4)
+
+#define ZKP_RP_OPEN 0      /* Response::Open  {w1,r1,w2,r2}            (range_proof.rs:54-66) */
+#define ZKP_RP_MASK1 1     /* Response::Mask  {j:1, masked_x, masked_r} (range_proof.rs:68-77) */
+#define ZKP_RP_MASK2 2     /* Response::Mask  {j:2, ...} */
+
+#define ZKP_CK_M2 11       /* correct_key_ni.rs:29 */
+
+typedef struct zkp_ctx zkp_ctx;
+
+/* ---- context ------------------------------------------------------------ */
+/* stream: a cudaStream_t to launch on (e.g. torch's current stream), or NULL
+ * for a private stream. */
+int zkp_ctx_create(int device, void* stream, zkp_ctx** out);
+void zkp_ctx_destroy(zkp_ctx* ctx);
+const char* zkp_last_error(const zkp_ctx* ctx);
+int zkp_version(void);
+int zkp_sm_count(const zkp_ctx* ctx);
+int zkp_sync(zkp_ctx* ctx);
+
+/* Per-kernel device-time accounting (CUDA events on the launch stream).
+ * kernel ids: 0 = modexp_shared (K1), 1 = modexp_var (K2), 2 = modmul (K3),
+ * 3 = sha256_transcript (K4), 4 = everything else. */
+int zkp_profile_enable(zkp_ctx* ctx, int on);
+int zkp_profile_reset(zkp_ctx* ctx);
+int zkp_profile_get(zkp_ctx* ctx, int kernel, double* ms_total, long long* launches, double* units);
+
+/* ---- key ---------------------------------------------------------------- */
+/* Paillier EncryptionKey{n, nn} (kzen-paillier): derives nn = n^2, Montgomery
+ * constants for nn and n, and the sliding-window schedule of the exponent n. */
+int zkp_set_key(zkp_ctx* ctx, const uint32_t* n, int n_limbs);
+/* Generic shared (modulus, exponent) for zkp_modexp_shared. */
+int zkp_set_modulus(zkp_ctx* ctx, const uint32_t* mod, int mod_limbs, const uint32_t* exp, int exp_limbs);
+int zkp_nn_limbs(const zkp_ctx* ctx); /* 2*n_limbs after zkp_set_key */
+
+/* ---- K1: BigInt::mod_pow(base, E, M) with one (M,E) per call ---------------
+ * out[j] = bases[j]^E mod M.  bases: [batch][base_limbs] (< 2^(32*mod_limbs)),
+ * out: [batch][mod_limbs].  After zkp_set_key: M = nn, E = n. */
+int zkp_modexp_shared(zkp_ctx* ctx, const uint32_t* bases, int base_limbs, int batch, uint32_t* out);
+
+/* Paillier::encrypt_with_chosen_randomness(ek, m, r) = (1 + m*n) * r^n mod nn
+ * (kzen-paillier; called at range_proof.rs:165,179,280,286,330).
+ * m: [batch][m_limbs], r: [batch][r_limbs], out: [batch][nn_limbs]. */
+int zkp_paillier_enc(zkp_ctx* ctx, const uint32_t* m, int m_limbs, const uint32_t* r, int r_limbs, int batch,
+                     uint32_t* out);
+
+/* ---- K2: BigInt::mod_pow with per-instance modulus / exponent --------------
+ * out[j] = bases[j]^exps[j/per] mod mods[j/per]   (correct_key_ni.rs:90-93 with
+ * per = 11; Paillier::mul / mod_pow sites of the sigma protocols with per = 1).
+ * bases, out: [batch][mod_limbs]; mods: [ceil(batch/per)][mod_limbs] (odd);
+ * exps: [ceil(batch/per)][exp_limbs]; exp_bits: bits scanned (>= max bit length). */
+int zkp_modexp_var(zkp_ctx* ctx, const uint32_t* bases, const uint32_t* exps, int exp_limbs, int exp_bits,
+                   const uint32_t* mods, int mod_limbs, int per, int batch, uint32_t* out);
+
+/* ---- K3: BigInt::mod_mul / Paillier::add under the key ----------------------
+ * out[j] = a[j] * b[j/b_per] mod (which ? nn : n).  Widths = that modulus. */
+int zkp_modmul(zkp_ctx* ctx, int which_nn, const uint32_t* a, const uint32_t* b, int b_per, int batch,
+               uint32_t* out);
+
+/* ---- K4: compute_digest (utils.rs:9-22) -----------------------------------
+ * digest[b] = SHA-256( to_bytes(items[b][0]) || ... || to_bytes(items[b][count-1]) )
+ * where to_bytes is the minimal-length big-endian magnitude and zero -> 0x00
+ * (curv-kzen BigInt::to_bytes over GMP).  items: [batch][count][limbs]. */
+int zkp_sha256_transcript(zkp_ctx* ctx, const uint32_t* items, int limbs, int count, int batch,
+                          uint8_t* digest /* [batch][32] */);
+
+/* ---- RangeProofNi (range_proof_ni.rs:47-107, range_proof.rs:128-355) --------
+ * All proofs of a batch are under the key set by zkp_set_key.
+ * ef = error_factor (SECURITY_PARAMETER = 128, range_proof_ni.rs:23).
+ * w_limbs: row width of range / x / w / masked_x values (>= bits(10000*range)/32+1
+ * is always enough), n_limbs / nn_limbs: widths of n / n^2.
+ *
+ * prove inputs  range[b][w], x[b][w], r[b][n]             secret_x, secret_r
+ *               w1[b][ef][w]   samples of [third, 2*third) (range_proof.rs:136-139)
+ *               swap[b][ef]    the coin flips            (range_proof.rs:144-149)
+ *               r1[b][ef][n], r2[b][ef][n]                (range_proof.rs:151-159)
+ * prove outputs c1[b][ef][nn], c2[b][ef][nn]              EncryptedPairs
+ *               digest[b][32]                             compute_digest(n, c1.., c2..)
+ *               kind[b][ef]                               ZKP_RP_*
+ *               resp_w[b][ef][2][w]  Open: (w1,w2)  Mask: (masked_x, 0)
+ *               resp_r[b][ef][2][n]  Open: (r1,r2)  Mask: (masked_r, 0)
+ * Any output pointer may be NULL (not fetched). */
+int zkp_rangeproof_ni_prove(zkp_ctx* ctx, int batch, int ef, int w_limbs, const uint32_t* range, const uint32_t* x,
+                            const uint32_t* r, const uint32_t* w1, const uint8_t* swap, const uint32_t* r1,
+                            const uint32_t* r2, uint32_t* c1, uint32_t* c2, uint8_t* digest, uint8_t* kind,
+                            uint32_t* resp_w, uint32_t* resp_r);
+int zkp_rp_prove_stage(zkp_ctx* ctx, int batch, int ef, int w_limbs, const uint32_t* range, const uint32_t* x,
+                       const uint32_t* r, const uint32_t* w1, const uint8_t* swap, const uint32_t* r1,
+                       const uint32_t* r2);
+int zkp_rp_prove_run(zkp_ctx* ctx);
+int zkp_rp_prove_fetch(zkp_ctx* ctx, uint32_t* c1, uint32_t* c2, uint8_t* digest, uint8_t* kind, uint32_t* resp_w,
+                       uint32_t* resp_r);
+
+/* verify inputs: range[b][w], cipher_x[b][nn] and the proof arrays as produced
+ * by prove.  accept[b] = 1 iff RangeProofNi::verify returns Ok(()); fault[b] = 1
+ * where the reference would panic (kind byte out of range).  digest (optional
+ * out) receives the recomputed challenge hash. */
+int zkp_rangeproof_ni_verify(zkp_ctx* ctx, int batch, int ef, int w_limbs, const uint32_t* range,
+                             const uint32_t* cipher_x, const uint32_t* c1, const uint32_t* c2, const uint8_t* kind,
+                             const uint32_t* resp_w, const uint32_t* resp_r, uint8_t* accept, uint8_t* fault,
+                             uint8_t* digest);
+int zkp_rp_verify_stage(zkp_ctx* ctx, int batch, int ef, int w_limbs, const uint32_t* range,
+                        const uint32_t* cipher_x, const uint32_t* c1, const uint32_t* c2, const uint8_t* kind,
+                        const uint32_t* resp_w, const uint32_t* resp_r);
+/* Chain on the device: verify the batch most recently produced by
+ * zkp_rp_prove_run (no host round trip); only cipher_x comes from the host. */
+int zkp_rp_verify_stage_from_prove(zkp_ctx* ctx, const uint32_t* cipher_x);
+int zkp_rp_verify_run(zkp_ctx* ctx);
+int zkp_rp_verify_fetch(zkp_ctx* ctx, uint8_t* accept, uint8_t* fault, uint8_t* digest);
+/* Number of Paillier encryptions the last verify_run performed (ef + #Open per proof). */
+long long zkp_rp_verify_enc_count(zkp_ctx* ctx);
+
+/* ---- NiCorrectKeyProof::verify (correct_key_ni.rs:73-100) -------------------
+ * n[b][n_limbs] (one modulus per proof), sigma[b][11][n_limbs], salt shared.
+ * accept[b] = 1 iff all 11 sigma_i^N mod N equal the derived rho_i and
+ * gcd(primorial(6370), N) == 1.  rho (optional out): [b][11][n_limbs]. */
+int zkp_correct_key_ni_verify(zkp_ctx* ctx, int batch, int n_limbs, const uint32_t* n, const uint32_t* sigma,
+                              const uint8_t* salt, int salt_len, uint8_t* accept, uint32_t* rho);
+int zkp_ck_verify_stage(zkp_ctx* ctx, int batch, int n_limbs, const uint32_t* n, const uint32_t* sigma,
+                        const uint8_t* salt, int salt_len);
+int zkp_ck_verify_run(zkp_ctx* ctx);
+int zkp_ck_verify_fetch(zkp_ctx* ctx, uint8_t* accept, uint32_t* rho);
+
+/* ---- measurement ----------------------------------------------------------
+ * Register-only multiply-add issue-rate microbenchmark (the roofline denominator
+ * for the modexp kernels).  variant 0: independent IMAD.WIDE.U32, 1: the
+ * carry-chained IMAD.WIDE.U32.X rows the Montgomery loop is made of, 2: 32-bit
+ * IMAD.  Returns multiply-adds per second in *mads_per_s. */
+int zkp_imad_peak(zkp_ctx* ctx, int variant, double* mads_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZKP_B200_H */

@@ -1,0 +1,413 @@
+// C-ABI layer, part 1: context, key setup, the raw modexp / modmul / Enc calls and
+// the measurement hooks declared in include/zkp_b200.h.
+//
+// Host code here only marshals buffers and derives per-key constants; every
+// big-integer operation on caller data runs in the CUDA kernels of modexp.cu.
+// There is deliberately no CPU fallback: zkp_ctx_create fails without a device.
+#include <algorithm>
+#include <cstring>
+#include <new>
+
+#include "ctx.h"
+
+using namespace zkp;
+
+namespace zkp {
+
+int fail(zkp_ctx* c, int code, const char* what) {
+  if (c) c->err = what;
+  return code;
+}
+int fail_cuda(zkp_ctx* c, cudaError_t e, const char* what) {
+  if (c) {
+    c->err = std::string(cudaGetErrorName(e)) + ": " + cudaGetErrorString(e) + " in " + what;
+  }
+  cudaGetLastError();
+  return ZKP_E_CUDA;
+}
+
+ProfScope::ProfScope(zkp_ctx* ctx, int kid, double units) : c(ctx) {
+  if (!c->profiling) return;
+  ProfEntry e;
+  e.kid = kid;
+  e.units = units;
+  auto get = [&]() {
+    cudaEvent_t ev;
+    if (!c->ev_pool.empty()) {
+      ev = c->ev_pool.back();
+      c->ev_pool.pop_back();
+    } else {
+      cudaEventCreate(&ev);
+    }
+    return ev;
+  };
+  e.a = get();
+  e.b = get();
+  cudaEventRecord(e.a, c->stream);
+  c->prof.push_back(e);
+  idx = (int)c->prof.size() - 1;
+}
+ProfScope::~ProfScope() {
+  if (idx >= 0) cudaEventRecord(c->prof[idx].b, c->stream);
+}
+
+cudaError_t ensure_table(zkp_ctx* c, int S, int entries) {
+  size_t bytes = (size_t)resident_groups(S, c->num_sms) * entries * S * sizeof(uint32_t);
+  return c->table.ensure(bytes);
+}
+
+// Sliding-window (width kWindowShared) recoding of a public exponent, most
+// significant bit first.  Entry k: low byte = table index of the odd power
+// x^(2*idx+1) to multiply by (0xff = none), upper 24 bits = squarings to do first.
+// Entry 0 only loads the accumulator.
+static std::vector<uint32_t> recode_exponent(const uint32_t* e, int limbs) {
+  std::vector<uint32_t> out;
+  int top = limbs * 32 - 1;
+  auto bit = [&](int i) { return (e[i >> 5] >> (i & 31)) & 1u; };
+  while (top >= 0 && !bit(top)) --top;
+  if (top < 0) return out;  // exponent zero
+  int i = top;
+  uint32_t pending_sq = 0;
+  bool first = true;
+  while (i >= 0) {
+    if (!bit(i)) {
+      ++pending_sq;
+      --i;
+      continue;
+    }
+    int l = std::max(i - kWindowShared + 1, 0);
+    while (!bit(l)) ++l;  // window [i .. l] ends in a one
+    uint32_t v = 0;
+    for (int k = i; k >= l; --k) v = (v << 1) | bit(k);
+    uint32_t width = (uint32_t)(i - l + 1);
+    if (first) {
+      out.push_back(v >> 1);
+      first = false;
+    } else {
+      out.push_back(((pending_sq + width) << 8) | (v >> 1));
+    }
+    pending_sq = 0;
+    i = l - 1;
+  }
+  if (pending_sq) out.push_back((pending_sq << 8) | 0xffu);
+  return out;
+}
+
+int setup_slot(zkp_ctx* c, KeySlot& slot, const uint32_t* mod, int limbs, const uint32_t* exp, int exp_limbs) {
+  slot.ready = false;
+  if (!mod || limbs <= 0 || (limbs % 4)) return fail(c, ZKP_E_ARG, "modulus width must be a positive multiple of 4 limbs");
+  if (!(mod[0] & 1u)) return fail(c, ZKP_E_ARG, "modulus must be odd");
+  int S = pick_width(limbs);
+  if (S < 0) return fail(c, ZKP_E_ARG, "modulus wider than 8192 bits");
+  slot.S = S;
+  slot.limbs = limbs;
+  slot.h_mod.assign(S, 0u);
+  memcpy(slot.h_mod.data(), mod, (size_t)limbs * 4);
+  ZKP_CU(c, slot.mod.ensure((size_t)S * 4));
+  ZKP_CU(c, slot.r2.ensure((size_t)S * 4));
+  ZKP_CU(c, slot.nR.ensure((size_t)S * 4));
+  ZKP_CU(c, slot.n0.ensure(16));
+  ZKP_CU(c, cudaMemcpyAsync(slot.mod.p, slot.h_mod.data(), (size_t)S * 4, cudaMemcpyHostToDevice, c->stream));
+  ZKP_CU(c, cudaMemsetAsync(slot.nR.p, 0, (size_t)S * 4, c->stream));
+  ZKP_CU(c, launch_mont_setup(slot.mod.as<uint32_t>(), S, S, 1, slot.r2.as<uint32_t>(), slot.n0.as<uint32_t>(), c->stream));
+  ZKP_CU(c, cudaMemcpyAsync(&slot.n0inv, slot.n0.p, 4, cudaMemcpyDeviceToHost, c->stream));
+  slot.nsteps = 0;
+  if (exp) {
+    std::vector<uint32_t> sched = recode_exponent(exp, exp_limbs);
+    if (sched.empty()) return fail(c, ZKP_E_ARG, "shared exponent must be non-zero");
+    if ((int)sched.size() > kMaxSchedSteps) return fail(c, ZKP_E_ARG, "shared exponent too long");
+    slot.nsteps = (int)sched.size();
+    sched.resize((sched.size() + 3) & ~size_t(3), 0xffu);
+    ZKP_CU(c, slot.sched.ensure(sched.size() * 4));
+    ZKP_CU(c, cudaMemcpyAsync(slot.sched.p, sched.data(), sched.size() * 4, cudaMemcpyHostToDevice, c->stream));
+  }
+  ZKP_CU(c, cudaStreamSynchronize(c->stream));
+  slot.ready = true;
+  return ZKP_OK;
+}
+
+}  // namespace zkp
+
+extern "C" {
+
+int zkp_version(void) { return 100; }
+
+int zkp_ctx_create(int device, void* stream, zkp_ctx** out) {
+  if (!out) return ZKP_E_ARG;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) {
+    cudaGetLastError();
+    return ZKP_E_CUDA;  // no CUDA device: there is no CPU path behind this ABI
+  }
+  zkp_ctx* c = new (std::nothrow) zkp_ctx();
+  if (!c) return ZKP_E_NOMEM;
+  c->device = device;
+  if (cudaSetDevice(device) != cudaSuccess) {
+    delete c;
+    return ZKP_E_CUDA;
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+    delete c;
+    return ZKP_E_CUDA;
+  }
+  c->num_sms = prop.multiProcessorCount;
+  if (stream) {
+    c->stream = (cudaStream_t)stream;
+  } else {
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+      delete c;
+      return ZKP_E_CUDA;
+    }
+    c->own_stream = true;
+  }
+  *out = c;
+  return ZKP_OK;
+}
+
+void zkp_ctx_destroy(zkp_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  for (auto& e : c->prof) {
+    cudaEventDestroy(e.a);
+    cudaEventDestroy(e.b);
+  }
+  for (auto e : c->ev_pool) cudaEventDestroy(e);
+  c->nn.release();
+  c->n.release();
+  DevBuf* bufs[] = {&c->table, &c->in0, &c->in1, &c->in2, &c->in3, &c->out0,
+                    &c->rp.range, &c->rp.x, &c->rp.r, &c->rp.w, &c->rp.swap, &c->rp.rr, &c->rp.c, &c->rp.digest,
+                    &c->rp.kind, &c->rp.resp_w, &c->rp.resp_r, &c->rp.rmul, &c->rp.v_range, &c->rp.v_cx, &c->rp.v_c,
+                    &c->rp.v_kind, &c->rp.v_resp_w, &c->rp.v_resp_r, &c->rp.v_digest, &c->rp.v_jobs_base,
+                    &c->rp.v_jobs_plain, &c->rp.v_jobs_tag, &c->rp.v_jobs_out, &c->rp.v_count, &c->rp.v_cmul,
+                    &c->rp.v_ok, &c->rp.v_accept, &c->rp.v_fault,
+                    &c->ck.n, &c->ck.sigma, &c->ck.r2, &c->ck.n0inv, &c->ck.rho, &c->ck.mask, &c->ck.out,
+                    &c->ck.accept, &c->ck.salt, &c->ck.aux};
+  for (DevBuf* b : bufs) b->release();
+  if (c->own_stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+const char* zkp_last_error(const zkp_ctx* c) { return c ? c->err.c_str() : "null context"; }
+int zkp_sm_count(const zkp_ctx* c) { return c ? c->num_sms : 0; }
+
+int zkp_sync(zkp_ctx* c) {
+  if (!c) return ZKP_E_ARG;
+  ZKP_CU(c, cudaStreamSynchronize(c->stream));
+  return ZKP_OK;
+}
+
+int zkp_profile_enable(zkp_ctx* c, int on) {
+  if (!c) return ZKP_E_ARG;
+  c->profiling = on != 0;
+  return ZKP_OK;
+}
+int zkp_profile_reset(zkp_ctx* c) {
+  if (!c) return ZKP_E_ARG;
+  cudaStreamSynchronize(c->stream);
+  for (auto& e : c->prof) {
+    c->ev_pool.push_back(e.a);
+    c->ev_pool.push_back(e.b);
+  }
+  c->prof.clear();
+  return ZKP_OK;
+}
+int zkp_profile_get(zkp_ctx* c, int kernel, double* ms_total, long long* launches, double* units) {
+  if (!c || kernel < 0 || kernel >= KID_COUNT) return ZKP_E_ARG;
+  ZKP_CU(c, cudaStreamSynchronize(c->stream));
+  double ms = 0, u = 0;
+  long long n = 0;
+  for (auto& e : c->prof) {
+    if (e.kid != kernel) continue;
+    float t = 0;
+    ZKP_CU(c, cudaEventElapsedTime(&t, e.a, e.b));
+    ms += t;
+    u += e.units;
+    ++n;
+  }
+  if (ms_total) *ms_total = ms;
+  if (launches) *launches = n;
+  if (units) *units = u;
+  return ZKP_OK;
+}
+
+int zkp_set_key(zkp_ctx* c, const uint32_t* n, int n_limbs) {
+  if (!c) return ZKP_E_ARG;
+  c->paillier = false;
+  if (!n || n_limbs <= 0 || (n_limbs % 4) || 2 * n_limbs > 256) return fail(c, ZKP_E_ARG, "n_limbs must be a multiple of 4, at most 128");
+  ZKP_CU(c, cudaSetDevice(c->device));
+  // nn = n * n (host schoolbook; once per key)
+  std::vector<uint32_t> nn((size_t)2 * n_limbs, 0u);
+  for (int i = 0; i < n_limbs; ++i) {
+    uint64_t carry = 0;
+    for (int j = 0; j < n_limbs; ++j) {
+      uint64_t t = (uint64_t)n[i] * n[j] + nn[i + j] + carry;
+      nn[i + j] = (uint32_t)t;
+      carry = t >> 32;
+    }
+    nn[i + n_limbs] = (uint32_t)carry;
+  }
+  int rc = setup_slot(c, c->nn, nn.data(), 2 * n_limbs, n, n_limbs);
+  if (rc) return rc;
+  rc = setup_slot(c, c->n, n, n_limbs, nullptr, 0);
+  if (rc) return rc;
+  // nR = n * R mod nn (Montgomery form of n, used by the Enc epilogue)
+  SharedKey k = c->nn.view();
+  ZKP_CU(c, launch_modmul_shared(k, 1, c->n.mod.as<uint32_t>(), c->n.S, nullptr, 0, 1, c->nn.nR.as<uint32_t>(), k.S, 1,
+                                 c->stream));
+  ZKP_CU(c, cudaStreamSynchronize(c->stream));
+  c->n_limbs = n_limbs;
+  c->paillier = true;
+  c->rp.prove_staged = c->rp.prove_done = c->rp.verify_staged = c->rp.verify_done = false;
+  return ZKP_OK;
+}
+
+int zkp_set_modulus(zkp_ctx* c, const uint32_t* mod, int mod_limbs, const uint32_t* exp, int exp_limbs) {
+  if (!c) return ZKP_E_ARG;
+  if (!exp || exp_limbs <= 0) return fail(c, ZKP_E_ARG, "exponent required");
+  ZKP_CU(c, cudaSetDevice(c->device));
+  c->paillier = false;
+  c->n.ready = false;
+  return setup_slot(c, c->nn, mod, mod_limbs, exp, exp_limbs);
+}
+
+int zkp_nn_limbs(const zkp_ctx* c) { return (c && c->nn.ready) ? c->nn.limbs : 0; }
+
+int zkp_modexp_shared(zkp_ctx* c, const uint32_t* bases, int base_limbs, int batch, uint32_t* out) {
+  if (!c) return ZKP_E_ARG;
+  if (!c->nn.ready) return fail(c, ZKP_E_STATE, "no key / modulus set");
+  if (batch < 0 || !bases || !out) return fail(c, ZKP_E_ARG, "null buffer or negative batch");
+  if (base_limbs <= 0 || base_limbs % 4 || base_limbs > c->nn.S) return fail(c, ZKP_E_ARG, "bad base_limbs");
+  if (batch == 0) return ZKP_OK;
+  ZKP_CU(c, cudaSetDevice(c->device));
+  const int ol = c->nn.limbs;
+  ZKP_CU(c, c->in0.ensure((size_t)batch * base_limbs * 4));
+  ZKP_CU(c, c->out0.ensure((size_t)batch * ol * 4));
+  ZKP_CU(c, ensure_table(c, c->nn.S, kTableShared));
+  ZKP_CU(c, cudaMemcpyAsync(c->in0.p, bases, (size_t)batch * base_limbs * 4, cudaMemcpyHostToDevice, c->stream));
+  {
+    ProfScope ps(c, KID_MODEXP_SHARED, batch);
+    ZKP_CU(c, launch_modexp_shared(c->nn.view(), c->in0.as<uint32_t>(), base_limbs, nullptr, 0, c->out0.as<uint32_t>(), ol,
+                                   batch, c->table.as<uint32_t>(), c->num_sms, c->stream));
+  }
+  ZKP_CU(c, cudaMemcpyAsync(out, c->out0.p, (size_t)batch * ol * 4, cudaMemcpyDeviceToHost, c->stream));
+  ZKP_CU(c, cudaStreamSynchronize(c->stream));
+  return ZKP_OK;
+}
+
+int zkp_paillier_enc(zkp_ctx* c, const uint32_t* m, int m_limbs, const uint32_t* r, int r_limbs, int batch,
+                     uint32_t* out) {
+  if (!c) return ZKP_E_ARG;
+  if (!c->paillier) return fail(c, ZKP_E_STATE, "zkp_set_key not called");
+  if (batch < 0 || !m || !r || !out) return fail(c, ZKP_E_ARG, "null buffer or negative batch");
+  if (m_limbs <= 0 || m_limbs % 4 || m_limbs > c->nn.S || r_limbs <= 0 || r_limbs % 4 || r_limbs > c->nn.S)
+    return fail(c, ZKP_E_ARG, "bad m_limbs / r_limbs");
+  if (batch == 0) return ZKP_OK;
+  ZKP_CU(c, cudaSetDevice(c->device));
+  const int ol = c->nn.limbs;
+  ZKP_CU(c, c->in0.ensure((size_t)batch * r_limbs * 4));
+  ZKP_CU(c, c->in1.ensure((size_t)batch * m_limbs * 4));
+  ZKP_CU(c, c->out0.ensure((size_t)batch * ol * 4));
+  ZKP_CU(c, ensure_table(c, c->nn.S, kTableShared));
+  ZKP_CU(c, cudaMemcpyAsync(c->in0.p, r, (size_t)batch * r_limbs * 4, cudaMemcpyHostToDevice, c->stream));
+  ZKP_CU(c, cudaMemcpyAsync(c->in1.p, m, (size_t)batch * m_limbs * 4, cudaMemcpyHostToDevice, c->stream));
+  {
+    ProfScope ps(c, KID_MODEXP_SHARED, batch);
+    ZKP_CU(c, launch_modexp_shared(c->nn.view(), c->in0.as<uint32_t>(), r_limbs, c->in1.as<uint32_t>(), m_limbs,
+                                   c->out0.as<uint32_t>(), ol, batch, c->table.as<uint32_t>(), c->num_sms, c->stream));
+  }
+  ZKP_CU(c, cudaMemcpyAsync(out, c->out0.p, (size_t)batch * ol * 4, cudaMemcpyDeviceToHost, c->stream));
+  ZKP_CU(c, cudaStreamSynchronize(c->stream));
+  return ZKP_OK;
+}
+
+int zkp_modexp_var(zkp_ctx* c, const uint32_t* bases, const uint32_t* exps, int exp_limbs, int exp_bits,
+                   const uint32_t* mods, int mod_limbs, int per, int batch, uint32_t* out) {
+  if (!c) return ZKP_E_ARG;
+  if (batch < 0 || !bases || !exps || !mods || !out) return fail(c, ZKP_E_ARG, "null buffer or negative batch");
+  if (mod_limbs <= 0 || mod_limbs % 4 || exp_limbs <= 0 || exp_bits <= 0 || exp_bits > 32 * exp_limbs || per <= 0)
+    return fail(c, ZKP_E_ARG, "bad widths");
+  int S = pick_width(mod_limbs);
+  if (S < 0) return fail(c, ZKP_E_ARG, "modulus wider than 8192 bits");
+  if (batch == 0) return ZKP_OK;
+  const int count = (batch + per - 1) / per;
+  for (int i = 0; i < count; ++i)
+    if (!(mods[(size_t)i * mod_limbs] & 1u)) return fail(c, ZKP_E_ARG, "every modulus must be odd");
+  ZKP_CU(c, cudaSetDevice(c->device));
+  ZKP_CU(c, c->in0.ensure((size_t)batch * mod_limbs * 4));
+  ZKP_CU(c, c->in1.ensure((size_t)count * exp_limbs * 4));
+  ZKP_CU(c, c->in2.ensure((size_t)count * mod_limbs * 4));
+  ZKP_CU(c, c->in3.ensure((size_t)count * (S + 1) * 4));
+  ZKP_CU(c, c->out0.ensure((size_t)batch * mod_limbs * 4));
+  ZKP_CU(c, ensure_table(c, S, kTableVar));
+  uint32_t* d_r2 = c->in3.as<uint32_t>();
+  uint32_t* d_n0 = d_r2 + (size_t)count * S;
+  ZKP_CU(c, cudaMemcpyAsync(c->in0.p, bases, (size_t)batch * mod_limbs * 4, cudaMemcpyHostToDevice, c->stream));
+  ZKP_CU(c, cudaMemcpyAsync(c->in1.p, exps, (size_t)count * exp_limbs * 4, cudaMemcpyHostToDevice, c->stream));
+  ZKP_CU(c, cudaMemcpyAsync(c->in2.p, mods, (size_t)count * mod_limbs * 4, cudaMemcpyHostToDevice, c->stream));
+  {
+    ProfScope ps(c, KID_OTHER, count);
+    ZKP_CU(c, launch_mont_setup(c->in2.as<uint32_t>(), mod_limbs, S, count, d_r2, d_n0, c->stream));
+  }
+  {
+    ProfScope ps(c, KID_MODEXP_VAR, batch);
+    ZKP_CU(c, launch_modexp_var(c->in0.as<uint32_t>(), c->in2.as<uint32_t>(), mod_limbs, d_r2, d_n0, c->in1.as<uint32_t>(),
+                                exp_limbs, exp_bits, per, c->out0.as<uint32_t>(), batch, S, c->table.as<uint32_t>(),
+                                c->num_sms, c->stream));
+  }
+  ZKP_CU(c, cudaMemcpyAsync(out, c->out0.p, (size_t)batch * mod_limbs * 4, cudaMemcpyDeviceToHost, c->stream));
+  ZKP_CU(c, cudaStreamSynchronize(c->stream));
+  return ZKP_OK;
+}
+
+int zkp_modmul(zkp_ctx* c, int which_nn, const uint32_t* a, const uint32_t* b, int b_per, int batch, uint32_t* out) {
+  if (!c) return ZKP_E_ARG;
+  KeySlot& slot = which_nn ? c->nn : c->n;
+  if (!slot.ready) return fail(c, ZKP_E_STATE, "no key set");
+  if (batch < 0 || !a || !b || !out || b_per <= 0) return fail(c, ZKP_E_ARG, "null buffer / bad batch");
+  if (batch == 0) return ZKP_OK;
+  ZKP_CU(c, cudaSetDevice(c->device));
+  const int w = slot.limbs;
+  const int nb = (batch + b_per - 1) / b_per;
+  ZKP_CU(c, c->in0.ensure((size_t)batch * w * 4));
+  ZKP_CU(c, c->in1.ensure((size_t)nb * w * 4));
+  ZKP_CU(c, c->out0.ensure((size_t)batch * w * 4));
+  ZKP_CU(c, cudaMemcpyAsync(c->in0.p, a, (size_t)batch * w * 4, cudaMemcpyHostToDevice, c->stream));
+  ZKP_CU(c, cudaMemcpyAsync(c->in1.p, b, (size_t)nb * w * 4, cudaMemcpyHostToDevice, c->stream));
+  {
+    ProfScope ps(c, KID_MODMUL, batch);
+    ZKP_CU(c, launch_modmul_shared(slot.view(), 0, c->in0.as<uint32_t>(), w, c->in1.as<uint32_t>(), w, b_per,
+                                   c->out0.as<uint32_t>(), w, batch, c->stream));
+  }
+  ZKP_CU(c, cudaMemcpyAsync(out, c->out0.p, (size_t)batch * w * 4, cudaMemcpyDeviceToHost, c->stream));
+  ZKP_CU(c, cudaStreamSynchronize(c->stream));
+  return ZKP_OK;
+}
+
+int zkp_imad_peak(zkp_ctx* c, int variant, double* mads_per_s) {
+  if (!c || !mads_per_s) return ZKP_E_ARG;
+  ZKP_CU(c, cudaSetDevice(c->device));
+  ZKP_CU(c, c->out0.ensure(256));
+  const int blocks = c->num_sms * 8;
+  double ops = 0;
+  cudaEvent_t a, b;
+  ZKP_CU(c, cudaEventCreate(&a));
+  ZKP_CU(c, cudaEventCreate(&b));
+  // warm-up, then a launch long enough (~100+ ms) to settle at sustained clocks
+  ZKP_CU(c, launch_imad_peak(variant, blocks, 2000, c->out0.as<uint32_t>(), &ops, c->stream));
+  ZKP_CU(c, cudaStreamSynchronize(c->stream));
+  ZKP_CU(c, cudaEventRecord(a, c->stream));
+  ZKP_CU(c, launch_imad_peak(variant, blocks, 400000, c->out0.as<uint32_t>(), &ops, c->stream));
+  ZKP_CU(c, cudaEventRecord(b, c->stream));
+  ZKP_CU(c, cudaStreamSynchronize(c->stream));
+  float ms = 0;
+  ZKP_CU(c, cudaEventElapsedTime(&ms, a, b));
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  *mads_per_s = ops / (ms * 1e-3);
+  return ZKP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,138 @@
+// Internal state behind the opaque zkp_ctx of include/zkp_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/zkp_b200.h"
+#include "kernels.h"
+
+namespace zkp {
+
+// Growable device allocation (never shrinks; freed with the context).
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + (bytes >> 3) + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class U>
+  U* as() const { return reinterpret_cast<U*>(p); }
+};
+
+// One shared (modulus, exponent) pair resident on the device.
+struct KeySlot {
+  int S = 0;          // kernel width (limbs)
+  int limbs = 0;      // caller's width of the modulus
+  DevBuf mod, r2, nR, sched, n0;
+  std::vector<uint32_t> h_mod;  // host copy, S limbs
+  int nsteps = 0;
+  uint32_t n0inv = 0;
+  bool ready = false;
+  SharedKey view() const {
+    SharedKey k;
+    k.mod = mod.as<uint32_t>();
+    k.r2 = r2.as<uint32_t>();
+    k.nR = nR.as<uint32_t>();
+    k.sched = sched.as<uint32_t>();
+    k.nsteps = nsteps;
+    k.n0inv = n0inv;
+    k.S = S;
+    return k;
+  }
+  void release() {
+    mod.release(); r2.release(); nR.release(); sched.release(); n0.release();
+    ready = false;
+  }
+};
+
+enum KernelId { KID_MODEXP_SHARED = 0, KID_MODEXP_VAR = 1, KID_MODMUL = 2, KID_SHA = 3, KID_OTHER = 4, KID_COUNT = 5 };
+
+struct ProfEntry {
+  int kid;
+  cudaEvent_t a, b;
+  double units;
+};
+
+struct RpState {  // RangeProofNi staging (api_rangeproof.cu)
+  int batch = 0, ef = 0, w_limbs = 0;
+  bool prove_staged = false, prove_done = false, verify_staged = false, verify_done = false;
+  bool verify_from_prove = false;
+  long long enc_count = 0;
+  // prove
+  DevBuf range, x, r, w, swap, rr;          // rr = [r1 | r2] bases, w = [w1' | w2'] plaintexts (after prep)
+  DevBuf c, digest, kind, resp_w, resp_r;   // c = [c1 | c2]
+  DevBuf rmul;                              // r*r1, r*r2 mod n
+  // verify
+  DevBuf v_range, v_cx, v_c, v_kind, v_resp_w, v_resp_r, v_digest;
+  DevBuf v_jobs_base, v_jobs_plain, v_jobs_tag, v_jobs_out, v_count, v_cmul, v_ok, v_accept, v_fault;
+};
+
+struct CkState {  // NiCorrectKeyProof staging (api_correctkey.cu)
+  int batch = 0, n_limbs = 0, S = 0;
+  bool staged = false, done = false;
+  DevBuf n, sigma, r2, n0inv, rho, mask, out, accept, salt, aux;
+  int salt_len = 0;
+};
+
+}  // namespace zkp
+
+struct zkp_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int num_sms = 0;
+  std::string err;
+  zkp::KeySlot nn;   // modulus n^2 (or the generic shared modulus), exponent n
+  zkp::KeySlot n;    // modulus n
+  bool paillier = false;
+  int n_limbs = 0;   // caller's width of n after zkp_set_key
+  zkp::DevBuf table;                 // window-table scratch
+  zkp::DevBuf in0, in1, in2, in3, out0;  // generic staging for the one-shot calls
+  bool profiling = false;
+  std::vector<zkp::ProfEntry> prof;
+  std::vector<cudaEvent_t> ev_pool;
+  zkp::RpState rp;
+  zkp::CkState ck;
+};
+
+namespace zkp {
+
+int fail(zkp_ctx* c, int code, const char* what);
+int fail_cuda(zkp_ctx* c, cudaError_t e, const char* what);
+
+#define ZKP_CU(ctx, call)                                        \
+  do {                                                           \
+    cudaError_t e__ = (call);                                    \
+    if (e__ != cudaSuccess) return zkp::fail_cuda(ctx, e__, #call); \
+  } while (0)
+
+// Scoped device-time accounting of one kernel launch (no-op unless profiling).
+struct ProfScope {
+  zkp_ctx* c;
+  int idx = -1;
+  ProfScope(zkp_ctx* ctx, int kid, double units);
+  ~ProfScope();
+};
+
+// table scratch large enough for K1/K2 at width S
+cudaError_t ensure_table(zkp_ctx* c, int S, int entries);
+
+// Montgomery/key helpers (api_core.cu)
+int setup_slot(zkp_ctx* c, KeySlot& slot, const uint32_t* mod, int limbs, const uint32_t* exp, int exp_limbs);
+
+}  // namespace zkp

@@ -1,0 +1,353 @@
+// Cooperative fixed-width multiword arithmetic for sm_100a.
+//
+// One big integer of S = T*L 32-bit limbs is spread over a group of T adjacent
+// lanes of a warp (T in {4,8,16,32}); lane g of the group holds limbs
+// [g*L, (g+1)*L) in registers.  All groups of a warp run in lock-step, so every
+// shuffle/ballot is issued with the full-warp mask and a sub-warp width of T.
+//
+// The arithmetic this replaces in the reference is GMP's mpz_powm / mpz_mul /
+// mpz_mod underneath curv-kzen's BigInt::{mod_pow, mod_mul} and kzen-paillier's
+// Paillier::encrypt_with_chosen_randomness (call sites: reference
+// src/zkproofs/range_proof.rs:161-187,280-291,325-334; correct_key_ni.rs:90-93).
+//
+// Machine unit: the 32x32+64 -> 64 multiply-add.  A mad.lo.cc.u32 / madc.hi.cc.u32
+// pair on the same operands is fused by ptxas into ONE IMAD.WIDE.U32(.X) with
+// carry-in/out in a predicate.  IMAD.WIDE needs 64-bit aligned register pairs, so
+// the accumulator is kept as TWO arrays: one takes the even-limb products (pairs
+// at limbs 2m,2m+1), the other the odd-limb products (pairs at 2m+1,2m+2).  The
+// per-step division by 2^32 swaps their roles, and the stale array is moved down
+// one aligned pair through the 3-operand form d = a*b + c, so a CIOS step is
+// 2L IMAD.WIDE + 3 SHFL + a handful of adds, with no register moves.
+#pragma once
+#include <stdint.h>
+
+namespace zkp {
+
+#define ZKP_FULL 0xffffffffu
+
+// ---- single-instruction carry-chain helpers (PTX) -------------------------
+__device__ __forceinline__ void add_cc(uint32_t& r, uint32_t a) {
+  asm volatile("add.cc.u32 %0, %0, %1;" : "+r"(r) : "r"(a));
+}
+__device__ __forceinline__ void addc_cc(uint32_t& r, uint32_t a) {
+  asm volatile("addc.cc.u32 %0, %0, %1;" : "+r"(r) : "r"(a));
+}
+__device__ __forceinline__ void addc(uint32_t& r, uint32_t a) {
+  asm volatile("addc.u32 %0, %0, %1;" : "+r"(r) : "r"(a));
+}
+__device__ __forceinline__ void sub_cc(uint32_t& r, uint32_t a, uint32_t b) {
+  asm volatile("sub.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+}
+__device__ __forceinline__ void subc_cc(uint32_t& r, uint32_t a, uint32_t b) {
+  asm volatile("subc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+}
+__device__ __forceinline__ uint32_t subc_out() {  // 0 if no borrow, 0xffffffff if borrow
+  uint32_t r;
+  asm volatile("subc.u32 %0, 0, 0;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t addc_out() {  // carry flag -> 0/1
+  uint32_t r;
+  asm volatile("addc.u32 %0, 0, 0;" : "=r"(r));
+  return r;
+}
+// (hi:lo) += a*b, starting a carry chain
+__device__ __forceinline__ void mad_wide_cc(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
+  asm volatile("mad.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.cc.u32 %1, %2, %3, %1;"
+               : "+r"(lo), "+r"(hi) : "r"(a), "r"(b));
+}
+// (hi:lo) += a*b + carry, continuing a carry chain
+__device__ __forceinline__ void madc_wide_cc(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
+  asm volatile("madc.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.cc.u32 %1, %2, %3, %1;"
+               : "+r"(lo), "+r"(hi) : "r"(a), "r"(b));
+}
+
+// (d1:d0) = a*b + (c1:c0) + carry, continuing a carry chain; the destination pair
+// may differ from the addend pair, which is how the accumulator is shifted down
+// by one aligned limb pair for free.
+__device__ __forceinline__ void madc_wide3_cc(uint32_t& d0, uint32_t& d1, uint32_t a, uint32_t b, uint32_t c0,
+                                              uint32_t c1) {
+  asm volatile("madc.lo.cc.u32 %0, %2, %3, %4;\n\tmadc.hi.cc.u32 %1, %2, %3, %5;"
+               : "=&r"(d0), "=r"(d1) : "r"(a), "r"(b), "r"(c0), "r"(c1));
+}
+
+template <int T, int L>
+struct Mp {
+  static_assert(T == 4 || T == 8 || T == 16 || T == 32, "group width");
+  static_assert(L >= 2 && (L % 2) == 0, "limbs per lane must be even");
+  static constexpr int S = T * L;  // limbs per integer
+  static constexpr uint32_t GM = (T == 32) ? 0xffffffffu : ((1u << T) - 1u);
+
+  // Group-wide resolution of per-lane carries (or borrows).  `gen` = this lane
+  // produced a carry out, `prop` = this lane would pass an incoming carry on
+  // (gen and prop are never both set).  Returns the carry INTO this lane and,
+  // in `top`, the carry out of the most significant lane of the group.
+  static __device__ __forceinline__ uint32_t resolve(bool gen, bool prop, int lane, uint32_t& top) {
+    uint32_t gb = __ballot_sync(ZKP_FULL, gen);
+    uint32_t pb = __ballot_sync(ZKP_FULL, prop);
+    int base = lane & ~(T - 1);
+    int g = lane & (T - 1);
+    if (T == 32) {
+      uint64_t a = (uint64_t)(gb | pb), b = (uint64_t)gb;
+      uint64_t s = a + b;
+      uint64_t cin = s ^ a ^ b;
+      top = (uint32_t)(s >> 32) & 1u;
+      return (uint32_t)(cin >> g) & 1u;
+    } else {
+      uint32_t G = (gb >> base) & GM, P = (pb >> base) & GM;
+      uint32_t a = G | P;
+      uint32_t s = a + G;
+      uint32_t cin = s ^ a ^ G;
+      top = (s >> T) & 1u;
+      return (cin >> g) & 1u;
+    }
+  }
+
+  static __device__ __forceinline__ bool all_ones(const uint32_t (&x)[L]) {
+    uint32_t m = x[0];
+#pragma unroll
+    for (int j = 1; j < L; ++j) m &= x[j];
+    return m == 0xffffffffu;
+  }
+  static __device__ __forceinline__ bool all_zero(const uint32_t (&x)[L]) {
+    uint32_t m = x[0];
+#pragma unroll
+    for (int j = 1; j < L; ++j) m |= x[j];
+    return m == 0u;
+  }
+
+  // x += c (c in {0,1}) rippled through this lane's limbs only.
+  static __device__ __forceinline__ void add_small(uint32_t (&x)[L], uint32_t c) {
+    add_cc(x[0], c);
+#pragma unroll
+    for (int j = 1; j < L - 1; ++j) addc_cc(x[j], 0);
+    addc(x[L - 1], 0);
+  }
+  static __device__ __forceinline__ void sub_small(uint32_t (&x)[L], uint32_t c) {
+    uint32_t t;
+    sub_cc(t, x[0], c);
+    x[0] = t;
+#pragma unroll
+    for (int j = 1; j < L; ++j) {
+      subc_cc(t, x[j], 0);
+      x[j] = t;
+    }
+  }
+
+  // d = a - b over the whole group. Returns the final borrow (1 iff a < b).
+  static __device__ __forceinline__ uint32_t sub_full(uint32_t (&d)[L], const uint32_t (&a)[L], const uint32_t (&b)[L], int lane) {
+    sub_cc(d[0], a[0], b[0]);
+#pragma unroll
+    for (int j = 1; j < L; ++j) subc_cc(d[j], a[j], b[j]);
+    uint32_t bo = subc_out() & 1u;
+    uint32_t top;
+    uint32_t bin = resolve(bo != 0, all_zero(d), lane, top);
+    sub_small(d, bin);
+    return top;
+  }
+
+  // a += b over the whole group. Returns the carry out of the top lane.
+  static __device__ __forceinline__ uint32_t add_full(uint32_t (&a)[L], const uint32_t (&b)[L], int lane) {
+    add_cc(a[0], b[0]);
+#pragma unroll
+    for (int j = 1; j < L; ++j) addc_cc(a[j], b[j]);
+    uint32_t co = addc_out();
+    uint32_t top;
+    uint32_t cin = resolve(co != 0, all_ones(a), lane, top);
+    add_small(a, cin);
+    return top;
+  }
+
+  // 1 iff a >= b (group-wide unsigned compare)
+  static __device__ __forceinline__ uint32_t geq(const uint32_t (&a)[L], const uint32_t (&b)[L], int lane) {
+    uint32_t d[L];
+    return sub_full(d, a, b, lane) ^ 1u;
+  }
+
+  // Group-wide equality; result uniform in the group.
+  static __device__ __forceinline__ bool equal(const uint32_t (&a)[L], const uint32_t (&b)[L], int lane) {
+    uint32_t m = 0;
+#pragma unroll
+    for (int j = 0; j < L; ++j) m |= a[j] ^ b[j];
+    uint32_t nb = __ballot_sync(ZKP_FULL, m != 0);
+    int base = lane & ~(T - 1);
+    return ((nb >> base) & GM) == 0u;
+  }
+
+  // Turn the redundant accumulator (L+1 significant limbs per lane: u[L] is the
+  // lane's overflow, weight 2^(32L)) into the canonical residue r in [0, n):
+  // push overflows one lane up, resolve carries, subtract n once if needed.
+  // Pre-condition: the represented value is < 2n.
+  static __device__ __forceinline__ void finish(uint32_t (&r)[L], uint32_t (&u)[L + 2], const uint32_t (&n)[L], int lane) {
+    const int g = lane & (T - 1);
+    uint32_t ov = __shfl_up_sync(ZKP_FULL, u[L], 1, T);
+    if (g == 0) ov = 0;
+    uint32_t x[L];
+#pragma unroll
+    for (int j = 0; j < L; ++j) x[j] = u[j];
+    add_cc(x[0], ov);
+#pragma unroll
+    for (int j = 1; j < L; ++j) addc_cc(x[j], 0);
+    uint32_t co = addc_out();
+    uint32_t topc;
+    uint32_t cin = resolve(co != 0, all_ones(x), lane, topc);
+    add_small(x, cin);
+    // value >= 2^(32 S) ?  (top lane's own overflow limb, plus the resolved carry)
+    uint32_t hi = __shfl_sync(ZKP_FULL, u[L], T - 1, T) + topc;
+    uint32_t d[L];
+    uint32_t borrow = sub_full(d, x, n, lane);
+    bool take = (hi != 0) || (borrow == 0);
+#pragma unroll
+    for (int j = 0; j < L; ++j) r[j] = take ? d[j] : x[j];
+  }
+
+  // X[0..L+1] += (a[0], a[2], ...) * b : the even-limb products, one carry chain
+  static __device__ __forceinline__ void mad_even(uint32_t (&X)[L + 2], const uint32_t (&a)[L], uint32_t b) {
+    mad_wide_cc(X[0], X[1], a[0], b);
+#pragma unroll
+    for (int j = 2; j < L; j += 2) madc_wide_cc(X[j], X[j + 1], a[j], b);
+    addc_cc(X[L], 0);
+    addc(X[L + 1], 0);
+  }
+  // Z[0..L+1] += (a[1], a[3], ...) * b : the odd-limb products (Z[w] has weight 2^(32(w+1)))
+  static __device__ __forceinline__ void mad_odd(uint32_t (&Z)[L + 2], const uint32_t (&a)[L], uint32_t b) {
+    mad_wide_cc(Z[0], Z[1], a[1], b);
+#pragma unroll
+    for (int j = 2; j < L; j += 2) madc_wide_cc(Z[j], Z[j + 1], a[j + 1], b);
+    addc_cc(Z[L], 0);
+    addc(Z[L + 1], 0);
+  }
+
+  // One CIOS step  acc = (acc + a*b + q*n) / 2^32  on the split accumulator.
+  // On entry X is the even-aligned array (X[w] at limb w) and Y is the array
+  // that was even-aligned one step ago (Y[w] at limb w-1, Y[0] belongs to the
+  // lane below).  On exit Y is the even-aligned array and X the stale one, so
+  // callers alternate step(X,Y) / step(Y,X).  Both operand-carrying IMAD.WIDE
+  // chains read/write 64-bit aligned register pairs only: no MOVs.
+  static __device__ __forceinline__ void cios_step(uint32_t (&X)[L + 2], uint32_t (&Y)[L + 2], const uint32_t (&a)[L],
+                                                   const uint32_t (&n)[L], uint32_t b, uint32_t n0inv, int g) {
+    uint32_t in = __shfl_down_sync(ZKP_FULL, Y[0], 1, T);
+    if (g == T - 1) in = 0;
+    add_cc(Y[L], in);
+    addc(Y[L + 1], 0);
+    uint32_t Z[L + 2];
+    add_cc(X[0], Y[1]);  // limb 0; the carry enters the odd chain at limb 1
+#pragma unroll
+    for (int j = 0; j < L; j += 2) madc_wide3_cc(Z[j], Z[j + 1], a[j + 1], b, Y[j + 2], Y[j + 3]);
+    Z[L] = addc_out();
+    Z[L + 1] = 0;
+    mad_even(X, a, b);
+    uint32_t q = __shfl_sync(ZKP_FULL, X[0], 0, T) * n0inv;
+    mad_even(X, n, q);
+    mad_odd(Z, n, q);
+#pragma unroll
+    for (int j = 0; j < L + 2; ++j) Y[j] = Z[j];
+  }
+
+  // r = a * b * 2^(-32 S) mod n     (CIOS Montgomery; a, b < n; n odd;
+  // n0inv = -n^{-1} mod 2^32).  r may alias a or b.
+  static __device__ __forceinline__ void mont_mul(uint32_t (&r)[L], const uint32_t (&a)[L], const uint32_t (&b)[L],
+                                                  const uint32_t (&n)[L], uint32_t n0inv, int lane) {
+    const int g = lane & (T - 1);
+    uint32_t E[L + 2], O[L + 2];
+#pragma unroll
+    for (int j = 0; j < L + 2; ++j) E[j] = O[j] = 0;
+#pragma unroll 1
+    for (int owner = 0; owner < T; ++owner) {
+#pragma unroll
+      for (int j = 0; j < L; j += 2) {
+        uint32_t b0 = __shfl_sync(ZKP_FULL, b[j], owner, T);
+        uint32_t b1 = __shfl_sync(ZKP_FULL, b[j + 1], owner, T);
+        cios_step(E, O, a, n, b0, n0inv, g);
+        cios_step(O, E, a, n, b1, n0inv, g);
+      }
+    }
+    // merge: value = E + (O >> 32), O[0] going to the lane below
+    uint32_t in = __shfl_down_sync(ZKP_FULL, O[0], 1, T);
+    if (g == T - 1) in = 0;
+    add_cc(O[L], in);
+    addc(O[L + 1], 0);
+    add_cc(E[0], O[1]);
+#pragma unroll
+    for (int j = 1; j <= L; ++j) addc_cc(E[j], O[j + 1]);
+    addc(E[L + 1], 0);
+    finish(r, E, n, lane);
+  }
+
+  static __device__ __forceinline__ void mont_sqr(uint32_t (&r)[L], const uint32_t (&a)[L], const uint32_t (&n)[L],
+                                                  uint32_t n0inv, int lane) {
+    mont_mul(r, a, a, n, n0inv, lane);
+  }
+
+  // x = 2x mod n  (x < n)
+  static __device__ __forceinline__ void mod_double(uint32_t (&x)[L], const uint32_t (&n)[L], int lane) {
+    const int g = lane & (T - 1);
+    uint32_t topbit = x[L - 1] >> 31;
+    uint32_t in = __shfl_up_sync(ZKP_FULL, topbit, 1, T);
+    if (g == 0) in = 0;
+    uint32_t hi = __shfl_sync(ZKP_FULL, topbit, T - 1, T);
+#pragma unroll
+    for (int j = L - 1; j > 0; --j) x[j] = (x[j] << 1) | (x[j - 1] >> 31);
+    x[0] = (x[0] << 1) | in;
+    uint32_t d[L];
+    uint32_t borrow = sub_full(d, x, n, lane);
+    bool take = (hi != 0) || (borrow == 0);
+#pragma unroll
+    for (int j = 0; j < L; ++j) x[j] = take ? d[j] : x[j];
+  }
+
+  // ---- coalesced, vectorised limb moves (this lane's L limbs) -------------
+  static __device__ __forceinline__ void load(uint32_t (&x)[L], const uint32_t* p) {
+    if (L % 4 == 0) {
+      const uint4* q = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+      for (int j = 0; j < L / 4; ++j) {
+        uint4 v = q[j];
+        x[4 * j] = v.x; x[4 * j + 1] = v.y; x[4 * j + 2] = v.z; x[4 * j + 3] = v.w;
+      }
+    } else {
+      const uint2* q = reinterpret_cast<const uint2*>(p);
+#pragma unroll
+      for (int j = 0; j < L / 2; ++j) {
+        uint2 v = q[j];
+        x[2 * j] = v.x; x[2 * j + 1] = v.y;
+      }
+    }
+  }
+  static __device__ __forceinline__ void store(uint32_t* p, const uint32_t (&x)[L]) {
+    if (L % 4 == 0) {
+      uint4* q = reinterpret_cast<uint4*>(p);
+#pragma unroll
+      for (int j = 0; j < L / 4; ++j) q[j] = make_uint4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+    } else {
+      uint2* q = reinterpret_cast<uint2*>(p);
+#pragma unroll
+      for (int j = 0; j < L / 2; ++j) q[j] = make_uint2(x[2 * j], x[2 * j + 1]);
+    }
+  }
+  // Load a narrower integer (`limbs` <= S limbs, multiple of 2) zero-extended.
+  static __device__ __forceinline__ void load_ext(uint32_t (&x)[L], const uint32_t* p, int limbs, int g) {
+#pragma unroll
+    for (int j = 0; j < L; j += 2) {
+      int idx = g * L + j;
+      uint2 v = make_uint2(0u, 0u);
+      if (idx < limbs) v = *reinterpret_cast<const uint2*>(p + idx);
+      x[j] = v.x; x[j + 1] = v.y;
+    }
+  }
+  // Store only the low `limbs` limbs (multiple of 2) of the integer.
+  static __device__ __forceinline__ void store_ext(uint32_t* p, const uint32_t (&x)[L], int limbs, int g) {
+#pragma unroll
+    for (int j = 0; j < L; j += 2) {
+      int idx = g * L + j;
+      if (idx < limbs) *reinterpret_cast<uint2*>(p + idx) = make_uint2(x[j], x[j + 1]);
+    }
+  }
+  static __device__ __forceinline__ void set_small(uint32_t (&x)[L], uint32_t v, int g) {
+#pragma unroll
+    for (int j = 0; j < L; ++j) x[j] = 0;
+    if (g == 0) x[0] = v;
+  }
+};
+
+}  // namespace zkp

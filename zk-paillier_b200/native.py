@@ -1,0 +1,330 @@
+"""ctypes binding of the C ABI in include/zkp_b200.h.
+
+Integers cross as little-endian uint32 limb arrays (numpy, C-contiguous).  There
+is no CPU implementation behind any of these calls: if libzkp_b200.so is missing
+or no CUDA device is present, they raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libzkp_b200.so")
+
+ZKP_OK = 0
+RP_OPEN, RP_MASK1, RP_MASK2 = 0, 1, 2
+CK_M2 = 11
+KID_MODEXP_SHARED, KID_MODEXP_VAR, KID_MODMUL, KID_SHA, KID_OTHER = range(5)
+
+_u32p = C.POINTER(C.c_uint32)
+_u8p = C.POINTER(C.c_uint8)
+
+# name -> (restype, argtypes); every symbol include/zkp_b200.h declares
+SIGNATURES = {
+    "zkp_ctx_create": (C.c_int, [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "zkp_ctx_destroy": (None, [C.c_void_p]),
+    "zkp_last_error": (C.c_char_p, [C.c_void_p]),
+    "zkp_version": (C.c_int, []),
+    "zkp_sm_count": (C.c_int, [C.c_void_p]),
+    "zkp_sync": (C.c_int, [C.c_void_p]),
+    "zkp_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
+    "zkp_profile_reset": (C.c_int, [C.c_void_p]),
+    "zkp_profile_get": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.POINTER(C.c_double)]),
+    "zkp_set_key": (C.c_int, [C.c_void_p, _u32p, C.c_int]),
+    "zkp_set_modulus": (C.c_int, [C.c_void_p, _u32p, C.c_int, _u32p, C.c_int]),
+    "zkp_nn_limbs": (C.c_int, [C.c_void_p]),
+    "zkp_modexp_shared": (C.c_int, [C.c_void_p, _u32p, C.c_int, C.c_int, _u32p]),
+    "zkp_paillier_enc": (C.c_int, [C.c_void_p, _u32p, C.c_int, _u32p, C.c_int, C.c_int, _u32p]),
+    "zkp_modexp_var": (C.c_int, [C.c_void_p, _u32p, _u32p, C.c_int, C.c_int, _u32p, C.c_int, C.c_int, C.c_int, _u32p]),
+    "zkp_modmul": (C.c_int, [C.c_void_p, C.c_int, _u32p, _u32p, C.c_int, C.c_int, _u32p]),
+    "zkp_sha256_transcript": (C.c_int, [C.c_void_p, _u32p, C.c_int, C.c_int, C.c_int, _u8p]),
+    "zkp_rangeproof_ni_prove": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, _u32p, _u32p, _u32p, _u32p, _u8p, _u32p, _u32p,
+                                          _u32p, _u32p, _u8p, _u8p, _u32p, _u32p]),
+    "zkp_rp_prove_stage": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, _u32p, _u32p, _u32p, _u32p, _u8p, _u32p, _u32p]),
+    "zkp_rp_prove_run": (C.c_int, [C.c_void_p]),
+    "zkp_rp_prove_fetch": (C.c_int, [C.c_void_p, _u32p, _u32p, _u8p, _u8p, _u32p, _u32p]),
+    "zkp_rangeproof_ni_verify": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, _u32p, _u32p, _u32p, _u32p, _u8p, _u32p, _u32p,
+                                           _u8p, _u8p, _u8p]),
+    "zkp_rp_verify_stage": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, _u32p, _u32p, _u32p, _u32p, _u8p, _u32p, _u32p]),
+    "zkp_rp_verify_stage_from_prove": (C.c_int, [C.c_void_p, _u32p]),
+    "zkp_rp_verify_run": (C.c_int, [C.c_void_p]),
+    "zkp_rp_verify_fetch": (C.c_int, [C.c_void_p, _u8p, _u8p, _u8p]),
+    "zkp_rp_verify_enc_count": (C.c_longlong, [C.c_void_p]),
+    "zkp_correct_key_ni_verify": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _u32p, _u32p, _u8p, C.c_int, _u8p, _u32p]),
+    "zkp_ck_verify_stage": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _u32p, _u32p, _u8p, C.c_int]),
+    "zkp_ck_verify_run": (C.c_int, [C.c_void_p]),
+    "zkp_ck_verify_fetch": (C.c_int, [C.c_void_p, _u8p, _u32p]),
+    "zkp_imad_peak": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double)]),
+}
+
+_lib = None
+
+
+class ZkpError(RuntimeError):
+    pass
+
+
+def load():
+    """Load libzkp_b200.so (built in-tree by `make lib` / __graft_entry__.build())."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ZkpError(f"{LIB_PATH} is not built (run `make lib`); there is no CPU fallback")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+# ---- limb helpers -----------------------------------------------------------
+def to_limbs(x: int, limbs: int) -> np.ndarray:
+    return np.frombuffer(int(x).to_bytes(limbs * 4, "little"), dtype="<u4").copy()
+
+
+def from_limbs(a) -> int:
+    return int.from_bytes(np.ascontiguousarray(a, dtype="<u4").tobytes(), "little")
+
+
+def ints_to_limbs(xs, limbs: int) -> np.ndarray:
+    """list (possibly nested) of non-negative ints -> uint32 array [..., limbs]."""
+    arr = np.asarray(xs, dtype=object)
+    flat = arr.reshape(-1)
+    buf = b"".join(int(v).to_bytes(limbs * 4, "little") for v in flat)
+    return np.frombuffer(buf, dtype="<u4").reshape(arr.shape + (limbs,)).copy()
+
+
+def limbs_to_ints(a):
+    a = np.ascontiguousarray(a, dtype="<u4")
+    limbs = a.shape[-1]
+    raw = a.tobytes()
+    n = a.size // limbs
+    vals = [int.from_bytes(raw[i * limbs * 4:(i + 1) * limbs * 4], "little") for i in range(n)]
+    return np.asarray(vals + [None], dtype=object)[:-1].reshape(a.shape[:-1]).tolist() if a.ndim > 1 else vals[0]
+
+
+def _p32(a):
+    return None if a is None else a.ctypes.data_as(_u32p)
+
+
+def _p8(a):
+    return None if a is None else a.ctypes.data_as(_u8p)
+
+
+def _c32(a):
+    a = np.ascontiguousarray(a, dtype=np.uint32)
+    return a
+
+
+def _c8(a):
+    return np.ascontiguousarray(a, dtype=np.uint8)
+
+
+class Context:
+    """One engine context = one GPU (zkp_ctx).  Single-threaded."""
+
+    def __init__(self, device: int = 0, stream=None):
+        self._lib = load()
+        h = C.c_void_p()
+        rc = self._lib.zkp_ctx_create(int(device), C.c_void_p(stream) if stream else None, C.byref(h))
+        if rc != ZKP_OK:
+            raise ZkpError(f"zkp_ctx_create(device={device}) failed with {rc}: no usable CUDA device (no CPU fallback)")
+        self._h = h
+        self.device = device
+        self.n_limbs = 0
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.zkp_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _ck(self, rc):
+        if rc != ZKP_OK:
+            raise ZkpError(f"zkp error {rc}: {self._lib.zkp_last_error(self._h).decode()}")
+
+    # -- misc
+    @property
+    def sm_count(self):
+        return self._lib.zkp_sm_count(self._h)
+
+    def sync(self):
+        self._ck(self._lib.zkp_sync(self._h))
+
+    def profile_enable(self, on=True):
+        self._ck(self._lib.zkp_profile_enable(self._h, 1 if on else 0))
+
+    def profile_reset(self):
+        self._ck(self._lib.zkp_profile_reset(self._h))
+
+    def profile_get(self, kernel):
+        ms, n, u = C.c_double(), C.c_longlong(), C.c_double()
+        self._ck(self._lib.zkp_profile_get(self._h, kernel, C.byref(ms), C.byref(n), C.byref(u)))
+        return ms.value, n.value, u.value
+
+    def imad_peak(self, variant=0):
+        v = C.c_double()
+        self._ck(self._lib.zkp_imad_peak(self._h, variant, C.byref(v)))
+        return v.value
+
+    # -- key
+    def set_key(self, n_limbs_arr):
+        n = _c32(n_limbs_arr)
+        self._ck(self._lib.zkp_set_key(self._h, _p32(n), n.shape[-1]))
+        self.n_limbs = n.shape[-1]
+
+    def set_modulus(self, mod, exp):
+        mod, exp = _c32(mod), _c32(exp)
+        self._ck(self._lib.zkp_set_modulus(self._h, _p32(mod), mod.shape[-1], _p32(exp), exp.shape[-1]))
+
+    @property
+    def nn_limbs(self):
+        return self._lib.zkp_nn_limbs(self._h)
+
+    # -- K1 / K2 / K3
+    def modexp_shared(self, bases):
+        bases = _c32(bases)
+        batch, bl = bases.shape
+        out = np.empty((batch, self.nn_limbs), dtype=np.uint32)
+        self._ck(self._lib.zkp_modexp_shared(self._h, _p32(bases), bl, batch, _p32(out)))
+        return out
+
+    def paillier_enc(self, m, r):
+        m, r = _c32(m), _c32(r)
+        batch = m.shape[0]
+        assert r.shape[0] == batch
+        out = np.empty((batch, self.nn_limbs), dtype=np.uint32)
+        self._ck(self._lib.zkp_paillier_enc(self._h, _p32(m), m.shape[1], _p32(r), r.shape[1], batch, _p32(out)))
+        return out
+
+    def modexp_var(self, bases, exps, mods, per=1, exp_bits=None):
+        bases, exps, mods = _c32(bases), _c32(exps), _c32(mods)
+        batch, ml = bases.shape
+        assert mods.shape[1] == ml and exps.shape[0] == mods.shape[0] == (batch + per - 1) // per
+        if exp_bits is None:
+            exp_bits = 32 * exps.shape[1]
+        out = np.empty((batch, ml), dtype=np.uint32)
+        self._ck(self._lib.zkp_modexp_var(self._h, _p32(bases), _p32(exps), exps.shape[1], exp_bits, _p32(mods), ml, per,
+                                          batch, _p32(out)))
+        return out
+
+    def modmul(self, a, b, which_nn=True, b_per=1):
+        a, b = _c32(a), _c32(b)
+        batch = a.shape[0]
+        out = np.empty_like(a)
+        self._ck(self._lib.zkp_modmul(self._h, 1 if which_nn else 0, _p32(a), _p32(b), b_per, batch, _p32(out)))
+        return out
+
+    # -- K4
+    def sha256_transcript(self, items):
+        items = _c32(items)
+        batch, count, limbs = items.shape
+        out = np.empty((batch, 32), dtype=np.uint8)
+        self._ck(self._lib.zkp_sha256_transcript(self._h, _p32(items), limbs, count, batch, _p8(out)))
+        return out
+
+    # -- RangeProofNi
+    def rp_prove_stage(self, ef, range_, x, r, w1, swap, r1, r2):
+        range_, x, r, w1, r1, r2 = map(_c32, (range_, x, r, w1, r1, r2))
+        swap = _c8(swap)
+        batch, wl = range_.shape
+        assert w1.shape == (batch, ef, wl) and swap.shape == (batch, ef)
+        assert r1.shape == r2.shape == (batch, ef, self.n_limbs) and r.shape == (batch, self.n_limbs) and x.shape == (batch, wl)
+        self._ck(self._lib.zkp_rp_prove_stage(self._h, batch, ef, wl, _p32(range_), _p32(x), _p32(r), _p32(w1), _p8(swap),
+                                              _p32(r1), _p32(r2)))
+        self._rp_shape = (batch, ef, wl)
+
+    def rp_prove_run(self):
+        self._ck(self._lib.zkp_rp_prove_run(self._h))
+
+    def rp_prove_fetch(self, want_pairs=True):
+        batch, ef, wl = self._rp_shape
+        nl, nnl = self.n_limbs, self.nn_limbs
+        out = {
+            "c1": np.empty((batch, ef, nnl), np.uint32) if want_pairs else None,
+            "c2": np.empty((batch, ef, nnl), np.uint32) if want_pairs else None,
+            "digest": np.empty((batch, 32), np.uint8),
+            "kind": np.empty((batch, ef), np.uint8),
+            "resp_w": np.empty((batch, ef, 2, wl), np.uint32),
+            "resp_r": np.empty((batch, ef, 2, nl), np.uint32),
+        }
+        self._ck(self._lib.zkp_rp_prove_fetch(self._h, _p32(out["c1"]), _p32(out["c2"]), _p8(out["digest"]), _p8(out["kind"]),
+                                              _p32(out["resp_w"]), _p32(out["resp_r"])))
+        return out
+
+    def rangeproof_ni_prove(self, ef, range_, x, r, w1, swap, r1, r2):
+        self.rp_prove_stage(ef, range_, x, r, w1, swap, r1, r2)
+        self.rp_prove_run()
+        return self.rp_prove_fetch()
+
+    def rp_verify_stage(self, ef, range_, cipher_x, c1, c2, kind, resp_w, resp_r):
+        range_, cipher_x, c1, c2, resp_w, resp_r = map(_c32, (range_, cipher_x, c1, c2, resp_w, resp_r))
+        kind = _c8(kind)
+        batch, wl = range_.shape
+        nl, nnl = self.n_limbs, self.nn_limbs
+        assert c1.shape == c2.shape == (batch, ef, nnl) and cipher_x.shape == (batch, nnl)
+        assert kind.shape == (batch, ef) and resp_w.shape == (batch, ef, 2, wl) and resp_r.shape == (batch, ef, 2, nl)
+        self._ck(self._lib.zkp_rp_verify_stage(self._h, batch, ef, wl, _p32(range_), _p32(cipher_x), _p32(c1), _p32(c2),
+                                               _p8(kind), _p32(resp_w), _p32(resp_r)))
+        self._rpv_batch = batch
+
+    def rp_verify_stage_from_prove(self, cipher_x):
+        cipher_x = _c32(cipher_x)
+        self._ck(self._lib.zkp_rp_verify_stage_from_prove(self._h, _p32(cipher_x)))
+        self._rpv_batch = cipher_x.shape[0]
+
+    def rp_verify_run(self):
+        self._ck(self._lib.zkp_rp_verify_run(self._h))
+
+    def rp_verify_fetch(self):
+        b = self._rpv_batch
+        accept, fault, digest = np.empty(b, np.uint8), np.empty(b, np.uint8), np.empty((b, 32), np.uint8)
+        self._ck(self._lib.zkp_rp_verify_fetch(self._h, _p8(accept), _p8(fault), _p8(digest)))
+        return accept, fault, digest
+
+    def rp_verify_enc_count(self):
+        return self._lib.zkp_rp_verify_enc_count(self._h)
+
+    def rangeproof_ni_verify(self, ef, range_, cipher_x, c1, c2, kind, resp_w, resp_r):
+        self.rp_verify_stage(ef, range_, cipher_x, c1, c2, kind, resp_w, resp_r)
+        self.rp_verify_run()
+        return self.rp_verify_fetch()
+
+    # -- NiCorrectKeyProof
+    def ck_verify_stage(self, n, sigma, salt: bytes):
+        n, sigma = _c32(n), _c32(sigma)
+        batch, nl = n.shape
+        assert sigma.shape == (batch, CK_M2, nl)
+        s = np.frombuffer(bytes(salt), dtype=np.uint8).copy() if len(salt) else np.zeros(1, np.uint8)
+        self._ck(self._lib.zkp_ck_verify_stage(self._h, batch, nl, _p32(n), _p32(sigma), _p8(s), len(salt)))
+        self._ck_shape = (batch, nl)
+
+    def ck_verify_run(self):
+        self._ck(self._lib.zkp_ck_verify_run(self._h))
+
+    def ck_verify_fetch(self, want_rho=False):
+        batch, nl = self._ck_shape
+        accept = np.empty(batch, np.uint8)
+        rho = np.empty((batch, CK_M2, nl), np.uint32) if want_rho else None
+        self._ck(self._lib.zkp_ck_verify_fetch(self._h, _p8(accept), _p32(rho)))
+        return (accept, rho) if want_rho else accept
+
+    def correct_key_ni_verify(self, n, sigma, salt: bytes, want_rho=False):
+        self.ck_verify_stage(n, sigma, salt)
+        self.ck_verify_run()
+        return self.ck_verify_fetch(want_rho)
