@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""bench.py -- RangeProofNi proofs+verifies/sec at 2048-bit n on 1..8 B200 (BASELINE.json metric).
+
+One "step" = RangeProofNi::prove followed by RangeProofNi::verify over one batch of synthetic statements
+under the reference's fixed 2048-bit test key (range_proof_ni.rs:141-145), error factor 128
+(range_proof_ni.rs:23), 256-bit ranges (range_proof_ni.rs:133) -- the shape of the reference's Criterion
+bench (benches/all.rs:55-71), batched.  Default workload = BASELINE.json configs[1]: batch 1024 per GPU.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (CUDA, sm_100a)
+  python bench.py --impl reference ...                            the CPU path (GMP mpz_powm, all host cores)
+
+Numbers printed (one JSON line, rank 0):
+  value       device-resident throughput: inputs already in HBM, prove_run + verify_run chained on the device,
+              CUDA events on the launch stream, max over ranks
+  e2e         the same metric through the public C ABI with HOST (pinned) buffers: H2D of the statement and the
+              randomness, prove, D2H of the whole proof, H2D of the proof again (the verifier is another party),
+              verify, D2H of the verdicts -- all inside the timed region
+  roofline    the dominant kernel K1 (modexp_shared): algorithmic multiply-adds per second
+              of K1 device time against the IMAD.WIDE.U32 issue peak measured in this run; plus its HBM view
+  cpu_baseline  oracle/oracle.c (the reference's loops on the reference's own backend, GMP) on a bounded sample
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_BITS = 2048
+EF = 128
+METRIC = "RangeProofNi proofs+verifies/sec at 2048-bit n"
+UNIT = "proofs+verifies/s"
+
+
+# ---- algorithmic work ---------------------------------------------------
+def mm(s):
+    return 2 * s * s + s
+
+
+def modexp_imads(mod_bits, exp_bits):
+    return (exp_bits + -(-exp_bits // 5) + 32) * mm(mod_bits // 32)
+
+
+ENC_IMADS = modexp_imads(2 * N_BITS, N_BITS)  # 81.9 M at 2048-bit n
+# algorithmic HBM bytes of one Enc inside RangeProofNi: base (|n|) + plaintext row in, ciphertext (2|n|) out
+ENC_BYTES = N_BITS // 8 + 48 + 2 * N_BITS // 8
+
+
+def test_key():
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import zkp_oracle as po  # constants only (the reference's fixed test primes)
+
+    return po.TEST_P * po.TEST_Q
+
+
+def cpu_sample(n_int, work, cx, sel, threads):
+    """prove+verify of the proofs `sel` on the CPU oracle; returns seconds."""
+    import c_oracle
+    from zk_paillier_b200.native import to_limbs
+
+    nl = work["n_limbs"]
+    nlimbs = to_limbs(n_int, nl)
+    t0 = time.perf_counter()
+    pr = c_oracle.rangeproof_ni_prove(nlimbs, EF, work["range"][sel], work["x"][sel], work["r"][sel], work["w1"][sel],
+                                      work["swap"][sel], work["r1"][sel], work["r2"][sel], threads)
+    acc, fault, dig, encs = c_oracle.rangeproof_ni_verify(nlimbs, EF, work["range"][sel], cx[sel], pr["c1"], pr["c2"], pr["kind"],
+                                                          pr["resp_w"], pr["resp_r"], threads)
+    dt = time.perf_counter() - t0
+    return dt, pr, acc
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
+        os.unlink(self.f.name)
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
+            except Exception:
+                continue
+            for nm, v in zip(names, r[3:7]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(nm)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), power_w_max=float(max(pw)), samples=len(sm))
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def pinned(shape, dtype):
+    import torch
+
+    t = torch.empty(tuple(shape), dtype={np.uint32: torch.int32, np.uint8: torch.uint8}[dtype], pin_memory=True)
+    return t.numpy().view(dtype)
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import zk_paillier_b200 as zk
+    from zk_paillier_b200 import workload
+    from zk_paillier_b200.native import KID_MODEXP_SHARED, KID_MODMUL, KID_OTHER, KID_SHA, to_limbs
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the engine has no CPU path (use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    batch = args.batch
+    nl = N_BITS // 32
+
+    # public key: rank 0 owns it, one NCCL broadcast (the only collective before the hot path)
+    n_t = torch.zeros(nl, dtype=torch.int32, device=dev)
+    if rank == 0:
+        n_t.copy_(torch.from_numpy(to_limbs(test_key(), nl).view(np.int32)))
+    if world > 1:
+        dist.broadcast(n_t, 0)
+    n_limbs_arr = n_t.cpu().numpy().view(np.uint32)
+    n_int = int.from_bytes(n_limbs_arr.tobytes(), "little")
+
+    stream = torch.cuda.Stream(dev)  # the library launches on this stream, so torch events on it time the kernels
+    torch.cuda.set_stream(stream)
+    ctx = zk.native.Context(local, stream=stream.cuda_stream)
+    ctx.set_key(n_limbs_arr)
+
+    # this rank's shard of independent statements (weak scaling: `batch` proofs per GPU)
+    work = workload.rangeproof_batch(n_int, batch, ef=EF, seed=workload.DEFAULT_SEED + rank, reject_every=100)
+    wl = work["w_limbs"]
+    cx = ctx.paillier_enc(work["x_n"], work["r"])  # statement ciphertexts c = Enc(x, r): not on the measured path
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    # ---------------- device-resident steps (value) ----------------
+    ctx.rp_prove_stage(EF, work["range"], work["x"], work["r"], work["w1"], work["swap"], work["r1"], work["r2"])
+    ctx.rp_prove_run()
+    ctx.rp_verify_stage_from_prove(cx)
+
+    def step_device():
+        ctx.rp_prove_run()
+        ctx.rp_verify_run()
+
+    for _ in range(args.warmup):
+        step_device()
+    ctx.profile_enable(True)
+    ctx.profile_reset()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_device()
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    ms = e0.elapsed_time(e1)
+    prof = {k: ctx.profile_get(k) for k in (KID_MODEXP_SHARED, KID_MODMUL, KID_SHA, KID_OTHER)}
+    ctx.profile_enable(False)
+    ctx.profile_reset()
+    accept, fault, digest = ctx.rp_verify_fetch()
+    expect = np.array([0 if b % 100 == 99 else 1 for b in range(batch)], np.uint8)
+    if not np.array_equal(accept, expect) or fault.any():
+        raise SystemExit("bench.py: wrong verdicts from the device path")
+    enc_verify = ctx.rp_verify_enc_count()
+
+    # ---------------- end-to-end steps through the C ABI with host buffers (e2e) ----------------
+    host_in = {k: pinned(work[k].shape, work[k].dtype.type) for k in ("range", "x", "r", "w1", "swap", "r1", "r2")}
+    for k in host_in:
+        host_in[k][...] = work[k]
+    cx_h = pinned(cx.shape, np.uint32)
+    cx_h[...] = cx
+    lib, h = ctx._lib, ctx._h
+    from zk_paillier_b200.native import _p32, _p8
+
+    nnl = 2 * nl
+    out = {"c1": pinned((batch, EF, nnl), np.uint32), "c2": pinned((batch, EF, nnl), np.uint32), "digest": pinned((batch, 32), np.uint8),
+           "kind": pinned((batch, EF), np.uint8), "resp_w": pinned((batch, EF, 2, wl), np.uint32), "resp_r": pinned((batch, EF, 2, nl), np.uint32)}
+    acc_h, fault_h, dig_h = pinned((batch,), np.uint8), pinned((batch,), np.uint8), pinned((batch, 32), np.uint8)
+
+    def step_e2e():
+        ctx._ck(lib.zkp_rangeproof_ni_prove(h, batch, EF, wl, _p32(host_in["range"]), _p32(host_in["x"]), _p32(host_in["r"]),
+                                            _p32(host_in["w1"]), _p8(host_in["swap"]), _p32(host_in["r1"]), _p32(host_in["r2"]),
+                                            _p32(out["c1"]), _p32(out["c2"]), _p8(out["digest"]), _p8(out["kind"]), _p32(out["resp_w"]),
+                                            _p32(out["resp_r"])))
+        ctx._ck(lib.zkp_rangeproof_ni_verify(h, batch, EF, wl, _p32(host_in["range"]), _p32(cx_h), _p32(out["c1"]), _p32(out["c2"]),
+                                             _p8(out["kind"]), _p32(out["resp_w"]), _p32(out["resp_r"]), _p8(acc_h), _p8(fault_h), _p8(dig_h)))
+
+    h2d = sum(host_in[k].nbytes for k in host_in) + cx_h.nbytes + host_in["range"].nbytes + sum(out[k].nbytes for k in ("c1", "c2", "kind", "resp_w", "resp_r"))
+    d2h = sum(v.nbytes for v in out.values()) + acc_h.nbytes + fault_h.nbytes + dig_h.nbytes
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record(stream)
+    for _ in range(args.e2e_steps):
+        step_e2e()
+    if world > 1:  # final gather of the verdicts + challenge hashes over NVLink (33 B per proof)
+        rec = torch.from_numpy(np.concatenate([acc_h[:, None], dig_h], axis=1)).to(dev)
+        allrec = torch.empty((world,) + tuple(rec.shape), dtype=rec.dtype, device=dev)
+        dist.all_gather_into_tensor(allrec, rec)
+    g1.record(stream)
+    barrier()
+    e2e_ms = g0.elapsed_time(g1)  # the ABI calls are host-synchronous, so the event pair brackets copies + kernels + host gaps
+    if not np.array_equal(acc_h, expect):
+        raise SystemExit("bench.py: wrong verdicts from the e2e path")
+
+    # max over ranks
+    times = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = times.tolist()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    value = world * batch * args.steps / (ms * 1e-3)
+    e2e_value = world * batch * args.e2e_steps / (e2e_ms * 1e-3)
+
+    # ---------------- roofline of the dominant kernel ----------------
+    k1_ms, k1_launches, k1_units = prof[KID_MODEXP_SHARED]
+    imad_peak = ctx.imad_peak(0)
+    achieved = k1_units * ENC_IMADS / (k1_ms * 1e-3)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    hbm_ach = k1_units * ENC_BYTES / (k1_ms * 1e-3) / 1e9
+    kernel_ms = {"modexp_shared": k1_ms, "modmul": prof[KID_MODMUL][0], "sha256_transcript": prof[KID_SHA][0], "other": prof[KID_OTHER][0]}
+    launches = int(sum(p[1] for p in prof.values()))
+
+    # ---------------- CPU baseline on a bounded sample (rank 0, N=1 only) ----------------
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import c_oracle
+
+        cores = c_oracle.hw_threads()
+        t1, pr1, acc1 = cpu_sample(n_int, work, cx, np.arange(1), cores)
+        m = int(max(1, min(64, args.cpu_seconds / max(t1, 1e-3))))
+        dt, pr, acc = cpu_sample(n_int, work, cx, np.arange(m), cores)
+        same = all(np.array_equal(pr[k], out[k][:m]) for k in ("c1", "c2", "digest", "kind", "resp_w", "resp_r")) and np.array_equal(acc, acc_h[:m])
+        if not same:
+            raise SystemExit("bench.py: CUDA outputs differ from the CPU oracle on the baseline sample")
+        cpu = {"value": m / dt, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{m} of the {batch} proofs (prove+verify, {m * 256} + {int((pr['kind'] == 0).sum()) + m * EF} Enc), GMP {c_oracle.gmp_version()} mpz_powm, outputs byte-identical to the GPU's"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (32x32+64 IMAD)",
+        "data": "synthetic (seeded PCG64; reference test key; 1% reject-path statements)",
+        "config": {"workload": f"RangeProofNi prove+verify, batch={batch} per GPU, 2048-bit n (reference test key), error_factor=128, 256-bit range",
+                   "batch_per_gpu": batch, "n_bits": N_BITS, "error_factor": EF, "enc_per_step_per_gpu": int(2 * batch * EF + enc_verify),
+                   "l2": "working set per step (approx 0.5 GB of bases, ciphertexts and responses) exceeds the 126 MB L2; no explicit flush",
+                   "sharding": "independent proofs, contiguous shard per rank; NCCL broadcast of n before, all_gather of verdicts after; no collective on the modexp path"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": args.e2e_steps},
+        "gpu_launches": launches,
+        "roofline": {"bound": "imad", "kernel": "modexp_shared_kernel<8,16> (K1)", "achieved": achieved / 1e12, "peak": imad_peak / 1e12, "unit": "T IMAD.WIDE.U32/s",
+                     "frac": achieved / imad_peak, "traffic": None,
+                     "peak_source": "IMAD.WIDE.U32 issue-rate microbenchmark measured in this run (MEASURED_PEAKS.json has no integer entry)",
+                     "alg_imads_per_enc": ENC_IMADS, "k1_launches": int(k1_launches), "k1_ms_avg": k1_ms / max(k1_launches, 1),
+                     "k1_share_of_step": k1_ms / ms},
+        "roofline_hbm": {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak, "traffic": None,
+                         "alg_bytes_per_enc": ENC_BYTES, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
+        "kernel_ms": kernel_ms,
+        "clocks": clocks,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_reference(args):
+    """The reference's CPU path (its loops restated on its own backend, GMP) on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import c_oracle
+    from zk_paillier_b200 import workload
+
+    n_int = test_key()
+    cores = c_oracle.hw_threads()
+    batch = args.batch
+    work = workload.rangeproof_batch(n_int, min(batch, 64), ef=EF, seed=workload.DEFAULT_SEED, reject_every=100)
+    from zk_paillier_b200.native import to_limbs
+
+    cx = c_oracle.paillier_enc(to_limbs(n_int, work["n_limbs"]), work["x_n"], work["r"], cores)
+    t1, _, _ = cpu_sample(n_int, work, cx, np.arange(1), cores)
+    budget = args.ref_seconds / max(1, args.steps + args.warmup)
+    m = int(max(1, min(len(work["range"]), budget / max(t1, 1e-3))))
+    sel = np.arange(m)
+    for _ in range(args.warmup):
+        cpu_sample(n_int, work, cx, sel, cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_sample(n_int, work, cx, sel, cores)
+    dt = time.perf_counter() - t0
+    value = m * args.steps / dt
+    sample = f"{m} of the {batch} proofs per step (prove+verify), GMP {c_oracle.gmp_version()} mpz_powm on {cores} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "GMP mpz (64-bit limbs)",
+        "data": "synthetic (seeded PCG64; reference test key)",
+        "config": {"workload": f"RangeProofNi prove+verify, batch={batch} per GPU, 2048-bit n (reference test key), error_factor=128, 256-bit range",
+                   "note": "the Rust reference cannot be built offline (no cargo; curv-kzen / kzen-paillier un-vendored): this arm is its loops restated in C on its own bigint backend (GMP), parallel over the security parameter like rayon"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=1024, help="proofs per GPU per step (configs[1])")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
+    ap.add_argument("--ref-seconds", type=float, default=120.0, help="target total time of the --impl reference run")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

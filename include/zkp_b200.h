@@ -91,12 +91,15 @@ int zkp_paillier_enc(zkp_ctx* ctx, const uint32_t* m, int m_limbs, const uint32_
                      uint32_t* out);
 
 /* ---- K2: BigInt::mod_pow with per-instance modulus / exponent --------------
- * out[j] = bases[j]^exps[j/per] mod mods[j/per]   (correct_key_ni.rs:90-93 with
- * per = 11; Paillier::mul / mod_pow sites of the sigma protocols with per = 1).
- * bases, out: [batch][mod_limbs]; mods: [ceil(batch/per)][mod_limbs] (odd);
- * exps: [ceil(batch/per)][exp_limbs]; exp_bits: bits scanned (>= max bit length). */
-int zkp_modexp_var(zkp_ctx* ctx, const uint32_t* bases, const uint32_t* exps, int exp_limbs, int exp_bits,
-                   const uint32_t* mods, int mod_limbs, int per, int batch, uint32_t* out);
+ * out[j] = bases[j]^exps[j/exp_per] mod mods[j/mod_per]
+ * (correct_key_ni.rs:90-93 with exp_per = mod_per = 11; the Paillier::mul / mod_pow
+ * sites of the sigma protocols -- zero_enc_proof.rs:60,81, correct_ciphertext.rs:60,81,
+ * multiplication_proof.rs:91-94,133-138, verlin_proof.rs:89,109,147,152 -- with
+ * exp_per = 1 and mod_per = batch for one shared key).
+ * bases, out: [batch][mod_limbs]; mods: [ceil(batch/mod_per)][mod_limbs] (odd);
+ * exps: [ceil(batch/exp_per)][exp_limbs]; exp_bits: bits scanned (every exponent < 2^exp_bits). */
+int zkp_modexp_var(zkp_ctx* ctx, const uint32_t* bases, const uint32_t* exps, int exp_limbs, int exp_bits, int exp_per,
+                   const uint32_t* mods, int mod_limbs, int mod_per, int batch, uint32_t* out);
 
 /* ---- K3: BigInt::mod_mul / Paillier::add under the key ----------------------
  * out[j] = a[j] * b[j/b_per] mod (which ? nn : n).  Widths = that modulus. */

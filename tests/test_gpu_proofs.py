@@ -1,0 +1,208 @@
+"""GPU parity (-m gpu) of the proof pipelines through the C ABI against the CPU oracles:
+RangeProofNi::{prove, verify} (range_proof_ni.rs:47-107), NiCorrectKeyProof::verify (correct_key_ni.rs:73-100)
+and the transcript hash (utils.rs:9-22).  Bit-exact: every output array must equal the oracle's."""
+import hashlib
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+from util import GOLDEN, c_oracle, keys, limbs_for, po
+from zk_paillier_b200 import workload
+from zk_paillier_b200.native import from_limbs, ints_to_limbs, limbs_to_ints, to_limbs
+
+pytestmark = pytest.mark.gpu
+
+
+def test_sha256_transcript_matches_hashlib(ctx):
+    rng = random.Random(3)
+    limbs = 128
+    rows = []
+    for b in range(70):
+        items = []
+        for k in range(9):
+            kind = (b + k) % 6
+            if kind == 0:
+                v = 0
+            elif kind == 1:
+                v = rng.getrandbits(rng.randrange(1, 4096))
+            elif kind == 2:
+                v = rng.getrandbits(4096) >> (8 * (b % 5))      # leading zero bytes
+            elif kind == 3:
+                v = (1 << 4096) - 1
+            elif kind == 4:
+                v = rng.getrandbits(32 * (k + 1))                 # whole leading zero limbs
+            else:
+                v = 1 << (8 * rng.randrange(0, 512) )
+            items.append(v)
+        rows.append(items)
+    dig = ctx.sha256_transcript(ints_to_limbs(rows, limbs))
+    for items, d in zip(rows, dig):
+        assert bytes(d) == hashlib.sha256(po.transcript_bytes(items)).digest()
+    # one long transcript crossing many blocks, one item
+    dig = ctx.sha256_transcript(ints_to_limbs([[7] * 300], 8))
+    assert bytes(dig[0]) == hashlib.sha256(b"\x07" * 300).digest()
+    # FIPS 180-4 "abc"
+    dig = ctx.sha256_transcript(ints_to_limbs([[int.from_bytes(b"abc", "big")]], 4))
+    assert bytes(dig[0]).hex() == "ba7816bf8f01cfea414140de5dae2223b00361a396177a9cb410ff61f20015ad"
+
+
+def _prove_both(ctx, n, nl, work):
+    ef = work["ef"]
+    ctx.set_key(to_limbs(n, nl))
+    gpu = ctx.rangeproof_ni_prove(ef, work["range"], work["x"], work["r"], work["w1"], work["swap"], work["r1"], work["r2"])
+    cpu = c_oracle.rangeproof_ni_prove(to_limbs(n, nl), ef, work["range"], work["x"], work["r"], work["w1"], work["swap"],
+                                       work["r1"], work["r2"])
+    return gpu, cpu
+
+
+@pytest.mark.parametrize("bits,batch,ef", [(1024, 40, 16), (2048, 3, 128), (1024, 5, 40), (3072, 2, 24)])
+def test_rangeproof_prove_and_verify_bit_exact(ctx, bits, batch, ef):
+    p, q = keys(bits)[0]
+    n = p * q
+    nl = limbs_for(bits)
+    work = workload.rangeproof_batch(n, batch, ef=ef, seed=bits + batch, reject_every=4)
+    gpu, cpu = _prove_both(ctx, n, nl, work)
+    for k in ("c1", "c2", "digest", "kind", "resp_w", "resp_r"):
+        assert np.array_equal(gpu[k], cpu[k]), k
+    cx = ctx.paillier_enc(work["x_n"], work["r"])
+    assert np.array_equal(cx, c_oracle.paillier_enc(to_limbs(n, nl), work["x_n"], work["r"]))
+    args = (ef, work["range"], cx, gpu["c1"], gpu["c2"], gpu["kind"], gpu["resp_w"], gpu["resp_r"])
+    acc, fault, dig = ctx.rangeproof_ni_verify(*args)
+    acc_c, fault_c, dig_c, encs_c = c_oracle.rangeproof_ni_verify(to_limbs(n, nl), *args)
+    assert np.array_equal(acc, acc_c) and np.array_equal(fault, fault_c) and np.array_equal(dig, dig_c)
+    assert acc.tolist() == [0 if b % 4 == 3 else 1 for b in range(batch)]
+    assert ctx.rp_verify_enc_count() == encs_c == int((gpu["kind"] == 0).sum()) + batch * ef
+    # device-chained verify (no host round trip of the proof) gives the same verdicts
+    ctx.rp_prove_stage(ef, work["range"], work["x"], work["r"], work["w1"], work["swap"], work["r1"], work["r2"])
+    ctx.rp_prove_run()
+    ctx.rp_verify_stage_from_prove(cx)
+    ctx.rp_verify_run()
+    acc2, fault2, dig2 = ctx.rp_verify_fetch()
+    assert np.array_equal(acc2, acc) and np.array_equal(dig2, dig) and not fault2.any()
+
+
+def test_rangeproof_verify_rejects_tampering(ctx):
+    p, q = keys(1024)[2]
+    n = p * q
+    nl, ef, batch = 32, 32, 12
+    work = workload.rangeproof_batch(n, batch, ef=ef, seed=77)
+    gpu, _ = _prove_both(ctx, n, nl, work)
+    cx = ctx.paillier_enc(work["x_n"], work["r"])
+    base = {k: gpu[k].copy() for k in ("c1", "c2", "kind", "resp_w", "resp_r")}
+    t = {k: v.copy() for k, v in base.items()}
+    cxt = cx.copy()
+    kind = base["kind"]
+    open_i = [int(np.argmax(kind[b] == 0)) for b in range(batch)]
+    mask_i = [int(np.argmax(kind[b] != 0)) for b in range(batch)]
+    t["resp_r"][1, open_i[1], 0, 0] ^= 1          # Open: wrong r1 -> c1 mismatch
+    t["resp_w"][2, open_i[2], 1, 0] ^= 1          # Open: wrong w2 -> c2 mismatch
+    t["resp_r"][3, mask_i[3], 0, 5] ^= 4          # Mask: wrong masked_r
+    t["resp_w"][4, mask_i[4], 0, 0] ^= 1          # Mask: wrong masked_x
+    t["kind"][5, open_i[5]] = 1                   # variant does not match the challenge bit -> false
+    t["kind"][6, mask_i[6]] = 0
+    t["c1"][7, 3, 0] ^= 1                         # changes the transcript hash (almost surely flips some bits) and c1
+    cxt[8, 0] ^= 2                                # wrong statement ciphertext
+    t["kind"][9, 0] = 7                           # not a variant at all -> fault
+    t["kind"][10, mask_i[10]] = 3 - kind[10, mask_i[10]]  # Mask with the other j
+    args = (ef, work["range"], cxt, t["c1"], t["c2"], t["kind"], t["resp_w"], t["resp_r"])
+    acc, fault, dig = ctx.rangeproof_ni_verify(*args)
+    acc_c, fault_c, dig_c, _ = c_oracle.rangeproof_ni_verify(to_limbs(n, nl), *args)
+    assert np.array_equal(acc, acc_c) and np.array_equal(fault, fault_c) and np.array_equal(dig, dig_c)
+    assert acc.tolist() == [1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1]
+    assert fault.tolist() == [0] * 9 + [1, 0, 0]
+    # Open response whose w1/w2 are both in the middle third fails the interval predicate only
+    t2 = {k: v.copy() for k, v in base.items()}
+    b, i = 0, open_i[0]
+    third = work["range_int"][b] // 3
+    w_mid = third + 5
+    t2["resp_w"][b, i, 0] = to_limbs(w_mid, 12)
+    t2["resp_w"][b, i, 1] = to_limbs(w_mid + 1, 12)
+    r1 = from_limbs(t2["resp_r"][b, i, 0]); r2 = from_limbs(t2["resp_r"][b, i, 1])
+    t2["c1"][b, i] = to_limbs(po.paillier_encrypt(n, w_mid, r1), 64)
+    t2["c2"][b, i] = to_limbs(po.paillier_encrypt(n, w_mid + 1, r2), 64)
+    args = (ef, work["range"], cx, t2["c1"], t2["c2"], t2["kind"], t2["resp_w"], t2["resp_r"])
+    acc, fault, dig = ctx.rangeproof_ni_verify(*args)
+    acc_c, fault_c, dig_c, _ = c_oracle.rangeproof_ni_verify(to_limbs(n, nl), *args)
+    assert np.array_equal(acc, acc_c) and np.array_equal(dig, dig_c)
+
+
+def test_rangeproof_digest_with_leading_zero_byte(ctx):
+    """to_bytes(digest) drops leading zero bytes BEFORE the challenge bits are indexed:
+    search (on the CPU oracle) for a transcript whose SHA-256 starts with 0x00 and check the GPU agrees."""
+    p, q = keys(1024)[3]
+    n = p * q
+    nl, ef = 32, 16
+    nlimbs = to_limbs(n, nl)
+    work = workload.rangeproof_batch(n, 1500, ef=1, seed=5)
+    cpu = c_oracle.rangeproof_ni_prove(nlimbs, 1, work["range"], work["x"], work["r"], work["w1"], work["swap"], work["r1"], work["r2"])
+    # grow the hit to ef=16 by keeping pair 0 and checking digests of full proofs is too slow; instead use ef=1
+    hits = np.nonzero(cpu["digest"][:, 0] == 0)[0]
+    assert len(hits) >= 1
+    sel = np.concatenate([hits, np.arange(3)])
+    sub = {k: work[k][sel] for k in ("range", "x", "r", "w1", "swap", "r1", "r2")}
+    ctx.set_key(nlimbs)
+    gpu = ctx.rangeproof_ni_prove(1, sub["range"], sub["x"], sub["r"], sub["w1"], sub["swap"], sub["r1"], sub["r2"])
+    for k in ("c1", "c2", "digest", "kind", "resp_w", "resp_r"):
+        assert np.array_equal(gpu[k], cpu[k][sel]), k
+    assert gpu["digest"][0, 0] == 0
+
+
+def test_rangeproof_golden_vector(ctx):
+    g = json.load(open(os.path.join(GOLDEN, "vectors.json")))
+    rp = g["range_proof_ni"]
+    n = int(g["n"])
+    ctx.set_key(to_limbs(n, 64))
+    wl = 12
+    one = lambda v, l: ints_to_limbs([int(v)], l)
+    out = ctx.rangeproof_ni_prove(128, one(rp["range"], wl), one(rp["x"], wl), one(rp["r"], 64),
+                                  ints_to_limbs([[int(v) for v in rp["w1"]]], wl), np.array([rp["swap"]], np.uint8),
+                                  ints_to_limbs([[int(v) for v in rp["r1"]]], 64), ints_to_limbs([[int(v) for v in rp["r2"]]], 64))
+    assert bytes(out["digest"][0]).hex() == rp["challenge_digest"]
+    assert out["kind"][0].tolist() == rp["kinds"]
+    acc, fault, _ = ctx.rangeproof_ni_verify(128, one(rp["range"], wl), one(rp["ciphertext"], 128), out["c1"], out["c2"], out["kind"],
+                                             out["resp_w"], out["resp_r"])
+    assert acc.tolist() == [1] and fault.tolist() == [0]
+    for v in g["enc"][:4]:
+        c = ctx.paillier_enc(one(v["m"], 64), one(v["r"], 64))
+        assert from_limbs(c[0]) == int(v["c"])
+
+
+@pytest.mark.parametrize("bits,batch", [(1024, 37), (2048, 9), (3072, 20), (4096, 5)])
+def test_correct_key_verify_bit_exact(ctx, bits, batch):
+    ks = keys(bits)
+    nl = limbs_for(bits)
+    salt = b"Zen Go X" if bits != 2048 else po.SALT_STRING
+    work = workload.correct_key_batch(ks, batch, salt, lambda p, q, s: po.NiCorrectKeyProof.proof(p, q, s).sigma_vec, nl, bad_every=5)
+    acc, rho = ctx.correct_key_ni_verify(work["n"], work["sigma"], salt, want_rho=True)
+    acc_c, rho_c = c_oracle.correct_key_ni_verify(work["n"], work["sigma"], salt)
+    assert np.array_equal(rho, rho_c)
+    assert np.array_equal(acc, acc_c)
+    assert acc.tolist() == [0 if b % 5 == 4 else 1 for b in range(batch)]
+
+
+def test_correct_key_edge_cases(ctx):
+    ks = keys(1024)
+    nl = 32
+    p, q = ks[0]
+    cases_n, cases_s = [], []
+    for salt in (b"", b"\x00\x00Zen", b"x" * 100):
+        sig = po.NiCorrectKeyProof.proof(p, q, salt).sigma_vec
+        acc, rho = ctx.correct_key_ni_verify(ints_to_limbs([p * q], nl), ints_to_limbs([sig], nl), salt, want_rho=True)
+        assert acc.tolist() == [1]
+        assert limbs_to_ints(rho[0]) == po.correct_key_rho(p * q, salt)
+    salt = b"KZen"
+    # modulus with a small prime factor (gcd test), shorter modulus in wider rows, sigma >= n
+    n_small = 6367 * q
+    n_short = ks[1][0] * 65537
+    sig_short = []
+    acc, rho = ctx.correct_key_ni_verify(ints_to_limbs([n_small, n_short], nl), ints_to_limbs([[1] * 11, [2] * 11], nl), salt, want_rho=True)
+    acc_c, rho_c = c_oracle.correct_key_ni_verify(ints_to_limbs([n_small, n_short], nl), ints_to_limbs([[1] * 11, [2] * 11], nl), salt)
+    assert np.array_equal(acc, acc_c) and np.array_equal(rho, rho_c) and acc.tolist() == [0, 0]
+    n = p * q
+    sig = po.NiCorrectKeyProof.proof(p, q, salt).sigma_vec
+    sig_big = [s + n if s + n < (1 << 1024) else s for s in sig]   # unreduced sigma: mod_pow reduces it
+    acc = ctx.correct_key_ni_verify(ints_to_limbs([n], nl), ints_to_limbs([sig_big], nl), salt)
+    assert acc.tolist() == [1]

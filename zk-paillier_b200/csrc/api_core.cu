@@ -177,14 +177,9 @@ void zkp_ctx_destroy(zkp_ctx* c) {
   for (auto e : c->ev_pool) cudaEventDestroy(e);
   c->nn.release();
   c->n.release();
-  DevBuf* bufs[] = {&c->table, &c->in0, &c->in1, &c->in2, &c->in3, &c->out0,
-                    &c->rp.range, &c->rp.x, &c->rp.r, &c->rp.w, &c->rp.swap, &c->rp.rr, &c->rp.c, &c->rp.digest,
-                    &c->rp.kind, &c->rp.resp_w, &c->rp.resp_r, &c->rp.rmul, &c->rp.v_range, &c->rp.v_cx, &c->rp.v_c,
-                    &c->rp.v_kind, &c->rp.v_resp_w, &c->rp.v_resp_r, &c->rp.v_digest, &c->rp.v_jobs_base,
-                    &c->rp.v_jobs_plain, &c->rp.v_jobs_tag, &c->rp.v_jobs_out, &c->rp.v_count, &c->rp.v_cmul,
-                    &c->rp.v_ok, &c->rp.v_accept, &c->rp.v_fault,
-                    &c->ck.n, &c->ck.sigma, &c->ck.r2, &c->ck.n0inv, &c->ck.rho, &c->ck.mask, &c->ck.out,
-                    &c->ck.accept, &c->ck.salt, &c->ck.aux};
+  std::vector<DevBuf*> bufs = {&c->table, &c->in0, &c->in1, &c->in2, &c->in3, &c->out0};
+  for (DevBuf* b : c->rp.all()) bufs.push_back(b);
+  for (DevBuf* b : c->ck.all()) bufs.push_back(b);
   for (DevBuf* b : bufs) b->release();
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -323,39 +318,41 @@ int zkp_paillier_enc(zkp_ctx* c, const uint32_t* m, int m_limbs, const uint32_t*
   return ZKP_OK;
 }
 
-int zkp_modexp_var(zkp_ctx* c, const uint32_t* bases, const uint32_t* exps, int exp_limbs, int exp_bits,
-                   const uint32_t* mods, int mod_limbs, int per, int batch, uint32_t* out) {
+int zkp_modexp_var(zkp_ctx* c, const uint32_t* bases, const uint32_t* exps, int exp_limbs, int exp_bits, int exp_per,
+                   const uint32_t* mods, int mod_limbs, int mod_per, int batch, uint32_t* out) {
   if (!c) return ZKP_E_ARG;
   if (batch < 0 || !bases || !exps || !mods || !out) return fail(c, ZKP_E_ARG, "null buffer or negative batch");
-  if (mod_limbs <= 0 || mod_limbs % 4 || exp_limbs <= 0 || exp_bits <= 0 || exp_bits > 32 * exp_limbs || per <= 0)
+  if (mod_limbs <= 0 || mod_limbs % 4 || exp_limbs <= 0 || exp_bits <= 0 || exp_bits > 32 * exp_limbs || exp_per <= 0 ||
+      mod_per <= 0)
     return fail(c, ZKP_E_ARG, "bad widths");
   int S = pick_width(mod_limbs);
   if (S < 0) return fail(c, ZKP_E_ARG, "modulus wider than 8192 bits");
   if (batch == 0) return ZKP_OK;
-  const int count = (batch + per - 1) / per;
-  for (int i = 0; i < count; ++i)
+  const int nmod = (batch + mod_per - 1) / mod_per;
+  const int nexp = (batch + exp_per - 1) / exp_per;
+  for (int i = 0; i < nmod; ++i)
     if (!(mods[(size_t)i * mod_limbs] & 1u)) return fail(c, ZKP_E_ARG, "every modulus must be odd");
   ZKP_CU(c, cudaSetDevice(c->device));
   ZKP_CU(c, c->in0.ensure((size_t)batch * mod_limbs * 4));
-  ZKP_CU(c, c->in1.ensure((size_t)count * exp_limbs * 4));
-  ZKP_CU(c, c->in2.ensure((size_t)count * mod_limbs * 4));
-  ZKP_CU(c, c->in3.ensure((size_t)count * (S + 1) * 4));
+  ZKP_CU(c, c->in1.ensure((size_t)nexp * exp_limbs * 4));
+  ZKP_CU(c, c->in2.ensure((size_t)nmod * mod_limbs * 4));
+  ZKP_CU(c, c->in3.ensure((size_t)nmod * (S + 1) * 4));
   ZKP_CU(c, c->out0.ensure((size_t)batch * mod_limbs * 4));
   ZKP_CU(c, ensure_table(c, S, kTableVar));
   uint32_t* d_r2 = c->in3.as<uint32_t>();
-  uint32_t* d_n0 = d_r2 + (size_t)count * S;
+  uint32_t* d_n0 = d_r2 + (size_t)nmod * S;
   ZKP_CU(c, cudaMemcpyAsync(c->in0.p, bases, (size_t)batch * mod_limbs * 4, cudaMemcpyHostToDevice, c->stream));
-  ZKP_CU(c, cudaMemcpyAsync(c->in1.p, exps, (size_t)count * exp_limbs * 4, cudaMemcpyHostToDevice, c->stream));
-  ZKP_CU(c, cudaMemcpyAsync(c->in2.p, mods, (size_t)count * mod_limbs * 4, cudaMemcpyHostToDevice, c->stream));
+  ZKP_CU(c, cudaMemcpyAsync(c->in1.p, exps, (size_t)nexp * exp_limbs * 4, cudaMemcpyHostToDevice, c->stream));
+  ZKP_CU(c, cudaMemcpyAsync(c->in2.p, mods, (size_t)nmod * mod_limbs * 4, cudaMemcpyHostToDevice, c->stream));
   {
-    ProfScope ps(c, KID_OTHER, count);
-    ZKP_CU(c, launch_mont_setup(c->in2.as<uint32_t>(), mod_limbs, S, count, d_r2, d_n0, c->stream));
+    ProfScope ps(c, KID_OTHER, nmod);
+    ZKP_CU(c, launch_mont_setup(c->in2.as<uint32_t>(), mod_limbs, S, nmod, d_r2, d_n0, c->stream));
   }
   {
     ProfScope ps(c, KID_MODEXP_VAR, batch);
     ZKP_CU(c, launch_modexp_var(c->in0.as<uint32_t>(), c->in2.as<uint32_t>(), mod_limbs, d_r2, d_n0, c->in1.as<uint32_t>(),
-                                exp_limbs, exp_bits, per, c->out0.as<uint32_t>(), batch, S, c->table.as<uint32_t>(),
-                                c->num_sms, c->stream));
+                                exp_limbs, exp_bits, exp_per, mod_per, c->out0.as<uint32_t>(), batch, S,
+                                c->table.as<uint32_t>(), c->num_sms, c->stream));
   }
   ZKP_CU(c, cudaMemcpyAsync(out, c->out0.p, (size_t)batch * mod_limbs * 4, cudaMemcpyDeviceToHost, c->stream));
   ZKP_CU(c, cudaStreamSynchronize(c->stream));

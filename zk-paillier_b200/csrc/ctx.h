@@ -69,24 +69,37 @@ struct ProfEntry {
 };
 
 struct RpState {  // RangeProofNi staging (api_rangeproof.cu)
-  int batch = 0, ef = 0, w_limbs = 0;
+  int batch = 0, ef = 0, wl = 0;  // prove shape
   bool prove_staged = false, prove_done = false, verify_staged = false, verify_done = false;
-  bool verify_from_prove = false;
-  long long enc_count = 0;
-  // prove
-  DevBuf range, x, r, w, swap, rr;          // rr = [r1 | r2] bases, w = [w1' | w2'] plaintexts (after prep)
+  // prove: inputs, then outputs
+  DevBuf range, x, r, w1in, w, swap, rr;    // w = [w1' | w2'] plaintexts, rr = [r1 | r2] bases
   DevBuf c, digest, kind, resp_w, resp_r;   // c = [c1 | c2]
-  DevBuf rmul;                              // r*r1, r*r2 mod n
-  // verify
-  DevBuf v_range, v_cx, v_c, v_kind, v_resp_w, v_resp_r, v_digest;
-  DevBuf v_jobs_base, v_jobs_plain, v_jobs_tag, v_jobs_out, v_count, v_cmul, v_ok, v_accept, v_fault;
+  DevBuf rmul, fault;                       // r*r1 | r*r2 mod n
+  // verify: owned copies of host inputs
+  DevBuf v_range, v_cx, v_c, v_kind, v_resp_w, v_resp_r;
+  // verify: work and outputs
+  DevBuf v_digest, v_jobs_base, v_jobs_plain, v_tag, v_jobs_out, v_count, v_cmul, v_sel, v_ok, v_accept, v_fault;
+  // verify: views of the inputs (own copies, or the prove buffers when chained on the device)
+  int vbatch = 0, vef = 0, vwl = 0;
+  const uint32_t* pv_range = nullptr;
+  const uint32_t* pv_c = nullptr;
+  const uint32_t* pv_resp_w = nullptr;
+  const uint32_t* pv_resp_r = nullptr;
+  const uint8_t* pv_kind = nullptr;
+  long long enc_count = 0;
+  std::vector<DevBuf*> all() {
+    return {&range, &x, &r, &w1in, &w, &swap, &rr, &c, &digest, &kind, &resp_w, &resp_r, &rmul, &fault,
+            &v_range, &v_cx, &v_c, &v_kind, &v_resp_w, &v_resp_r, &v_digest, &v_jobs_base, &v_jobs_plain,
+            &v_tag, &v_jobs_out, &v_count, &v_cmul, &v_sel, &v_ok, &v_accept, &v_fault};
+  }
 };
 
 struct CkState {  // NiCorrectKeyProof staging (api_correctkey.cu)
-  int batch = 0, n_limbs = 0, S = 0;
+  int batch = 0, nl = 0, S = 0, salt_len = 0;
   bool staged = false, done = false;
-  DevBuf n, sigma, r2, n0inv, rho, mask, out, accept, salt, aux;
-  int salt_len = 0;
+  DevBuf n, sigma, salt, r2, n0inv, mask, rho, derived, accept, primes;
+  int nprimes = 0;
+  std::vector<DevBuf*> all() { return {&n, &sigma, &salt, &r2, &n0inv, &mask, &rho, &derived, &accept, &primes}; }
 };
 
 }  // namespace zkp

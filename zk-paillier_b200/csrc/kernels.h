@@ -38,28 +38,104 @@ struct SharedKey {
 // bases: [jobs][base_limbs], plain: [jobs][plain_limbs], out: [jobs][out_limbs].
 // base_limbs / plain_limbs must be multiples of 4 (16-byte TMA rows).
 // table: scratch of resident_groups(S) * kTableShared * S limbs.
+// jobs_dev (optional): device pointer to the actual job count (<= jobs), read by the kernel.
 cudaError_t launch_modexp_shared(const SharedKey& key, const uint32_t* bases, int base_limbs,
                                  const uint32_t* plain, int plain_limbs, uint32_t* out, int out_limbs, int jobs,
-                                 uint32_t* table, int num_sms, cudaStream_t st);
+                                 uint32_t* table, int num_sms, cudaStream_t st, const unsigned* jobs_dev = nullptr);
 
 // Montgomery setup for per-instance moduli: r2[i] = R^2 mod mods[i] ([count][S]), n0inv[i].
 // mods: [count][mod_limbs].
 cudaError_t launch_mont_setup(const uint32_t* mods, int mod_limbs, int S, int count, uint32_t* r2, uint32_t* n0inv,
                               cudaStream_t st);
 
-// K2: out[j] = bases[j]^exps[j / per] mod mods[j / per], fixed 5-bit window.
-// bases/out: [jobs][mod_limbs]; mods: [count][mod_limbs]; r2: [count][S];
-// exps: [count][exp_limbs]; exp_bits: number of exponent bits scanned (uniform).
+// K2: out[j] = bases[j]^exps[j / exp_per] mod mods[j / mod_per], fixed 5-bit window.
+// bases/out: [jobs][mod_limbs]; mods: [ceil(jobs/mod_per)][mod_limbs]; r2: [..][S];
+// exps: [ceil(jobs/exp_per)][exp_limbs]; exp_bits: number of exponent bits scanned (uniform).
 cudaError_t launch_modexp_var(const uint32_t* bases, const uint32_t* mods, int mod_limbs, const uint32_t* r2,
                               const uint32_t* n0inv, const uint32_t* exps, int exp_limbs, int exp_bits,
-                              int per, uint32_t* out, int jobs, int S, uint32_t* table, int num_sms,
-                              cudaStream_t st);
+                              int exp_per, int mod_per, uint32_t* out, int jobs, int S, uint32_t* table,
+                              int num_sms, cudaStream_t st);
 
 // K3: shared modulus.  mode 0: out[j] = a[j] * b[j / b_per] mod M
 //                      mode 1: out[j] = a[j] * R mod M (to Montgomery form; b unused; out rows are S limbs)
 // a: [jobs][a_limbs], b: [ceil(jobs/b_per)][b_limbs], out: [jobs][out_limbs].
 cudaError_t launch_modmul_shared(const SharedKey& key, int mode, const uint32_t* a, int a_limbs, const uint32_t* b,
                                  int b_limbs, int b_per, uint32_t* out, int out_limbs, int jobs, cudaStream_t st);
+
+// K3 with a per-job operand selector (RangeProofNi verify, range_proof.rs:321-327):
+// out[t] = (sel[t] == 2 ? a1[t] : a0[t]) * b[t / b_per] mod M; rows with sel[t] == 0 are not stored.
+cudaError_t launch_modmul_select(const SharedKey& key, const uint8_t* sel, const uint32_t* a0, const uint32_t* a1,
+                                 int a_limbs, const uint32_t* b, int b_limbs, int b_per, uint32_t* out, int out_limbs,
+                                 int jobs, cudaStream_t st);
+
+// ---- K4: Fiat-Shamir transcript hash (utils.rs:9-22) -------------------------------------------
+constexpr int kShaThreads = 64;
+struct ShaSeg {
+  const uint32_t* base;    // items of proof b start at base + b * batch_stride
+  long long batch_stride;  // in limbs (0 = the same items for every proof, e.g. n)
+  int count;               // items per proof in this segment
+  int limbs;               // limbs per item
+};
+struct ShaSegs {
+  ShaSeg seg[4];
+  int nseg;
+};
+cudaError_t launch_sha256_transcript(const ShaSegs& segs, int batch, uint8_t* digest, cudaStream_t st);
+
+// ---- K5: RangeProofNi glue (rangeproof.cu) -----------------------------------------------------
+constexpr uint8_t ZKP_RP_OPEN_ = 0, ZKP_RP_MASK1_ = 1, ZKP_RP_MASK2_ = 2;
+
+struct RpProveArgs {
+  int batch, ef, wl, nl;
+  const uint32_t* range;   // [batch][wl]
+  const uint32_t* x;       // [batch][wl]
+  const uint32_t* w;       // [2][batch*ef][wl]  w1' | w2'
+  const uint32_t* rr;      // [2][batch*ef][nl]  r1 | r2
+  const uint32_t* rmul;    // [2][batch*ef][nl]  r*r1 mod n | r*r2 mod n
+  const uint8_t* digest;   // [batch][32]
+  uint8_t* kind;           // [batch*ef]
+  uint32_t* resp_w;        // [batch*ef][2][wl]
+  uint32_t* resp_r;        // [batch*ef][2][nl]
+  uint8_t* fault;          // [batch]
+};
+struct RpVerifyArgs {
+  int batch, ef, wl, nl;
+  const uint32_t* range;    // [batch][wl]
+  const uint32_t* c;        // [2][batch*ef][2nl]  c1 | c2
+  const uint8_t* kind;      // [batch*ef]
+  const uint32_t* resp_w;   // [batch*ef][2][wl]
+  const uint32_t* resp_r;   // [batch*ef][2][nl]
+  const uint8_t* digest;    // [batch][32]
+  const uint32_t* cmul;     // [batch*ef][2nl]     c_j * cipher_x mod n^2 (Mask rows)
+  uint32_t* jobs_base;      // [2*batch*ef][nl]
+  uint32_t* jobs_plain;     // [2*batch*ef][wl]
+  uint32_t* jobs_out;       // [2*batch*ef][2nl]
+  uint32_t* tag;            // [2*batch*ef]  (t << 1) | which
+  unsigned* count;          // number of jobs
+  uint8_t* sel;             // [batch*ef]
+  uint8_t* ok;              // [batch*ef]
+  uint8_t* fault;           // [batch]
+};
+cudaError_t launch_rp_prep(const uint32_t* range, const uint32_t* w1in, uint32_t* w, const uint8_t* swap, int batch,
+                           int ef, int wl, uint8_t* fault, cudaStream_t st);
+cudaError_t launch_rp_respond(const RpProveArgs& a, cudaStream_t st);
+cudaError_t launch_rp_plan(const RpVerifyArgs& a, cudaStream_t st);
+cudaError_t launch_rp_check(const RpVerifyArgs& a, cudaStream_t st);
+cudaError_t launch_rp_accept(const uint8_t* ok, const uint8_t* fault, int batch, int ef, uint8_t* accept,
+                             cudaStream_t st);
+
+// ---- NiCorrectKeyProof glue (correctkey.cu) ----------------------------------------------------
+constexpr int kCkM2 = 11;      // correct_key_ni.rs:29
+constexpr int kCkAlpha = 6370; // primes below alpha make up P (correct_key_ni.rs:25-26)
+// mask[b][i][ml] = mask_generation(bit_length(n_b), H(n_b || H(salt) || i)), ml = nl + 8
+cudaError_t launch_ck_rho(const uint32_t* n, int nl, const uint8_t* salt, int salt_len, int batch, uint32_t* mask, int ml,
+                          cudaStream_t st);
+// rho[b][i][nl] = mask[b][i] % n_b   (r2: [batch][S], n0inv: [batch] from launch_mont_setup)
+cudaError_t launch_ck_reduce(const uint32_t* mask, int ml, const uint32_t* mods, int nl, const uint32_t* r2,
+                             const uint32_t* n0inv, int S, int batch, uint32_t* rho, cudaStream_t st);
+// accept[b] = (rho[b] == derived[b]) && no prime in primes[] divides n_b
+cudaError_t launch_ck_check(const uint32_t* n, int nl, const uint32_t* rho, const uint32_t* derived,
+                            const uint16_t* primes, int nprimes, int batch, uint8_t* accept, cudaStream_t st);
 
 // IMAD.WIDE.U32 peak microbenchmark (register-only).  variant 0: independent
 // IMAD.WIDE.U32; 1: carry-chained IMAD.WIDE.U32.X rows; 2: plain IMAD (32-bit).

@@ -87,6 +87,7 @@ struct SharedParams {
   int plain_limbs;
   int out_limbs;
   int jobs;
+  const unsigned* jobs_dev;
   int sched_pad;  // schedule entries padded to a multiple of 4
 };
 
@@ -122,10 +123,11 @@ __global__ void __launch_bounds__(kCtaThreads, Occ<T, L>::kMinBlocks) modexp_sha
   phase ^= 1;
 
   uint32_t* tab = p.table + ((size_t)(blockIdx.x * G + grp) * kTableShared) * S + g * L;
-  const int npass = (p.jobs + G - 1) / G;
+  const int jobs = p.jobs_dev ? min((int)*p.jobs_dev, p.jobs) : p.jobs;
+  const int npass = (jobs + G - 1) / G;
   for (int cj = blockIdx.x; cj < npass; cj += gridDim.x) {
     const int job0 = cj * G;
-    const int nvalid = min(G, p.jobs - job0);
+    const int nvalid = min(G, jobs - job0);
     if (threadIdx.x == 0) {
       uint32_t bb = (uint32_t)(nvalid * p.base_limbs) * 4u;
       uint32_t pb = p.plain ? (uint32_t)(nvalid * p.plain_limbs) * 4u : 0u;
@@ -221,7 +223,8 @@ struct VarParams {
   int mod_limbs;
   int exp_limbs;
   int exp_bits;
-  int per;
+  int exp_per;
+  int mod_per;
   int jobs;
 };
 
@@ -247,9 +250,9 @@ __global__ void __launch_bounds__(kCtaThreads, Occ<T, L>::kMinBlocks) modexp_var
     const int job = cj * G + grp;
     const bool valid = job < p.jobs;
     const int src = valid ? job : 0;
-    const int mi = src / p.per;
+    const int mi = src / p.mod_per;
     const uint32_t n0inv = p.n0inv[mi];
-    const uint32_t* e = p.exps + (size_t)mi * p.exp_limbs;
+    const uint32_t* e = p.exps + (size_t)(src / p.exp_per) * p.exp_limbs;
     uint32_t n[L], acc[L], y[L];
     M::load_ext(n, p.mods + (size_t)mi * p.mod_limbs, p.mod_limbs, g);
     M::load(y, p.r2 + (size_t)mi * S + g * L);
@@ -318,6 +321,38 @@ __global__ void __launch_bounds__(kCtaThreads) modmul_shared_kernel(const MulPar
   if (valid) M::store_ext(p.out + (size_t)job * p.out_limbs, x, p.out_limbs, g);
 }
 
+struct MulSelParams {
+  SharedKey key;
+  const uint8_t* sel;
+  const uint32_t* a0;
+  const uint32_t* a1;
+  const uint32_t* b;
+  uint32_t* out;
+  int a_limbs, b_limbs, out_limbs, b_per, jobs;
+};
+
+template <int T, int L>
+__global__ void __launch_bounds__(kCtaThreads) modmul_select_kernel(const MulSelParams p) {
+  using M = Mp<T, L>;
+  constexpr int G = kCtaThreads / T;
+  const int lane = threadIdx.x & 31;
+  const int g = lane & (T - 1);
+  const int job = blockIdx.x * G + threadIdx.x / T;
+  const bool valid = job < p.jobs;
+  const int src = valid ? job : 0;
+  const uint8_t sel = p.sel[src];
+  // a warp is skipped only as a whole: its groups share shuffles
+  if (__ballot_sync(ZKP_FULL, valid && sel != 0) == 0u) return;
+  uint32_t n[L], x[L], y[L];
+  M::load(n, p.key.mod + g * L);
+  M::load_ext(x, (sel == 2 ? p.a1 : p.a0) + (size_t)src * p.a_limbs, p.a_limbs, g);
+  M::load(y, p.key.r2 + g * L);
+  M::mont_mul(x, x, y, n, p.key.n0inv, lane);
+  M::load_ext(y, p.b + (size_t)(src / p.b_per) * p.b_limbs, p.b_limbs, g);
+  M::mont_mul(x, x, y, n, p.key.n0inv, lane);
+  if (valid && sel != 0) M::store_ext(p.out + (size_t)job * p.out_limbs, x, p.out_limbs, g);
+}
+
 // ----------------------------------------------------------------- dispatch
 int pick_width(int limbs) {
   static const int w[] = {32, 64, 96, 128, 192, 256};
@@ -351,7 +386,7 @@ int resident_groups(int S, int num_sms) {
 
 cudaError_t launch_modexp_shared(const SharedKey& key, const uint32_t* bases, int base_limbs, const uint32_t* plain,
                                  int plain_limbs, uint32_t* out, int out_limbs, int jobs, uint32_t* table,
-                                 int num_sms, cudaStream_t st) {
+                                 int num_sms, cudaStream_t st, const unsigned* jobs_dev) {
   if (jobs <= 0) return cudaSuccess;
   if (base_limbs % 4 || (plain && plain_limbs % 4) || base_limbs > key.S || (plain && plain_limbs > key.S) ||
       out_limbs % 2 || out_limbs > key.S || key.nsteps <= 0)
@@ -366,6 +401,7 @@ cudaError_t launch_modexp_shared(const SharedKey& key, const uint32_t* bases, in
   p.plain_limbs = plain ? plain_limbs : 0;
   p.out_limbs = out_limbs;
   p.jobs = jobs;
+  p.jobs_dev = jobs_dev;
   p.sched_pad = (key.nsteps + 3) & ~3;
 #define CALL(T_, L_)                                                                                          \
   {                                                                                                           \
@@ -399,10 +435,11 @@ cudaError_t launch_mont_setup(const uint32_t* mods, int mod_limbs, int S, int co
 }
 
 cudaError_t launch_modexp_var(const uint32_t* bases, const uint32_t* mods, int mod_limbs, const uint32_t* r2,
-                              const uint32_t* n0inv, const uint32_t* exps, int exp_limbs, int exp_bits, int per,
-                              uint32_t* out, int jobs, int S, uint32_t* table, int num_sms, cudaStream_t st) {
+                              const uint32_t* n0inv, const uint32_t* exps, int exp_limbs, int exp_bits, int exp_per,
+                              int mod_per, uint32_t* out, int jobs, int S, uint32_t* table, int num_sms,
+                              cudaStream_t st) {
   if (jobs <= 0) return cudaSuccess;
-  if (per <= 0 || exp_bits <= 0 || exp_bits > 32 * exp_limbs || mod_limbs % 2 || mod_limbs > S)
+  if (exp_per <= 0 || mod_per <= 0 || exp_bits <= 0 || exp_bits > 32 * exp_limbs || mod_limbs % 2 || mod_limbs > S)
     return cudaErrorInvalidValue;
   VarParams p;
   p.bases = bases;
@@ -415,7 +452,8 @@ cudaError_t launch_modexp_var(const uint32_t* bases, const uint32_t* mods, int m
   p.mod_limbs = mod_limbs;
   p.exp_limbs = exp_limbs;
   p.exp_bits = exp_bits;
-  p.per = per;
+  p.exp_per = exp_per;
+  p.mod_per = mod_per;
   p.jobs = jobs;
 #define CALL(T_, L_)                                                   \
   {                                                                    \
@@ -451,6 +489,35 @@ cudaError_t launch_modmul_shared(const SharedKey& key, int mode, const uint32_t*
   {                                                                                  \
     constexpr int G = kCtaThreads / T_;                                              \
     modmul_shared_kernel<T_, L_><<<(jobs + G - 1) / G, kCtaThreads, 0, st>>>(p);     \
+  }
+  ZKP_DISPATCH(key.S, CALL)
+#undef CALL
+  return cudaGetLastError();
+}
+
+cudaError_t launch_modmul_select(const SharedKey& key, const uint8_t* sel, const uint32_t* a0, const uint32_t* a1,
+                                 int a_limbs, const uint32_t* b, int b_limbs, int b_per, uint32_t* out, int out_limbs,
+                                 int jobs, cudaStream_t st) {
+  if (jobs <= 0) return cudaSuccess;
+  if (b_per <= 0 || a_limbs % 2 || a_limbs > key.S || out_limbs % 2 || out_limbs > key.S || b_limbs % 2 ||
+      b_limbs > key.S)
+    return cudaErrorInvalidValue;
+  MulSelParams p;
+  p.key = key;
+  p.sel = sel;
+  p.a0 = a0;
+  p.a1 = a1;
+  p.b = b;
+  p.out = out;
+  p.a_limbs = a_limbs;
+  p.b_limbs = b_limbs;
+  p.out_limbs = out_limbs;
+  p.b_per = b_per;
+  p.jobs = jobs;
+#define CALL(T_, L_)                                                                 \
+  {                                                                                  \
+    constexpr int G = kCtaThreads / T_;                                              \
+    modmul_select_kernel<T_, L_><<<(jobs + G - 1) / G, kCtaThreads, 0, st>>>(p);     \
   }
   ZKP_DISPATCH(key.S, CALL)
 #undef CALL

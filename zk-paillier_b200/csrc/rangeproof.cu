@@ -1,0 +1,286 @@
+// K4 (Fiat-Shamir transcript hash) and the RangeProofNi glue kernels K5: everything of
+// RangeProof::{generate_encrypted_pairs, generate_proof, verifier_output}
+// (reference src/zkproofs/range_proof.rs:128-193, 210-252, 254-355) that is not a
+// Paillier encryption -- thirds of the range, w2 = w1 - third, the coin swap,
+// challenge bits, response selection, interval predicates, ciphertext equality
+// and the AND over the security parameter.  The encryptions themselves run in
+// K1 (modexp.cu); the two mulmods (r*r_j mod n, c_j*cipher_x mod n^2) in K3.
+#include "kernels.h"
+#include "sha256.cuh"
+
+namespace zkp {
+
+// ------------------------------------------------------------------------ K4
+// digest[b] = SHA-256( to_bytes(seg0 items of b) || to_bytes(seg1 items) || ... )
+__global__ void __launch_bounds__(kShaThreads) sha256_transcript_kernel(const ShaSegs segs, int batch, uint8_t* digest) {
+  __shared__ uint32_t wbuf[16 * kShaThreads];
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  Sha256 s;
+  s.init(wbuf + threadIdx.x, kShaThreads);
+  for (int k = 0; k < segs.nseg; ++k) {
+    const ShaSeg sg = segs.seg[k];
+    const uint32_t* base = sg.base + (size_t)b * sg.batch_stride;
+    for (int it = 0; it < sg.count; ++it) {
+      const uint32_t* p = base + (size_t)it * sg.limbs;
+      s.push_bigint(sg.limbs, [&](int i) { return __ldg(p + i); });
+    }
+  }
+  uint32_t out[8];
+  s.finish(out);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    uint32_t v = out[i];
+    digest[(size_t)b * 32 + 4 * i + 0] = (uint8_t)(v >> 24);
+    digest[(size_t)b * 32 + 4 * i + 1] = (uint8_t)(v >> 16);
+    digest[(size_t)b * 32 + 4 * i + 2] = (uint8_t)(v >> 8);
+    digest[(size_t)b * 32 + 4 * i + 3] = (uint8_t)v;
+  }
+}
+
+cudaError_t launch_sha256_transcript(const ShaSegs& segs, int batch, uint8_t* digest, cudaStream_t st) {
+  if (batch <= 0) return cudaSuccess;
+  sha256_transcript_kernel<<<(batch + kShaThreads - 1) / kShaThreads, kShaThreads, 0, st>>>(segs, batch, digest);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------ small fixed-width helpers
+// (values of w limbs, w <= kMaxW, one thread each; these are ~256-bit numbers)
+constexpr int kMaxW = 64;
+
+// q = floor(a / 3)     range.div_floor(3)  (range_proof.rs:133, 218, 264)
+__device__ __forceinline__ void div3(uint32_t* q, const uint32_t* a, int w) {
+  uint32_t rem = 0;
+  for (int i = w - 1; i >= 0; --i) {
+    unsigned long long cur = ((unsigned long long)rem << 32) | a[i];
+    q[i] = (uint32_t)(cur / 3ull);
+    rem = (uint32_t)(cur % 3ull);
+  }
+}
+// -1, 0, 1
+__device__ __forceinline__ int cmpw(const uint32_t* a, const uint32_t* b, int w) {
+  for (int i = w - 1; i >= 0; --i) {
+    if (a[i] != b[i]) return a[i] < b[i] ? -1 : 1;
+  }
+  return 0;
+}
+// d = a + b, returns carry out
+__device__ __forceinline__ uint32_t addw(uint32_t* d, const uint32_t* a, const uint32_t* b, int w) {
+  uint32_t c = 0;
+  for (int i = 0; i < w; ++i) {
+    unsigned long long t = (unsigned long long)a[i] + b[i] + c;
+    d[i] = (uint32_t)t;
+    c = (uint32_t)(t >> 32);
+  }
+  return c;
+}
+// d = a - b, returns borrow out
+__device__ __forceinline__ uint32_t subw(uint32_t* d, const uint32_t* a, const uint32_t* b, int w) {
+  uint32_t br = 0;
+  for (int i = 0; i < w; ++i) {
+    unsigned long long t = (unsigned long long)a[i] - b[i] - br;
+    d[i] = (uint32_t)t;
+    br = (uint32_t)(t >> 63);
+  }
+  return br;
+}
+
+// ------------------------------------------------------------- prove: prep
+// w1in: [batch*ef][wl] the w1 samples; w: [2][batch*ef][wl] receives w1' (half 0) and
+// w2' (half 1) after the swap.  range_proof.rs:141-149.
+__global__ void rp_prep_kernel(const uint32_t* range, const uint32_t* w1in, uint32_t* w, const uint8_t* swap, int batch,
+                               int ef, int wl, uint8_t* fault) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= batch * ef) return;
+  const int b = t / ef;
+  uint32_t third[kMaxW], w1[kMaxW], w2[kMaxW];
+  div3(third, range + (size_t)b * wl, wl);
+  uint32_t* p1 = w + (size_t)t * wl;
+  uint32_t* p2 = w + ((size_t)batch * ef + t) * wl;
+  for (int i = 0; i < wl; ++i) w1[i] = w1in[(size_t)t * wl + i];
+  uint32_t borrow = subw(w2, w1, third, wl);
+  if (borrow) fault[b] = 1;  // w1 < third: negative plaintext, outside the engine's domain
+  const bool sw = swap[t] != 0;
+  for (int i = 0; i < wl; ++i) {
+    p1[i] = sw ? w2[i] : w1[i];
+    p2[i] = sw ? w1[i] : w2[i];
+  }
+}
+
+// ---------------------------------------------------------- prove: respond
+// range_proof.rs:210-252 for one (proof, i).
+__global__ void rp_respond_kernel(RpProveArgs a) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= a.batch * a.ef) return;
+  const int b = t / a.ef, i = t % a.ef;
+  const int wl = a.wl, nl = a.nl;
+  const size_t half = (size_t)a.batch * a.ef;
+  uint32_t e = challenge_bit(a.digest + (size_t)b * 32, i);
+  if (e == 2u) {
+    a.fault[b] = 1;
+    e = 0;
+  }
+  const uint32_t* w1 = a.w + (size_t)t * wl;
+  const uint32_t* w2 = a.w + (half + t) * wl;
+  uint32_t* rw = a.resp_w + (size_t)t * 2 * wl;
+  uint32_t* rr = a.resp_r + (size_t)t * 2 * nl;
+  if (!e) {
+    a.kind[t] = ZKP_RP_OPEN_;
+    for (int k = 0; k < wl; ++k) {
+      rw[k] = w1[k];
+      rw[wl + k] = w2[k];
+    }
+    const uint32_t* r1 = a.rr + (size_t)t * nl;
+    const uint32_t* r2 = a.rr + (half + t) * nl;
+    for (int k = 0; k < nl; ++k) {
+      rr[k] = r1[k];
+      rr[nl + k] = r2[k];
+    }
+    return;
+  }
+  uint32_t third[kMaxW], two[kMaxW], s[kMaxW];
+  div3(third, a.range + (size_t)b * wl, wl);
+  addw(two, third, third, wl);
+  const uint32_t* x = a.x + (size_t)b * wl;
+  uint32_t carry = addw(s, x, w1, wl);
+  const bool first = !carry && cmpw(s, third, wl) > 0 && cmpw(s, two, wl) < 0;
+  if (!first) carry = addw(s, x, w2, wl);
+  if (carry) a.fault[b] = 1;  // masked_x does not fit w_limbs
+  a.kind[t] = first ? ZKP_RP_MASK1_ : ZKP_RP_MASK2_;
+  const uint32_t* mr = a.rmul + ((first ? 0 : half) + t) * nl;
+  for (int k = 0; k < wl; ++k) {
+    rw[k] = s[k];
+    rw[wl + k] = 0;
+  }
+  for (int k = 0; k < nl; ++k) {
+    rr[k] = mr[k];
+    rr[nl + k] = 0;
+  }
+}
+
+cudaError_t launch_rp_prep(const uint32_t* range, const uint32_t* w1in, uint32_t* w, const uint8_t* swap, int batch,
+                           int ef, int wl, uint8_t* fault, cudaStream_t st) {
+  if (wl > kMaxW) return cudaErrorInvalidValue;
+  const int total = batch * ef;
+  if (total <= 0) return cudaSuccess;
+  rp_prep_kernel<<<(total + 127) / 128, 128, 0, st>>>(range, w1in, w, swap, batch, ef, wl, fault);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_rp_respond(const RpProveArgs& a, cudaStream_t st) {
+  if (a.wl > kMaxW) return cudaErrorInvalidValue;
+  const int total = a.batch * a.ef;
+  if (total <= 0) return cudaSuccess;
+  rp_respond_kernel<<<(total + 127) / 128, 128, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------ verify: plan
+// For each (proof, i): the challenge bit, the (bit, variant) match of
+// range_proof.rs:276/314/345, the interval predicates (:300-309, :338-340), and
+// the Paillier encryptions to run, appended to a compact job list
+// (2 for Open, 1 for Mask).  sel[t] tells K3 which ciphertext to multiply by
+// cipher_x (0 none, 1 c1, 2 c2).
+__global__ void rp_plan_kernel(RpVerifyArgs a) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= a.batch * a.ef) return;
+  const int b = t / a.ef, i = t % a.ef;
+  const int wl = a.wl, nl = a.nl;
+  const uint32_t e = challenge_bit(a.digest + (size_t)b * 32, i);
+  const uint8_t k = a.kind[t];
+  a.sel[t] = 0;
+  if (e == 2u || k > ZKP_RP_MASK2_) {  // the reference panics (index out of range) / has no such variant
+    a.fault[b] = 1;
+    a.ok[t] = 0;
+    return;
+  }
+  if ((e == 0u) != (k == ZKP_RP_OPEN_)) {  // `_ => false`
+    a.ok[t] = 0;
+    return;
+  }
+  uint32_t third[kMaxW], two[kMaxW];
+  div3(third, a.range + (size_t)b * wl, wl);
+  addw(two, third, third, wl);
+  const uint32_t* rw = a.resp_w + (size_t)t * 2 * wl;
+  const uint32_t* rr = a.resp_r + (size_t)t * 2 * nl;
+  bool ok;
+  int njobs;
+  if (k == ZKP_RP_OPEN_) {
+    const uint32_t* w1 = rw;
+    const uint32_t* w2 = rw + wl;
+    const bool f1 = cmpw(w2, third, wl) < 0 && cmpw(w1, third, wl) > 0 && cmpw(w1, two, wl) < 0;
+    const bool f2 = cmpw(w1, third, wl) < 0 && cmpw(w2, third, wl) > 0 && cmpw(w2, two, wl) < 0;
+    ok = f1 || f2;
+    njobs = 2;
+  } else {
+    ok = !(cmpw(rw, third, wl) < 0 || cmpw(rw, two, wl) > 0);
+    njobs = 1;
+    a.sel[t] = k;  // 1 -> c1, 2 -> c2 (j == 1 ? c1 : c2; only 1 and 2 are representable here)
+  }
+  a.ok[t] = ok ? 1 : 0;
+  // The encryptions are still performed when a predicate already failed, as in the reference.
+  const unsigned slot = atomicAdd(a.count, (unsigned)njobs);
+  for (int j = 0; j < njobs; ++j) {
+    a.tag[slot + j] = ((uint32_t)t << 1) | (uint32_t)j;
+    uint32_t* jb = a.jobs_base + (size_t)(slot + j) * nl;
+    uint32_t* jp = a.jobs_plain + (size_t)(slot + j) * wl;
+    for (int q = 0; q < nl; ++q) jb[q] = rr[(size_t)j * nl + q];
+    for (int q = 0; q < wl; ++q) jp[q] = rw[(size_t)j * wl + q];
+  }
+}
+
+// ----------------------------------------------------------- verify: check
+// One warp per executed encryption: compare with the committed ciphertext
+// (Open: c1[i] / c2[i], range_proof.rs:293-298) or with c_j * cipher_x mod n^2
+// (Mask, :321-337); clear ok[t] on mismatch.
+__global__ void rp_check_kernel(RpVerifyArgs a) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const unsigned njobs = *a.count;
+  if ((unsigned)warp >= njobs) return;
+  const uint32_t tg = a.tag[warp];
+  const uint32_t t = tg >> 1, j = tg & 1u;
+  const int nnl = 2 * a.nl;
+  const size_t half = (size_t)a.batch * a.ef;
+  const uint32_t* want;
+  if (a.kind[t] == ZKP_RP_OPEN_) want = a.c + ((j ? half : 0) + t) * nnl;
+  else want = a.cmul + (size_t)t * nnl;
+  const uint32_t* got = a.jobs_out + (size_t)warp * nnl;
+  uint32_t diff = 0;
+  for (int q = lane; q < nnl; q += 32) diff |= got[q] ^ want[q];
+  diff = __reduce_or_sync(0xffffffffu, diff);
+  if (lane == 0 && diff) a.ok[t] = 0;
+}
+
+// accept[b] = AND_i ok[b][i], and not faulted (range_proof.rs:350-354)
+__global__ void rp_accept_kernel(const uint8_t* ok, const uint8_t* fault, int batch, int ef, uint8_t* accept) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= batch) return;
+  uint32_t all = 1;
+  for (int i = lane; i < ef; i += 32) all &= ok[(size_t)warp * ef + i];
+  all = __reduce_and_sync(0xffffffffu, all);
+  if (lane == 0) accept[warp] = (uint8_t)((all & 1u) && !fault[warp]);
+}
+
+cudaError_t launch_rp_plan(const RpVerifyArgs& a, cudaStream_t st) {
+  if (a.wl > kMaxW) return cudaErrorInvalidValue;
+  const int total = a.batch * a.ef;
+  if (total <= 0) return cudaSuccess;
+  rp_plan_kernel<<<(total + 127) / 128, 128, 0, st>>>(a);
+  return cudaGetLastError();
+}
+cudaError_t launch_rp_check(const RpVerifyArgs& a, cudaStream_t st) {
+  const long long maxjobs = 2ll * a.batch * a.ef;
+  if (maxjobs <= 0) return cudaSuccess;
+  rp_check_kernel<<<(unsigned)((maxjobs * 32 + 255) / 256), 256, 0, st>>>(a);
+  return cudaGetLastError();
+}
+cudaError_t launch_rp_accept(const uint8_t* ok, const uint8_t* fault, int batch, int ef, uint8_t* accept,
+                             cudaStream_t st) {
+  if (batch <= 0) return cudaSuccess;
+  rp_accept_kernel<<<(batch * 32 + 255) / 256, 256, 0, st>>>(ok, fault, batch, ef, accept);
+  return cudaGetLastError();
+}
+
+}  // namespace zkp

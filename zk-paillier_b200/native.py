@@ -36,7 +36,7 @@ SIGNATURES = {
     "zkp_nn_limbs": (C.c_int, [C.c_void_p]),
     "zkp_modexp_shared": (C.c_int, [C.c_void_p, _u32p, C.c_int, C.c_int, _u32p]),
     "zkp_paillier_enc": (C.c_int, [C.c_void_p, _u32p, C.c_int, _u32p, C.c_int, C.c_int, _u32p]),
-    "zkp_modexp_var": (C.c_int, [C.c_void_p, _u32p, _u32p, C.c_int, C.c_int, _u32p, C.c_int, C.c_int, C.c_int, _u32p]),
+    "zkp_modexp_var": (C.c_int, [C.c_void_p, _u32p, _u32p, C.c_int, C.c_int, C.c_int, _u32p, C.c_int, C.c_int, C.c_int, _u32p]),
     "zkp_modmul": (C.c_int, [C.c_void_p, C.c_int, _u32p, _u32p, C.c_int, C.c_int, _u32p]),
     "zkp_sha256_transcript": (C.c_int, [C.c_void_p, _u32p, C.c_int, C.c_int, C.c_int, _u8p]),
     "zkp_rangeproof_ni_prove": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, _u32p, _u32p, _u32p, _u32p, _u8p, _u32p, _u32p,
@@ -212,15 +212,19 @@ class Context:
         self._ck(self._lib.zkp_paillier_enc(self._h, _p32(m), m.shape[1], _p32(r), r.shape[1], batch, _p32(out)))
         return out
 
-    def modexp_var(self, bases, exps, mods, per=1, exp_bits=None):
+    def modexp_var(self, bases, exps, mods, per=1, exp_bits=None, exp_per=None, mod_per=None):
+        """out[j] = bases[j]^exps[j // exp_per] mod mods[j // mod_per]; `per` sets both."""
         bases, exps, mods = _c32(bases), _c32(exps), _c32(mods)
+        exp_per = per if exp_per is None else exp_per
+        mod_per = per if mod_per is None else mod_per
         batch, ml = bases.shape
-        assert mods.shape[1] == ml and exps.shape[0] == mods.shape[0] == (batch + per - 1) // per
+        assert mods.shape[1] == ml and mods.shape[0] == (batch + mod_per - 1) // mod_per
+        assert exps.shape[0] == (batch + exp_per - 1) // exp_per
         if exp_bits is None:
             exp_bits = 32 * exps.shape[1]
         out = np.empty((batch, ml), dtype=np.uint32)
-        self._ck(self._lib.zkp_modexp_var(self._h, _p32(bases), _p32(exps), exps.shape[1], exp_bits, _p32(mods), ml, per,
-                                          batch, _p32(out)))
+        self._ck(self._lib.zkp_modexp_var(self._h, _p32(bases), _p32(exps), exps.shape[1], exp_bits, exp_per, _p32(mods), ml,
+                                          mod_per, batch, _p32(out)))
         return out
 
     def modmul(self, a, b, which_nn=True, b_per=1):
