@@ -144,12 +144,9 @@ def run_b200(args):
     nl = N_BITS // 32
 
     # public key: rank 0 owns it, one NCCL broadcast (the only collective before the hot path)
-    n_t = torch.zeros(nl, dtype=torch.int32, device=dev)
-    if rank == 0:
-        n_t.copy_(torch.from_numpy(to_limbs(test_key(), nl).view(np.int32)))
-    if world > 1:
-        dist.broadcast(n_t, 0)
-    n_limbs_arr = n_t.cpu().numpy().view(np.uint32)
+    from zk_paillier_b200 import sharding
+
+    n_limbs_arr = sharding.broadcast_key(to_limbs(test_key(), nl) if rank == 0 else np.zeros(1, np.uint32), dev)
     n_int = int.from_bytes(n_limbs_arr.tobytes(), "little")
 
     stream = torch.cuda.Stream(dev)  # the library launches on this stream, so torch events on it time the kernels
@@ -232,9 +229,8 @@ def run_b200(args):
     for _ in range(args.e2e_steps):
         step_e2e()
     if world > 1:  # final gather of the verdicts + challenge hashes over NVLink (33 B per proof)
-        rec = torch.from_numpy(np.concatenate([acc_h[:, None], dig_h], axis=1)).to(dev)
-        allrec = torch.empty((world,) + tuple(rec.shape), dtype=rec.dtype, device=dev)
-        dist.all_gather_into_tensor(allrec, rec)
+        allrec = sharding.gather_records(np.concatenate([acc_h[:, None], dig_h], axis=1), dev, counts=[batch] * world)
+        assert allrec.shape == (world * batch, 33)
     g1.record(stream)
     barrier()
     e2e_ms = g0.elapsed_time(g1)  # the ABI calls are host-synchronous, so the event pair brackets copies + kernels + host gaps

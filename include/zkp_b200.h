@@ -170,6 +170,42 @@ int zkp_ck_verify_stage(zkp_ctx* ctx, int batch, int n_limbs, const uint32_t* n,
 int zkp_ck_verify_run(zkp_ctx* ctx);
 int zkp_ck_verify_fetch(zkp_ctx* ctx, uint8_t* accept, uint32_t* rho);
 
+/* ---- sigma protocols under the key of zkp_set_key -----------------------------
+ * One row per proof; n-wide rows are [batch][n_limbs], ciphertext-wide rows are
+ * [batch][nn_limbs].  The Fiat-Shamir challenge e = compute_digest(n, ...) is
+ * computed on the device.  Randomness (r_prime, x_prime, d, r_d, a.., r_a) is an
+ * input.  z_limbs: row width of the UNREDUCED responses x' + x*e (correct_ciphertext.rs:59,
+ * verlin_proof.rs:87-89), a multiple of 4 with n_limbs + 12 <= z_limbs <= nn_limbs.
+ * accept[b] = 1 iff verify returns Ok(()).
+ *
+ * ZeroProof (zero_enc_proof.rs:44-94): witness r, statement c; proof (z, a). */
+int zkp_zero_prove(zkp_ctx* ctx, int batch, const uint32_t* r, const uint32_t* c, const uint32_t* r_prime, uint32_t* z,
+                   uint32_t* a);
+int zkp_zero_verify(zkp_ctx* ctx, int batch, const uint32_t* c, const uint32_t* z, const uint32_t* a, uint8_t* accept);
+/* CiphertextProof (correct_ciphertext.rs:42-98): witness (x, r), statement c; proof (z1, z2, c_prime). */
+int zkp_ciphertext_prove(zkp_ctx* ctx, int batch, int z_limbs, const uint32_t* x, const uint32_t* r, const uint32_t* c,
+                         const uint32_t* x_prime, const uint32_t* r_prime, uint32_t* z1, uint32_t* z2, uint32_t* c_prime);
+int zkp_ciphertext_verify(zkp_ctx* ctx, int batch, int z_limbs, const uint32_t* c, const uint32_t* z1, const uint32_t* z2,
+                          const uint32_t* c_prime, uint8_t* accept);
+/* MulProof (multiplication_proof.rs:60-145): witness (a, b, r_a, r_b, r_c), statement (e_a, e_b, e_c),
+ * randomness (d, r_d); proof (f, z1, z2, e_d, e_db).  fault[b] = 1 where BigInt::mod_inv(..).unwrap()
+ * (:96, :137) would panic (value not invertible mod n^2); such proofs are not accepted. */
+int zkp_mul_prove(zkp_ctx* ctx, int batch, const uint32_t* a, const uint32_t* b, const uint32_t* r_a, const uint32_t* r_b,
+                  const uint32_t* r_c, const uint32_t* e_a, const uint32_t* e_b, const uint32_t* e_c, const uint32_t* d,
+                  const uint32_t* r_d, uint32_t* f, uint32_t* z1, uint32_t* z2, uint32_t* e_d, uint32_t* e_db, uint8_t* fault);
+int zkp_mul_verify(zkp_ctx* ctx, int batch, const uint32_t* e_a, const uint32_t* e_b, const uint32_t* e_c, const uint32_t* f,
+                   const uint32_t* z1, const uint32_t* z2, const uint32_t* e_d, const uint32_t* e_db, uint8_t* accept,
+                   uint8_t* fault);
+/* VerlinProof (verlin_proof.rs:60-165): witness (x, x', x'', r_x), statement (c, c', phi_x),
+ * randomness (a, a', a'', r_a); proof (phi_a, z, z', z'', r_z). */
+int zkp_verlin_prove(zkp_ctx* ctx, int batch, int z_limbs, const uint32_t* x, const uint32_t* x_prime, const uint32_t* x_dp,
+                     const uint32_t* r_x, const uint32_t* c, const uint32_t* c_prime, const uint32_t* phi_x,
+                     const uint32_t* a, const uint32_t* a_prime, const uint32_t* a_dp, const uint32_t* r_a, uint32_t* phi_a,
+                     uint32_t* z, uint32_t* z_prime, uint32_t* z_dp, uint32_t* r_z);
+int zkp_verlin_verify(zkp_ctx* ctx, int batch, int z_limbs, const uint32_t* c, const uint32_t* c_prime, const uint32_t* phi_x,
+                      const uint32_t* phi_a, const uint32_t* z, const uint32_t* z_prime, const uint32_t* z_dp,
+                      const uint32_t* r_z, uint8_t* accept);
+
 /* ---- measurement ----------------------------------------------------------
  * Register-only multiply-add issue-rate microbenchmark (the roofline denominator
  * for the modexp kernels).  variant 0: independent IMAD.WIDE.U32, 1: the

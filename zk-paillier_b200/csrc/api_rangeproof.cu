@@ -23,7 +23,6 @@ ShaSegs rp_transcript(zkp_ctx* c, const uint32_t* cpairs, int batch, int ef) {
   s.seg[0] = {c->n.mod.as<uint32_t>(), 0, 1, c->n.limbs};                       // ek.n
   s.seg[1] = {cpairs, (long long)ef * nnl, ef, nnl};                             // c1[0..ef)
   s.seg[2] = {cpairs + (size_t)batch * ef * nnl, (long long)ef * nnl, ef, nnl};  // c2[0..ef)
-  s.seg[3] = {nullptr, 0, 0, 0};
   return s;
 }
 
@@ -43,7 +42,6 @@ int zkp_sha256_transcript(zkp_ctx* c, const uint32_t* items, int limbs, int coun
   ShaSegs s;
   s.nseg = 1;
   s.seg[0] = {c->in0.as<uint32_t>(), (long long)count * limbs, count, limbs};
-  s.seg[1] = s.seg[2] = s.seg[3] = {nullptr, 0, 0, 0};
   {
     ProfScope ps(c, KID_SHA, batch);
     ZKP_CU(c, launch_sha256_transcript(s, batch, c->out0.as<uint8_t>(), c->stream));

@@ -1,0 +1,373 @@
+// C-ABI layer, part 4: the sigma-protocol proofs for a batch of statements under one key:
+//   ZeroProof        reference src/zkproofs/zero_enc_proof.rs:44-94
+//   CiphertextProof  reference src/zkproofs/correct_ciphertext.rs:42-98
+//   MulProof         reference src/zkproofs/multiplication_proof.rs:60-145
+//   VerlinProof      reference src/zkproofs/verlin_proof.rs:60-165
+// Each call uploads the statement/witness/randomness rows, sequences K1 (Enc), K2 (mod_pow with the
+// per-proof challenge / response exponents), K3 (mod_mul), K4 (the Fiat-Shamir hash) and the
+// per-proof helpers of sigma.cu on the device, and downloads the proof rows or verdicts.
+#include "ctx.h"
+
+using namespace zkp;
+
+namespace {
+
+// Bump allocator over one device buffer for the temporaries of a call.
+struct Arena {
+  zkp_ctx* c;
+  size_t off = 0, cap = 0;
+  uint8_t* base = nullptr;
+  std::vector<size_t> wants;
+  explicit Arena(zkp_ctx* ctx) : c(ctx) {}
+  cudaError_t reserve(size_t bytes) {
+    cudaError_t e = c->in0.ensure(bytes);
+    base = c->in0.as<uint8_t>();
+    cap = bytes;
+    off = 0;
+    return e;
+  }
+  template <class U>
+  U* get(size_t count) {
+    size_t bytes = (count * sizeof(U) + 255) & ~size_t(255);
+    if (off + bytes > cap) return nullptr;
+    U* p = reinterpret_cast<U*>(base + off);
+    off += bytes;
+    return p;
+  }
+};
+
+struct Sig {
+  zkp_ctx* c;
+  cudaStream_t st;
+  int batch, nl, nnl;
+  Arena ar;
+  bool bad = false;
+  Sig(zkp_ctx* ctx, int b) : c(ctx), st(ctx->stream), batch(b), nl(ctx->n.limbs), nnl(ctx->nn.limbs), ar(ctx) {}
+
+  uint32_t* rows(int limbs) {
+    uint32_t* p = ar.get<uint32_t>((size_t)batch * limbs);
+    if (!p) bad = true;
+    return p;
+  }
+  uint32_t* up(const uint32_t* host, int limbs) {  // upload [batch][limbs]
+    uint32_t* p = rows(limbs);
+    if (p && cudaMemcpyAsync(p, host, (size_t)batch * limbs * 4, cudaMemcpyHostToDevice, st) != cudaSuccess) bad = true;
+    return p;
+  }
+  void down(uint32_t* host, const uint32_t* dev, int limbs) {
+    if (host && cudaMemcpyAsync(host, dev, (size_t)batch * limbs * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) bad = true;
+  }
+  void ck(cudaError_t e) {
+    if (e != cudaSuccess) {
+      bad = true;
+      fail_cuda(c, e, "sigma-protocol launch");
+    }
+  }
+  // Paillier::encrypt_with_chosen_randomness(ek, m, r); m == nullptr means the plaintext 0 (c = r^n mod nn)
+  uint32_t* enc(const uint32_t* m, int m_limbs, const uint32_t* r, int r_limbs) {
+    uint32_t* out = rows(nnl);
+    if (bad) return out;
+    ProfScope ps(c, KID_MODEXP_SHARED, batch);
+    ck(launch_modexp_shared(c->nn.view(), r, r_limbs, m, m_limbs, out, nnl, batch, c->table.as<uint32_t>(), c->num_sms, st));
+    return out;
+  }
+  // BigInt::mod_pow(base, exp, nn) / Paillier::mul, per-proof exponent
+  uint32_t* powm(const uint32_t* base, int base_limbs, const uint32_t* exp, int exp_limbs) {
+    uint32_t* out = rows(nnl);
+    if (bad) return out;
+    ProfScope ps(c, KID_MODEXP_VAR, batch);
+    ck(launch_modexp_var(base, c->nn.mod.as<uint32_t>(), nnl, c->nn.r2.as<uint32_t>(), c->nn.n0.as<uint32_t>(), exp, exp_limbs,
+                         32 * exp_limbs, 1, 0x7fffffff, out, batch, c->nn.S, c->table.as<uint32_t>(), c->num_sms, st, base_limbs));
+    return out;
+  }
+  // BigInt::mod_mul(a, b, nn) / Paillier::add
+  uint32_t* mulm(const uint32_t* a, int a_limbs, const uint32_t* b, int b_limbs) {
+    uint32_t* out = rows(nnl);
+    if (bad) return out;
+    ProfScope ps(c, KID_MODMUL, batch);
+    ck(launch_modmul_shared(c->nn.view(), 0, a, a_limbs, b, b_limbs, 1, out, nnl, batch, st));
+    return out;
+  }
+  // e = compute_digest(n, items...) as 8 limbs
+  uint32_t* challenge(std::initializer_list<const uint32_t*> items) {
+    uint8_t* dig = ar.get<uint8_t>((size_t)batch * 32);
+    uint32_t* e = rows(8);
+    if (!dig || bad) { bad = true; return e; }
+    ShaSegs s;
+    s.nseg = 0;
+    s.seg[s.nseg++] = {c->n.mod.as<uint32_t>(), 0, 1, nl};
+    for (const uint32_t* p : items) s.seg[s.nseg++] = {p, (long long)nnl, 1, nnl};
+    {
+      ProfScope ps(c, KID_SHA, batch);
+      ck(launch_sha256_transcript(s, batch, dig, st));
+    }
+    ProfScope ps(c, KID_OTHER, batch);
+    ck(launch_digest_to_limbs(dig, batch, e, st));
+    return e;
+  }
+  int finish(const char* what) {
+    if (bad) {
+      cudaStreamSynchronize(st);
+      if (c->err.empty()) c->err = what;
+      return ZKP_E_CUDA;
+    }
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return fail_cuda(c, e, what);
+    return ZKP_OK;
+  }
+};
+
+int sigma_begin(zkp_ctx* c, int batch, int z_limbs, size_t rows_nnl, size_t rows_other_bytes, Sig& s) {
+  if (!c->paillier) return fail(c, ZKP_E_STATE, "zkp_set_key not called");
+  if (batch <= 0) return fail(c, ZKP_E_ARG, "batch must be positive");
+  if (z_limbs && (z_limbs % 4 || z_limbs < c->n.limbs + 12 || z_limbs > c->nn.S))
+    return fail(c, ZKP_E_ARG, "z_limbs must be a multiple of 4 in [n_limbs + 12, nn_limbs]");
+  cudaError_t e = cudaSetDevice(c->device);
+  if (e != cudaSuccess) return fail_cuda(c, e, "cudaSetDevice");
+  c->err.clear();
+  // generous: every helper result is one [batch][nn_limbs] row array
+  size_t bytes = (size_t)batch * ((rows_nnl + 12) * s.nnl * 4 + rows_other_bytes + 256) + 64 * 256;
+  e = s.ar.reserve(bytes);
+  if (e != cudaSuccess) return fail_cuda(c, e, "arena");
+  e = ensure_table(c, c->nn.S, kTableVar);
+  if (e != cudaSuccess) return fail_cuda(c, e, "table");
+  return ZKP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+// ------------------------------------------------------------------ ZeroProof
+int zkp_zero_prove(zkp_ctx* c, int batch, const uint32_t* r, const uint32_t* cc, const uint32_t* r_prime, uint32_t* z,
+                   uint32_t* a) {
+  if (!c || !r || !cc || !r_prime || !z || !a) return c ? fail(c, ZKP_E_ARG, "null buffer") : ZKP_E_ARG;
+  Sig s(c, batch);
+  int rc = sigma_begin(c, batch, 0, 6, 4 * 4 * (size_t)s.nl, s);
+  if (rc) return rc;
+  uint32_t* d_r = s.up(r, s.nl);
+  uint32_t* d_c = s.up(cc, s.nnl);
+  uint32_t* d_rp = s.up(r_prime, s.nl);
+  uint32_t* d_a = s.enc(nullptr, 0, d_rp, s.nl);                 // a = Enc(0, r')            :46-52
+  uint32_t* e = s.challenge({d_c, d_a});                         // e = H(n, c, a)            :54-58
+  uint32_t* r_e = s.powm(d_r, s.nl, e, 8);                       // r^e mod nn                :60
+  uint32_t* d_z = s.mulm(d_rp, s.nl, r_e, s.nnl);                // z = r' * r^e mod nn       :61
+  s.down(z, d_z, s.nnl);
+  s.down(a, d_a, s.nnl);
+  return s.finish("zkp_zero_prove");
+}
+
+int zkp_zero_verify(zkp_ctx* c, int batch, const uint32_t* cc, const uint32_t* z, const uint32_t* a, uint8_t* accept) {
+  if (!c || !cc || !z || !a || !accept) return c ? fail(c, ZKP_E_ARG, "null buffer") : ZKP_E_ARG;
+  Sig s(c, batch);
+  int rc = sigma_begin(c, batch, 0, 7, 64, s);
+  if (rc) return rc;
+  uint32_t* d_c = s.up(cc, s.nnl);
+  uint32_t* d_z = s.up(z, s.nnl);
+  uint32_t* d_a = s.up(a, s.nnl);
+  uint8_t* d_acc = s.ar.get<uint8_t>((size_t)batch);
+  uint32_t* e = s.challenge({d_c, d_a});                         // :67-71
+  uint32_t* c_z = s.enc(nullptr, 0, d_z, s.nnl);                 // Enc(0, z)                 :73-79
+  uint32_t* c_e = s.powm(d_c, s.nnl, e, 8);                      // Paillier::mul(c, e)       :81-85
+  uint32_t* c_z_test = s.mulm(c_e, s.nnl, d_a, s.nnl);           // Paillier::add(c_e, a)     :86-88
+  if (!s.bad) s.ck(launch_rows_equal(c_z, c_z_test, s.nnl, batch, 0, d_acc, s.st));
+  if (cudaMemcpyAsync(accept, d_acc, (size_t)batch, cudaMemcpyDeviceToHost, s.st) != cudaSuccess) s.bad = true;
+  return s.finish("zkp_zero_verify");
+}
+
+// ------------------------------------------------------------ CiphertextProof
+int zkp_ciphertext_prove(zkp_ctx* c, int batch, int z_limbs, const uint32_t* x, const uint32_t* r, const uint32_t* cc,
+                         const uint32_t* x_prime, const uint32_t* r_prime, uint32_t* z1, uint32_t* z2, uint32_t* c_prime) {
+  if (!c || !x || !r || !cc || !x_prime || !r_prime || !z1 || !z2 || !c_prime) return c ? fail(c, ZKP_E_ARG, "null buffer") : ZKP_E_ARG;
+  Sig s(c, batch);
+  int rc = sigma_begin(c, batch, z_limbs, 6, 4 * (4 * (size_t)s.nl + z_limbs) + 64, s);
+  if (rc) return rc;
+  uint32_t* d_x = s.up(x, s.nl);
+  uint32_t* d_r = s.up(r, s.nl);
+  uint32_t* d_c = s.up(cc, s.nnl);
+  uint32_t* d_xp = s.up(x_prime, s.nl);
+  uint32_t* d_rp = s.up(r_prime, s.nl);
+  uint8_t* d_fault = s.ar.get<uint8_t>((size_t)batch);
+  cudaMemsetAsync(d_fault, 0, (size_t)batch, s.st);
+  uint32_t* d_cp = s.enc(d_xp, s.nl, d_rp, s.nl);                // c' = Enc(x', r')          :45-51
+  uint32_t* e = s.challenge({d_c, d_cp});                        // :53-57
+  uint32_t* d_z1 = s.rows(z_limbs);
+  if (!s.bad) s.ck(launch_muladd(d_xp, s.nl, d_x, s.nl, e, 8, batch, d_z1, z_limbs, d_fault, s.st));  // z1 = x' + x*e (unreduced) :59
+  uint32_t* r_e = s.powm(d_r, s.nl, e, 8);                       // :60
+  uint32_t* d_z2 = s.mulm(d_rp, s.nl, r_e, s.nnl);               // :61
+  s.down(z1, d_z1, z_limbs);
+  s.down(z2, d_z2, s.nnl);
+  s.down(c_prime, d_cp, s.nnl);
+  return s.finish("zkp_ciphertext_prove");
+}
+
+int zkp_ciphertext_verify(zkp_ctx* c, int batch, int z_limbs, const uint32_t* cc, const uint32_t* z1, const uint32_t* z2,
+                          const uint32_t* c_prime, uint8_t* accept) {
+  if (!c || !cc || !z1 || !z2 || !c_prime || !accept) return c ? fail(c, ZKP_E_ARG, "null buffer") : ZKP_E_ARG;
+  Sig s(c, batch);
+  int rc = sigma_begin(c, batch, z_limbs, 7, 4 * (size_t)z_limbs + 64, s);
+  if (rc) return rc;
+  uint32_t* d_c = s.up(cc, s.nnl);
+  uint32_t* d_z1 = s.up(z1, z_limbs);
+  uint32_t* d_z2 = s.up(z2, s.nnl);
+  uint32_t* d_cp = s.up(c_prime, s.nnl);
+  uint8_t* d_acc = s.ar.get<uint8_t>((size_t)batch);
+  uint32_t* e = s.challenge({d_c, d_cp});                        // :67-71
+  uint32_t* c_z = s.enc(d_z1, z_limbs, d_z2, s.nnl);             // Enc(z1, z2)               :73-79
+  uint32_t* c_e = s.powm(d_c, s.nnl, e, 8);                      // :81-85
+  uint32_t* c_z_test = s.mulm(c_e, s.nnl, d_cp, s.nnl);          // :86-92
+  if (!s.bad) s.ck(launch_rows_equal(c_z, c_z_test, s.nnl, batch, 0, d_acc, s.st));
+  if (cudaMemcpyAsync(accept, d_acc, (size_t)batch, cudaMemcpyDeviceToHost, s.st) != cudaSuccess) s.bad = true;
+  return s.finish("zkp_ciphertext_verify");
+}
+
+// -------------------------------------------------------------------- MulProof
+int zkp_mul_prove(zkp_ctx* c, int batch, const uint32_t* a, const uint32_t* b, const uint32_t* r_a, const uint32_t* r_b,
+                  const uint32_t* r_c, const uint32_t* e_a, const uint32_t* e_b, const uint32_t* e_c, const uint32_t* d,
+                  const uint32_t* r_d, uint32_t* f, uint32_t* z1, uint32_t* z2, uint32_t* e_d, uint32_t* e_db, uint8_t* fault) {
+  if (!c || !a || !b || !r_a || !r_b || !r_c || !e_a || !e_b || !e_c || !d || !r_d || !f || !z1 || !z2 || !e_d || !e_db || !fault)
+    return c ? fail(c, ZKP_E_ARG, "null buffer") : ZKP_E_ARG;
+  Sig s(c, batch);
+  int rc = sigma_begin(c, batch, 0, 22, 4 * 12 * (size_t)s.nl + 64, s);
+  if (rc) return rc;
+  const int nl = s.nl, nnl = s.nnl;
+  uint32_t *d_a = s.up(a, nl), *d_b = s.up(b, nl), *d_ra = s.up(r_a, nl), *d_rb = s.up(r_b, nl), *d_rc = s.up(r_c, nl);
+  uint32_t *d_ea = s.up(e_a, nnl), *d_eb = s.up(e_b, nnl), *d_ec = s.up(e_c, nnl), *d_d = s.up(d, nl), *d_rd = s.up(r_d, nl);
+  uint8_t* d_fault = s.ar.get<uint8_t>((size_t)batch);
+  cudaMemsetAsync(d_fault, 0, (size_t)batch, s.st);
+  uint32_t* d_ed = s.enc(d_d, nl, d_rd, nl);                                   // e_d = Enc(d, r_d)             :63-69
+  uint32_t* r_db = s.rows(nnl);
+  uint32_t* db = s.rows(nnl);
+  if (!s.bad) s.ck(launch_muladd(nullptr, 0, d_rd, nl, d_rb, nl, batch, r_db, nnl, d_fault, s.st));  // r_db = r_d * r_b (unreduced) :70
+  if (!s.bad) s.ck(launch_muladd(nullptr, 0, d_d, nl, d_b, nl, batch, db, nnl, d_fault, s.st));      // db = d * b (unreduced)       :71
+  uint32_t* d_edb = s.enc(db, nnl, r_db, nnl);                                 // e_db = Enc(db, r_db)          :72-78
+  uint32_t* e = s.challenge({d_ea, d_eb, d_ec, d_ed, d_edb});                  // :80-87
+  uint32_t* ea = s.rows(nl);
+  {
+    ProfScope ps(c, KID_MODMUL, batch);
+    s.ck(launch_modmul_shared(c->n.view(), 0, e, 8, d_a, nl, 1, ea, nl, batch, s.st));  // ea = e*a mod n       :89
+  }
+  uint32_t* d_f = s.rows(nl);
+  if (!s.bad) s.ck(launch_modadd(ea, d_d, c->n.mod.as<uint32_t>(), nl, batch, d_f, s.st));           // f = ea + d mod n     :90
+  uint32_t* r_a_e = s.powm(d_ra, nl, e, 8);                                    // :91
+  uint32_t* d_z1 = s.mulm(r_a_e, nnl, d_rd, nl);                               // :92
+  uint32_t* r_b_f = s.powm(d_rb, nl, d_f, nl);                                 // :93
+  uint32_t* r_c_e = s.powm(d_rc, nl, e, 8);                                    // :94
+  uint32_t* v = s.mulm(r_db, nnl, r_c_e, nnl);                                 // :95
+  uint32_t* vinv = s.rows(nnl);
+  uint32_t* scratch = s.rows(4 * nnl);
+  if (!s.bad) s.ck(launch_modinv(v, c->nn.mod.as<uint32_t>(), nnl, batch, scratch, vinv, d_fault, s.st));  // mod_inv(..).unwrap() :96
+  uint32_t* d_z2 = s.mulm(r_b_f, nnl, vinv, nnl);                              // :97
+  s.down(f, d_f, nl);
+  s.down(z1, d_z1, nnl);
+  s.down(z2, d_z2, nnl);
+  s.down(e_d, d_ed, nnl);
+  s.down(e_db, d_edb, nnl);
+  if (cudaMemcpyAsync(fault, d_fault, (size_t)batch, cudaMemcpyDeviceToHost, s.st) != cudaSuccess) s.bad = true;
+  return s.finish("zkp_mul_prove");
+}
+
+int zkp_mul_verify(zkp_ctx* c, int batch, const uint32_t* e_a, const uint32_t* e_b, const uint32_t* e_c, const uint32_t* f,
+                   const uint32_t* z1, const uint32_t* z2, const uint32_t* e_d, const uint32_t* e_db, uint8_t* accept,
+                   uint8_t* fault) {
+  if (!c || !e_a || !e_b || !e_c || !f || !z1 || !z2 || !e_d || !e_db || !accept || !fault)
+    return c ? fail(c, ZKP_E_ARG, "null buffer") : ZKP_E_ARG;
+  Sig s(c, batch);
+  int rc = sigma_begin(c, batch, 0, 22, 4 * (size_t)s.nl + 128, s);
+  if (rc) return rc;
+  const int nl = s.nl, nnl = s.nnl;
+  uint32_t *d_ea = s.up(e_a, nnl), *d_eb = s.up(e_b, nnl), *d_ec = s.up(e_c, nnl), *d_f = s.up(f, nl);
+  uint32_t *d_z1 = s.up(z1, nnl), *d_z2 = s.up(z2, nnl), *d_ed = s.up(e_d, nnl), *d_edb = s.up(e_db, nnl);
+  uint8_t* d_fault = s.ar.get<uint8_t>((size_t)batch);
+  uint8_t* d_acc = s.ar.get<uint8_t>((size_t)batch);
+  cudaMemsetAsync(d_fault, 0, (size_t)batch, s.st);
+  uint32_t* e = s.challenge({d_ea, d_eb, d_ec, d_ed, d_edb});                  // :109-116
+  uint32_t* enc_f_z1 = s.enc(d_f, nl, d_z1, nnl);                              // :118-124
+  uint32_t* enc_0_z2 = s.enc(nullptr, 0, d_z2, nnl);                           // :125-131
+  uint32_t* e_a_e = s.powm(d_ea, nnl, e, 8);                                   // :133
+  uint32_t* lhs1 = s.mulm(e_a_e, nnl, d_ed, nnl);                              // :134
+  uint32_t* e_c_e = s.powm(d_ec, nnl, e, 8);                                   // :135
+  uint32_t* v = s.mulm(d_edb, nnl, e_c_e, nnl);                                // :136
+  uint32_t* vinv = s.rows(nnl);
+  uint32_t* scratch = s.rows(4 * nnl);
+  if (!s.bad) s.ck(launch_modinv(v, c->nn.mod.as<uint32_t>(), nnl, batch, scratch, vinv, d_fault, s.st));  // :137 (unwrap -> fault)
+  uint32_t* e_b_f = s.powm(d_eb, nnl, d_f, nl);                                // :138
+  uint32_t* lhs2 = s.mulm(e_b_f, nnl, vinv, nnl);                              // :139
+  if (!s.bad) s.ck(launch_rows_equal(lhs1, enc_f_z1, nnl, batch, 0, d_acc, s.st));         // :141
+  if (!s.bad) s.ck(launch_rows_equal(lhs2, enc_0_z2, nnl, batch, 1, d_acc, s.st));
+  if (cudaMemcpyAsync(accept, d_acc, (size_t)batch, cudaMemcpyDeviceToHost, s.st) != cudaSuccess) s.bad = true;
+  if (cudaMemcpyAsync(fault, d_fault, (size_t)batch, cudaMemcpyDeviceToHost, s.st) != cudaSuccess) s.bad = true;
+  rc = s.finish("zkp_mul_verify");
+  if (rc == ZKP_OK)
+    for (int i = 0; i < batch; ++i)
+      if (fault[i]) accept[i] = 0;
+  return rc;
+}
+
+// ----------------------------------------------------------------- VerlinProof
+namespace {
+// gen_phi (verlin_proof.rs:138-165): c^y * c'^y' * Enc(y'', r_y) mod nn
+uint32_t* gen_phi(Sig& s, const uint32_t* cc, const uint32_t* cp, const uint32_t* y, const uint32_t* yp, const uint32_t* ydp,
+                  int y_limbs, const uint32_t* r_y, int r_limbs) {
+  uint32_t* c_y = s.powm(cc, s.nnl, y, y_limbs);
+  uint32_t* cp_yp = s.powm(cp, s.nnl, yp, y_limbs);
+  uint32_t* en = s.enc(ydp, y_limbs, r_y, r_limbs);
+  uint32_t* t = s.mulm(c_y, s.nnl, cp_yp, s.nnl);
+  return s.mulm(t, s.nnl, en, s.nnl);
+}
+}  // namespace
+
+int zkp_verlin_prove(zkp_ctx* c, int batch, int z_limbs, const uint32_t* x, const uint32_t* x_prime, const uint32_t* x_dp,
+                     const uint32_t* r_x, const uint32_t* cc, const uint32_t* c_prime, const uint32_t* phi_x,
+                     const uint32_t* a, const uint32_t* a_prime, const uint32_t* a_dp, const uint32_t* r_a, uint32_t* phi_a,
+                     uint32_t* z, uint32_t* z_prime, uint32_t* z_dp, uint32_t* r_z) {
+  if (!c || !x || !x_prime || !x_dp || !r_x || !cc || !c_prime || !phi_x || !a || !a_prime || !a_dp || !r_a || !phi_a || !z ||
+      !z_prime || !z_dp || !r_z)
+    return c ? fail(c, ZKP_E_ARG, "null buffer") : ZKP_E_ARG;
+  Sig s(c, batch);
+  int rc = sigma_begin(c, batch, z_limbs, 12, 4 * (8 * (size_t)s.nl + 3 * (size_t)z_limbs) + 128, s);
+  if (rc) return rc;
+  const int nl = s.nl, nnl = s.nnl;
+  uint32_t *d_x = s.up(x, nl), *d_xp = s.up(x_prime, nl), *d_xdp = s.up(x_dp, nl), *d_rx = s.up(r_x, nl);
+  uint32_t *d_c = s.up(cc, nnl), *d_cp = s.up(c_prime, nnl), *d_phix = s.up(phi_x, nnl);
+  uint32_t *d_a = s.up(a, nl), *d_ap = s.up(a_prime, nl), *d_adp = s.up(a_dp, nl), *d_ra = s.up(r_a, nl);
+  uint8_t* d_fault = s.ar.get<uint8_t>((size_t)batch);
+  cudaMemsetAsync(d_fault, 0, (size_t)batch, s.st);
+  uint32_t* d_phia = gen_phi(s, d_c, d_cp, d_a, d_ap, d_adp, nl, d_ra, nl);    // :70-78
+  uint32_t* e = s.challenge({d_c, d_cp, d_phix, d_phia});                      // :80-86
+  uint32_t *d_z = s.rows(z_limbs), *d_zp = s.rows(z_limbs), *d_zdp = s.rows(z_limbs);
+  if (!s.bad) s.ck(launch_muladd(d_a, nl, d_x, nl, e, 8, batch, d_z, z_limbs, d_fault, s.st));       // z = x*e + a      :87
+  if (!s.bad) s.ck(launch_muladd(d_ap, nl, d_xp, nl, e, 8, batch, d_zp, z_limbs, d_fault, s.st));    // :88
+  if (!s.bad) s.ck(launch_muladd(d_adp, nl, d_xdp, nl, e, 8, batch, d_zdp, z_limbs, d_fault, s.st)); // :89
+  uint32_t* r_x_e = s.powm(d_rx, nl, e, 8);                                    // :90
+  uint32_t* d_rz = s.mulm(r_x_e, nnl, d_ra, nl);                               // :91
+  s.down(phi_a, d_phia, nnl);
+  s.down(z, d_z, z_limbs);
+  s.down(z_prime, d_zp, z_limbs);
+  s.down(z_dp, d_zdp, z_limbs);
+  s.down(r_z, d_rz, nnl);
+  return s.finish("zkp_verlin_prove");
+}
+
+int zkp_verlin_verify(zkp_ctx* c, int batch, int z_limbs, const uint32_t* cc, const uint32_t* c_prime, const uint32_t* phi_x,
+                      const uint32_t* phi_a, const uint32_t* z, const uint32_t* z_prime, const uint32_t* z_dp,
+                      const uint32_t* r_z, uint8_t* accept) {
+  if (!c || !cc || !c_prime || !phi_x || !phi_a || !z || !z_prime || !z_dp || !r_z || !accept)
+    return c ? fail(c, ZKP_E_ARG, "null buffer") : ZKP_E_ARG;
+  Sig s(c, batch);
+  int rc = sigma_begin(c, batch, z_limbs, 13, 4 * 3 * (size_t)z_limbs + 128, s);
+  if (rc) return rc;
+  const int nnl = s.nnl;
+  uint32_t *d_c = s.up(cc, nnl), *d_cp = s.up(c_prime, nnl), *d_phix = s.up(phi_x, nnl), *d_phia = s.up(phi_a, nnl);
+  uint32_t *d_z = s.up(z, z_limbs), *d_zp = s.up(z_prime, z_limbs), *d_zdp = s.up(z_dp, z_limbs), *d_rz = s.up(r_z, nnl);
+  uint8_t* d_acc = s.ar.get<uint8_t>((size_t)batch);
+  uint32_t* e = s.challenge({d_c, d_cp, d_phix, d_phia});                      // :102-108
+  uint32_t* phi_x_e = s.powm(d_phix, nnl, e, 8);                               // :109-113
+  uint32_t* rhs = s.mulm(phi_x_e, nnl, d_phia, nnl);                           // :114-118
+  uint32_t* phi_z = gen_phi(s, d_c, d_cp, d_z, d_zp, d_zdp, z_limbs, d_rz, nnl);  // :120-128
+  if (!s.bad) s.ck(launch_rows_equal(phi_z, rhs, nnl, batch, 0, d_acc, s.st));
+  if (cudaMemcpyAsync(accept, d_acc, (size_t)batch, cudaMemcpyDeviceToHost, s.st) != cudaSuccess) s.bad = true;
+  return s.finish("zkp_verlin_verify");
+}
+
+}  // extern "C"

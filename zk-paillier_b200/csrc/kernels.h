@@ -54,7 +54,7 @@ cudaError_t launch_mont_setup(const uint32_t* mods, int mod_limbs, int S, int co
 cudaError_t launch_modexp_var(const uint32_t* bases, const uint32_t* mods, int mod_limbs, const uint32_t* r2,
                               const uint32_t* n0inv, const uint32_t* exps, int exp_limbs, int exp_bits,
                               int exp_per, int mod_per, uint32_t* out, int jobs, int S, uint32_t* table,
-                              int num_sms, cudaStream_t st);
+                              int num_sms, cudaStream_t st, int base_limbs = 0 /* 0: bases are mod_limbs wide */);
 
 // K3: shared modulus.  mode 0: out[j] = a[j] * b[j / b_per] mod M
 //                      mode 1: out[j] = a[j] * R mod M (to Montgomery form; b unused; out rows are S limbs)
@@ -77,7 +77,7 @@ struct ShaSeg {
   int limbs;               // limbs per item
 };
 struct ShaSegs {
-  ShaSeg seg[4];
+  ShaSeg seg[8];
   int nseg;
 };
 cudaError_t launch_sha256_transcript(const ShaSegs& segs, int batch, uint8_t* digest, cudaStream_t st);
@@ -136,6 +136,21 @@ cudaError_t launch_ck_reduce(const uint32_t* mask, int ml, const uint32_t* mods,
 // accept[b] = (rho[b] == derived[b]) && no prime in primes[] divides n_b
 cudaError_t launch_ck_check(const uint32_t* n, int nl, const uint32_t* rho, const uint32_t* derived,
                             const uint16_t* primes, int nprimes, int batch, uint8_t* accept, cudaStream_t st);
+
+// ---- sigma-protocol helpers (sigma.cu), one thread per proof ------------------------------------
+cudaError_t launch_digest_to_limbs(const uint8_t* digest, int batch, uint32_t* out /* [batch][8] */, cudaStream_t st);
+// out[b] = a[b] + x[b] * e[b] as plain integers (a may be null); sets fault[b] on overflow of out_limbs
+cudaError_t launch_muladd(const uint32_t* a, int a_limbs, const uint32_t* x, int x_limbs, const uint32_t* e, int e_limbs,
+                          int batch, uint32_t* out, int out_limbs, uint8_t* fault, cudaStream_t st);
+// out[b] = (a[b] + c[b]) mod m, a and c already below m (m: one shared modulus of `limbs` limbs)
+cudaError_t launch_modadd(const uint32_t* a, const uint32_t* c, const uint32_t* m, int limbs, int batch, uint32_t* out,
+                          cudaStream_t st);
+// accept[b] = (and_in ? accept[b] : 1) && x[b] == y[b]
+cudaError_t launch_rows_equal(const uint32_t* x, const uint32_t* y, int limbs, int batch, int and_in, uint8_t* accept,
+                              cudaStream_t st);
+// out[b] = v[b]^-1 mod m (m odd, shared); fault[b] = 1 when not invertible.  scratch: [batch][4*limbs]
+cudaError_t launch_modinv(const uint32_t* v, const uint32_t* m, int limbs, int batch, uint32_t* scratch, uint32_t* out,
+                          uint8_t* fault, cudaStream_t st);
 
 // IMAD.WIDE.U32 peak microbenchmark (register-only).  variant 0: independent
 // IMAD.WIDE.U32; 1: carry-chained IMAD.WIDE.U32.X rows; 2: plain IMAD (32-bit).

@@ -221,6 +221,7 @@ struct VarParams {
   uint32_t* out;
   uint32_t* table;
   int mod_limbs;
+  int base_limbs;
   int exp_limbs;
   int exp_bits;
   int exp_per;
@@ -256,7 +257,7 @@ __global__ void __launch_bounds__(kCtaThreads, Occ<T, L>::kMinBlocks) modexp_var
     uint32_t n[L], acc[L], y[L];
     M::load_ext(n, p.mods + (size_t)mi * p.mod_limbs, p.mod_limbs, g);
     M::load(y, p.r2 + (size_t)mi * S + g * L);
-    M::load_ext(acc, p.bases + (size_t)src * p.mod_limbs, p.mod_limbs, g);
+    M::load_ext(acc, p.bases + (size_t)src * p.base_limbs, p.base_limbs, g);
     M::mont_mul(acc, acc, y, n, n0inv, lane);  // x R
     {
       uint32_t one[L];
@@ -437,7 +438,9 @@ cudaError_t launch_mont_setup(const uint32_t* mods, int mod_limbs, int S, int co
 cudaError_t launch_modexp_var(const uint32_t* bases, const uint32_t* mods, int mod_limbs, const uint32_t* r2,
                               const uint32_t* n0inv, const uint32_t* exps, int exp_limbs, int exp_bits, int exp_per,
                               int mod_per, uint32_t* out, int jobs, int S, uint32_t* table, int num_sms,
-                              cudaStream_t st) {
+                              cudaStream_t st, int base_limbs) {
+  if (base_limbs <= 0) base_limbs = mod_limbs;
+  if (base_limbs % 2 || base_limbs > S) return cudaErrorInvalidValue;
   if (jobs <= 0) return cudaSuccess;
   if (exp_per <= 0 || mod_per <= 0 || exp_bits <= 0 || exp_bits > 32 * exp_limbs || mod_limbs % 2 || mod_limbs > S)
     return cudaErrorInvalidValue;
@@ -450,6 +453,7 @@ cudaError_t launch_modexp_var(const uint32_t* bases, const uint32_t* mods, int m
   p.out = out;
   p.table = table;
   p.mod_limbs = mod_limbs;
+  p.base_limbs = base_limbs;
   p.exp_limbs = exp_limbs;
   p.exp_bits = exp_bits;
   p.exp_per = exp_per;

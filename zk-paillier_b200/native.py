@@ -55,6 +55,14 @@ SIGNATURES = {
     "zkp_ck_verify_stage": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _u32p, _u32p, _u8p, C.c_int]),
     "zkp_ck_verify_run": (C.c_int, [C.c_void_p]),
     "zkp_ck_verify_fetch": (C.c_int, [C.c_void_p, _u8p, _u32p]),
+    "zkp_zero_prove": (C.c_int, [C.c_void_p, C.c_int] + [_u32p] * 5),
+    "zkp_zero_verify": (C.c_int, [C.c_void_p, C.c_int] + [_u32p] * 3 + [_u8p]),
+    "zkp_ciphertext_prove": (C.c_int, [C.c_void_p, C.c_int, C.c_int] + [_u32p] * 8),
+    "zkp_ciphertext_verify": (C.c_int, [C.c_void_p, C.c_int, C.c_int] + [_u32p] * 4 + [_u8p]),
+    "zkp_mul_prove": (C.c_int, [C.c_void_p, C.c_int] + [_u32p] * 15 + [_u8p]),
+    "zkp_mul_verify": (C.c_int, [C.c_void_p, C.c_int] + [_u32p] * 8 + [_u8p, _u8p]),
+    "zkp_verlin_prove": (C.c_int, [C.c_void_p, C.c_int, C.c_int] + [_u32p] * 16),
+    "zkp_verlin_verify": (C.c_int, [C.c_void_p, C.c_int, C.c_int] + [_u32p] * 8 + [_u8p]),
     "zkp_imad_peak": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double)]),
 }
 
@@ -332,3 +340,81 @@ class Context:
         self.ck_verify_stage(n, sigma, salt)
         self.ck_verify_run()
         return self.ck_verify_fetch(want_rho)
+
+    # -- sigma protocols (rows: [batch][n_limbs] or [batch][nn_limbs]; z rows [batch][z_limbs])
+    @property
+    def z_limbs(self):
+        return self.n_limbs + 12
+
+    def _rows(self, arrs, widths):
+        out = []
+        batch = None
+        for a, w in zip(arrs, widths):
+            a = _c32(a)
+            assert a.ndim == 2 and a.shape[1] == w, (a.shape, w)
+            batch = a.shape[0] if batch is None else batch
+            assert a.shape[0] == batch
+            out.append(a)
+        return batch, out
+
+    def zero_prove(self, r, c, r_prime):
+        nl, nnl = self.n_limbs, self.nn_limbs
+        batch, (r, c, r_prime) = self._rows((r, c, r_prime), (nl, nnl, nl))
+        z, a = np.empty((batch, nnl), np.uint32), np.empty((batch, nnl), np.uint32)
+        self._ck(self._lib.zkp_zero_prove(self._h, batch, _p32(r), _p32(c), _p32(r_prime), _p32(z), _p32(a)))
+        return z, a
+
+    def zero_verify(self, c, z, a):
+        nnl = self.nn_limbs
+        batch, (c, z, a) = self._rows((c, z, a), (nnl, nnl, nnl))
+        acc = np.empty(batch, np.uint8)
+        self._ck(self._lib.zkp_zero_verify(self._h, batch, _p32(c), _p32(z), _p32(a), _p8(acc)))
+        return acc
+
+    def ciphertext_prove(self, x, r, c, x_prime, r_prime):
+        nl, nnl, zl = self.n_limbs, self.nn_limbs, self.z_limbs
+        batch, (x, r, c, x_prime, r_prime) = self._rows((x, r, c, x_prime, r_prime), (nl, nl, nnl, nl, nl))
+        z1, z2, cp = np.empty((batch, zl), np.uint32), np.empty((batch, nnl), np.uint32), np.empty((batch, nnl), np.uint32)
+        self._ck(self._lib.zkp_ciphertext_prove(self._h, batch, zl, _p32(x), _p32(r), _p32(c), _p32(x_prime), _p32(r_prime),
+                                                _p32(z1), _p32(z2), _p32(cp)))
+        return z1, z2, cp
+
+    def ciphertext_verify(self, c, z1, z2, c_prime):
+        nnl, zl = self.nn_limbs, self.z_limbs
+        batch, (c, z1, z2, c_prime) = self._rows((c, z1, z2, c_prime), (nnl, zl, nnl, nnl))
+        acc = np.empty(batch, np.uint8)
+        self._ck(self._lib.zkp_ciphertext_verify(self._h, batch, zl, _p32(c), _p32(z1), _p32(z2), _p32(c_prime), _p8(acc)))
+        return acc
+
+    def mul_prove(self, a, b, r_a, r_b, r_c, e_a, e_b, e_c, d, r_d):
+        nl, nnl = self.n_limbs, self.nn_limbs
+        batch, ins = self._rows((a, b, r_a, r_b, r_c, e_a, e_b, e_c, d, r_d), (nl,) * 5 + (nnl,) * 3 + (nl, nl))
+        f = np.empty((batch, nl), np.uint32)
+        z1, z2, e_d, e_db = (np.empty((batch, nnl), np.uint32) for _ in range(4))
+        fault = np.empty(batch, np.uint8)
+        self._ck(self._lib.zkp_mul_prove(self._h, batch, *[_p32(v) for v in ins], _p32(f), _p32(z1), _p32(z2), _p32(e_d), _p32(e_db),
+                                         _p8(fault)))
+        return f, z1, z2, e_d, e_db, fault
+
+    def mul_verify(self, e_a, e_b, e_c, f, z1, z2, e_d, e_db):
+        nl, nnl = self.n_limbs, self.nn_limbs
+        batch, ins = self._rows((e_a, e_b, e_c, f, z1, z2, e_d, e_db), (nnl, nnl, nnl, nl, nnl, nnl, nnl, nnl))
+        acc, fault = np.empty(batch, np.uint8), np.empty(batch, np.uint8)
+        self._ck(self._lib.zkp_mul_verify(self._h, batch, *[_p32(v) for v in ins], _p8(acc), _p8(fault)))
+        return acc, fault
+
+    def verlin_prove(self, x, x_prime, x_dp, r_x, c, c_prime, phi_x, a, a_prime, a_dp, r_a):
+        nl, nnl, zl = self.n_limbs, self.nn_limbs, self.z_limbs
+        batch, ins = self._rows((x, x_prime, x_dp, r_x, c, c_prime, phi_x, a, a_prime, a_dp, r_a), (nl,) * 4 + (nnl,) * 3 + (nl,) * 4)
+        phi_a, r_z = np.empty((batch, nnl), np.uint32), np.empty((batch, nnl), np.uint32)
+        z, zp, zdp = (np.empty((batch, zl), np.uint32) for _ in range(3))
+        self._ck(self._lib.zkp_verlin_prove(self._h, batch, zl, *[_p32(v) for v in ins], _p32(phi_a), _p32(z), _p32(zp), _p32(zdp),
+                                            _p32(r_z)))
+        return phi_a, z, zp, zdp, r_z
+
+    def verlin_verify(self, c, c_prime, phi_x, phi_a, z, z_prime, z_dp, r_z):
+        nnl, zl = self.nn_limbs, self.z_limbs
+        batch, ins = self._rows((c, c_prime, phi_x, phi_a, z, z_prime, z_dp, r_z), (nnl,) * 4 + (zl,) * 3 + (nnl,))
+        acc = np.empty(batch, np.uint8)
+        self._ck(self._lib.zkp_verlin_verify(self._h, batch, zl, *[_p32(v) for v in ins], _p8(acc)))
+        return acc
