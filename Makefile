@@ -10,10 +10,16 @@ BUILD     := build
 CU        := $(wildcard $(CSRC)/*.cu)
 OBJ       := $(patsubst $(CSRC)/%.cu,$(BUILD)/%.o,$(CU))
 LIB       := zk-paillier_b200/libzkp_b200.so
+HOSTLIB   := zk-paillier_b200/libzkp_host.so
+HOSTSRC   := zk-paillier_b200/host
 
 all: lib oracle
 
-lib: $(LIB)
+lib: $(LIB) $(HOSTLIB)
+
+# C++ host mirror of the reference's zkproofs::* interface (JSON C shim for the tests); links the CUDA library
+$(HOSTLIB): $(HOSTSRC)/host_capi.cpp $(wildcard $(HOSTSRC)/*.hpp) include/zkp_b200.h $(LIB)
+	g++ -O2 -std=c++17 -fPIC -shared -Wall -o $@ $(HOSTSRC)/host_capi.cpp -Lzk-paillier_b200 -lzkp_b200 -Wl,-rpath,'$$ORIGIN'
 
 $(BUILD)/%.o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.h) $(wildcard $(CSRC)/*.cuh) include/zkp_b200.h
 	@mkdir -p $(BUILD)
@@ -26,7 +32,7 @@ oracle:
 	$(MAKE) -C oracle
 
 clean:
-	rm -rf $(BUILD) $(LIB)
+	rm -rf $(BUILD) $(LIB) $(HOSTLIB)
 	$(MAKE) -C oracle clean
 
 .PHONY: all lib oracle clean

@@ -6,7 +6,7 @@
  * zkproofs::RangeProofNi::{prove,verify} and NiCorrectKeyProof::verify (plus
  * the modexps of ZeroProof / CiphertextProof / MulProof / VerlinProof).  The
  * reference has no FFI of its own: its seam is the Rust call surface between the
- * proof protocols (src/zkproofs/*.rs) and curv-kzen / kzen-paillier (GMP).  Each
+ * proof protocols (src/zkproofs/) and curv-kzen / kzen-paillier (GMP).  Each
  * entry point below names the reference code it replaces; the Rust `extern "C"`
  * block a maintainer would add is in INTEGRATION.md and rust/src/ffi.rs.
  *
@@ -165,6 +165,11 @@ long long zkp_rp_verify_enc_count(zkp_ctx* ctx);
  * gcd(primorial(6370), N) == 1.  rho (optional out): [b][11][n_limbs]. */
 int zkp_correct_key_ni_verify(zkp_ctx* ctx, int batch, int n_limbs, const uint32_t* n, const uint32_t* sigma,
                               const uint8_t* salt, int salt_len, uint8_t* accept, uint32_t* rho);
+/* The prover's half of the same derivation (correct_key_ni.rs:44-63): rho[b][11][n_limbs] =
+ * mask_generation(|N_b|, H(N_b, H(salt), i)) % N_b.  NiCorrectKeyProof::proof then takes N-th roots of
+ * these with the decryption key (extract_nroot: two half-width zkp_modexp_var calls + CRT on the host). */
+int zkp_correct_key_ni_rho(zkp_ctx* ctx, int batch, int n_limbs, const uint32_t* n, const uint8_t* salt, int salt_len,
+                           uint32_t* rho);
 int zkp_ck_verify_stage(zkp_ctx* ctx, int batch, int n_limbs, const uint32_t* n, const uint32_t* sigma,
                         const uint8_t* salt, int salt_len);
 int zkp_ck_verify_run(zkp_ctx* ctx);

@@ -1,0 +1,200 @@
+"""GPU suite: the reference-shaped C++ interface (zkproofs.hpp) end to end -- prove / verify, Err vs panic,
+and the serde wire format -- cross-checked BOTH ways against the Python oracle on identical randomness:
+the JSON a C++ prover emits must be byte-identical to the oracle's, and each side must accept the other's proofs."""
+import json
+import random
+
+import pytest
+
+from hostlib import Stream, call
+from util import keys, po
+
+pytestmark = pytest.mark.gpu
+N2048 = po.TEST_P * po.TEST_Q
+
+
+def _range_statements(rng, n, count, bad=()):
+    st = []
+    for i in range(count):
+        q = rng.getrandbits(256) | (1 << 255)
+        x = q * rng.randrange(100, 10000) if i in bad else rng.randrange(q // 3)
+        r = rng.randrange(1, n)
+        st.append({"range": q, "x": x, "r": r, "ciphertext": po.paillier_encrypt(n, x, r)})
+    return st
+
+
+def _oracle_range_prove(n, s, stream, ef):
+    third = s["range"] // 3
+    w1 = [po.sample_range(stream, third, 2 * third) for _ in range(ef)]
+    swap = [b & 1 for b in stream(ef)]
+    r1 = [po.sample_below(stream, n) for _ in range(ef)]
+    r2 = [po.sample_below(stream, n) for _ in range(ef)]
+    return po.RangeProofNi.prove(n, s["range"], s["ciphertext"], s["x"], s["r"], w1, swap, r1, r2)
+
+
+@pytest.mark.parametrize("n,ef", [(N2048, 128), (None, 40)])
+def test_rangeproof_wire_format_and_cross_verification(n, ef):
+    if n is None:
+        p, q = keys(1024)[0]
+        n = p * q
+    rng = random.Random(ef)
+    st = _range_statements(rng, n, 3, bad={2})
+    data = rng.randbytes(3 * ef * (64 + 1 + 2 * 3 * 256) + 4096)   # rejection sampling: leave slack
+    r = call("rangeproof_ni.prove", n=str(n), error_factor=ef, rng_hex=data.hex(),
+             statements=[{k: str(v) for k, v in s.items()} for s in st])
+    assert r["ok"], r
+    stream = Stream(data)
+    for s, js in zip(st, r["proofs"]):
+        want = _oracle_range_prove(n, s, stream, ef)
+        assert js == want.to_json()                       # byte-identical serde output
+        back = po.RangeProofNi.from_json(js)
+        ok = True
+        try:
+            back.verify(n, s["ciphertext"])               # the oracle accepts / rejects the C++ prover's proof
+        except po.IncorrectProof:
+            ok = False
+        assert ok == (s["x"] < s["range"] // 3)
+    res = call("rangeproof_ni.verify", n=str(n), proofs=r["proofs"], ciphertexts=[str(s["ciphertext"]) for s in st])
+    assert res["results"] == ["ok", "ok", "incorrect"]
+    assert call("rangeproof_ni.verify_batch", proofs=r["proofs"])["accept"] == [1, 1, 0]
+    # precondition failures panic in the reference (assert_eq!): wrong ciphertext / wrong key
+    res = call("rangeproof_ni.verify", n=str(n), proofs=r["proofs"][:1], ciphertexts=[str(st[0]["ciphertext"] + 1)])
+    assert res["results"][0].startswith("panic")
+    res = call("rangeproof_ni.verify", n=str(n + 2), proofs=r["proofs"][:1], ciphertexts=[str(st[0]["ciphertext"])])
+    assert res["results"][0].startswith("panic")
+    # a proof claiming more responses than it carries indexes out of range in the reference
+    d = json.loads(r["proofs"][0])
+    d["proof"] = d["proof"][:-1]
+    res = call("rangeproof_ni.verify", n=str(n), proofs=[json.dumps(d)], ciphertexts=[str(st[0]["ciphertext"])])
+    assert res["results"][0].startswith("panic")
+    # tampered wire values
+    d = json.loads(r["proofs"][1])
+    k = next(i for i, o in enumerate(d["proof"]) if "Mask" in o)
+    d["proof"][k]["Mask"]["masked_x"] = str(int(d["proof"][k]["Mask"]["masked_x"]) + 1)
+    res = call("rangeproof_ni.verify", n=str(n), proofs=[json.dumps(d)], ciphertexts=[str(st[1]["ciphertext"])])
+    assert res["results"] == ["incorrect"]
+
+
+def test_oracle_proofs_verify_through_the_host_mirror():
+    p, q = keys(1024)[1]
+    n = p * q
+    rng = random.Random(4)
+    st = _range_statements(rng, n, 2, bad={1})
+    proofs = []
+    for s in st:
+        third = s["range"] // 3
+        ef = 128
+        pr = po.RangeProofNi.prove(n, s["range"], s["ciphertext"], s["x"], s["r"], [rng.randrange(third, 2 * third) for _ in range(ef)],
+                                   [rng.getrandbits(1) for _ in range(ef)], [rng.randrange(n) for _ in range(ef)], [rng.randrange(n) for _ in range(ef)])
+        proofs.append(pr.to_json())
+    res = call("rangeproof_ni.verify", n=str(n), proofs=proofs, ciphertexts=[str(s["ciphertext"]) for s in st])
+    assert res["results"] == ["ok", "incorrect"]
+
+
+@pytest.mark.parametrize("bits", [1024, 2048, 3072])
+def test_correct_key_proof_and_verify(bits):
+    p, q = keys(bits)[0]
+    n = p * q
+    for salt in (None, b"Zen Go X"):
+        req = {"p": str(p), "q": str(q)}
+        if salt is not None:
+            req["salt_hex"] = salt.hex()
+        r = call("correct_key_ni.proof", **req)
+        assert r["ok"], r
+        want = po.NiCorrectKeyProof.proof(p, q, salt)
+        assert r["proof"] == want.to_json()                # NiCorrectKeyProof::proof, CRT n-th roots, wire format
+        s = po.SALT_STRING if salt is None else salt
+        bad = po.NiCorrectKeyProof(list(want.sigma_vec))
+        bad.sigma_vec[10] = (bad.sigma_vec[10] * 2) % n
+        short = json.dumps({"sigma_vec": [str(v) for v in want.sigma_vec[:10]]})
+        res = call("correct_key_ni.verify", n=[str(n)] * 3, salt_hex=s.hex(), proofs=[r["proof"], bad.to_json(), short])
+        assert res["results"][:2] == ["ok", "incorrect"] and res["results"][2].startswith("panic")
+        res = call("correct_key_ni.verify", n=[str(n)], salt_hex=(s + b"!").hex(), proofs=[r["proof"]])
+        assert res["results"] == ["incorrect"]
+
+
+def _sigma_roundtrip(name, n, items, make_want, data, bad_expected):
+    r = call(f"{name}.prove", n=str(n), items=[{k: str(v) for k, v in it.items()} for it in items], rng_hex=data.hex())
+    assert r["ok"], r
+    stream = Stream(data)
+    wants = [make_want(it, stream) for it in items]
+    assert r["proofs"] == [w[0] for w in wants]             # wire format + values on identical randomness
+    vitems = [dict({k: str(v) for k, v in it.items()}, proof=js) for it, js in zip(items, r["proofs"])]
+    res = call(f"{name}.verify", n=str(n), items=vitems)
+    assert res["results"] == bad_expected, res
+    return r["proofs"]
+
+
+def test_sigma_protocols_through_the_host_mirror():
+    p, q = keys(1024)[2]
+    n = p * q
+    rng = random.Random(9)
+    rnd = lambda: rng.randrange(1, n)
+    hexs = lambda *vals: json.dumps({k: po.serde_bigint_native(v) for k, v in vals}, separators=(",", ":"))
+    data = rng.randbytes(20000)
+
+    # ZeroProof: {"z","a"}; statement 1 encrypts 1 (zero_enc_proof.rs:135)
+    items = []
+    for m in (0, 1):
+        r = rnd()
+        items.append({"r": r, "c": po.paillier_encrypt(n, m, r)})
+
+    def want_zero(it, s):
+        pr = po.ZeroProof.prove(it["r"], n, it["c"], po.sample_below(s, n))
+        return (hexs(("z", pr.z), ("a", pr.a)),)
+
+    _sigma_roundtrip("zero", n, items, want_zero, data, ["ok", "incorrect"])
+
+    # CiphertextProof: {"z1","z2","c_prime"}; witness r+1 in item 1 (correct_ciphertext.rs:140)
+    items = []
+    for bad in (0, 1):
+        x, r = rnd(), rnd()
+        items.append({"x": x, "r": r + bad, "c": po.paillier_encrypt(n, x, r)})
+
+    def want_ct(it, s):
+        xp = po.sample_below(s, n)
+        rp = po.sample_below(s, n)
+        pr = po.CiphertextProof.prove(it["x"], it["r"], n, it["c"], xp, rp)
+        return (hexs(("z1", pr.z1), ("z2", pr.z2), ("c_prime", pr.c_prime)),)
+
+    _sigma_roundtrip("ciphertext", n, items, want_ct, data, ["ok", "incorrect"])
+
+    # MulProof: {"f","z1","z2","e_d","e_db"}; c != a*b in item 1 (multiplication_proof.rs:223)
+    import math
+    items = []
+    for bad in (0, 1):
+        a, b = rnd(), rnd()
+        c = (a * b + bad) % n
+        r_a, r_b, r_c = rnd(), rnd(), rnd()
+        items.append({"a": a, "b": b, "c": c, "r_a": r_a, "r_b": r_b, "r_c": r_c, "e_a": po.paillier_encrypt(n, a, r_a),
+                      "e_b": po.paillier_encrypt(n, b, r_b), "e_c": po.paillier_encrypt(n, c, r_c)})
+
+    def coprime(s):
+        while True:
+            v = po.sample_below(s, n)
+            if math.gcd(v, n) == 1:
+                return v
+
+    def want_mul(it, s):
+        d = po.sample_below(s, n)
+        r_d = coprime(s)
+        pr = po.MulProof.prove(it["a"], it["b"], it["c"], it["r_a"], it["r_b"], it["r_c"], n, it["e_a"], it["e_b"], it["e_c"], d, r_d)
+        return (hexs(("f", pr.f), ("z1", pr.z1), ("z2", pr.z2), ("e_d", pr.e_d), ("e_db", pr.e_db)),)
+
+    _sigma_roundtrip("mul", n, items, want_mul, data, ["ok", "incorrect"])
+
+    # VerlinProof: {"phi_a","z","z_prime","z_double_prime","r_z"}; wrong x in item 1 (verlin_proof.rs:219)
+    items = []
+    for bad in (0, 1):
+        x, xp, xdp, r_x = rnd(), rnd(), rnd(), rnd()
+        c, cp = po.paillier_encrypt(n, rnd(), rnd()), po.paillier_encrypt(n, rnd(), rnd())
+        items.append({"x": x + bad, "x_prime": xp, "x_double_prime": xdp, "r_x": r_x, "c": c, "c_prime": cp,
+                      "phi_x": po.gen_phi(n, c, cp, x, xp, xdp, r_x)})
+
+    def want_verlin(it, s):
+        a, ap, adp = po.sample_below(s, n), po.sample_below(s, n), po.sample_below(s, n)
+        r_a = coprime(s)
+        pr = po.VerlinProof.prove(it["x"], it["x_prime"], it["x_double_prime"], it["r_x"], n, it["c"], it["c_prime"], it["phi_x"], a, ap, adp, r_a)
+        return (hexs(("phi_a", pr.phi_a), ("z", pr.z), ("z_prime", pr.z_prime), ("z_double_prime", pr.z_double_prime), ("r_z", pr.r_z)),)
+
+    _sigma_roundtrip("verlin", n, items, want_verlin, data, ["ok", "incorrect"])

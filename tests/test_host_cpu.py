@@ -1,0 +1,54 @@
+"""CPU suite: the C++ host mirror's own big-integer / codec layer (no GPU needed) against Python ints and the
+oracle's sampling rule."""
+import random
+
+from hostlib import Stream, call
+from util import po
+
+
+def test_bigint_against_python_ints():
+    rng = random.Random(1)
+    cases = [(0, 1), (1, 1), (2**32 - 1, 2**32), (2**64, 2**32 - 1), (10**40, 10**20 + 1)]
+    for _ in range(200):
+        ab, bb = rng.choice([8, 64, 300, 2048, 4096]), rng.choice([8, 33, 64, 1024, 2047])
+        cases.append((rng.getrandbits(ab), rng.getrandbits(bb) | 1))
+    for a, b in cases:
+        r = call("bigint.selftest", a=str(a), b=str(b))
+        assert r["ok"], r
+        assert int(r["sum"]) == a + b and int(r["prod"]) == a * b
+        assert int(r["quot"]) == a // b and int(r["rem"]) == a % b
+        if a >= b:
+            assert int(r["diff"]) == a - b
+        import math
+        g = math.gcd(a, b)
+        assert int(r["gcd"]) == g
+        if g == 1 and b > 1:
+            assert int(r["inv"]) == pow(a, -1, b)
+        else:
+            assert "inv" not in r or b == 1
+        assert r["hex"] == po.serde_bigint_native(a) and r["bits"] == a.bit_length() and r["roundtrip"] is True
+
+
+def test_knuth_division_corner_cases():
+    # qhat over-estimation and add-back paths of algorithm D
+    B = 2**32
+    cases = [((B**4 - 1), (B**2 - 1)), (B**3, B**2 - 1), ((B - 1) * B**3, (B // 2) * B + 1), (B**5 - B**2, B**3 - 1),
+             (0x7fffffff800000010000000000000000, 0x800000008000000200000005)]
+    for a, b in cases:
+        r = call("bigint.selftest", a=str(a), b=str(b))
+        assert int(r["quot"]) == a // b and int(r["rem"]) == a % b
+
+
+def test_sampling_rule_matches_oracle():
+    data = random.Random(2).randbytes(4000)
+    lo, hi = 12345, (1 << 255) // 3
+    r = call("sample", lo=str(lo), hi=str(hi), count=20, rng_hex=data.hex())
+    s = Stream(data)
+    assert [int(v) for v in r["values"]] == [po.sample_range(s, lo, hi) for _ in range(20)]
+
+
+def test_errors_are_reported_not_thrown():
+    r = call("bigint.selftest", a="12x", b="1")
+    assert r["ok"] is False and r["kind"] == "error"
+    r = call("nope")
+    assert r["ok"] is False

@@ -103,6 +103,37 @@ int zkp_ck_verify_fetch(zkp_ctx* c, uint8_t* accept, uint32_t* rho) {
   return ZKP_OK;
 }
 
+int zkp_correct_key_ni_rho(zkp_ctx* c, int batch, int nl, const uint32_t* n, const uint8_t* salt, int salt_len, uint32_t* rho) {
+  if (!c) return ZKP_E_ARG;
+  if (batch <= 0 || nl <= 0 || nl % 4 || !n || !rho || salt_len < 0 || (salt_len > 0 && !salt))
+    return fail(c, ZKP_E_ARG, "bad correct-key batch shape");
+  const int S = pick_width(nl);
+  if (S < 0) return fail(c, ZKP_E_ARG, "modulus wider than 8192 bits");
+  for (int b = 0; b < batch; ++b)
+    if (!(n[(size_t)b * nl] & 1u)) return fail(c, ZKP_E_ARG, "every modulus must be odd");
+  ZKP_CU(c, cudaSetDevice(c->device));
+  CkState& s = c->ck;
+  s.staged = s.done = false;
+  const size_t bm = (size_t)batch * kCkM2;
+  const int ml = nl + 8;
+  ZKP_CU(c, s.n.ensure((size_t)batch * nl * 4));
+  ZKP_CU(c, s.salt.ensure((size_t)salt_len + 16));
+  ZKP_CU(c, s.r2.ensure((size_t)batch * S * 4));
+  ZKP_CU(c, s.n0inv.ensure((size_t)batch * 4));
+  ZKP_CU(c, s.mask.ensure(bm * ml * 4 + (size_t)S * 4));
+  ZKP_CU(c, s.rho.ensure(bm * nl * 4));
+  cudaStream_t st = c->stream;
+  ZKP_CU(c, cudaMemcpyAsync(s.n.p, n, (size_t)batch * nl * 4, cudaMemcpyHostToDevice, st));
+  if (salt_len) ZKP_CU(c, cudaMemcpyAsync(s.salt.p, salt, (size_t)salt_len, cudaMemcpyHostToDevice, st));
+  ZKP_CU(c, launch_mont_setup(s.n.as<uint32_t>(), nl, S, batch, s.r2.as<uint32_t>(), s.n0inv.as<uint32_t>(), st));
+  ZKP_CU(c, launch_ck_rho(s.n.as<uint32_t>(), nl, s.salt.as<uint8_t>(), salt_len, batch, s.mask.as<uint32_t>(), ml, st));
+  ZKP_CU(c, launch_ck_reduce(s.mask.as<uint32_t>(), ml, s.n.as<uint32_t>(), nl, s.r2.as<uint32_t>(), s.n0inv.as<uint32_t>(), S, batch,
+                             s.rho.as<uint32_t>(), st));
+  ZKP_CU(c, cudaMemcpyAsync(rho, s.rho.p, bm * nl * 4, cudaMemcpyDeviceToHost, st));
+  ZKP_CU(c, cudaStreamSynchronize(st));
+  return ZKP_OK;
+}
+
 int zkp_correct_key_ni_verify(zkp_ctx* c, int batch, int nl, const uint32_t* n, const uint32_t* sigma, const uint8_t* salt,
                               int salt_len, uint8_t* accept, uint32_t* rho) {
   int rc = zkp_ck_verify_stage(c, batch, nl, n, sigma, salt, salt_len);

@@ -1,0 +1,218 @@
+// JSON-in / JSON-out C entry point over the C++ host mirror (zkproofs.hpp), so the pytest suite can drive
+// the reference-shaped interface (prove / verify, serde wire format, panics vs Err) end to end:
+//     char* zkh_call(const char* op, const char* request_json);   // caller frees with zkh_free
+// Every response is {"ok": true, ...} or {"ok": false, "error": "...", "kind": "panic" | "error"}.
+#include <cstdlib>
+#include <cstring>
+#include <map>
+
+#include "zkproofs.hpp"
+
+using namespace zkproofs;
+
+namespace {
+
+Engine& engine(int device) {
+  static std::map<int, std::unique_ptr<Engine>> engines;
+  auto& e = engines[device];
+  if (!e) e.reset(new Engine(device));
+  return *e;
+}
+
+// deterministic byte source from a hex string (tests); falls back to OsRng when absent
+ByteSource rng_from(const Json& req) {
+  const Json* h = req.find("rng_hex");
+  if (!h) return os_rng();
+  auto buf = std::make_shared<std::vector<uint8_t>>();
+  const std::string& s = h->as_str();
+  for (size_t i = 0; i + 1 < s.size(); i += 2) buf->push_back((uint8_t)std::stoi(s.substr(i, 2), nullptr, 16));
+  auto pos = std::make_shared<size_t>(0);
+  return [buf, pos](uint8_t* p, size_t n) {
+    if (*pos + n > buf->size()) throw std::runtime_error("rng_hex exhausted");
+    memcpy(p, buf->data() + *pos, n);
+    *pos += n;
+  };
+}
+
+BigInt dec(const Json& j, const char* k) { return BigInt::from_dec(j.at(k).as_str()); }
+std::vector<uint8_t> unhex(const std::string& s) {
+  std::vector<uint8_t> v;
+  for (size_t i = 0; i + 1 < s.size(); i += 2) v.push_back((uint8_t)std::stoi(s.substr(i, 2), nullptr, 16));
+  return v;
+}
+
+// run `fn` per item, mapping the three outcomes of a reference verify
+template <class F>
+Json outcomes(size_t n, F fn) {
+  Json arr = Json::array();
+  for (size_t i = 0; i < n; ++i) {
+    try {
+      fn(i);
+      arr.push(Json::string("ok"));
+    } catch (const IncorrectProof&) {
+      arr.push(Json::string("incorrect"));
+    } catch (const ReferencePanic& e) {
+      arr.push(Json::string(std::string("panic: ") + e.what()));
+    }
+  }
+  return arr;
+}
+
+Json dispatch(const std::string& op, const Json& req) {
+  const int device = req.find("device") ? (int)req.at("device").as_num() : 0;
+  Json out = Json::object();
+  out.set("ok", Json::boolean(true));
+  if (op == "bigint.selftest") {
+    BigInt a = dec(req, "a"), b = dec(req, "b");
+    out.set("sum", ser_dec(a + b));
+    out.set("prod", ser_dec(a * b));
+    if (a >= b) out.set("diff", ser_dec(a - b));
+    if (!b.is_zero()) {
+      out.set("quot", ser_dec(a / b));
+      out.set("rem", ser_dec(a % b));
+      BigInt inv;
+      if (BigInt::mod_inv(a, b, inv)) out.set("inv", ser_dec(inv));
+    }
+    out.set("gcd", ser_dec(BigInt::gcd(a, b)));
+    out.set("hex", ser_native(a));
+    out.set("bits", Json::number((int64_t)a.bit_length()));
+    BigInt back;
+    BigInt::parse_hex_bytes(a.to_hex_bytes(), back);
+    out.set("roundtrip", Json::boolean(back == a && BigInt::from_dec(a.to_dec()) == a && BigInt::from_limbs(a.to_limbs(a.d.size() + 3).data(), a.d.size() + 3) == a));
+    return out;
+  }
+  if (op == "sample") {  // the sampling rules of SURVEY 8a a15 on a given byte stream
+    ByteSource rng = rng_from(req);
+    Json arr = Json::array();
+    BigInt lo = dec(req, "lo"), hi = dec(req, "hi");
+    for (int64_t i = 0; i < req.at("count").as_num(); ++i) arr.push(ser_dec(BigInt::sample_range(rng, lo, hi)));
+    out.set("values", arr);
+    return out;
+  }
+  Engine& eng = engine(device);
+  if (op == "rangeproof_ni.prove") {
+    EncryptionKey ek(dec(req, "n"));
+    std::vector<RangeStatement> st;
+    for (auto& s : req.at("statements").arr) st.push_back({dec(s, "range"), dec(s, "ciphertext"), dec(s, "x"), dec(s, "r")});
+    size_t ef = req.find("error_factor") ? (size_t)req.at("error_factor").as_num() : SECURITY_PARAMETER;
+    auto proofs = RangeProofNi::prove_batch(eng, ek, st, rng_from(req), ef);
+    Json arr = Json::array();
+    for (auto& p : proofs) arr.push(Json::string(p.to_json()));
+    out.set("proofs", arr);
+    return out;
+  }
+  if (op == "rangeproof_ni.verify") {  // one proof at a time through verify(ek, ciphertext), like a caller of the crate
+    EncryptionKey ek(dec(req, "n"));
+    std::vector<RangeProofNi> ps;
+    for (auto& s : req.at("proofs").arr) ps.push_back(RangeProofNi::from_json(s.as_str()));
+    const Json& cts = req.at("ciphertexts");
+    out.set("results", outcomes(ps.size(), [&](size_t i) { ps[i].verify(eng, ek, BigInt::from_dec(cts.arr[i].as_str())); }));
+    return out;
+  }
+  if (op == "rangeproof_ni.verify_batch") {
+    std::vector<RangeProofNi> ps;
+    for (auto& s : req.at("proofs").arr) ps.push_back(RangeProofNi::from_json(s.as_str()));
+    std::vector<const RangeProofNi*> ptrs;
+    for (auto& p : ps) ptrs.push_back(&p);
+    Json arr = Json::array();
+    for (int v : RangeProofNi::verify_batch(eng, ptrs)) arr.push(Json::number(v));
+    out.set("accept", arr);
+    return out;
+  }
+  if (op == "correct_key_ni.proof") {
+    DecryptionKey dk{dec(req, "p"), dec(req, "q")};
+    NiCorrectKeyProof pr;
+    if (req.find("salt_hex")) {
+      auto salt = unhex(req.at("salt_hex").as_str());
+      static const uint8_t none = 0;
+      pr = NiCorrectKeyProof::proof(eng, dk, salt.empty() ? &none : salt.data(), salt.size());
+    } else {
+      pr = NiCorrectKeyProof::proof(eng, dk);
+    }
+    out.set("proof", Json::string(pr.to_json()));
+    return out;
+  }
+  if (op == "correct_key_ni.verify") {
+    auto salt = unhex(req.at("salt_hex").as_str());
+    static const uint8_t none = 0;
+    std::vector<NiCorrectKeyProof> ps;
+    std::vector<EncryptionKey> eks;
+    for (auto& s : req.at("proofs").arr) ps.push_back(NiCorrectKeyProof::from_json(s.as_str()));
+    for (auto& s : req.at("n").arr) eks.push_back(EncryptionKey(BigInt::from_dec(s.as_str())));
+    out.set("results", outcomes(ps.size(), [&](size_t i) { ps[i].verify(eng, eks[i], salt.empty() ? &none : salt.data(), salt.size()); }));
+    return out;
+  }
+  // sigma protocols: {"n", "items": [{witness/statement/proof fields as decimal strings}], "rng_hex"}
+  EncryptionKey ek(dec(req, "n"));
+  const auto& items = req.at("items").arr;
+  if (op == "zero.prove") {
+    std::vector<ZeroWitness> w; std::vector<ZeroStatement> st;
+    for (auto& it : items) { w.push_back({dec(it, "r")}); st.push_back({ek, dec(it, "c")}); }
+    Json arr = Json::array();
+    for (auto& p : ZeroProof::prove_batch(eng, w, st, rng_from(req))) arr.push(Json::string(p.to_json()));
+    out.set("proofs", arr);
+  } else if (op == "zero.verify") {
+    out.set("results", outcomes(items.size(), [&](size_t i) { ZeroProof::from_json(items[i].at("proof").as_str()).verify(eng, {ek, dec(items[i], "c")}); }));
+  } else if (op == "ciphertext.prove") {
+    std::vector<CiphertextWitness> w; std::vector<CiphertextStatement> st;
+    for (auto& it : items) { w.push_back({dec(it, "x"), dec(it, "r")}); st.push_back({ek, dec(it, "c")}); }
+    Json arr = Json::array();
+    for (auto& p : CiphertextProof::prove_batch(eng, w, st, rng_from(req))) arr.push(Json::string(p.to_json()));
+    out.set("proofs", arr);
+  } else if (op == "ciphertext.verify") {
+    out.set("results", outcomes(items.size(), [&](size_t i) { CiphertextProof::from_json(items[i].at("proof").as_str()).verify(eng, {ek, dec(items[i], "c")}); }));
+  } else if (op == "mul.prove") {
+    std::vector<MulWitness> w; std::vector<MulStatement> st;
+    for (auto& it : items) {
+      w.push_back({dec(it, "a"), dec(it, "b"), dec(it, "c"), dec(it, "r_a"), dec(it, "r_b"), dec(it, "r_c")});
+      st.push_back({ek, dec(it, "e_a"), dec(it, "e_b"), dec(it, "e_c")});
+    }
+    Json arr = Json::array();
+    for (auto& p : MulProof::prove_batch(eng, w, st, rng_from(req))) arr.push(Json::string(p.to_json()));
+    out.set("proofs", arr);
+  } else if (op == "mul.verify") {
+    out.set("results", outcomes(items.size(), [&](size_t i) {
+      MulProof::from_json(items[i].at("proof").as_str()).verify(eng, {ek, dec(items[i], "e_a"), dec(items[i], "e_b"), dec(items[i], "e_c")});
+    }));
+  } else if (op == "verlin.prove") {
+    std::vector<VerlinWitness> w; std::vector<VerlinStatement> st;
+    for (auto& it : items) {
+      w.push_back({dec(it, "x"), dec(it, "x_prime"), dec(it, "x_double_prime"), dec(it, "r_x")});
+      st.push_back({ek, dec(it, "c"), dec(it, "c_prime"), dec(it, "phi_x")});
+    }
+    Json arr = Json::array();
+    for (auto& p : VerlinProof::prove_batch(eng, w, st, rng_from(req))) arr.push(Json::string(p.to_json()));
+    out.set("proofs", arr);
+  } else if (op == "verlin.verify") {
+    out.set("results", outcomes(items.size(), [&](size_t i) {
+      VerlinProof::from_json(items[i].at("proof").as_str()).verify(eng, {ek, dec(items[i], "c"), dec(items[i], "c_prime"), dec(items[i], "phi_x")});
+    }));
+  } else {
+    throw std::runtime_error("unknown op " + op);
+  }
+  return out;
+}
+
+char* dup(const std::string& s) {
+  char* p = (char*)malloc(s.size() + 1);
+  memcpy(p, s.c_str(), s.size() + 1);
+  return p;
+}
+
+}  // namespace
+
+extern "C" {
+
+char* zkh_call(const char* op, const char* request_json) {
+  try {
+    return dup(dispatch(op, Json::parse(request_json)).dump());
+  } catch (const ReferencePanic& e) {
+    return dup(Json::object().set("ok", Json::boolean(false)).set("kind", Json::string("panic")).set("error", Json::string(e.what())).dump());
+  } catch (const std::exception& e) {
+    return dup(Json::object().set("ok", Json::boolean(false)).set("kind", Json::string("error")).set("error", Json::string(e.what())).dump());
+  }
+}
+
+void zkh_free(char* p) { free(p); }
+
+}  // extern "C"

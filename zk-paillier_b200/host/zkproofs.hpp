@@ -1,0 +1,696 @@
+// Host-side mirror of the reference's `zkproofs` call surface (reference src/zkproofs/mod.rs:29-43), in
+// C++ because the reference's own toolchain (Rust) is absent from the build image.  Same names, argument
+// meaning, error behaviour and serde wire format as the Rust structs; all big-integer loops go through the
+// C ABI of include/zkp_b200.h (CUDA, no CPU fallback).  Every proof type also has a `*_batch` form -- the
+// one thing the engine adds (the reference takes exactly one statement per call and fans out on rayon).
+//
+//   reference                                      here
+//   RangeProofNi::prove / verify / verify_self      RangeProofNi::prove / verify / verify_self (+ _batch)
+//   NiCorrectKeyProof::proof / verify               NiCorrectKeyProof::proof / verify (+ verify_batch)
+//   {Zero,Ciphertext,Mul,Verlin}Proof::prove/verify same (+ _batch)
+//   Err(IncorrectProof)                             throw IncorrectProof   (batch forms return 0/1 per proof)
+//   panic (assert_eq!, unwrap, index out of range)  throw ReferencePanic
+#pragma once
+#include <cstdio>
+#include <cstring>
+#include <exception>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/zkp_b200.h"
+#include "bigint.hpp"
+#include "json.hpp"
+
+namespace zkproofs {
+
+using zkhost::BigInt;
+using zkhost::Json;
+using ByteSource = BigInt::ByteSource;
+
+struct IncorrectProof : std::exception {  // errors.rs:5-13
+  const char* what() const noexcept override { return "given proof doesn't match a statement"; }
+};
+struct ReferencePanic : std::logic_error {  // where the reference panics instead of returning Err
+  using std::logic_error::logic_error;
+};
+
+constexpr size_t SECURITY_PARAMETER = 128;  // range_proof_ni.rs:23
+constexpr size_t M2 = 11;                   // correct_key_ni.rs:29
+static const uint8_t SALT_STRING[4] = {75, 90, 101, 110};  // correct_key_ni.rs:28
+
+inline ByteSource os_rng() {  // OsRng
+  return [](uint8_t* p, size_t n) {
+    FILE* f = fopen("/dev/urandom", "rb");
+    if (!f || fread(p, 1, n, f) != n) throw std::runtime_error("cannot read /dev/urandom");
+    fclose(f);
+  };
+}
+
+struct EncryptionKey {  // kzen-paillier EncryptionKey {n, nn}
+  BigInt n, nn;
+  EncryptionKey() {}
+  explicit EncryptionKey(const BigInt& n_) : n(n_), nn(n_ * n_) {}
+  bool operator==(const EncryptionKey& o) const { return n == o.n; }
+  Json to_json() const { return Json::object().set("n", Json::string(n.to_dec())); }  // minimal form (RECALLED)
+  static EncryptionKey from_json(const Json& j) { return EncryptionKey(BigInt::from_dec(j.at("n").as_str())); }
+};
+struct DecryptionKey {
+  BigInt p, q;
+};
+
+inline size_t round4(size_t limbs) { return (limbs + 3) / 4 * 4; }
+inline size_t limbs_for_bits(size_t bits) { return round4((bits + 31) / 32); }
+
+// serde helpers: src/serialize.rs (decimal strings) and curv's native BigInt serde (hex of to_bytes, RECALLED)
+inline Json ser_dec(const BigInt& x) { return Json::string(x.to_dec()); }
+inline BigInt de_dec(const Json& j, bool panic_on_error) {
+  BigInt v;
+  if (!BigInt::parse_dec(j.as_str(), v)) {
+    if (panic_on_error) throw ReferencePanic("from_str_radix(..).unwrap() on a malformed decimal string (serialize.rs:69)");
+    throw std::runtime_error("invalid decimal BigInt");
+  }
+  return v;
+}
+inline Json ser_native(const BigInt& x) { return Json::string(x.to_hex_bytes()); }
+inline BigInt de_native(const Json& j) {
+  BigInt v;
+  if (!BigInt::parse_hex_bytes(j.as_str(), v)) throw std::runtime_error("invalid hex BigInt");
+  return v;
+}
+inline Json ser_vec(const std::vector<BigInt>& v) {
+  Json a = Json::array();
+  for (auto& x : v) a.push(ser_dec(x));
+  return a;
+}
+inline std::vector<BigInt> de_vec(const Json& j) {
+  std::vector<BigInt> v;
+  for (auto& x : j.arr) v.push_back(de_dec(x, true));
+  return v;
+}
+
+// One engine context = one GPU.  Single-threaded, like zkp_ctx.
+class Engine {
+ public:
+  explicit Engine(int device = 0) {
+    int rc = zkp_ctx_create(device, nullptr, &h_);
+    if (rc != ZKP_OK) throw std::runtime_error("zkp_ctx_create failed: no usable CUDA device (the engine has no CPU fallback)");
+  }
+  ~Engine() { zkp_ctx_destroy(h_); }
+  Engine(const Engine&) = delete;
+  Engine& operator=(const Engine&) = delete;
+  zkp_ctx* handle() { return h_; }
+  void check(int rc) const {
+    if (rc != ZKP_OK) throw std::runtime_error(std::string("zkp_b200: ") + zkp_last_error(h_));
+  }
+  void use_key(const EncryptionKey& ek) {
+    if (have_key_ && key_ == ek.n) return;
+    nl_ = limbs_for_bits(ek.n.bit_length());
+    std::vector<uint32_t> n = ek.n.to_limbs(nl_);
+    check(zkp_set_key(h_, n.data(), (int)nl_));
+    key_ = ek.n;
+    have_key_ = true;
+  }
+  size_t nl() const { return nl_; }
+  size_t nnl() const { return 2 * nl_; }
+  size_t zl() const { return nl_ + 12; }
+
+ private:
+  zkp_ctx* h_ = nullptr;
+  BigInt key_;
+  bool have_key_ = false;
+  size_t nl_ = 0;
+};
+
+// [rows] BigInts -> dense limb matrix
+inline std::vector<uint32_t> pack(const std::vector<BigInt>& v, size_t limbs) {
+  std::vector<uint32_t> out(v.size() * limbs);
+  for (size_t i = 0; i < v.size(); ++i) v[i].to_limbs(out.data() + i * limbs, limbs);
+  return out;
+}
+inline std::vector<BigInt> unpack(const std::vector<uint32_t>& m, size_t limbs) {
+  std::vector<BigInt> v;
+  for (size_t i = 0; i + limbs <= m.size(); i += limbs) v.push_back(BigInt::from_limbs(m.data() + i, limbs));
+  return v;
+}
+
+// ------------------------------------------------------------------------------------ RangeProofNi
+struct EncryptedPairs {  // range_proof.rs:32-39
+  std::vector<BigInt> c1, c2;
+};
+struct Response {  // range_proof.rs:53-78
+  bool open = true;
+  BigInt w1, r1, w2, r2;        // Open
+  uint8_t j = 0;                // Mask
+  BigInt masked_x, masked_r;
+};
+struct Proof {  // range_proof.rs:80-81
+  std::vector<Response> responses;
+};
+struct RangeStatement {
+  BigInt range, ciphertext, secret_x, secret_r;
+};
+
+class RangeProofNi {  // range_proof_ni.rs:36-44
+ public:
+  EncryptionKey ek;
+  BigInt range, ciphertext;
+  EncryptedPairs encrypted_pairs;
+  Proof proof;
+  size_t error_factor = 0;
+
+  // range_proof_ni.rs:47-82.  Randomness: per proof, w1[0..ef) <- sample_range(third, two_thirds), then ef coin
+  // bytes (low bit), then r1[0..ef), r2[0..ef) <- sample_below(n)  (range_proof.rs:136-159; the reference's draw
+  // order under rayon is nondeterministic, so any fixed order is as faithful as another).
+  static std::vector<RangeProofNi> prove_batch(Engine& eng, const EncryptionKey& ek, const std::vector<RangeStatement>& st,
+                                               const ByteSource& rng = os_rng(), size_t ef = SECURITY_PARAMETER) {
+    eng.use_key(ek);
+    const size_t B = st.size(), nl = eng.nl(), nnl = eng.nnl();
+    if (B == 0) return {};
+    size_t wbits = 0;
+    for (auto& s : st) wbits = std::max({wbits, s.range.bit_length() + 2, s.secret_x.bit_length() + 2});
+    const size_t wl = limbs_for_bits(wbits);
+    if (wl > 64) throw std::length_error("range / secret_x wider than 2048 bits");
+    std::vector<BigInt> range, x, r, w1, r1, r2;
+    std::vector<uint8_t> swap(B * ef);
+    for (auto& s : st) {
+      range.push_back(s.range);
+      x.push_back(s.secret_x);
+      r.push_back(s.secret_r);
+      BigInt third = s.range.div_floor(BigInt(3)), two = third + third;
+      if (third.is_zero()) throw ReferencePanic("sample_range on an empty interval (range < 3)");
+      for (size_t i = 0; i < ef; ++i) w1.push_back(BigInt::sample_range(rng, third, two));
+      rng(swap.data() + (&s - &st[0]) * ef, ef);
+      for (size_t i = 0; i < ef; ++i) r1.push_back(BigInt::sample_below(rng, ek.n));
+      for (size_t i = 0; i < ef; ++i) r2.push_back(BigInt::sample_below(rng, ek.n));
+    }
+    for (auto& b : swap) b &= 1;
+    std::vector<uint32_t> c1(B * ef * nnl), c2(B * ef * nnl), resp_w(B * ef * 2 * wl), resp_r(B * ef * 2 * nl);
+    std::vector<uint8_t> kind(B * ef), digest(B * 32);
+    eng.check(zkp_rangeproof_ni_prove(eng.handle(), (int)B, (int)ef, (int)wl, pack(range, wl).data(), pack(x, wl).data(),
+                                      pack(r, nl).data(), pack(w1, wl).data(), swap.data(), pack(r1, nl).data(), pack(r2, nl).data(),
+                                      c1.data(), c2.data(), digest.data(), kind.data(), resp_w.data(), resp_r.data()));
+    std::vector<RangeProofNi> out(B);
+    for (size_t b = 0; b < B; ++b) {
+      RangeProofNi& p = out[b];
+      p.ek = ek;
+      p.range = st[b].range;
+      p.ciphertext = st[b].ciphertext;
+      p.error_factor = ef;
+      for (size_t i = 0; i < ef; ++i) {
+        const size_t t = b * ef + i;
+        p.encrypted_pairs.c1.push_back(BigInt::from_limbs(&c1[t * nnl], nnl));
+        p.encrypted_pairs.c2.push_back(BigInt::from_limbs(&c2[t * nnl], nnl));
+        Response rs;
+        const uint32_t* w = &resp_w[t * 2 * wl];
+        const uint32_t* rr = &resp_r[t * 2 * nl];
+        if (kind[t] == ZKP_RP_OPEN) {
+          rs.open = true;
+          rs.w1 = BigInt::from_limbs(w, wl);
+          rs.w2 = BigInt::from_limbs(w + wl, wl);
+          rs.r1 = BigInt::from_limbs(rr, nl);
+          rs.r2 = BigInt::from_limbs(rr + nl, nl);
+        } else {
+          rs.open = false;
+          rs.j = kind[t];
+          rs.masked_x = BigInt::from_limbs(w, wl);
+          rs.masked_r = BigInt::from_limbs(rr, nl);
+        }
+        p.proof.responses.push_back(rs);
+      }
+    }
+    return out;
+  }
+  static RangeProofNi prove(Engine& eng, const EncryptionKey& ek, const BigInt& range, const BigInt& ciphertext,
+                            const BigInt& secret_x, const BigInt& secret_r, const ByteSource& rng = os_rng()) {
+    return prove_batch(eng, ek, {RangeStatement{range, ciphertext, secret_x, secret_r}}, rng)[0];
+  }
+
+  // range_proof_ni.rs:109-128 for many proofs under ONE key and error factor.  1 = Ok(()), 0 = Err(IncorrectProof).
+  static std::vector<int> verify_batch(Engine& eng, const std::vector<const RangeProofNi*>& ps) {
+    const size_t B = ps.size();
+    if (B == 0) return {};
+    const EncryptionKey& ek = ps[0]->ek;
+    const size_t ef = ps[0]->error_factor;
+    eng.use_key(ek);
+    const size_t nl = eng.nl(), nnl = eng.nnl();
+    size_t wbits = 0;
+    for (auto* p : ps) {
+      if (!(p->ek == ek) || p->error_factor != ef) throw std::invalid_argument("verify_batch: proofs must share key and error factor");
+      // bits_of_e[i] / responses[i] index out of range in the reference (range_proof.rs:273-274)
+      if (p->proof.responses.size() < ef || p->encrypted_pairs.c1.size() < ef || p->encrypted_pairs.c2.size() < ef || ef > 256)
+        throw ReferencePanic("index out of bounds: proof shorter than error_factor");
+      wbits = std::max(wbits, p->range.bit_length() + 1);
+      for (size_t i = 0; i < ef; ++i) {
+        const Response& r = p->proof.responses[i];
+        wbits = std::max({wbits, r.w1.bit_length(), r.w2.bit_length(), r.masked_x.bit_length()});
+      }
+    }
+    const size_t wl = limbs_for_bits(wbits);
+    std::vector<uint32_t> range(B * wl), cx(B * nnl), c1(B * ef * nnl), c2(B * ef * nnl), resp_w(B * ef * 2 * wl, 0), resp_r(B * ef * 2 * nl, 0);
+    std::vector<uint8_t> kind(B * ef), accept(B), fault(B);
+    std::vector<int> out(B, -1);
+    auto fits = [](const BigInt& v, size_t limbs) { return v.d.size() <= limbs; };
+    for (size_t b = 0; b < B; ++b) {
+      const RangeProofNi& p = *ps[b];
+      bool representable = wl <= 64 && fits(p.ciphertext, nnl);
+      for (size_t i = 0; i < ef && representable; ++i) {
+        const Response& r = p.proof.responses[i];
+        representable = fits(p.encrypted_pairs.c1[i], nnl) && fits(p.encrypted_pairs.c2[i], nnl) && fits(r.r1, nl) && fits(r.r2, nl) &&
+                        fits(r.masked_r, nl);
+      }
+      if (!representable) {  // a value >= 2^(row width) can never equal a canonical residue: Err(IncorrectProof)
+        out[b] = 0;
+        continue;
+      }
+      p.range.to_limbs(&range[b * wl], wl);
+      p.ciphertext.to_limbs(&cx[b * nnl], nnl);
+      for (size_t i = 0; i < ef; ++i) {
+        const size_t t = b * ef + i;
+        const Response& r = p.proof.responses[i];
+        p.encrypted_pairs.c1[i].to_limbs(&c1[t * nnl], nnl);
+        p.encrypted_pairs.c2[i].to_limbs(&c2[t * nnl], nnl);
+        if (r.open) {
+          kind[t] = ZKP_RP_OPEN;
+          r.w1.to_limbs(&resp_w[t * 2 * wl], wl);
+          r.w2.to_limbs(&resp_w[t * 2 * wl + wl], wl);
+          r.r1.to_limbs(&resp_r[t * 2 * nl], nl);
+          r.r2.to_limbs(&resp_r[t * 2 * nl + nl], nl);
+        } else {
+          kind[t] = r.j == 1 ? ZKP_RP_MASK1 : ZKP_RP_MASK2;  // `if *j == 1 { c1 } else { c2 }` (range_proof.rs:321-325)
+          r.masked_x.to_limbs(&resp_w[t * 2 * wl], wl);
+          r.masked_r.to_limbs(&resp_r[t * 2 * nl], nl);
+        }
+      }
+    }
+    eng.check(zkp_rangeproof_ni_verify(eng.handle(), (int)B, (int)ef, (int)wl, range.data(), cx.data(), c1.data(), c2.data(), kind.data(),
+                                       resp_w.data(), resp_r.data(), accept.data(), fault.data(), nullptr));
+    for (size_t b = 0; b < B; ++b) {
+      if (out[b] == 0) continue;
+      if (fault[b]) throw ReferencePanic("index out of bounds in verifier_output (range_proof.rs:273)");
+      out[b] = accept[b];
+    }
+    return out;
+  }
+  void verify_self(Engine& eng) const {
+    if (!verify_batch(eng, {this})[0]) throw IncorrectProof();
+  }
+  // range_proof_ni.rs:84-107
+  void verify(Engine& eng, const EncryptionKey& ek_, const BigInt& ciphertext_) const {
+    if (!(ek_ == ek)) throw ReferencePanic("assertion failed: `(left == right)` ek (range_proof_ni.rs:86)");
+    if (ciphertext_ != ciphertext) throw ReferencePanic("assertion failed: `(left == right)` ciphertext (range_proof_ni.rs:88)");
+    verify_self(eng);
+  }
+
+  Json to_json_value() const {
+    Json j = Json::object();
+    j.set("ek", ek.to_json());
+    j.set("range", ser_native(range));
+    j.set("ciphertext", ser_native(ciphertext));
+    j.set("encrypted_pairs", Json::object().set("c1", ser_vec(encrypted_pairs.c1)).set("c2", ser_vec(encrypted_pairs.c2)));
+    Json arr = Json::array();
+    for (auto& r : proof.responses) {
+      if (r.open)
+        arr.push(Json::object().set("Open", Json::object().set("w1", ser_dec(r.w1)).set("r1", ser_dec(r.r1)).set("w2", ser_dec(r.w2)).set("r2", ser_dec(r.r2))));
+      else
+        arr.push(Json::object().set("Mask", Json::object().set("j", Json::number(r.j)).set("masked_x", ser_dec(r.masked_x)).set("masked_r", ser_dec(r.masked_r))));
+    }
+    j.set("proof", arr);
+    j.set("error_factor", Json::number((int64_t)error_factor));
+    return j;
+  }
+  std::string to_json() const { return to_json_value().dump(); }
+  static RangeProofNi from_json_value(const Json& j) {
+    RangeProofNi p;
+    p.ek = EncryptionKey::from_json(j.at("ek"));
+    p.range = de_native(j.at("range"));
+    p.ciphertext = de_native(j.at("ciphertext"));
+    p.encrypted_pairs.c1 = de_vec(j.at("encrypted_pairs").at("c1"));
+    p.encrypted_pairs.c2 = de_vec(j.at("encrypted_pairs").at("c2"));
+    for (auto& o : j.at("proof").arr) {
+      Response r;
+      if (const Json* v = o.find("Open")) {
+        r.open = true;
+        r.w1 = de_dec(v->at("w1"), false); r.r1 = de_dec(v->at("r1"), false);
+        r.w2 = de_dec(v->at("w2"), false); r.r2 = de_dec(v->at("r2"), false);
+      } else {
+        const Json& m = o.at("Mask");
+        r.open = false;
+        int64_t jj = m.at("j").as_num();
+        if (jj < 0 || jj > 255) throw std::runtime_error("j out of range for u8");
+        r.j = (uint8_t)jj;
+        r.masked_x = de_dec(m.at("masked_x"), false);
+        r.masked_r = de_dec(m.at("masked_r"), false);
+      }
+      p.proof.responses.push_back(r);
+    }
+    p.error_factor = (size_t)j.at("error_factor").as_num();
+    return p;
+  }
+  static RangeProofNi from_json(const std::string& s) { return from_json_value(Json::parse(s)); }
+};
+
+// ------------------------------------------------------------------------------- NiCorrectKeyProof
+class NiCorrectKeyProof {  // correct_key_ni.rs:34-39
+ public:
+  std::vector<BigInt> sigma_vec;
+
+  // correct_key_ni.rs:42-71.  rho on the device (zkp_correct_key_ni_rho); extract_nroot(dk, rho_i) =
+  // rho_i^(n^-1 mod phi) mod n through CRT: two half-width K2 modexps per i, recombined on the host.
+  static NiCorrectKeyProof proof(Engine& eng, const DecryptionKey& dk, const uint8_t* salt = nullptr, size_t salt_len = 0) {
+    if (!salt) { salt = SALT_STRING; salt_len = sizeof(SALT_STRING); }
+    const BigInt n = dk.p * dk.q;
+    const size_t nl = limbs_for_bits(n.bit_length());
+    std::vector<uint32_t> rho(M2 * nl), nrow = n.to_limbs(nl);
+    eng.check(zkp_correct_key_ni_rho(eng.handle(), 1, (int)nl, nrow.data(), salt, (int)salt_len, rho.data()));
+    const BigInt pm1 = dk.p - BigInt(1), qm1 = dk.q - BigInt(1);
+    BigInt dp, dq, pinv;
+    if (!BigInt::mod_inv(n % pm1, pm1, dp) || !BigInt::mod_inv(n % qm1, qm1, dq) || !BigInt::mod_inv(dk.p % dk.q, dk.q, pinv))
+      throw ReferencePanic("extract_nroot: n is not invertible mod phi(n)");
+    const size_t hl = limbs_for_bits(std::max(dk.p.bit_length(), dk.q.bit_length()));
+    std::vector<BigInt> bases, exps{dp, dq}, mods{dk.p, dk.q};
+    std::vector<BigInt> rhos = unpack(rho, nl);
+    for (auto& r : rhos) bases.push_back(r % dk.p);
+    for (auto& r : rhos) bases.push_back(r % dk.q);
+    std::vector<uint32_t> out(2 * M2 * hl);
+    eng.check(zkp_modexp_var(eng.handle(), pack(bases, hl).data(), pack(exps, hl).data(), (int)hl, (int)(32 * hl), (int)M2,
+                             pack(mods, hl).data(), (int)hl, (int)M2, (int)(2 * M2), out.data()));
+    std::vector<BigInt> s = unpack(out, hl);
+    NiCorrectKeyProof pr;
+    for (size_t i = 0; i < M2; ++i) {
+      const BigInt& sp = s[i];
+      const BigInt& sq = s[M2 + i];
+      BigInt diff = (sq + dk.q - (sp % dk.q)) % dk.q;      // (sq - sp) mod q
+      BigInt h = (diff * pinv) % dk.q;
+      pr.sigma_vec.push_back(sp + dk.p * h);
+    }
+    return pr;
+  }
+
+  // correct_key_ni.rs:73-100 for many (proof, key) pairs with one salt; every modulus padded to a common width.
+  static std::vector<int> verify_batch(Engine& eng, const std::vector<const NiCorrectKeyProof*>& ps, const std::vector<EncryptionKey>& eks,
+                                       const uint8_t* salt, size_t salt_len) {
+    const size_t B = ps.size();
+    if (B == 0) return {};
+    size_t bits = 0;
+    for (auto& ek : eks) bits = std::max(bits, ek.n.bit_length());
+    const size_t nl = limbs_for_bits(bits);
+    std::vector<uint32_t> n(B * nl), sigma(B * M2 * nl);
+    std::vector<uint8_t> accept(B);
+    std::vector<int> out(B, -1);
+    for (size_t b = 0; b < B; ++b) {
+      if (ps[b]->sigma_vec.size() < M2) throw ReferencePanic("index out of bounds: sigma_vec shorter than M2 (correct_key_ni.rs:92)");
+      eks[b].n.to_limbs(&n[b * nl], nl);
+      for (size_t i = 0; i < M2; ++i) {
+        BigInt s = ps[b]->sigma_vec[i];
+        if (s.d.size() > nl) s = s % eks[b].n;  // mod_pow reduces its base; same residue
+        s.to_limbs(&sigma[(b * M2 + i) * nl], nl);
+      }
+    }
+    eng.check(zkp_correct_key_ni_verify(eng.handle(), (int)B, (int)nl, n.data(), sigma.data(), salt, (int)salt_len, accept.data(), nullptr));
+    for (size_t b = 0; b < B; ++b) out[b] = accept[b];
+    return out;
+  }
+  void verify(Engine& eng, const EncryptionKey& ek, const uint8_t* salt, size_t salt_len) const {
+    if (!verify_batch(eng, {this}, {ek}, salt, salt_len)[0]) throw IncorrectProof();
+  }
+  std::string to_json() const { return Json::object().set("sigma_vec", ser_vec(sigma_vec)).dump(); }
+  static NiCorrectKeyProof from_json(const std::string& s) {
+    NiCorrectKeyProof p;
+    p.sigma_vec = de_vec(Json::parse(s).at("sigma_vec"));
+    return p;
+  }
+};
+
+// ----------------------------------------------------------------------------------- sigma protocols
+// Field names and order follow the reference structs; BigInt fields use curv's native serde.
+struct ZeroStatement { EncryptionKey ek; BigInt c; };        // zero_enc_proof.rs:37-41
+struct ZeroWitness { BigInt r; };                            // :32-35
+class ZeroProof {                                            // :26-30
+ public:
+  BigInt z, a;
+  static std::vector<ZeroProof> prove_batch(Engine& eng, const std::vector<ZeroWitness>& w, const std::vector<ZeroStatement>& st,
+                                            const ByteSource& rng = os_rng()) {
+    const size_t B = st.size();
+    if (B == 0) return {};
+    eng.use_key(st[0].ek);
+    const size_t nl = eng.nl(), nnl = eng.nnl();
+    std::vector<BigInt> r, c, rp;
+    for (size_t b = 0; b < B; ++b) {
+      r.push_back(w[b].r);
+      c.push_back(st[b].c);
+      rp.push_back(BigInt::sample_below(rng, st[b].ek.n));  // :45
+    }
+    std::vector<uint32_t> z(B * nnl), a(B * nnl);
+    eng.check(zkp_zero_prove(eng.handle(), (int)B, pack(r, nl).data(), pack(c, nnl).data(), pack(rp, nl).data(), z.data(), a.data()));
+    std::vector<ZeroProof> out(B);
+    for (size_t b = 0; b < B; ++b) {
+      out[b].z = BigInt::from_limbs(&z[b * nnl], nnl);
+      out[b].a = BigInt::from_limbs(&a[b * nnl], nnl);
+    }
+    return out;
+  }
+  static ZeroProof prove(Engine& eng, const ZeroWitness& w, const ZeroStatement& st, const ByteSource& rng = os_rng()) {
+    return prove_batch(eng, {w}, {st}, rng)[0];
+  }
+  static std::vector<int> verify_batch(Engine& eng, const std::vector<const ZeroProof*>& ps, const std::vector<ZeroStatement>& st) {
+    const size_t B = ps.size();
+    if (B == 0) return {};
+    eng.use_key(st[0].ek);
+    const size_t nnl = eng.nnl();
+    std::vector<BigInt> c, z, a;
+    for (size_t b = 0; b < B; ++b) {
+      c.push_back(st[b].c);   // rows are hashed and exponentiated as given (mod_pow reduces its base itself)
+      z.push_back(ps[b]->z);
+      a.push_back(ps[b]->a);
+    }
+    std::vector<uint8_t> acc(B);
+    std::vector<int> out(B);
+    for (size_t b = 0; b < B; ++b)
+      if (st[b].c.d.size() > nnl || ps[b]->a.d.size() > nnl || ps[b]->z.d.size() > nnl) throw std::length_error("operand wider than n^2 rows");
+    eng.check(zkp_zero_verify(eng.handle(), (int)B, pack(c, nnl).data(), pack(z, nnl).data(), pack(a, nnl).data(), acc.data()));
+    for (size_t b = 0; b < B; ++b) out[b] = acc[b];
+    return out;
+  }
+  void verify(Engine& eng, const ZeroStatement& st) const {
+    if (!verify_batch(eng, {this}, {st})[0]) throw IncorrectProof();
+  }
+  std::string to_json() const { return Json::object().set("z", ser_native(z)).set("a", ser_native(a)).dump(); }
+  static ZeroProof from_json(const std::string& s) {
+    Json j = Json::parse(s);
+    ZeroProof p;
+    p.z = de_native(j.at("z"));
+    p.a = de_native(j.at("a"));
+    return p;
+  }
+};
+
+struct CiphertextStatement { EncryptionKey ek; BigInt c; };  // correct_ciphertext.rs:35-39
+struct CiphertextWitness { BigInt x, r; };                   // :29-33
+class CiphertextProof {                                      // :22-27
+ public:
+  BigInt z1, z2, c_prime;
+  static std::vector<CiphertextProof> prove_batch(Engine& eng, const std::vector<CiphertextWitness>& w,
+                                                  const std::vector<CiphertextStatement>& st, const ByteSource& rng = os_rng()) {
+    const size_t B = st.size();
+    if (B == 0) return {};
+    eng.use_key(st[0].ek);
+    const size_t nl = eng.nl(), nnl = eng.nnl(), zl = eng.zl();
+    std::vector<BigInt> x, r, c, xp, rp;
+    for (size_t b = 0; b < B; ++b) {
+      x.push_back(w[b].x); r.push_back(w[b].r); c.push_back(st[b].c);
+      xp.push_back(BigInt::sample_below(rng, st[b].ek.n));  // :43
+      rp.push_back(BigInt::sample_below(rng, st[b].ek.n));  // :44
+    }
+    std::vector<uint32_t> z1(B * zl), z2(B * nnl), cp(B * nnl);
+    eng.check(zkp_ciphertext_prove(eng.handle(), (int)B, (int)zl, pack(x, nl).data(), pack(r, nl).data(), pack(c, nnl).data(),
+                                   pack(xp, nl).data(), pack(rp, nl).data(), z1.data(), z2.data(), cp.data()));
+    std::vector<CiphertextProof> out(B);
+    for (size_t b = 0; b < B; ++b) {
+      out[b].z1 = BigInt::from_limbs(&z1[b * zl], zl);
+      out[b].z2 = BigInt::from_limbs(&z2[b * nnl], nnl);
+      out[b].c_prime = BigInt::from_limbs(&cp[b * nnl], nnl);
+    }
+    return out;
+  }
+  static CiphertextProof prove(Engine& eng, const CiphertextWitness& w, const CiphertextStatement& st, const ByteSource& rng = os_rng()) {
+    return prove_batch(eng, {w}, {st}, rng)[0];
+  }
+  static std::vector<int> verify_batch(Engine& eng, const std::vector<const CiphertextProof*>& ps, const std::vector<CiphertextStatement>& st) {
+    const size_t B = ps.size();
+    if (B == 0) return {};
+    eng.use_key(st[0].ek);
+    const size_t nnl = eng.nnl(), zl = eng.zl();
+    std::vector<BigInt> c, z1, z2, cp;
+    for (size_t b = 0; b < B; ++b) {
+      c.push_back(st[b].c);
+      z1.push_back(ps[b]->z1.d.size() > zl ? ps[b]->z1 % st[b].ek.n : ps[b]->z1);  // (m*n + 1) % nn depends on m mod n only
+      z2.push_back(ps[b]->z2);
+      cp.push_back(ps[b]->c_prime);
+    }
+    std::vector<uint8_t> acc(B);
+    eng.check(zkp_ciphertext_verify(eng.handle(), (int)B, (int)zl, pack(c, nnl).data(), pack(z1, zl).data(), pack(z2, nnl).data(),
+                                    pack(cp, nnl).data(), acc.data()));
+    return std::vector<int>(acc.begin(), acc.end());
+  }
+  void verify(Engine& eng, const CiphertextStatement& st) const {
+    if (!verify_batch(eng, {this}, {st})[0]) throw IncorrectProof();
+  }
+  std::string to_json() const {
+    return Json::object().set("z1", ser_native(z1)).set("z2", ser_native(z2)).set("c_prime", ser_native(c_prime)).dump();
+  }
+  static CiphertextProof from_json(const std::string& s) {
+    Json j = Json::parse(s);
+    CiphertextProof p;
+    p.z1 = de_native(j.at("z1")); p.z2 = de_native(j.at("z2")); p.c_prime = de_native(j.at("c_prime"));
+    return p;
+  }
+};
+
+struct MulStatement { EncryptionKey ek; BigInt e_a, e_b, e_c; };        // multiplication_proof.rs:51-57
+struct MulWitness { BigInt a, b, c, r_a, r_b, r_c; };                   // :41-49
+class MulProof {                                                        // :32-39
+ public:
+  BigInt f, z1, z2, e_d, e_db;
+  static BigInt sample_paillier_random(const ByteSource& rng, const BigInt& modulo) {  // :148-154
+    for (;;) {
+      BigInt r = BigInt::sample_below(rng, modulo);
+      if (BigInt::gcd(r, modulo) == BigInt(1)) return r;
+    }
+  }
+  static std::vector<MulProof> prove_batch(Engine& eng, const std::vector<MulWitness>& w, const std::vector<MulStatement>& st,
+                                           const ByteSource& rng = os_rng()) {
+    const size_t B = st.size();
+    if (B == 0) return {};
+    eng.use_key(st[0].ek);
+    const size_t nl = eng.nl(), nnl = eng.nnl();
+    std::vector<BigInt> a, b, ra, rb, rc, ea, eb, ec, d, rd;
+    for (size_t i = 0; i < B; ++i) {
+      a.push_back(w[i].a); b.push_back(w[i].b); ra.push_back(w[i].r_a); rb.push_back(w[i].r_b); rc.push_back(w[i].r_c);
+      ea.push_back(st[i].e_a); eb.push_back(st[i].e_b); ec.push_back(st[i].e_c);
+      d.push_back(BigInt::sample_below(rng, st[i].ek.n));          // :61
+      rd.push_back(sample_paillier_random(rng, st[i].ek.n));       // :62
+    }
+    std::vector<uint32_t> f(B * nl), z1(B * nnl), z2(B * nnl), ed(B * nnl), edb(B * nnl);
+    std::vector<uint8_t> fault(B);
+    eng.check(zkp_mul_prove(eng.handle(), (int)B, pack(a, nl).data(), pack(b, nl).data(), pack(ra, nl).data(), pack(rb, nl).data(),
+                            pack(rc, nl).data(), pack(ea, nnl).data(), pack(eb, nnl).data(), pack(ec, nnl).data(), pack(d, nl).data(),
+                            pack(rd, nl).data(), f.data(), z1.data(), z2.data(), ed.data(), edb.data(), fault.data()));
+    std::vector<MulProof> out(B);
+    for (size_t i = 0; i < B; ++i) {
+      if (fault[i]) throw ReferencePanic("called `Option::unwrap()` on a `None` value (mod_inv, multiplication_proof.rs:96)");
+      out[i].f = BigInt::from_limbs(&f[i * nl], nl);
+      out[i].z1 = BigInt::from_limbs(&z1[i * nnl], nnl);
+      out[i].z2 = BigInt::from_limbs(&z2[i * nnl], nnl);
+      out[i].e_d = BigInt::from_limbs(&ed[i * nnl], nnl);
+      out[i].e_db = BigInt::from_limbs(&edb[i * nnl], nnl);
+    }
+    return out;
+  }
+  static MulProof prove(Engine& eng, const MulWitness& w, const MulStatement& st, const ByteSource& rng = os_rng()) {
+    return prove_batch(eng, {w}, {st}, rng)[0];
+  }
+  static std::vector<int> verify_batch(Engine& eng, const std::vector<const MulProof*>& ps, const std::vector<MulStatement>& st) {
+    const size_t B = ps.size();
+    if (B == 0) return {};
+    eng.use_key(st[0].ek);
+    const size_t nl = eng.nl(), nnl = eng.nnl();
+    std::vector<BigInt> ea, eb, ec, f, z1, z2, ed, edb;
+    for (size_t i = 0; i < B; ++i) {
+      ea.push_back(st[i].e_a); eb.push_back(st[i].e_b); ec.push_back(st[i].e_c);
+      f.push_back(ps[i]->f); z1.push_back(ps[i]->z1); z2.push_back(ps[i]->z2); ed.push_back(ps[i]->e_d); edb.push_back(ps[i]->e_db);
+    }
+    std::vector<uint8_t> acc(B), fault(B);
+    eng.check(zkp_mul_verify(eng.handle(), (int)B, pack(ea, nnl).data(), pack(eb, nnl).data(), pack(ec, nnl).data(), pack(f, nl).data(),
+                             pack(z1, nnl).data(), pack(z2, nnl).data(), pack(ed, nnl).data(), pack(edb, nnl).data(), acc.data(), fault.data()));
+    for (size_t i = 0; i < B; ++i)
+      if (fault[i]) throw ReferencePanic("called `Option::unwrap()` on a `None` value (mod_inv, multiplication_proof.rs:137)");
+    return std::vector<int>(acc.begin(), acc.end());
+  }
+  void verify(Engine& eng, const MulStatement& st) const {
+    if (!verify_batch(eng, {this}, {st})[0]) throw IncorrectProof();
+  }
+  std::string to_json() const {
+    return Json::object().set("f", ser_native(f)).set("z1", ser_native(z1)).set("z2", ser_native(z2)).set("e_d", ser_native(e_d)).set("e_db", ser_native(e_db)).dump();
+  }
+  static MulProof from_json(const std::string& s) {
+    Json j = Json::parse(s);
+    MulProof p;
+    p.f = de_native(j.at("f")); p.z1 = de_native(j.at("z1")); p.z2 = de_native(j.at("z2")); p.e_d = de_native(j.at("e_d")); p.e_db = de_native(j.at("e_db"));
+    return p;
+  }
+};
+
+struct VerlinStatement { EncryptionKey ek; BigInt c, c_prime, phi_x; };         // verlin_proof.rs:51-57
+struct VerlinWitness { BigInt x, x_prime, x_double_prime, r_x; };               // :43-49
+class VerlinProof {                                                            // :34-41
+ public:
+  BigInt phi_a, z, z_prime, z_double_prime, r_z;
+  static std::vector<VerlinProof> prove_batch(Engine& eng, const std::vector<VerlinWitness>& w, const std::vector<VerlinStatement>& st,
+                                              const ByteSource& rng = os_rng()) {
+    const size_t B = st.size();
+    if (B == 0) return {};
+    eng.use_key(st[0].ek);
+    const size_t nl = eng.nl(), nnl = eng.nnl(), zl = eng.zl();
+    std::vector<BigInt> x, xp, xdp, rx, c, cp, phix, a, ap, adp, ra;
+    for (size_t i = 0; i < B; ++i) {
+      x.push_back(w[i].x); xp.push_back(w[i].x_prime); xdp.push_back(w[i].x_double_prime); rx.push_back(w[i].r_x);
+      c.push_back(st[i].c); cp.push_back(st[i].c_prime); phix.push_back(st[i].phi_x);
+      const BigInt& n = st[i].ek.n;
+      a.push_back(BigInt::sample_below(rng, n));             // :61
+      ap.push_back(BigInt::sample_below(rng, n));            // :62
+      adp.push_back(BigInt::sample_below(rng, n));           // :63
+      ra.push_back(MulProof::sample_paillier_random(rng, n));  // :64-67
+    }
+    std::vector<uint32_t> phia(B * nnl), z(B * zl), zp(B * zl), zdp(B * zl), rz(B * nnl);
+    eng.check(zkp_verlin_prove(eng.handle(), (int)B, (int)zl, pack(x, nl).data(), pack(xp, nl).data(), pack(xdp, nl).data(), pack(rx, nl).data(),
+                               pack(c, nnl).data(), pack(cp, nnl).data(), pack(phix, nnl).data(), pack(a, nl).data(), pack(ap, nl).data(),
+                               pack(adp, nl).data(), pack(ra, nl).data(), phia.data(), z.data(), zp.data(), zdp.data(), rz.data()));
+    std::vector<VerlinProof> out(B);
+    for (size_t i = 0; i < B; ++i) {
+      out[i].phi_a = BigInt::from_limbs(&phia[i * nnl], nnl);
+      out[i].z = BigInt::from_limbs(&z[i * zl], zl);
+      out[i].z_prime = BigInt::from_limbs(&zp[i * zl], zl);
+      out[i].z_double_prime = BigInt::from_limbs(&zdp[i * zl], zl);
+      out[i].r_z = BigInt::from_limbs(&rz[i * nnl], nnl);
+    }
+    return out;
+  }
+  static VerlinProof prove(Engine& eng, const VerlinWitness& w, const VerlinStatement& st, const ByteSource& rng = os_rng()) {
+    return prove_batch(eng, {w}, {st}, rng)[0];
+  }
+  static std::vector<int> verify_batch(Engine& eng, const std::vector<const VerlinProof*>& ps, const std::vector<VerlinStatement>& st) {
+    const size_t B = ps.size();
+    if (B == 0) return {};
+    eng.use_key(st[0].ek);
+    const size_t nnl = eng.nnl(), zl = eng.zl();
+    std::vector<BigInt> c, cp, phix, phia, z, zp, zdp, rz;
+    for (size_t i = 0; i < B; ++i) {
+      c.push_back(st[i].c); cp.push_back(st[i].c_prime); phix.push_back(st[i].phi_x);
+      phia.push_back(ps[i]->phi_a); z.push_back(ps[i]->z); zp.push_back(ps[i]->z_prime); zdp.push_back(ps[i]->z_double_prime);
+      rz.push_back(ps[i]->r_z);
+    }
+    std::vector<uint8_t> acc(B);
+    eng.check(zkp_verlin_verify(eng.handle(), (int)B, (int)zl, pack(c, nnl).data(), pack(cp, nnl).data(), pack(phix, nnl).data(),
+                                pack(phia, nnl).data(), pack(z, zl).data(), pack(zp, zl).data(), pack(zdp, zl).data(), pack(rz, nnl).data(),
+                                acc.data()));
+    return std::vector<int>(acc.begin(), acc.end());
+  }
+  void verify(Engine& eng, const VerlinStatement& st) const {
+    if (!verify_batch(eng, {this}, {st})[0]) throw IncorrectProof();
+  }
+  std::string to_json() const {
+    return Json::object().set("phi_a", ser_native(phi_a)).set("z", ser_native(z)).set("z_prime", ser_native(z_prime))
+        .set("z_double_prime", ser_native(z_double_prime)).set("r_z", ser_native(r_z)).dump();
+  }
+  static VerlinProof from_json(const std::string& s) {
+    Json j = Json::parse(s);
+    VerlinProof p;
+    p.phi_a = de_native(j.at("phi_a")); p.z = de_native(j.at("z")); p.z_prime = de_native(j.at("z_prime"));
+    p.z_double_prime = de_native(j.at("z_double_prime")); p.r_z = de_native(j.at("r_z"));
+    return p;
+  }
+};
+
+}  // namespace zkproofs

@@ -52,6 +52,7 @@ SIGNATURES = {
     "zkp_rp_verify_fetch": (C.c_int, [C.c_void_p, _u8p, _u8p, _u8p]),
     "zkp_rp_verify_enc_count": (C.c_longlong, [C.c_void_p]),
     "zkp_correct_key_ni_verify": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _u32p, _u32p, _u8p, C.c_int, _u8p, _u32p]),
+    "zkp_correct_key_ni_rho": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _u32p, _u8p, C.c_int, _u32p]),
     "zkp_ck_verify_stage": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _u32p, _u32p, _u8p, C.c_int]),
     "zkp_ck_verify_run": (C.c_int, [C.c_void_p]),
     "zkp_ck_verify_fetch": (C.c_int, [C.c_void_p, _u8p, _u32p]),
@@ -325,6 +326,14 @@ class Context:
         s = np.frombuffer(bytes(salt), dtype=np.uint8).copy() if len(salt) else np.zeros(1, np.uint8)
         self._ck(self._lib.zkp_ck_verify_stage(self._h, batch, nl, _p32(n), _p32(sigma), _p8(s), len(salt)))
         self._ck_shape = (batch, nl)
+
+    def correct_key_ni_rho(self, n, salt: bytes):
+        n = _c32(n)
+        batch, nl = n.shape
+        rho = np.empty((batch, CK_M2, nl), np.uint32)
+        s = np.frombuffer(bytes(salt), dtype=np.uint8).copy() if len(salt) else np.zeros(1, np.uint8)
+        self._ck(self._lib.zkp_correct_key_ni_rho(self._h, batch, nl, _p32(n), _p8(s), len(salt), _p32(rho)))
+        return rho
 
     def ck_verify_run(self):
         self._ck(self._lib.zkp_ck_verify_run(self._h))
