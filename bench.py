@@ -346,8 +346,122 @@ def run_reference(args):
     }))
 
 
+def run_other(args):
+    """Secondary configs (not the driver's headline): BASELINE.json configs[2] and configs[4] on one GPU.
+      --config correct_key : NiCorrectKeyProof verify, batch 4096, 3072-bit n (16 committed keys cycled; distinct-modulus kernel path)
+      --config sigma       : MulProof + VerlinProof verify, 4096-bit n, batch 512 + 512 (the per-GPU share of 8192 over 8 GPUs)"""
+    import torch
+    import zk_paillier_b200 as zk
+    from zk_paillier_b200 import workload
+    from zk_paillier_b200.native import KID_MODEXP_SHARED, KID_MODEXP_VAR, to_limbs, ints_to_limbs, limbs_to_ints
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import c_oracle
+    import zkp_oracle as po
+    from util import keys
+
+    dev = torch.device("cuda", 0)
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
+    ctx = zk.native.Context(0, stream=stream.cuda_stream)
+    imad_peak = ctx.imad_peak(0)
+    line = {"n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32 limbs (32x32+64 IMAD)", "data": "synthetic"}
+    if args.config == "correct_key":
+        bits, batch, salt = 3072, args.batch if args.batch != 1024 else 4096, b"Zen Go X"
+        nl = bits // 32
+        work = workload.correct_key_batch(keys(bits), batch, salt, lambda p, q, s: po.NiCorrectKeyProof.proof(p, q, s).sigma_vec, nl, bad_every=64)
+        ctx.ck_verify_stage(work["n"], work["sigma"], salt)
+        for _ in range(args.warmup):
+            ctx.ck_verify_run()
+        ctx.profile_enable(True); ctx.profile_reset()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            ctx.ck_verify_run()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        k2_ms, k2_n, k2_units = ctx.profile_get(KID_MODEXP_VAR)
+        ctx.profile_enable(False)
+        acc = ctx.ck_verify_fetch()
+        assert acc.tolist() == [0 if b % 64 == 63 else 1 for b in range(batch)]
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            acc = ctx.correct_key_ni_verify(work["n"], work["sigma"], salt)
+        e2e_s = time.perf_counter() - t0
+        cores = c_oracle.hw_threads()
+        m = min(batch, 16 * cores)
+        t0 = time.perf_counter()
+        acc_c, _ = c_oracle.correct_key_ni_verify(work["n"][:m], work["sigma"][:m], salt, cores)
+        cpu_s = time.perf_counter() - t0
+        assert np.array_equal(acc_c, acc[:m])
+        per = modexp_imads(bits, bits)
+        line.update(metric="NiCorrectKeyProof verifies/sec at 3072-bit n", unit="verifies/s", value=batch * args.steps / (ms * 1e-3),
+                    ms_per_step=ms / args.steps,
+                    config={"workload": f"NiCorrectKeyProof verify, batch={batch}, 3072-bit n, 16 distinct committed keys cycled, salt 'Zen Go X', 1/64 bad proofs"},
+                    e2e={"value": batch * args.e2e_steps / e2e_s, "unit": "verifies/s", "h2d_bytes_per_step": int(work["n"].nbytes + work["sigma"].nbytes),
+                         "d2h_bytes_per_step": batch},
+                    roofline={"bound": "imad", "kernel": "modexp_var_kernel<8,12> (K2)", "achieved": k2_units * per / (k2_ms * 1e-3) / 1e12, "peak": imad_peak / 1e12,
+                              "unit": "T IMAD.WIDE.U32/s", "frac": k2_units * per / (k2_ms * 1e-3) / imad_peak, "traffic": None, "alg_imads_per_modexp": per,
+                              "k2_share_of_step": k2_ms / ms},
+                    cpu_baseline={"value": m / cpu_s, "unit": "verifies/s", "cores": cores, "kind": "port", "sample": f"{m} of the {batch} proofs, GMP mpz_powm"})
+    else:
+        bits, B = 4096, args.batch if args.batch != 1024 else 512
+        p, q = keys(bits)[0]
+        n = p * q
+        nl, nnl = bits // 32, bits // 16
+        ctx.set_key(to_limbs(n, nl))
+        g = np.random.Generator(np.random.PCG64(5))
+        rows = lambda: workload._rand_limbs_below_pow2(g, (B,), nl, bits - 1)
+        a, b = rows(), rows()
+        c = ints_to_limbs([x * y % n for x, y in zip(limbs_to_ints(a), limbs_to_ints(b))], nl)
+        r_a, r_b, r_c, d, r_d = (rows() | 1 for _ in range(5))
+        e_a, e_b, e_c = ctx.paillier_enc(a, r_a), ctx.paillier_enc(b, r_b), ctx.paillier_enc(c, r_c)
+        f, z1, z2, e_d, e_db, fault = ctx.mul_prove(a, b, r_a, r_b, r_c, e_a, e_b, e_c, d, r_d)
+        x, xp, xdp, r_x = rows(), rows(), rows(), rows() | 1
+        cc, cp = ctx.paillier_enc(rows(), rows() | 1), ctx.paillier_enc(rows(), rows() | 1)
+        pad = lambda v: np.concatenate([v, np.zeros((B, nnl - nl), np.uint32)], axis=1)
+        nn_rows = to_limbs(n * n, nnl)[None, :]
+        phi_x = ctx.modmul(ctx.modmul(ctx.modexp_var(cc, pad(x), nn_rows, exp_per=1, mod_per=B, exp_bits=bits),
+                                      ctx.modexp_var(cp, pad(xp), nn_rows, exp_per=1, mod_per=B, exp_bits=bits)), ctx.paillier_enc(xdp, r_x))
+        phi_a, z, zp, zdp, r_z = ctx.verlin_prove(x, xp, xdp, r_x, cc, cp, phi_x, rows(), rows(), rows(), rows() | 1)
+
+        def step():
+            acc1, flt = ctx.mul_verify(e_a, e_b, e_c, f, z1, z2, e_d, e_db)
+            acc2 = ctx.verlin_verify(cc, cp, phi_x, phi_a, z, zp, zdp, r_z)
+            assert acc1.all() and acc2.all() and not flt.any()
+
+        for _ in range(args.warmup):
+            step()
+        ctx.profile_enable(True); ctx.profile_reset()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        k1_ms, _, k1_units = ctx.profile_get(KID_MODEXP_SHARED)
+        k2_ms, _, k2_units = ctx.profile_get(KID_MODEXP_VAR)
+        mul_imads = 3 * modexp_imads(2 * bits, bits) + 2 * modexp_imads(2 * bits, 256)
+        ver_imads = modexp_imads(2 * bits, 256) + 2 * modexp_imads(2 * bits, bits + 256) + modexp_imads(2 * bits, bits)
+        alg = B * (mul_imads + ver_imads) * args.steps
+        bytes_in = sum(v.nbytes for v in (e_a, e_b, e_c, f, z1, z2, e_d, e_db, cc, cp, phi_x, phi_a, z, zp, zdp, r_z))
+        line.update(metric="MulProof+VerlinProof verifies/sec at 4096-bit n", unit="verifies/s", value=2 * B * args.steps / dt, ms_per_step=dt / args.steps * 1e3,
+                    config={"workload": f"MulProof verify x{B} + VerlinProof verify x{B}, 4096-bit n (8192-bit modulus), one key; through the host-buffer ABI"},
+                    e2e={"value": 2 * B * args.steps / dt, "unit": "verifies/s", "h2d_bytes_per_step": int(bytes_in), "d2h_bytes_per_step": 3 * B},
+                    roofline={"bound": "imad", "kernel": "modexp_shared_kernel<16,16> + modexp_var_kernel<16,16>", "achieved": alg / ((k1_ms + k2_ms) * 1e-3) / 1e12,
+                              "peak": imad_peak / 1e12, "unit": "T IMAD.WIDE.U32/s", "frac": alg / ((k1_ms + k2_ms) * 1e-3) / imad_peak, "traffic": None,
+                              "modexp_share_of_step": (k1_ms + k2_ms) * 1e-3 / dt},
+                    cpu_baseline=None)
+    print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--config", default="rangeproof", choices=["rangeproof", "correct_key", "sigma"])
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
@@ -360,6 +474,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.config != "rangeproof":
+        run_other(args)
     else:
         run_b200(args)
 

@@ -5,6 +5,7 @@
 // big-integer operation on caller data runs in the CUDA kernels of modexp.cu.
 // There is deliberately no CPU fallback: zkp_ctx_create fails without a device.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -53,7 +54,20 @@ ProfScope::~ProfScope() {
 
 cudaError_t ensure_table(zkp_ctx* c, int S, int entries) {
   size_t bytes = (size_t)resident_groups(S, c->num_sms) * entries * S * sizeof(uint32_t);
+  if (c->enc2d_key && c->enc2d_enabled) {
+    size_t b2 = (size_t)enc2d_resident_groups(c->num_sms) * kTableShared * 128 * sizeof(uint32_t);
+    if (b2 > bytes) bytes = b2;
+  }
   return c->table.ensure(bytes);
+}
+
+cudaError_t launch_enc(zkp_ctx* c, const uint32_t* bases, int base_limbs, const uint32_t* plain, int plain_limbs, uint32_t* out,
+                       int jobs, const unsigned* jobs_dev) {
+  if (c->enc2d_key && c->enc2d_enabled && base_limbs == 64 && (!plain || (plain_limbs <= 64 && plain_limbs % 2 == 0)))
+    return launch_enc2d(c->n.h_mod.data(), c->nn.sched.as<uint32_t>(), c->nn.nsteps, bases, plain, plain_limbs, out, jobs,
+                        c->table.as<uint32_t>(), c->num_sms, c->stream, jobs_dev);
+  return launch_modexp_shared(c->nn.view(), bases, base_limbs, plain, plain_limbs, out, c->nn.limbs, jobs, c->table.as<uint32_t>(),
+                              c->num_sms, c->stream, jobs_dev);
 }
 
 // Sliding-window (width kWindowShared) recoding of a public exponent, most
@@ -255,6 +269,11 @@ int zkp_set_key(zkp_ctx* c, const uint32_t* n, int n_limbs) {
   ZKP_CU(c, cudaStreamSynchronize(c->stream));
   c->n_limbs = n_limbs;
   c->paillier = true;
+  c->enc2d_key = n_limbs == 64 && enc2d_supported(n, n_limbs);
+  {
+    const char* env = getenv("ZKP_B200_ENC2D");
+    c->enc2d_enabled = !(env && env[0] == '0');
+  }
   c->rp.prove_staged = c->rp.prove_done = c->rp.verify_staged = c->rp.verify_done = false;
   return ZKP_OK;
 }
@@ -310,8 +329,7 @@ int zkp_paillier_enc(zkp_ctx* c, const uint32_t* m, int m_limbs, const uint32_t*
   ZKP_CU(c, cudaMemcpyAsync(c->in1.p, m, (size_t)batch * m_limbs * 4, cudaMemcpyHostToDevice, c->stream));
   {
     ProfScope ps(c, KID_MODEXP_SHARED, batch);
-    ZKP_CU(c, launch_modexp_shared(c->nn.view(), c->in0.as<uint32_t>(), r_limbs, c->in1.as<uint32_t>(), m_limbs,
-                                   c->out0.as<uint32_t>(), ol, batch, c->table.as<uint32_t>(), c->num_sms, c->stream));
+    ZKP_CU(c, launch_enc(c, c->in0.as<uint32_t>(), r_limbs, c->in1.as<uint32_t>(), m_limbs, c->out0.as<uint32_t>(), batch));
   }
   ZKP_CU(c, cudaMemcpyAsync(out, c->out0.p, (size_t)batch * ol * 4, cudaMemcpyDeviceToHost, c->stream));
   ZKP_CU(c, cudaStreamSynchronize(c->stream));

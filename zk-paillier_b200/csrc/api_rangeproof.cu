@@ -110,8 +110,7 @@ int zkp_rp_prove_run(zkp_ctx* c) {
   }
   {  // c1 | c2 = Enc(w1' | w2', r1 | r2)  (:161-187)
     ProfScope ps(c, KID_MODEXP_SHARED, 2.0 * be);
-    ZKP_CU(c, launch_modexp_shared(c->nn.view(), s.rr.as<uint32_t>(), nl, s.w.as<uint32_t>(), wl, s.c.as<uint32_t>(), nnl,
-                                   2 * be, c->table.as<uint32_t>(), c->num_sms, st));
+    ZKP_CU(c, launch_enc(c, s.rr.as<uint32_t>(), nl, s.w.as<uint32_t>(), wl, s.c.as<uint32_t>(), 2 * be));
   }
   {  // e = H(n, c1.., c2..)  (range_proof_ni.rs:58-61)
     ProfScope ps(c, KID_SHA, batch);
@@ -282,8 +281,7 @@ int zkp_rp_verify_run(zkp_ctx* c) {
   {
     ProfScope ps(c, KID_MODEXP_SHARED, 0.0);
     prof_idx = ps.idx;
-    ZKP_CU(c, launch_modexp_shared(c->nn.view(), a.jobs_base, nl, a.jobs_plain, wl, a.jobs_out, nnl, 2 * be,
-                                   c->table.as<uint32_t>(), c->num_sms, st, a.count));
+    ZKP_CU(c, launch_enc(c, a.jobs_base, nl, a.jobs_plain, wl, a.jobs_out, 2 * be, a.count));
   }
   {  // c_j * cipher_x mod n^2 for the Mask rows (range_proof.rs:321-327)
     ProfScope ps(c, KID_MODMUL, be);

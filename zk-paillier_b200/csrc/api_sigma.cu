@@ -68,7 +68,7 @@ struct Sig {
     uint32_t* out = rows(nnl);
     if (bad) return out;
     ProfScope ps(c, KID_MODEXP_SHARED, batch);
-    ck(launch_modexp_shared(c->nn.view(), r, r_limbs, m, m_limbs, out, nnl, batch, c->table.as<uint32_t>(), c->num_sms, st));
+    ck(launch_enc(c, r, r_limbs, m, m_limbs, out, batch));
     return out;
   }
   // BigInt::mod_pow(base, exp, nn) / Paillier::mul, per-proof exponent

@@ -114,6 +114,8 @@ struct zkp_ctx {
   zkp::KeySlot n;    // modulus n
   bool paillier = false;
   int n_limbs = 0;   // caller's width of n after zkp_set_key
+  bool enc2d_enabled = true;  // ZKP_B200_ENC2D=0 forces the Montgomery kernel K1 for Paillier encryptions
+  bool enc2d_key = false;     // the current key qualifies for the two-digit kernel (|n| = 2048 exactly)
   zkp::DevBuf table;                 // window-table scratch
   zkp::DevBuf in0, in1, in2, in3, out0;  // generic staging for the one-shot calls
   bool profiling = false;
@@ -144,6 +146,11 @@ struct ProfScope {
 
 // table scratch large enough for K1/K2 at width S
 cudaError_t ensure_table(zkp_ctx* c, int S, int entries);
+// Paillier::encrypt_with_chosen_randomness for `jobs` rows under the current key: picks K1v2 (two-digit base-n)
+// when the key and row widths qualify, else K1 (Montgomery mod n^2).  plain == nullptr encrypts 0.
+// Returns 1 if K1v2 ran, 0 if K1 ran, negative cudaError as -(int)err - 1000 on failure (see enc_failed()).
+cudaError_t launch_enc(zkp_ctx* c, const uint32_t* bases, int base_limbs, const uint32_t* plain, int plain_limbs, uint32_t* out,
+                       int jobs, const unsigned* jobs_dev = nullptr);
 
 // Montgomery/key helpers (api_core.cu)
 int setup_slot(zkp_ctx* c, KeySlot& slot, const uint32_t* mod, int limbs, const uint32_t* exp, int exp_limbs);

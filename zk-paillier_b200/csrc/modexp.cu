@@ -17,6 +17,7 @@
 // 1-D TMA bulk copy (cp.async.bulk -> UBLKCP) per array and an mbarrier.
 #include "kernels.h"
 #include "mp_coop.cuh"
+#include "blockmul.cuh"
 
 namespace zkp {
 
@@ -566,7 +567,44 @@ __global__ void __launch_bounds__(256) imad_peak_kernel(int iters, uint32_t* sin
   if (x == 0x12345678u) sink[0] = x;
 }
 
+// In-lane 32x32 block products by product scanning (blockmul.cuh): the building block of a
+// two-digit base-n engine.  MINB = resident CTAs of 128 threads per SM (register budget).
+template <int MINB, class Shape>
+__global__ void __launch_bounds__(128, MINB) blockmul_peak_kernel(int iters, uint32_t* sink) {
+  uint32_t a[32], b[32], out[64];
+  uint32_t seed = threadIdx.x * 2654435761u + blockIdx.x;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    a[j] = seed = seed * 1664525u + 1013904223u;
+    b[j] = seed = seed * 1664525u + 1013904223u;
+  }
+  for (int it = 0; it < iters; ++it) {
+    block_mul<32, 32, Shape>(out, a, b);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      a[j] ^= out[j];
+      b[j] += out[32 + j];
+    }
+  }
+  uint32_t x = 0;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) x ^= a[j] ^ b[j];
+  if (x == 0x12345678u) sink[0] = x;
+}
+
 cudaError_t launch_imad_peak(int variant, int blocks, int iters, uint32_t* sink, double* ops, cudaStream_t st) {
+  if (variant >= 3 && variant <= 6) {
+    // 3: full block, 4 CTAs/SM (16 warps); 4: full, 2 CTAs/SM (8 warps); 5: lower triangle, 4 CTAs/SM; 6: full, 3 CTAs/SM
+    const int it2 = iters / 64 > 0 ? iters / 64 : 1;
+    const int per_sm = variant == 4 ? 2 : (variant == 6 ? 3 : 4);
+    const int grid = blocks / 8 * per_sm;
+    if (variant == 3) blockmul_peak_kernel<4, ShapeFull><<<grid, 128, 0, st>>>(it2, sink);
+    if (variant == 4) blockmul_peak_kernel<2, ShapeFull><<<grid, 128, 0, st>>>(it2, sink);
+    if (variant == 5) blockmul_peak_kernel<4, ShapeLowTri><<<grid, 128, 0, st>>>(it2, sink);
+    if (variant == 6) blockmul_peak_kernel<3, ShapeFull><<<grid, 128, 0, st>>>(it2, sink);
+    *ops = (double)grid * 128.0 * (double)it2 * (variant == 5 ? 528.0 : 1024.0);
+    return cudaGetLastError();
+  }
   switch (variant) {
     case 0: imad_peak_kernel<0><<<blocks, 256, 0, st>>>(iters, sink); break;
     case 1: imad_peak_kernel<1><<<blocks, 256, 0, st>>>(iters, sink); break;

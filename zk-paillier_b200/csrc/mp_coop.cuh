@@ -73,7 +73,7 @@ __device__ __forceinline__ void madc_wide3_cc(uint32_t& d0, uint32_t& d1, uint32
 
 template <int T, int L>
 struct Mp {
-  static_assert(T == 4 || T == 8 || T == 16 || T == 32, "group width");
+  static_assert(T == 2 || T == 4 || T == 8 || T == 16 || T == 32, "group width");
   static_assert(L >= 2 && (L % 2) == 0, "limbs per lane must be even");
   static constexpr int S = T * L;  // limbs per integer
   static constexpr uint32_t GM = (T == 32) ? 0xffffffffu : ((1u << T) - 1u);

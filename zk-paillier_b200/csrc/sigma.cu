@@ -5,10 +5,11 @@
 //   digest -> exponent limbs, z = a + x*e (unreduced), (a + b) mod n, row equality, and
 //   BigInt::mod_inv (multiplication_proof.rs:96,137) by the binary extended Euclid.
 #include "kernels.h"
+#include "mp_coop.cuh"
 
 namespace zkp {
 
-constexpr int kMaxLimbs = 272;  // 8192-bit modulus + slack
+constexpr int kMaxLimbs = 256;  // 8192-bit modulus
 
 // e = compute_digest(...) as a BigInt (utils.rs:21): 32 big-endian bytes -> 8 little-endian limbs
 __global__ void digest_to_limbs_kernel(const uint8_t* digest, int batch, uint32_t* out) {
@@ -90,60 +91,101 @@ __global__ void rows_equal_kernel(const uint32_t* x, const uint32_t* y, int limb
   if (lane == 0) accept[warp] = (uint8_t)((and_in ? accept[warp] : 1) && diff == 0);
 }
 
-// ---- BigInt::mod_inv(v, m) for odd m: binary extended Euclid, one thread per instance.
-// Invariants: u = x1 * v (mod m), w = x2 * v (mod m).  Ends with u == 1 (inverse x1), or u == 0
-// (gcd(v, m) = w != 1: not invertible -> fault, where the reference's unwrap() panics).
-struct Big {
-  uint32_t* d;
-  int n;
-  __device__ bool is_zero() const { for (int i = 0; i < n; ++i) if (d[i]) return false; return true; }
-  __device__ bool is_one() const { if (d[0] != 1u) return false; for (int i = 1; i < n; ++i) if (d[i]) return false; return true; }
-  __device__ bool even() const { return !(d[0] & 1u); }
-  __device__ void shr1(uint32_t top) { for (int i = 0; i < n - 1; ++i) d[i] = (d[i] >> 1) | (d[i + 1] << 31); d[n - 1] = (d[n - 1] >> 1) | (top << 31); }
-  __device__ uint32_t add(const uint32_t* o) { uint32_t c = 0; for (int i = 0; i < n; ++i) { unsigned long long t = (unsigned long long)d[i] + o[i] + c; d[i] = (uint32_t)t; c = (uint32_t)(t >> 32); } return c; }
-  __device__ uint32_t sub(const uint32_t* o) { uint32_t b = 0; for (int i = 0; i < n; ++i) { unsigned long long t = (unsigned long long)d[i] - o[i] - b; d[i] = (uint32_t)t; b = (uint32_t)(t >> 63); } return b; }
-  __device__ int cmp(const uint32_t* o) const { for (int i = n - 1; i >= 0; --i) if (d[i] != o[i]) return d[i] < o[i] ? -1 : 1; return 0; }
+// ---- BigInt::mod_inv(v, m) for odd m: binary extended Euclid, ONE WARP per instance.
+// The four working integers (u, w and the cofactors x1, x2) are spread over the 32 lanes, L limbs per lane in
+// registers (Mp<32, L>): shifts borrow one bit from the neighbouring lane, add / sub / compare resolve
+// their carries with one ballot.  Control flow depends only on the instance, so it is uniform per warp.
+// Invariants: u = x1 * v (mod m), w = x2 * v (mod m).  Ends with u == 1 (inverse x1), or a common factor
+// (u == 0 or u == w): not invertible -> fault, where the reference's unwrap() panics.
+template <int L>
+struct Inv {
+  using M = Mp<32, L>;
+  static __device__ __forceinline__ void shr1(uint32_t (&x)[L], uint32_t top, int lane) {
+    uint32_t nb = __shfl_down_sync(ZKP_FULL, x[0], 1);
+    if (lane == 31) nb = top;
+#pragma unroll
+    for (int j = 0; j < L - 1; ++j) x[j] = (x[j] >> 1) | (x[j + 1] << 31);
+    x[L - 1] = (x[L - 1] >> 1) | (nb << 31);
+  }
+  static __device__ __forceinline__ bool is_odd(const uint32_t (&x)[L]) { return (__shfl_sync(ZKP_FULL, x[0], 0) & 1u) != 0; }
+  static __device__ __forceinline__ bool is_small(const uint32_t (&x)[L], uint32_t v, int lane) {  // x == v (v < 2^32)
+    uint32_t m = (lane == 0) ? (x[0] ^ v) : x[0];
+#pragma unroll
+    for (int j = 1; j < L; ++j) m |= x[j];
+    return __ballot_sync(ZKP_FULL, m != 0) == 0u;
+  }
+  // x = (x + m) >> 1 if x is odd else x >> 1   (halving modulo the odd m)
+  static __device__ __forceinline__ void half_mod(uint32_t (&x)[L], const uint32_t (&m)[L], int lane) {
+    uint32_t top = 0;
+    if (is_odd(x)) top = M::add_full(x, m, lane);
+    shr1(x, top, lane);
+  }
+  // x = (x - y) mod m
+  static __device__ __forceinline__ void sub_mod(uint32_t (&x)[L], const uint32_t (&y)[L], const uint32_t (&m)[L], int lane) {
+    uint32_t d[L];
+    uint32_t borrow = M::sub_full(d, x, y, lane);
+#pragma unroll
+    for (int j = 0; j < L; ++j) x[j] = d[j];
+    if (borrow) M::add_full(x, m, lane);
+  }
 };
 
-__global__ void modinv_kernel(const uint32_t* v, const uint32_t* m, int limbs, int batch, uint32_t* scratch,
-                              uint32_t* out, uint8_t* fault) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+template <int L>
+__global__ void __launch_bounds__(128) modinv_kernel(const uint32_t* v, const uint32_t* m, int limbs, int batch, uint32_t* out,
+                                                     uint8_t* fault) {
+  using M = Mp<32, L>;
+  using I = Inv<L>;
+  const int lane = threadIdx.x & 31;
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (b >= batch) return;
-  uint32_t* base = scratch + (size_t)b * 4 * limbs;
-  Big u{base, limbs}, w{base + limbs, limbs}, x1{base + 2 * limbs, limbs}, x2{base + 3 * limbs, limbs};
-  for (int i = 0; i < limbs; ++i) {
-    u.d[i] = v[(size_t)b * limbs + i];
-    w.d[i] = m[i];
-    x1.d[i] = i == 0 ? 1u : 0u;
-    x2.d[i] = 0u;
+  uint32_t u[L], w[L], x1[L], x2[L], mm[L], d[L];
+  M::load_ext(u, v + (size_t)b * limbs, limbs, lane);
+  M::load_ext(mm, m, limbs, lane);
+#pragma unroll
+  for (int j = 0; j < L; ++j) {
+    w[j] = mm[j];
+    x1[j] = 0;
+    x2[j] = 0;
   }
-  // reduce v below m first (v < 2^(32 limbs); m has its top limb set in practice, a few subtractions at most)
-  while (u.cmp(m) >= 0) u.sub(m);
-  bool ok = !u.is_zero();
-  while (ok && !u.is_one()) {
-    while (u.even()) {
-      u.shr1(0);
-      uint32_t c = x1.even() ? 0u : x1.add(m);
-      x1.shr1(c);
+  if (lane == 0) x1[0] = 1;
+  // v < 2^(32 limbs) may exceed m by a small factor when m's top limb is set: reduce by subtraction
+  bool ok = true;
+  for (int k = 0; k < 64; ++k) {
+    if (M::sub_full(d, u, mm, lane)) break;  // u < m
+#pragma unroll
+    for (int j = 0; j < L; ++j) u[j] = d[j];
+    if (k == 63) ok = false;
+  }
+  if (I::is_small(u, 0u, lane)) ok = false;
+  while (ok && !I::is_small(u, 1u, lane)) {
+    while (!I::is_odd(u)) {
+      I::shr1(u, 0, lane);
+      I::half_mod(x1, mm, lane);
     }
-    while (w.even()) {
-      w.shr1(0);
-      uint32_t c = x2.even() ? 0u : x2.add(m);
-      x2.shr1(c);
+    while (!I::is_odd(w)) {
+      I::shr1(w, 0, lane);
+      I::half_mod(x2, mm, lane);
     }
-    if (u.is_one()) break;
-    int c = u.cmp(w.d);
-    if (c == 0) { ok = false; break; }  // u == w != 1: common factor
-    if (c > 0) {
-      u.sub(w.d);
-      if (x1.sub(x2.d)) x1.add(m);
+    if (I::is_small(u, 1u, lane)) break;
+    const uint32_t borrow = M::sub_full(d, u, w, lane);  // d = u - w
+    if (!borrow) {
+      if (I::is_small(d, 0u, lane)) { ok = false; break; }  // u == w != 1: common factor
+#pragma unroll
+      for (int j = 0; j < L; ++j) u[j] = d[j];
+      I::sub_mod(x1, x2, mm, lane);
     } else {
-      w.sub(u.d);
-      if (x2.sub(x1.d)) x2.add(m);
+      M::sub_full(d, w, u, lane);
+#pragma unroll
+      for (int j = 0; j < L; ++j) w[j] = d[j];
+      I::sub_mod(x2, x1, mm, lane);
     }
   }
-  for (int i = 0; i < limbs; ++i) out[(size_t)b * limbs + i] = ok ? x1.d[i] : 0u;
-  if (!ok) fault[b] = 1;
+  if (!ok) {
+#pragma unroll
+    for (int j = 0; j < L; ++j) x1[j] = 0;
+    if (lane == 0) fault[b] = 1;
+  }
+  M::store_ext(out + (size_t)b * limbs, x1, limbs, lane);
 }
 
 static inline unsigned blocks_for(long long n, int t) { return (unsigned)((n + t - 1) / t); }
@@ -173,9 +215,15 @@ cudaError_t launch_rows_equal(const uint32_t* x, const uint32_t* y, int limbs, i
 }
 cudaError_t launch_modinv(const uint32_t* v, const uint32_t* m, int limbs, int batch, uint32_t* scratch, uint32_t* out,
                           uint8_t* fault, cudaStream_t st) {
+  (void)scratch;
   if (batch <= 0) return cudaSuccess;
-  if (limbs > kMaxLimbs) return cudaErrorInvalidValue;
-  modinv_kernel<<<blocks_for(batch, 32), 32, 0, st>>>(v, m, limbs, batch, scratch, out, fault);
+  if (limbs > kMaxLimbs || limbs % 2) return cudaErrorInvalidValue;
+  const unsigned grid = blocks_for(batch * 32ll, 128);
+  const int per_lane = (limbs + 31) / 32;
+  if (per_lane <= 2) modinv_kernel<2><<<grid, 128, 0, st>>>(v, m, limbs, batch, out, fault);
+  else if (per_lane <= 4) modinv_kernel<4><<<grid, 128, 0, st>>>(v, m, limbs, batch, out, fault);
+  else if (per_lane <= 6) modinv_kernel<6><<<grid, 128, 0, st>>>(v, m, limbs, batch, out, fault);
+  else modinv_kernel<8><<<grid, 128, 0, st>>>(v, m, limbs, batch, out, fault);
   return cudaGetLastError();
 }
 
