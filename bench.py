@@ -260,6 +260,12 @@ def run_b200(args):
     except Exception:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    traffic = None
+    try:  # DRAM bytes of K1 from the committed ncu capture, scaled to this run's Enc per launch
+        tr = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json")))
+        traffic = tr["dram_bytes_per_enc"] * k1_units / max(k1_launches, 1)
+    except Exception:
+        pass
     hbm_ach = k1_units * ENC_BYTES / (k1_ms * 1e-3) / 1e9
     kernel_ms = {"modexp_shared": k1_ms, "modmul": prof[KID_MODMUL][0], "sha256_transcript": prof[KID_SHA][0], "other": prof[KID_OTHER][0]}
     launches = int(sum(p[1] for p in prof.values()))
@@ -291,11 +297,12 @@ def run_b200(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": args.e2e_steps},
         "gpu_launches": launches,
         "roofline": {"bound": "imad", "kernel": "modexp_shared_kernel<8,16> (K1)", "achieved": achieved / 1e12, "peak": imad_peak / 1e12, "unit": "T IMAD.WIDE.U32/s",
-                     "frac": achieved / imad_peak, "traffic": None,
+                     "frac": achieved / imad_peak, "traffic": traffic,
+                     "traffic_note": "DRAM bytes per launch = ncu dram_bytes per Enc (profiles/k1_traffic.json) x Enc per launch",
                      "peak_source": "IMAD.WIDE.U32 issue-rate microbenchmark measured in this run (MEASURED_PEAKS.json has no integer entry)",
                      "alg_imads_per_enc": ENC_IMADS, "k1_launches": int(k1_launches), "k1_ms_avg": k1_ms / max(k1_launches, 1),
                      "k1_share_of_step": k1_ms / ms},
-        "roofline_hbm": {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak, "traffic": None,
+        "roofline_hbm": {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak, "traffic": traffic,
                          "alg_bytes_per_enc": ENC_BYTES, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
         "kernel_ms": kernel_ms,
         "clocks": clocks,

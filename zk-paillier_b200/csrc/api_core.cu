@@ -55,7 +55,7 @@ ProfScope::~ProfScope() {
 cudaError_t ensure_table(zkp_ctx* c, int S, int entries) {
   size_t bytes = (size_t)resident_groups(S, c->num_sms) * entries * S * sizeof(uint32_t);
   if (c->enc2d_key && c->enc2d_enabled) {
-    size_t b2 = (size_t)enc2d_resident_groups(c->num_sms) * kTableShared * 128 * sizeof(uint32_t);
+    size_t b2 = enc2d_scratch_limbs(c->num_sms) * sizeof(uint32_t);
     if (b2 > bytes) bytes = b2;
   }
   return c->table.ensure(bytes);
@@ -271,8 +271,10 @@ int zkp_set_key(zkp_ctx* c, const uint32_t* n, int n_limbs) {
   c->paillier = true;
   c->enc2d_key = n_limbs == 64 && enc2d_supported(n, n_limbs);
   {
+    // K1v2 (two-digit base-n, modexp2d.cu) is bit-exact but measured 7 % slower than K1 on B200 in round 1
+    // (DESIGN.md section 3.7): opt in with ZKP_B200_ENC2D=1.
     const char* env = getenv("ZKP_B200_ENC2D");
-    c->enc2d_enabled = !(env && env[0] == '0');
+    c->enc2d_enabled = env && env[0] == '1';
   }
   c->rp.prove_staged = c->rp.prove_done = c->rp.verify_staged = c->rp.verify_done = false;
   return ZKP_OK;

@@ -114,7 +114,7 @@ struct zkp_ctx {
   zkp::KeySlot n;    // modulus n
   bool paillier = false;
   int n_limbs = 0;   // caller's width of n after zkp_set_key
-  bool enc2d_enabled = true;  // ZKP_B200_ENC2D=0 forces the Montgomery kernel K1 for Paillier encryptions
+  bool enc2d_enabled = false; // ZKP_B200_ENC2D=1 selects the experimental two-digit kernel K1v2 for Paillier encryptions
   bool enc2d_key = false;     // the current key qualifies for the two-digit kernel (|n| = 2048 exactly)
   zkp::DevBuf table;                 // window-table scratch
   zkp::DevBuf in0, in1, in2, in3, out0;  // generic staging for the one-shot calls

@@ -274,6 +274,50 @@ struct Mp {
     finish(r, E, n, lane);
   }
 
+  // ---- plain (non-modular) product on the same split accumulator -----------------------------------
+  // One step  acc = (acc + a*b) / 2^32 : cios_step without the q*n rows.  The limb shifted out of lane 0 is
+  // the next limb of the low half of the product: it is left in lane 0's X[0] (callers capture it there).
+  static __device__ __forceinline__ void mul_step(uint32_t (&X)[L + 2], uint32_t (&Y)[L + 2], const uint32_t (&a)[L], uint32_t b, int g) {
+    uint32_t in = __shfl_down_sync(ZKP_FULL, Y[0], 1, T);
+    if (g == T - 1) in = 0;
+    add_cc(Y[L], in);
+    addc(Y[L + 1], 0);
+    uint32_t Z[L + 2];
+    add_cc(X[0], Y[1]);
+#pragma unroll
+    for (int j = 0; j < L; j += 2) madc_wide3_cc(Z[j], Z[j + 1], a[j + 1], b, Y[j + 2], Y[j + 3]);
+    Z[L] = addc_out();
+    Z[L + 1] = 0;
+    mad_even(X, a, b);
+#pragma unroll
+    for (int j = 0; j < L + 2; ++j) Y[j] = Z[j];
+  }
+
+  // After the last step: fold the two accumulator arrays and resolve the lane overflows into the exact
+  // S-limb value (the high half of a product; nothing can be left above the top lane).
+  static __device__ __forceinline__ void mul_finish(uint32_t (&r)[L], uint32_t (&E)[L + 2], uint32_t (&O)[L + 2], int lane) {
+    const int g = lane & (T - 1);
+    uint32_t in = __shfl_down_sync(ZKP_FULL, O[0], 1, T);
+    if (g == T - 1) in = 0;
+    add_cc(O[L], in);
+    addc(O[L + 1], 0);
+    add_cc(E[0], O[1]);
+#pragma unroll
+    for (int j = 1; j <= L; ++j) addc_cc(E[j], O[j + 1]);
+    addc(E[L + 1], 0);
+    uint32_t ov = __shfl_up_sync(ZKP_FULL, E[L], 1, T);
+    if (g == 0) ov = 0;
+#pragma unroll
+    for (int j = 0; j < L; ++j) r[j] = E[j];
+    add_cc(r[0], ov);
+#pragma unroll
+    for (int j = 1; j < L; ++j) addc_cc(r[j], 0);
+    uint32_t co = addc_out();
+    uint32_t topc;
+    uint32_t cin = resolve(co != 0, all_ones(r), lane, topc);
+    add_small(r, cin);
+  }
+
   static __device__ __forceinline__ void mont_sqr(uint32_t (&r)[L], const uint32_t (&a)[L], const uint32_t (&n)[L],
                                                   uint32_t n0inv, int lane) {
     mont_mul(r, a, a, n, n0inv, lane);
