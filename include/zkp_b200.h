@@ -137,6 +137,13 @@ int zkp_rp_prove_stage(zkp_ctx* ctx, int batch, int ef, int w_limbs, const uint3
                        const uint32_t* r, const uint32_t* w1, const uint8_t* swap, const uint32_t* r1,
                        const uint32_t* r2);
 int zkp_rp_prove_run(zkp_ctx* ctx);
+/* The same run in the two phases of the INTERACTIVE RangeProof (range_proof.rs): the encrypted pairs first
+ * (generate_encrypted_pairs, :128-193; fetch c1/c2 with zkp_rp_prove_fetch and NULL response pointers), then,
+ * once the verifier has opened its commitment, the responses to ITS ChallengeBits bytes (generate_proof,
+ * :210-252): challenge[b][chal_bytes], bit i = (byte[i/8] >> (7 - i%8)) & 1 as BitVec::from_bytes reads them.
+ * challenge == NULL uses the Fiat-Shamir bits of the transcript hash (= zkp_rp_prove_run). */
+int zkp_rp_prove_run_pairs(zkp_ctx* ctx);
+int zkp_rp_prove_run_responses(zkp_ctx* ctx, const uint8_t* challenge, int chal_bytes);
 int zkp_rp_prove_fetch(zkp_ctx* ctx, uint32_t* c1, uint32_t* c2, uint8_t* digest, uint8_t* kind, uint32_t* resp_w,
                        uint32_t* resp_r);
 
@@ -155,6 +162,8 @@ int zkp_rp_verify_stage(zkp_ctx* ctx, int batch, int ef, int w_limbs, const uint
  * zkp_rp_prove_run (no host round trip); only cipher_x comes from the host. */
 int zkp_rp_verify_stage_from_prove(zkp_ctx* ctx, const uint32_t* cipher_x);
 int zkp_rp_verify_run(zkp_ctx* ctx);
+/* RangeProof::verifier_output against the verifier's own ChallengeBits (interactive proof, range_proof.rs:254-355). */
+int zkp_rp_verify_run_with_challenge(zkp_ctx* ctx, const uint8_t* challenge, int chal_bytes);
 int zkp_rp_verify_fetch(zkp_ctx* ctx, uint8_t* accept, uint8_t* fault, uint8_t* digest);
 /* Number of Paillier encryptions the last verify_run performed (ef + #Open per proof). */
 long long zkp_rp_verify_enc_count(zkp_ctx* ctx);

@@ -30,6 +30,7 @@ def load():
         lib.orc_gmp_version.restype = C.c_char_p
         lib.orc_hw_threads.restype = C.c_int
         lib.orc_rangeproof_ni_verify.restype = C.c_longlong
+        lib.orc_rangeproof_verify.restype = C.c_longlong
         _lib = lib
     return _lib
 
@@ -82,7 +83,8 @@ def sha256_transcript(items):
     return out
 
 
-def rangeproof_ni_prove(n, ef, range_, x, r, w1, swap, r1, r2, threads=0):
+def rangeproof_ni_prove(n, ef, range_, x, r, w1, swap, r1, r2, threads=0, challenge=None):
+    """challenge: uint8 [batch, nbytes] -> the interactive RangeProof with the verifier's raw ChallengeBits."""
     n, range_, x, r, w1, r1, r2 = map(_c32, (n, range_, x, r, w1, r1, r2))
     swap = _c8(swap)
     batch, wl = range_.shape
@@ -96,20 +98,23 @@ def rangeproof_ni_prove(n, ef, range_, x, r, w1, swap, r1, r2, threads=0):
         "resp_r": np.zeros((batch, ef, 2, nl), np.uint32),
         "fault": np.zeros(batch, np.uint8),
     }
-    load().orc_rangeproof_ni_prove(_p32(n), nl, batch, ef, wl, _p32(range_), _p32(x), _p32(r), _p32(w1), _p8(swap), _p32(r1),
-                                   _p32(r2), _p32(out["c1"]), _p32(out["c2"]), _p8(out["digest"]), _p8(out["kind"]),
-                                   _p32(out["resp_w"]), _p32(out["resp_r"]), _p8(out["fault"]), threads)
+    ch = None if challenge is None else _c8(challenge)
+    load().orc_rangeproof_prove(_p32(n), nl, batch, ef, wl, _p32(range_), _p32(x), _p32(r), _p32(w1), _p8(swap), _p32(r1),
+                                _p32(r2), _p8(ch), 0 if ch is None else ch.shape[1], _p32(out["c1"]), _p32(out["c2"]),
+                                _p8(out["digest"]), _p8(out["kind"]), _p32(out["resp_w"]), _p32(out["resp_r"]), _p8(out["fault"]), threads)
     return out
 
 
-def rangeproof_ni_verify(n, ef, range_, cipher_x, c1, c2, kind, resp_w, resp_r, threads=0):
+def rangeproof_ni_verify(n, ef, range_, cipher_x, c1, c2, kind, resp_w, resp_r, threads=0, challenge=None):
     n, range_, cipher_x, c1, c2, resp_w, resp_r = map(_c32, (n, range_, cipher_x, c1, c2, resp_w, resp_r))
     kind = _c8(kind)
     batch, wl = range_.shape
     nl = n.shape[-1]
     accept, fault, digest = np.empty(batch, np.uint8), np.empty(batch, np.uint8), np.empty((batch, 32), np.uint8)
-    encs = load().orc_rangeproof_ni_verify(_p32(n), nl, batch, ef, wl, _p32(range_), _p32(cipher_x), _p32(c1), _p32(c2),
-                                           _p8(kind), _p32(resp_w), _p32(resp_r), _p8(accept), _p8(fault), _p8(digest), threads)
+    ch = None if challenge is None else _c8(challenge)
+    encs = load().orc_rangeproof_verify(_p32(n), nl, batch, ef, wl, _p32(range_), _p32(cipher_x), _p32(c1), _p32(c2),
+                                        _p8(kind), _p32(resp_w), _p32(resp_r), _p8(ch), 0 if ch is None else ch.shape[1],
+                                        _p8(accept), _p8(fault), _p8(digest), threads)
     return accept, fault, digest, encs
 
 

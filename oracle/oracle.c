@@ -225,6 +225,8 @@ typedef struct {
   uint8_t *digest, *kind, *ok, *fault;
   mpz_t zn, znn;
   uint8_t* ebits; /* [batch][ef] challenge bits, 2 = index out of range */
+  const uint8_t* chal; /* interactive proof: raw ChallengeBits bytes [batch][chal_bytes], or NULL */
+  int chal_bytes;
 } rp_job;
 
 /* third = range.div_floor(3), two_thirds = 2*third (range_proof.rs:133-134) */
@@ -282,7 +284,11 @@ static void rp_challenge(rp_job* j, const uint32_t* c1, const uint32_t* c2) {
     int len = 32 - lead;
     for (int i = 0; i < j->ef; ++i) {
       int byte = i / 8;
-      j->ebits[(size_t)b * j->ef + i] = byte < len ? (uint8_t)((d[lead + byte] >> (7 - i % 8)) & 1) : 2;
+      if (j->chal) /* BitVec::from_bytes(&e.0)[i] on the verifier's bytes as they are (range_proof.rs:221,267) */
+        j->ebits[(size_t)b * j->ef + i] =
+            byte < j->chal_bytes ? (uint8_t)((j->chal[(size_t)b * j->chal_bytes + byte] >> (7 - i % 8)) & 1) : 2;
+      else
+        j->ebits[(size_t)b * j->ef + i] = byte < len ? (uint8_t)((d[lead + byte] >> (7 - i % 8)) & 1) : 2;
     }
   }
   mpz_clear(z);
@@ -330,12 +336,25 @@ static void rp_response_task(void* a, long t) {
 }
 
 /* RangeProofNi::prove (range_proof_ni.rs:47-82) for a batch under one key; layouts as zkp_rangeproof_ni_prove. */
+void orc_rangeproof_prove(const uint32_t* n, int n_limbs, int batch, int ef, int w_limbs, const uint32_t* range,
+                          const uint32_t* x, const uint32_t* r, const uint32_t* w1, const uint8_t* swap, const uint32_t* r1,
+                          const uint32_t* r2, const uint8_t* challenge, int chal_bytes, uint32_t* c1, uint32_t* c2,
+                          uint8_t* digest, uint8_t* kind, uint32_t* resp_w, uint32_t* resp_r, uint8_t* fault, int threads);
 void orc_rangeproof_ni_prove(const uint32_t* n, int n_limbs, int batch, int ef, int w_limbs, const uint32_t* range,
                              const uint32_t* x, const uint32_t* r, const uint32_t* w1, const uint8_t* swap,
                              const uint32_t* r1, const uint32_t* r2, uint32_t* c1, uint32_t* c2, uint8_t* digest,
                              uint8_t* kind, uint32_t* resp_w, uint32_t* resp_r, uint8_t* fault, int threads) {
+  orc_rangeproof_prove(n, n_limbs, batch, ef, w_limbs, range, x, r, w1, swap, r1, r2, NULL, 0, c1, c2, digest, kind, resp_w,
+                       resp_r, fault, threads);
+}
+/* challenge != NULL: the interactive RangeProof (generate_encrypted_pairs + generate_proof with the verifier's e). */
+void orc_rangeproof_prove(const uint32_t* n, int n_limbs, int batch, int ef, int w_limbs, const uint32_t* range,
+                          const uint32_t* x, const uint32_t* r, const uint32_t* w1, const uint8_t* swap, const uint32_t* r1,
+                          const uint32_t* r2, const uint8_t* challenge, int chal_bytes, uint32_t* c1, uint32_t* c2,
+                          uint8_t* digest, uint8_t* kind, uint32_t* resp_w, uint32_t* resp_r, uint8_t* fault, int threads) {
   rp_job j;
   memset(&j, 0, sizeof j);
+  j.chal = challenge; j.chal_bytes = chal_bytes;
   j.batch = batch; j.ef = ef; j.w = w_limbs; j.nl = n_limbs;
   j.range = range; j.x = x; j.r = r; j.w1 = w1; j.swap = swap; j.r1 = r1; j.r2 = r2;
   j.c1 = c1; j.c2 = c2; j.digest = digest; j.kind = kind; j.resp_w = resp_w; j.resp_r = resp_r;
@@ -404,12 +423,25 @@ static void rp_verify_task(void* a, long t) {
 
 /* RangeProofNi::verify (range_proof_ni.rs:84-107); layouts as zkp_rangeproof_ni_verify.
  * Returns the number of Paillier encryptions performed. */
+long long orc_rangeproof_verify(const uint32_t* n, int n_limbs, int batch, int ef, int w_limbs, const uint32_t* range,
+                                const uint32_t* cipher_x, const uint32_t* c1, const uint32_t* c2, const uint8_t* kind,
+                                const uint32_t* resp_w, const uint32_t* resp_r, const uint8_t* challenge, int chal_bytes,
+                                uint8_t* accept, uint8_t* fault, uint8_t* digest, int threads);
 long long orc_rangeproof_ni_verify(const uint32_t* n, int n_limbs, int batch, int ef, int w_limbs, const uint32_t* range,
                                    const uint32_t* cipher_x, const uint32_t* c1, const uint32_t* c2, const uint8_t* kind,
                                    const uint32_t* resp_w, const uint32_t* resp_r, uint8_t* accept, uint8_t* fault,
                                    uint8_t* digest, int threads) {
+  return orc_rangeproof_verify(n, n_limbs, batch, ef, w_limbs, range, cipher_x, c1, c2, kind, resp_w, resp_r, NULL, 0, accept,
+                               fault, digest, threads);
+}
+/* challenge != NULL: RangeProof::verifier_output with the verifier's own e (interactive proof). */
+long long orc_rangeproof_verify(const uint32_t* n, int n_limbs, int batch, int ef, int w_limbs, const uint32_t* range,
+                                const uint32_t* cipher_x, const uint32_t* c1, const uint32_t* c2, const uint8_t* kind,
+                                const uint32_t* resp_w, const uint32_t* resp_r, const uint8_t* challenge, int chal_bytes,
+                                uint8_t* accept, uint8_t* fault, uint8_t* digest, int threads) {
   rp_job j;
   memset(&j, 0, sizeof j);
+  j.chal = challenge; j.chal_bytes = chal_bytes;
   j.batch = batch; j.ef = ef; j.w = w_limbs; j.nl = n_limbs;
   j.range = range; j.cx = cipher_x; j.c1in = c1; j.c2in = c2; j.kind_in = kind; j.resp_w_in = resp_w; j.resp_r_in = resp_r;
   j.digest = digest;

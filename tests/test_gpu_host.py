@@ -198,3 +198,28 @@ def test_sigma_protocols_through_the_host_mirror():
         return (hexs(("phi_a", pr.phi_a), ("z", pr.z), ("z_prime", pr.z_prime), ("z_double_prime", pr.z_double_prime), ("r_z", pr.r_z)),)
 
     _sigma_roundtrip("verlin", n, items, want_verlin, data, ["ok", "incorrect"])
+
+
+def test_interactive_range_proof_flow():
+    """range_proof.rs:431-525 through the C++ mirror: verifier_commit / generate_encrypted_pairs / verify_commit /
+    generate_proof / verifier_output, and the same transcript judged by the Python oracle."""
+    import hashlib
+    p, q = keys(2048)[1]
+    n = p * q
+    rng = random.Random(77)
+    for bad in (False, True):
+        s = _range_statements(rng, n, 1, bad={0} if bad else ())[0]
+        data = rng.randbytes(200000)
+        r = call("rangeproof.flow", n=str(n), rng_hex=data.hex(), **{k: str(v) for k, v in s.items()})
+        assert r["ok"], r
+        assert r["result"] == ("incorrect" if bad else "ok") and r["tampered_opening_rejected"] is True
+        e = bytes.fromhex(r["e_hex"])
+        assert len(e) == 5 and e == data[:5]
+        # commitment = Enc(H(e), r_c)  (range_proof.rs:118-126)
+        m = int.from_bytes(hashlib.sha256(e).digest(), "big")
+        assert int(r["com"]) == po.paillier_encrypt(n, m, int(r["com_r"]))
+        t = po.RangeProofNi.from_json(r["transcript"])
+        bits = po.verifier_output_bits(n, e, t.encrypted_pairs, t.proof, s["range"], s["ciphertext"], 40)
+        assert all(bits) == (not bad)
+        kinds = [0 if resp[0] == "Open" else 1 for resp in t.proof]
+        assert kinds == [po.challenge_bit(e, i) for i in range(40)]

@@ -206,3 +206,40 @@ def test_correct_key_edge_cases(ctx):
     sig_big = [s + n if s + n < (1 << 1024) else s for s in sig]   # unreduced sigma: mod_pow reduces it
     acc = ctx.correct_key_ni_verify(ints_to_limbs([n], nl), ints_to_limbs([sig_big], nl), salt)
     assert acc.tolist() == [1]
+
+
+def test_interactive_rangeproof_two_phase(ctx):
+    """Interactive RangeProof (range_proof.rs, error factor 40): pairs first, responses to the verifier's raw
+    ChallengeBits afterwards; verifier_output with its own e.  Bit-exact vs the C oracle."""
+    p, q = keys(2048)[0]
+    n = p * q
+    nl, ef, batch = 64, 40, 6
+    work = workload.rangeproof_batch(n, batch, ef=ef, seed=4040, reject_every=3)
+    chal = np.frombuffer(random.Random(2).randbytes(batch * 5), np.uint8).reshape(batch, 5).copy()
+    chal[1] = 0
+    chal[4] = 0xFF
+    nlimbs = to_limbs(n, nl)
+    ctx.set_key(nlimbs)
+    ctx.rp_prove_stage(ef, work["range"], work["x"], work["r"], work["w1"], work["swap"], work["r1"], work["r2"])
+    ctx.rp_prove_run_pairs()
+    c1, c2 = ctx.rp_prove_fetch_pairs()                      # what the prover sends before seeing e
+    ctx.rp_prove_run_responses(chal)
+    gpu = ctx.rp_prove_fetch()
+    cpu = c_oracle.rangeproof_ni_prove(nlimbs, ef, work["range"], work["x"], work["r"], work["w1"], work["swap"], work["r1"], work["r2"],
+                                       challenge=chal)
+    assert np.array_equal(c1, cpu["c1"]) and np.array_equal(c2, cpu["c2"])
+    for k in ("c1", "c2", "kind", "resp_w", "resp_r"):
+        assert np.array_equal(gpu[k], cpu[k]), k
+    assert (gpu["kind"][1] == 0).all() and (gpu["kind"][4] != 0).all()
+    cx = ctx.paillier_enc(work["x_n"], work["r"])
+    args = (ef, work["range"], cx, gpu["c1"], gpu["c2"], gpu["kind"], gpu["resp_w"], gpu["resp_r"])
+    for ch in (chal, chal ^ np.uint8(0x10), chal[:, :4]):
+        ctx.rp_verify_stage(*args)
+        ctx.rp_verify_run_with_challenge(ch)
+        acc, fault, _ = ctx.rp_verify_fetch()
+        acc_c, fault_c, _, _ = c_oracle.rangeproof_ni_verify(nlimbs, *args, challenge=ch)
+        assert np.array_equal(acc, acc_c) and np.array_equal(fault, fault_c)
+    ctx.rp_verify_stage(*args)
+    ctx.rp_verify_run_with_challenge(chal)
+    acc, fault, _ = ctx.rp_verify_fetch()
+    assert acc.tolist() == [1, 1, 0, 1, 1, 0] and not fault.any()

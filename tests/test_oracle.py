@@ -282,3 +282,44 @@ def test_golden_vectors():
     ck = g["correct_key_ni"]
     assert [str(s) for s in po.NiCorrectKeyProof.proof(int(ck["p"]), int(ck["q"]), bytes.fromhex(ck["salt_hex"])).sigma_vec] == ck["sigma_vec"]
     assert [str(s) for s in po.correct_key_rho(int(ck["p"]) * int(ck["q"]), bytes.fromhex(ck["salt_hex"]))] == ck["rho_vec"]
+
+
+def test_interactive_range_proof_oracles_agree():
+    """The interactive RangeProof (range_proof.rs:431-525, error factor 40): the verifier's ChallengeBits bytes are used
+    as they are.  C oracle vs the Python restatement of generate_proof / verifier_output."""
+    p, q = keys(1024)[0]
+    n = p * q
+    nl, ef, batch = 32, 40, 4
+    work = workload.rangeproof_batch(n, batch, ef=ef, seed=40, reject_every=4)
+    chal = np.frombuffer(random.Random(1).randbytes(batch * 5), np.uint8).reshape(batch, 5).copy()
+    chal[1] = 0            # all Open, first byte zero: would be stripped if it went through a BigInt
+    nlimbs = to_limbs(n, nl)
+    got = c_oracle.rangeproof_ni_prove(nlimbs, ef, work["range"], work["x"], work["r"], work["w1"], work["swap"], work["r1"], work["r2"],
+                                       challenge=chal)
+    cx = []
+    for b in range(batch):
+        w1 = limbs_to_ints(work["w1"][b]); r1 = limbs_to_ints(work["r1"][b]); r2 = limbs_to_ints(work["r2"][b])
+        r, x, rg = from_limbs(work["r"][b]), work["x_int"][b], work["range_int"][b]
+        pairs, data = po.generate_encrypted_pairs(n, rg, w1, [int(v) for v in work["swap"][b]], r1, r2)
+        e = bytes(chal[b])
+        proof = po.generate_proof(n, x, r, e, rg, data, ef)
+        c = po.paillier_encrypt(n, x, r)
+        cx.append(c)
+        assert limbs_to_ints(got["c1"][b]) == pairs["c1"]
+        assert [int(k) for k in got["kind"][b]] == [0 if t[0] == "Open" else t[1] for t in proof]
+        bits = po.verifier_output_bits(n, e, pairs, proof, rg, c, ef)
+        assert all(bits) == (b != 3)
+    assert (got["kind"][1] == 0).all()
+    acc, fault, _, _ = c_oracle.rangeproof_ni_verify(nlimbs, ef, work["range"], ints_to_limbs(cx, 2 * nl), got["c1"], got["c2"], got["kind"],
+                                                     got["resp_w"], got["resp_r"], challenge=chal)
+    assert acc.tolist() == [1, 1, 1, 0] and not fault.any()
+    # a different challenge than the one answered -> variant mismatch -> reject
+    chal2 = chal.copy()
+    chal2[0, 0] ^= 0x80
+    acc, _, _, _ = c_oracle.rangeproof_ni_verify(nlimbs, ef, work["range"], ints_to_limbs(cx, 2 * nl), got["c1"], got["c2"], got["kind"],
+                                                 got["resp_w"], got["resp_r"], challenge=chal2)
+    assert acc.tolist() == [0, 1, 1, 0]
+    # challenge shorter than error_factor bits: index out of range panics in the reference
+    acc, fault, _, _ = c_oracle.rangeproof_ni_verify(nlimbs, ef, work["range"], ints_to_limbs(cx, 2 * nl), got["c1"], got["c2"], got["kind"],
+                                                     got["resp_w"], got["resp_r"], challenge=chal[:, :4])
+    assert fault.all() and not acc.any()

@@ -60,7 +60,7 @@ int zkp_rp_prove_stage(zkp_ctx* c, int batch, int ef, int wl, const uint32_t* ra
   if (!range || !x || !r || !w1 || !swap || !r1 || !r2) return fail(c, ZKP_E_ARG, "null input");
   ZKP_CU(c, cudaSetDevice(c->device));
   RpState& s = c->rp;
-  s.prove_staged = s.prove_done = false;
+  s.prove_staged = s.prove_done = s.pairs_done = false;
   const int nl = c->n.limbs, nnl = c->nn.limbs;
   const size_t be = (size_t)batch * ef;
   ZKP_CU(c, s.range.ensure((size_t)batch * wl * 4));
@@ -94,14 +94,17 @@ int zkp_rp_prove_stage(zkp_ctx* c, int batch, int ef, int wl, const uint32_t* ra
   return ZKP_OK;
 }
 
-int zkp_rp_prove_run(zkp_ctx* c) {
+// Phase 1 of prove: the encrypted pairs and their transcript hash (RangeProof::generate_encrypted_pairs,
+// range_proof.rs:128-193, + range_proof_ni.rs:58-61).  Does not depend on the challenge.
+int zkp_rp_prove_run_pairs(zkp_ctx* c) {
   if (!c) return ZKP_E_ARG;
   RpState& s = c->rp;
   if (!s.prove_staged || !c->paillier) return fail(c, ZKP_E_STATE, "nothing staged for prove");
   ZKP_CU(c, cudaSetDevice(c->device));
   cudaStream_t st = c->stream;
-  const int batch = s.batch, ef = s.ef, wl = s.wl, nl = c->n.limbs, nnl = c->nn.limbs;
+  const int batch = s.batch, ef = s.ef, wl = s.wl, nl = c->n.limbs;
   const int be = batch * ef;
+  s.pairs_done = s.prove_done = false;
   ZKP_CU(c, cudaMemsetAsync(s.fault.p, 0, (size_t)batch, st));
   {  // w2 = w1 - third, coin swap (range_proof.rs:141-149)
     ProfScope ps(c, KID_OTHER, be);
@@ -116,6 +119,27 @@ int zkp_rp_prove_run(zkp_ctx* c) {
     ProfScope ps(c, KID_SHA, batch);
     ZKP_CU(c, launch_sha256_transcript(rp_transcript(c, s.c.as<uint32_t>(), batch, ef), batch, s.digest.as<uint8_t>(), st));
   }
+  s.pairs_done = true;
+  return ZKP_OK;
+}
+
+// Phase 2 of prove: the responses (RangeProof::generate_proof, range_proof.rs:210-252).  challenge == NULL: the
+// Fiat-Shamir bits of phase 1's hash (RangeProofNi); otherwise the verifier's raw ChallengeBits bytes,
+// [batch][chal_bytes] (the interactive proof).
+int zkp_rp_prove_run_responses(zkp_ctx* c, const uint8_t* challenge, int chal_bytes) {
+  if (!c) return ZKP_E_ARG;
+  RpState& s = c->rp;
+  if (!s.pairs_done || !c->paillier) return fail(c, ZKP_E_STATE, "zkp_rp_prove_run_pairs has not run");
+  if (challenge && chal_bytes <= 0) return fail(c, ZKP_E_ARG, "chal_bytes must be positive");
+  ZKP_CU(c, cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  const int batch = s.batch, ef = s.ef, wl = s.wl, nl = c->n.limbs;
+  const int be = batch * ef;
+  if (challenge) {
+    ZKP_CU(c, s.chal.ensure((size_t)batch * chal_bytes));
+    ZKP_CU(c, cudaMemcpyAsync(s.chal.p, challenge, (size_t)batch * chal_bytes, cudaMemcpyHostToDevice, st));
+  }
+  s.chal_bytes = challenge ? chal_bytes : 0;
   {  // secret_r * r_j % n for both j (range_proof.rs:239,245)
     ProfScope ps(c, KID_MODMUL, 2.0 * be);
     SharedKey kn = c->n.view();
@@ -129,6 +153,7 @@ int zkp_rp_prove_run(zkp_ctx* c) {
     a.batch = batch; a.ef = ef; a.wl = wl; a.nl = nl;
     a.range = s.range.as<uint32_t>(); a.x = s.x.as<uint32_t>(); a.w = s.w.as<uint32_t>(); a.rr = s.rr.as<uint32_t>();
     a.rmul = s.rmul.as<uint32_t>(); a.digest = s.digest.as<uint8_t>(); a.kind = s.kind.as<uint8_t>();
+    a.chal = challenge ? s.chal.as<uint8_t>() : nullptr; a.chal_bytes = s.chal_bytes;
     a.resp_w = s.resp_w.as<uint32_t>(); a.resp_r = s.resp_r.as<uint32_t>(); a.fault = s.fault.as<uint8_t>();
     ZKP_CU(c, launch_rp_respond(a, st));
   }
@@ -136,11 +161,18 @@ int zkp_rp_prove_run(zkp_ctx* c) {
   return ZKP_OK;
 }
 
+int zkp_rp_prove_run(zkp_ctx* c) {
+  int rc = zkp_rp_prove_run_pairs(c);
+  if (rc) return rc;
+  return zkp_rp_prove_run_responses(c, nullptr, 0);
+}
+
 int zkp_rp_prove_fetch(zkp_ctx* c, uint32_t* c1, uint32_t* c2, uint8_t* digest, uint8_t* kind, uint32_t* resp_w,
                        uint32_t* resp_r) {
   if (!c) return ZKP_E_ARG;
   RpState& s = c->rp;
-  if (!s.prove_done) return fail(c, ZKP_E_STATE, "prove has not run");
+  if (!s.pairs_done) return fail(c, ZKP_E_STATE, "prove has not run");
+  if (!s.prove_done && (kind || resp_w || resp_r)) return fail(c, ZKP_E_STATE, "responses have not been computed yet");
   ZKP_CU(c, cudaSetDevice(c->device));
   cudaStream_t st = c->stream;
   const size_t be = (size_t)s.batch * s.ef;
@@ -250,12 +282,22 @@ int zkp_rp_verify_stage_from_prove(zkp_ctx* c, const uint32_t* cipher_x) {
   return ZKP_OK;
 }
 
-int zkp_rp_verify_run(zkp_ctx* c) {
+int zkp_rp_verify_run(zkp_ctx* c) { return zkp_rp_verify_run_with_challenge(c, nullptr, 0); }
+
+// RangeProof::verifier_output with the verifier's own ChallengeBits (interactive proof, range_proof.rs:254-355);
+// challenge == NULL recomputes the Fiat-Shamir bits (RangeProofNi::verify).
+int zkp_rp_verify_run_with_challenge(zkp_ctx* c, const uint8_t* challenge, int chal_bytes) {
   if (!c) return ZKP_E_ARG;
   RpState& s = c->rp;
   if (!s.verify_staged || !c->paillier) return fail(c, ZKP_E_STATE, "nothing staged for verify");
+  if (challenge && chal_bytes <= 0) return fail(c, ZKP_E_ARG, "chal_bytes must be positive");
   ZKP_CU(c, cudaSetDevice(c->device));
   cudaStream_t st = c->stream;
+  if (challenge) {
+    ZKP_CU(c, s.v_chal.ensure((size_t)s.vbatch * chal_bytes));
+    ZKP_CU(c, cudaMemcpyAsync(s.v_chal.p, challenge, (size_t)s.vbatch * chal_bytes, cudaMemcpyHostToDevice, st));
+  }
+  s.v_chal_bytes = challenge ? chal_bytes : 0;
   const int batch = s.vbatch, ef = s.vef, wl = s.vwl, nl = c->n.limbs, nnl = c->nn.limbs;
   const int be = batch * ef;
   ZKP_CU(c, cudaMemsetAsync(s.v_fault.p, 0, (size_t)batch, st));
@@ -268,6 +310,7 @@ int zkp_rp_verify_run(zkp_ctx* c) {
   a.batch = batch; a.ef = ef; a.wl = wl; a.nl = nl;
   a.range = s.pv_range; a.c = s.pv_c; a.kind = s.pv_kind; a.resp_w = s.pv_resp_w; a.resp_r = s.pv_resp_r;
   a.digest = s.v_digest.as<uint8_t>(); a.cmul = s.v_cmul.as<uint32_t>();
+  a.chal = challenge ? s.v_chal.as<uint8_t>() : nullptr; a.chal_bytes = s.v_chal_bytes;
   a.jobs_base = s.v_jobs_base.as<uint32_t>(); a.jobs_plain = s.v_jobs_plain.as<uint32_t>();
   a.jobs_out = s.v_jobs_out.as<uint32_t>(); a.tag = s.v_tag.as<uint32_t>(); a.count = s.v_count.as<unsigned>();
   a.sel = s.v_sel.as<uint8_t>(); a.ok = s.v_ok.as<uint8_t>(); a.fault = s.v_fault.as<uint8_t>();

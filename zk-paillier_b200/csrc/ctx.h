@@ -75,6 +75,9 @@ struct RpState {  // RangeProofNi staging (api_rangeproof.cu)
   DevBuf range, x, r, w1in, w, swap, rr;    // w = [w1' | w2'] plaintexts, rr = [r1 | r2] bases
   DevBuf c, digest, kind, resp_w, resp_r;   // c = [c1 | c2]
   DevBuf rmul, fault;                       // r*r1 | r*r2 mod n
+  DevBuf chal, v_chal;                      // interactive proof: the verifier's raw challenge bytes
+  int chal_bytes = 0, v_chal_bytes = 0;
+  bool pairs_done = false;
   // verify: owned copies of host inputs
   DevBuf v_range, v_cx, v_c, v_kind, v_resp_w, v_resp_r;
   // verify: work and outputs
@@ -90,7 +93,7 @@ struct RpState {  // RangeProofNi staging (api_rangeproof.cu)
   std::vector<DevBuf*> all() {
     return {&range, &x, &r, &w1in, &w, &swap, &rr, &c, &digest, &kind, &resp_w, &resp_r, &rmul, &fault,
             &v_range, &v_cx, &v_c, &v_kind, &v_resp_w, &v_resp_r, &v_digest, &v_jobs_base, &v_jobs_plain,
-            &v_tag, &v_jobs_out, &v_count, &v_cmul, &v_sel, &v_ok, &v_accept, &v_fault};
+            &v_tag, &v_jobs_out, &v_count, &v_cmul, &v_sel, &v_ok, &v_accept, &v_fault, &chal, &v_chal};
   }
 };
 

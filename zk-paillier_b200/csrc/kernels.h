@@ -103,6 +103,8 @@ struct RpProveArgs {
   const uint32_t* rr;      // [2][batch*ef][nl]  r1 | r2
   const uint32_t* rmul;    // [2][batch*ef][nl]  r*r1 mod n | r*r2 mod n
   const uint8_t* digest;   // [batch][32]
+  const uint8_t* chal;     // interactive proof: raw ChallengeBits bytes [batch][chal_bytes] instead of the digest (or null)
+  int chal_bytes;
   uint8_t* kind;           // [batch*ef]
   uint32_t* resp_w;        // [batch*ef][2][wl]
   uint32_t* resp_r;        // [batch*ef][2][nl]
@@ -116,6 +118,8 @@ struct RpVerifyArgs {
   const uint32_t* resp_w;   // [batch*ef][2][wl]
   const uint32_t* resp_r;   // [batch*ef][2][nl]
   const uint8_t* digest;    // [batch][32]
+  const uint8_t* chal;      // interactive proof: raw ChallengeBits bytes [batch][chal_bytes] (or null)
+  int chal_bytes;
   const uint32_t* cmul;     // [batch*ef][2nl]     c_j * cipher_x mod n^2 (Mask rows)
   uint32_t* jobs_base;      // [2*batch*ef][nl]
   uint32_t* jobs_plain;     // [2*batch*ef][wl]

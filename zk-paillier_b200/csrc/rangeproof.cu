@@ -115,7 +115,8 @@ __global__ void rp_respond_kernel(RpProveArgs a) {
   const int b = t / a.ef, i = t % a.ef;
   const int wl = a.wl, nl = a.nl;
   const size_t half = (size_t)a.batch * a.ef;
-  uint32_t e = challenge_bit(a.digest + (size_t)b * 32, i);
+  uint32_t e = a.chal ? challenge_bit_raw(a.chal + (size_t)b * a.chal_bytes, a.chal_bytes, i)
+                      : challenge_bit(a.digest + (size_t)b * 32, i);
   if (e == 2u) {
     a.fault[b] = 1;
     e = 0;
@@ -186,7 +187,8 @@ __global__ void rp_plan_kernel(RpVerifyArgs a) {
   if (t >= a.batch * a.ef) return;
   const int b = t / a.ef, i = t % a.ef;
   const int wl = a.wl, nl = a.nl;
-  const uint32_t e = challenge_bit(a.digest + (size_t)b * 32, i);
+  const uint32_t e = a.chal ? challenge_bit_raw(a.chal + (size_t)b * a.chal_bytes, a.chal_bytes, i)
+                            : challenge_bit(a.digest + (size_t)b * 32, i);
   const uint8_t k = a.kind[t];
   a.sel[t] = 0;
   if (e == 2u || k > ZKP_RP_MASK2_) {  // the reference panics (index out of range) / has no such variant

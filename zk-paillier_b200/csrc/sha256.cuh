@@ -145,4 +145,12 @@ __device__ __forceinline__ uint32_t challenge_bit(const uint8_t* digest, int i) 
   return (digest[lead + byte] >> (7 - (i & 7))) & 1u;
 }
 
+// The interactive RangeProof hands the verifier's ChallengeBits bytes over as they are (range_proof.rs:86-91,
+// 221): BitVec::from_bytes(&e.0)[i] without any BigInt round trip, hence no stripping.
+__device__ __forceinline__ uint32_t challenge_bit_raw(const uint8_t* e, int nbytes, int i) {
+  const int byte = i >> 3;
+  if (byte >= nbytes) return 2u;
+  return (e[byte] >> (7 - (i & 7))) & 1u;
+}
+
 }  // namespace zkp

@@ -119,6 +119,41 @@ Json dispatch(const std::string& op, const Json& req) {
     out.set("accept", arr);
     return out;
   }
+  if (op == "rangeproof.flow") {  // the whole interactive protocol (range_proof.rs:431-525), both parties on this engine
+    EncryptionKey ek(dec(req, "n"));
+    const BigInt range = dec(req, "range"), x = dec(req, "x"), r = dec(req, "r"), cx = dec(req, "ciphertext");
+    ByteSource rng = rng_from(req);
+    const size_t ef = STATISTICAL_ERROR_FACTOR;
+    auto vc = RangeProof::verifier_commit(eng, ek, rng);                        // verifier
+    auto pd = RangeProof::generate_encrypted_pairs(eng, ek, range, ef, rng);    // prover
+    RangeProof::verify_commit(eng, ek, vc.com, vc.r, vc.e);                     // prover checks the opening
+    Proof proof = RangeProof::generate_proof(ek, x, r, vc.e, range, pd.second, ef);
+    std::string result = "ok";
+    try {
+      RangeProof::verifier_output(eng, ek, vc.e, pd.first, proof, range, cx, ef);
+    } catch (const IncorrectProof&) {
+      result = "incorrect";
+    }
+    bool bad_open = false;
+    try {
+      ChallengeBits e2 = vc.e;
+      e2.bytes[0] ^= 1;
+      RangeProof::verify_commit(eng, ek, vc.com, vc.r, e2);
+    } catch (const IncorrectProof&) {
+      bad_open = true;
+    }
+    RangeProofNi carrier;  // reuse the serde of the NI struct to ship pairs + responses to the test
+    carrier.ek = ek; carrier.range = range; carrier.ciphertext = cx; carrier.encrypted_pairs = pd.first; carrier.proof = proof; carrier.error_factor = ef;
+    std::string ehex;
+    for (uint8_t b : vc.e.bytes) { char t[3]; snprintf(t, 3, "%02x", b); ehex += t; }
+    out.set("result", Json::string(result));
+    out.set("e_hex", Json::string(ehex));
+    out.set("com", ser_dec(vc.com.com));
+    out.set("com_r", ser_dec(vc.r.r));
+    out.set("tampered_opening_rejected", Json::boolean(bad_open));
+    out.set("transcript", Json::string(carrier.to_json()));
+    return out;
+  }
   if (op == "correct_key_ni.proof") {
     DecryptionKey dk{dec(req, "p"), dec(req, "q")};
     NiCorrectKeyProof pr;

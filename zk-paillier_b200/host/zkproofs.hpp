@@ -22,6 +22,7 @@
 #include "../../include/zkp_b200.h"
 #include "bigint.hpp"
 #include "json.hpp"
+#include "sha256.hpp"
 
 namespace zkproofs {
 
@@ -228,7 +229,8 @@ class RangeProofNi {  // range_proof_ni.rs:36-44
   }
 
   // range_proof_ni.rs:109-128 for many proofs under ONE key and error factor.  1 = Ok(()), 0 = Err(IncorrectProof).
-  static std::vector<int> verify_batch(Engine& eng, const std::vector<const RangeProofNi*>& ps) {
+  // `interactive_e`: the verifier's raw ChallengeBits (interactive RangeProof), same bytes for every proof of the batch
+  static std::vector<int> verify_batch(Engine& eng, const std::vector<const RangeProofNi*>& ps, const std::vector<uint8_t>* interactive_e = nullptr) {
     const size_t B = ps.size();
     if (B == 0) return {};
     const EncryptionKey& ek = ps[0]->ek;
@@ -284,8 +286,18 @@ class RangeProofNi {  // range_proof_ni.rs:36-44
         }
       }
     }
-    eng.check(zkp_rangeproof_ni_verify(eng.handle(), (int)B, (int)ef, (int)wl, range.data(), cx.data(), c1.data(), c2.data(), kind.data(),
-                                       resp_w.data(), resp_r.data(), accept.data(), fault.data(), nullptr));
+    if (!interactive_e) {
+      eng.check(zkp_rangeproof_ni_verify(eng.handle(), (int)B, (int)ef, (int)wl, range.data(), cx.data(), c1.data(), c2.data(), kind.data(),
+                                         resp_w.data(), resp_r.data(), accept.data(), fault.data(), nullptr));
+    } else {
+      std::vector<uint8_t> ch;
+      for (size_t b = 0; b < B; ++b) ch.insert(ch.end(), interactive_e->begin(), interactive_e->end());
+      static const uint8_t none = 0;
+      eng.check(zkp_rp_verify_stage(eng.handle(), (int)B, (int)ef, (int)wl, range.data(), cx.data(), c1.data(), c2.data(), kind.data(),
+                                    resp_w.data(), resp_r.data()));
+      eng.check(zkp_rp_verify_run_with_challenge(eng.handle(), ch.empty() ? &none : ch.data(), (int)std::max<size_t>(1, interactive_e->size())));
+      eng.check(zkp_rp_verify_fetch(eng.handle(), accept.data(), fault.data(), nullptr));
+    }
     for (size_t b = 0; b < B; ++b) {
       if (out[b] == 0) continue;
       if (fault[b]) throw ReferencePanic("index out of bounds in verifier_output (range_proof.rs:273)");
@@ -349,6 +361,102 @@ class RangeProofNi {  // range_proof_ni.rs:36-44
     return p;
   }
   static RangeProofNi from_json(const std::string& s) { return from_json_value(Json::parse(s)); }
+};
+
+// ------------------------------------------------------------------------------------- RangeProof
+// The interactive proof (range_proof.rs:100-363), STATISTICAL_ERROR_FACTOR = 40 (:30).  The verifier commits
+// to its challenge, the prover sends the encrypted pairs, the verifier opens, the prover answers.
+constexpr size_t STATISTICAL_ERROR_FACTOR = 40;
+struct ChallengeBits { std::vector<uint8_t> bytes; };          // range_proof.rs:49-50
+struct Commitment { BigInt com; };                             // :83
+struct ChallengeRandomness { BigInt r; };                      // :100
+struct DataRandomnessPairs { std::vector<BigInt> w1, w2, r1, r2; };  // :41-47
+
+class RangeProof {
+ public:
+  // local compute_digest(bytes) (range_proof.rs:365-369): SHA-256 of the raw bytes as a BigInt
+  static BigInt digest_of_bytes(const std::vector<uint8_t>& b) { return BigInt::from_bytes(zkhost::sha256(b.data(), b.size())); }
+  // get_paillier_commitment (range_proof.rs:359-363): Enc(ek, x, r)
+  static BigInt paillier_commitment(Engine& eng, const EncryptionKey& ek, const BigInt& x, const BigInt& r) {
+    eng.use_key(ek);
+    const size_t nl = eng.nl(), nnl = eng.nnl();
+    std::vector<uint32_t> out(nnl);
+    eng.check(zkp_paillier_enc(eng.handle(), x.to_limbs(nl).data(), (int)nl, r.to_limbs(nl).data(), (int)nl, 1, out.data()));
+    return BigInt::from_limbs(out.data(), nnl);
+  }
+  struct VerifierCommit { Commitment com; ChallengeRandomness r; ChallengeBits e; };
+  // range_proof.rs:118-126
+  static VerifierCommit verifier_commit(Engine& eng, const EncryptionKey& ek, const ByteSource& rng = os_rng()) {
+    VerifierCommit v;
+    v.e.bytes.resize(STATISTICAL_ERROR_FACTOR / 8);            // ChallengeBits::sample (:86-91)
+    rng(v.e.bytes.data(), v.e.bytes.size());
+    BigInt m = digest_of_bytes(v.e.bytes);
+    v.r.r = BigInt::sample_below(rng, ek.n);
+    v.com.com = paillier_commitment(eng, ek, m, v.r.r);
+    return v;
+  }
+  // range_proof.rs:195-208
+  static void verify_commit(Engine& eng, const EncryptionKey& ek, const Commitment& com, const ChallengeRandomness& r, const ChallengeBits& e) {
+    if (paillier_commitment(eng, ek, digest_of_bytes(e.bytes), r.r) != com.com) throw IncorrectProof();
+  }
+  // range_proof.rs:128-193: 2 * error_factor Paillier encryptions on the device
+  static std::pair<EncryptedPairs, DataRandomnessPairs> generate_encrypted_pairs(Engine& eng, const EncryptionKey& ek, const BigInt& range,
+                                                                                 size_t error_factor, const ByteSource& rng = os_rng()) {
+    eng.use_key(ek);
+    const size_t nl = eng.nl(), nnl = eng.nnl(), ef = error_factor;
+    const BigInt third = range.div_floor(BigInt(3)), two = third + third;
+    DataRandomnessPairs d;
+    for (size_t i = 0; i < ef; ++i) d.w1.push_back(BigInt::sample_range(rng, third, two));     // :136-139
+    for (size_t i = 0; i < ef; ++i) d.w2.push_back(d.w1[i] - third);                           // :141
+    std::vector<uint8_t> coin(ef);
+    rng(coin.data(), ef);
+    for (size_t i = 0; i < ef; ++i)
+      if (coin[i] & 1) std::swap(d.w1[i], d.w2[i]);                                            // :144-149
+    for (size_t i = 0; i < ef; ++i) d.r1.push_back(BigInt::sample_below(rng, ek.n));           // :151-154
+    for (size_t i = 0; i < ef; ++i) d.r2.push_back(BigInt::sample_below(rng, ek.n));           // :156-159
+    std::vector<BigInt> m(d.w1), r(d.r1);
+    m.insert(m.end(), d.w2.begin(), d.w2.end());
+    r.insert(r.end(), d.r2.begin(), d.r2.end());
+    std::vector<uint32_t> out(2 * ef * nnl);
+    eng.check(zkp_paillier_enc(eng.handle(), pack(m, nl).data(), (int)nl, pack(r, nl).data(), (int)nl, (int)(2 * ef), out.data()));
+    EncryptedPairs p;
+    for (size_t i = 0; i < ef; ++i) p.c1.push_back(BigInt::from_limbs(&out[i * nnl], nnl));
+    for (size_t i = 0; i < ef; ++i) p.c2.push_back(BigInt::from_limbs(&out[(ef + i) * nnl], nnl));
+    return {p, d};
+  }
+  // range_proof.rs:210-252.  No modexp here: error_factor comparisons and (on average half as many) products
+  // secret_r * r_j % n, done with the host BigInt.
+  static Proof generate_proof(const EncryptionKey& ek, const BigInt& secret_x, const BigInt& secret_r, const ChallengeBits& e, const BigInt& range,
+                              const DataRandomnessPairs& data, size_t error_factor) {
+    const BigInt third = range.div_floor(BigInt(3)), two = third + third;
+    Proof pr;
+    for (size_t i = 0; i < error_factor; ++i) {
+      if (i / 8 >= e.bytes.size()) throw ReferencePanic("index out of bounds: bits_of_e[i] (range_proof.rs:225)");
+      const bool ei = (e.bytes[i / 8] >> (7 - i % 8)) & 1;
+      Response r;
+      if (!ei) {
+        r.open = true;
+        r.w1 = data.w1[i]; r.r1 = data.r1[i]; r.w2 = data.w2[i]; r.r2 = data.r2[i];
+      } else {
+        r.open = false;
+        const BigInt s1 = secret_x + data.w1[i];
+        if (s1 > third && s1 < two) {
+          r.j = 1; r.masked_x = s1; r.masked_r = (secret_r * data.r1[i]) % ek.n;
+        } else {
+          r.j = 2; r.masked_x = secret_x + data.w2[i]; r.masked_r = (secret_r * data.r2[i]) % ek.n;
+        }
+      }
+      pr.responses.push_back(r);
+    }
+    return pr;
+  }
+  // range_proof.rs:254-355 against the verifier's own ChallengeBits, on the device
+  static void verifier_output(Engine& eng, const EncryptionKey& ek, const ChallengeBits& e, const EncryptedPairs& pairs, const Proof& proof,
+                              const BigInt& range, const BigInt& cipher_x, size_t error_factor) {
+    RangeProofNi p;
+    p.ek = ek; p.range = range; p.ciphertext = cipher_x; p.encrypted_pairs = pairs; p.proof = proof; p.error_factor = error_factor;
+    if (!RangeProofNi::verify_batch(eng, {&p}, &e.bytes)[0]) throw IncorrectProof();
+  }
 };
 
 // ------------------------------------------------------------------------------- NiCorrectKeyProof

@@ -43,6 +43,9 @@ SIGNATURES = {
                                           _u32p, _u32p, _u8p, _u8p, _u32p, _u32p]),
     "zkp_rp_prove_stage": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, _u32p, _u32p, _u32p, _u32p, _u8p, _u32p, _u32p]),
     "zkp_rp_prove_run": (C.c_int, [C.c_void_p]),
+    "zkp_rp_prove_run_pairs": (C.c_int, [C.c_void_p]),
+    "zkp_rp_prove_run_responses": (C.c_int, [C.c_void_p, _u8p, C.c_int]),
+    "zkp_rp_verify_run_with_challenge": (C.c_int, [C.c_void_p, _u8p, C.c_int]),
     "zkp_rp_prove_fetch": (C.c_int, [C.c_void_p, _u32p, _u32p, _u8p, _u8p, _u32p, _u32p]),
     "zkp_rangeproof_ni_verify": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, _u32p, _u32p, _u32p, _u32p, _u8p, _u32p, _u32p,
                                            _u8p, _u8p, _u8p]),
@@ -264,6 +267,30 @@ class Context:
 
     def rp_prove_run(self):
         self._ck(self._lib.zkp_rp_prove_run(self._h))
+
+    def rp_prove_run_pairs(self):
+        self._ck(self._lib.zkp_rp_prove_run_pairs(self._h))
+
+    def rp_prove_run_responses(self, challenge=None):
+        """challenge: uint8 [batch, nbytes] raw ChallengeBits of the interactive proof, or None for Fiat-Shamir."""
+        if challenge is None:
+            self._ck(self._lib.zkp_rp_prove_run_responses(self._h, None, 0))
+        else:
+            ch = _c8(challenge)
+            assert ch.ndim == 2 and ch.shape[0] == self._rp_shape[0]
+            self._ck(self._lib.zkp_rp_prove_run_responses(self._h, _p8(ch), ch.shape[1]))
+
+    def rp_prove_fetch_pairs(self):
+        batch, ef, wl = self._rp_shape
+        nnl = self.nn_limbs
+        c1, c2 = np.empty((batch, ef, nnl), np.uint32), np.empty((batch, ef, nnl), np.uint32)
+        self._ck(self._lib.zkp_rp_prove_fetch(self._h, _p32(c1), _p32(c2), None, None, None, None))
+        return c1, c2
+
+    def rp_verify_run_with_challenge(self, challenge):
+        ch = _c8(challenge)
+        assert ch.ndim == 2 and ch.shape[0] == self._rpv_batch
+        self._ck(self._lib.zkp_rp_verify_run_with_challenge(self._h, _p8(ch), ch.shape[1]))
 
     def rp_prove_fetch(self, want_pairs=True):
         batch, ef, wl = self._rp_shape
