@@ -517,3 +517,50 @@ def deserialize_vecbigint(seq) -> list:
             raise ReferencePanic("from_str_radix(...).unwrap() on a malformed decimal string")
         out.append(int(s))
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+# CorrectKey, the interactive proof of correct_key.rs:64-172 (STATISTICAL_ERROR_FACTOR = 40, :26).
+class CorrectKeyProveError(Exception):
+    """correct_key.rs:174-184"""
+
+
+class CorrectKey:
+    @staticmethod
+    def challenge(n, s, r):
+        """correct_key.rs:65-107 with the draws s_i, r_i <- sample_below(n) made explicit.
+        Returns (Challenge {sn, e, z}, VerificationAid {s_digest})."""
+        sn = [pow(si, n, n) for si in s]
+        rn = [pow(ri, n, n) for ri in r]
+        e = compute_digest([n] + sn + rn)
+        z = [ri * pow(si, e, n) % n for ri, si in zip(r, s)]
+        return {"sn": sn, "e": e, "z": z}, {"s_digest": compute_digest(s)}
+
+    @staticmethod
+    def prove(p, q, ch):
+        """correct_key.rs:109-162"""
+        import math
+
+        n = p * q
+        if any(math.gcd(n, v) != 1 for v in ch["sn"]):
+            raise CorrectKeyProveError("`challenge.sn[i]` isn't co-prime with `n`")
+        if any(math.gcd(n, v) != 1 for v in ch["z"]):
+            raise CorrectKeyProveError("`challenge.z[i]` isn't co-prime with `n`")
+        phi = (q - 1) * (p - 1)
+        phimine = phi - (ch["e"] % phi)
+        rn = [pow(zi, n, n) * pow(sni, phimine, n) % n for zi, sni in zip(ch["z"], ch["sn"])]
+        if any(math.gcd(n, v) != 1 for v in rn):
+            raise CorrectKeyProveError("`rn[i]` isn't co-prime with `n`")
+        if ch["e"] != compute_digest([n] + ch["sn"] + rn):
+            raise CorrectKeyProveError("`challenge.e` wasn't computed correctly")
+        return {"s_digest": compute_digest([extract_nroot(p, q, sni) for sni in ch["sn"]])}
+
+    @staticmethod
+    def verify(proof, va):
+        """correct_key.rs:164-171"""
+        if proof["s_digest"] != va["s_digest"]:
+            raise IncorrectProof()
+
+    @staticmethod
+    def challenge_to_json(ch):
+        return json.dumps({"sn": [str(v) for v in ch["sn"]], "e": str(ch["e"]), "z": [str(v) for v in ch["z"]]}, separators=(",", ":"))

@@ -223,3 +223,31 @@ def test_interactive_range_proof_flow():
         assert all(bits) == (not bad)
         kinds = [0 if resp[0] == "Open" else 1 for resp in t.proof]
         assert kinds == [po.challenge_bit(e, i) for i in range(40)]
+
+
+@pytest.mark.parametrize("bits", [1024, 2048])
+def test_interactive_correct_key(bits):
+    """correct_key.rs:199-232 through the C++ mirror, checked against the Python oracle on the same randomness."""
+    p, q = keys(bits)[0]
+    n = p * q
+    data = random.Random(bits).randbytes(80 * (bits // 8) * 4)
+    r = call("correct_key.challenge", n=str(n), rng_hex=data.hex())
+    assert r["ok"], r
+    st = Stream(data)
+    s = [po.sample_below(st, n) for _ in range(40)]
+    rr = [po.sample_below(st, n) for _ in range(40)]
+    ch, va = po.CorrectKey.challenge(n, s, rr)
+    assert r["challenge"] == po.CorrectKey.challenge_to_json(ch)
+    assert int(r["verification_aid"]["s_digest"]) == va["s_digest"]
+    pr = call("correct_key.prove", p=str(p), q=str(q), challenge=r["challenge"], s_digest=str(va["s_digest"]))
+    assert pr["ok"] and pr["verify"] == "ok"
+    assert int(pr["proof"]["s_digest"]) == po.CorrectKey.prove(p, q, ch)["s_digest"]
+    # a key whose modulus is not what the verifier challenged (wrong dk): the e check fails
+    p2, q2 = keys(bits)[1]
+    pr = call("correct_key.prove", p=str(p2), q=str(q2), challenge=r["challenge"], s_digest=str(va["s_digest"]))
+    assert "prove_error" in pr
+    # tampered e
+    d = json.loads(r["challenge"])
+    d["e"] = str(int(d["e"]) ^ 1)
+    pr = call("correct_key.prove", p=str(p), q=str(q), challenge=json.dumps(d), s_digest=str(va["s_digest"]))
+    assert pr["prove_error"] == "`challenge.e` wasn't computed correctly"

@@ -323,3 +323,20 @@ def test_interactive_range_proof_oracles_agree():
     acc, fault, _, _ = c_oracle.rangeproof_ni_verify(nlimbs, ef, work["range"], ints_to_limbs(cx, 2 * nl), got["c1"], got["c2"], got["kind"],
                                                      got["resp_w"], got["resp_r"], challenge=chal[:, :4])
     assert fault.all() and not acc.any()
+
+
+def test_correct_key_interactive_oracle():
+    # correct_key.rs:199-232: honest key accepts; a tampered challenge is refused by the prover
+    p, q = keys(1024)[0]
+    n = p * q
+    rng = random.Random(40)
+    s = [rng.randrange(1, n) for _ in range(40)]
+    r = [rng.randrange(1, n) for _ in range(40)]
+    ch, va = po.CorrectKey.challenge(n, s, r)
+    proof = po.CorrectKey.prove(p, q, ch)
+    po.CorrectKey.verify(proof, va)
+    bad = dict(ch, e=ch["e"] + 1)
+    with pytest.raises(po.CorrectKeyProveError):
+        po.CorrectKey.prove(p, q, bad)
+    with pytest.raises(po.IncorrectProof):
+        po.CorrectKey.verify({"s_digest": proof["s_digest"] + 1}, va)

@@ -154,6 +154,29 @@ Json dispatch(const std::string& op, const Json& req) {
     out.set("transcript", Json::string(carrier.to_json()));
     return out;
   }
+  if (op == "correct_key.challenge") {
+    EncryptionKey ek(dec(req, "n"));
+    auto cv = CorrectKey::challenge(eng, ek, rng_from(req));
+    out.set("challenge", Json::string(cv.first.to_json()));
+    out.set("verification_aid", Json::object().set("s_digest", ser_dec(cv.second.s_digest)));
+    return out;
+  }
+  if (op == "correct_key.prove") {
+    DecryptionKey dk{dec(req, "p"), dec(req, "q")};
+    try {
+      CorrectKeyProof pr = CorrectKey::prove(eng, dk, Challenge::from_json(req.at("challenge").as_str()));
+      out.set("proof", Json::object().set("s_digest", ser_dec(pr.s_digest)));
+      try {
+        CorrectKey::verify(pr, VerificationAid{dec(req, "s_digest")});
+        out.set("verify", Json::string("ok"));
+      } catch (const IncorrectProof&) {
+        out.set("verify", Json::string("incorrect"));
+      }
+    } catch (const CorrectKeyProveError& e) {
+      out.set("prove_error", Json::string(e.what()));
+    }
+    return out;
+  }
   if (op == "correct_key_ni.proof") {
     DecryptionKey dk{dec(req, "p"), dec(req, "q")};
     NiCorrectKeyProof pr;

@@ -531,6 +531,116 @@ class NiCorrectKeyProof {  // correct_key_ni.rs:34-39
   }
 };
 
+// ------------------------------------------------------------------------------ shared device helpers
+// BigInt::mod_pow(base_i, exp_(i or shared), mod) for a batch under ONE modulus (K2 through zkp_modexp_var).
+inline std::vector<BigInt> powm_batch(Engine& eng, const std::vector<BigInt>& bases, const std::vector<BigInt>& exps, const BigInt& mod) {
+  const size_t B = bases.size();
+  if (B == 0) return {};
+  if (exps.size() != 1 && exps.size() != B) throw std::invalid_argument("powm_batch: one exponent, or one per base");
+  const size_t nl = limbs_for_bits(mod.bit_length());
+  size_t ebits = 1;
+  for (auto& e : exps) ebits = std::max(ebits, e.bit_length());
+  const size_t el = limbs_for_bits(ebits);
+  std::vector<BigInt> b2;
+  for (auto& b : bases) b2.push_back(b.d.size() > nl ? b % mod : b);
+  std::vector<uint32_t> out(B * nl);
+  eng.check(zkp_modexp_var(eng.handle(), pack(b2, nl).data(), pack(exps, el).data(), (int)el, (int)(32 * el), exps.size() == 1 ? (int)B : 1,
+                           mod.to_limbs(nl).data(), (int)nl, (int)B, (int)B, out.data()));
+  return unpack(out, nl);
+}
+// compute_digest (utils.rs:9-22) of one item list, on the device (K4)
+inline BigInt compute_digest(Engine& eng, const std::vector<BigInt>& items) {
+  size_t bits = 32;
+  for (auto& v : items) bits = std::max(bits, v.bit_length());
+  const size_t l = limbs_for_bits(bits);
+  uint8_t dig[32];
+  eng.check(zkp_sha256_transcript(eng.handle(), pack(items, l).data(), (int)l, (int)items.size(), 1, dig));
+  return BigInt::from_bytes(dig, 32);
+}
+// kzen-paillier extract_nroot(dk, z) = z^(n^-1 mod phi) mod n for a batch: two half-width K2 batches + CRT
+inline std::vector<BigInt> extract_nroots(Engine& eng, const DecryptionKey& dk, const std::vector<BigInt>& zs) {
+  const BigInt n = dk.p * dk.q, pm1 = dk.p - BigInt(1), qm1 = dk.q - BigInt(1);
+  BigInt dp, dq, pinv;
+  if (!BigInt::mod_inv(n % pm1, pm1, dp) || !BigInt::mod_inv(n % qm1, qm1, dq) || !BigInt::mod_inv(dk.p % dk.q, dk.q, pinv))
+    throw ReferencePanic("extract_nroot: n is not invertible mod phi(n)");
+  std::vector<BigInt> bp, bq;
+  for (auto& z : zs) { bp.push_back(z % dk.p); bq.push_back(z % dk.q); }
+  std::vector<BigInt> sp = powm_batch(eng, bp, {dp}, dk.p), sq = powm_batch(eng, bq, {dq}, dk.q), out;
+  for (size_t i = 0; i < zs.size(); ++i) {
+    BigInt diff = (sq[i] + dk.q - (sp[i] % dk.q)) % dk.q;
+    out.push_back(sp[i] + dk.p * ((diff * pinv) % dk.q));
+  }
+  return out;
+}
+
+// --------------------------------------------------------------------------------------- CorrectKey
+// The interactive proof of co-primality of n and phi(n) (correct_key.rs:64-172).
+struct Challenge {  // correct_key.rs:28-38
+  std::vector<BigInt> sn;
+  BigInt e;
+  std::vector<BigInt> z;
+  std::string to_json() const { return Json::object().set("sn", ser_vec(sn)).set("e", ser_dec(e)).set("z", ser_vec(z)).dump(); }
+  static Challenge from_json(const std::string& s) {
+    Json j = Json::parse(s);
+    Challenge c;
+    c.sn = de_vec(j.at("sn")); c.e = de_dec(j.at("e"), false); c.z = de_vec(j.at("z"));
+    return c;
+  }
+};
+struct VerificationAid { BigInt s_digest; };   // :40-44
+struct CorrectKeyProof { BigInt s_digest; };   // :46-50
+struct CorrectKeyProveError : std::runtime_error {  // :174-184
+  enum Kind { SniNotCoprimeWithN, ZiNotCoprimeWithN, RniNotCoprimeWithN, EWasntComputedCorrectly } kind;
+  CorrectKeyProveError(Kind k, const char* what) : std::runtime_error(what), kind(k) {}
+};
+
+class CorrectKey {
+ public:
+  // correct_key.rs:65-107: s_i, then r_i <- sample_below(n); 80 x^n mod n and 40 s^e mod n on the device
+  static std::pair<Challenge, VerificationAid> challenge(Engine& eng, const EncryptionKey& ek, const ByteSource& rng = os_rng()) {
+    const size_t k = STATISTICAL_ERROR_FACTOR;
+    std::vector<BigInt> s, r;
+    for (size_t i = 0; i < k; ++i) s.push_back(BigInt::sample_below(rng, ek.n));
+    for (size_t i = 0; i < k; ++i) r.push_back(BigInt::sample_below(rng, ek.n));
+    std::vector<BigInt> both(s);
+    both.insert(both.end(), r.begin(), r.end());
+    std::vector<BigInt> pw = powm_batch(eng, both, {ek.n}, ek.n);
+    Challenge ch;
+    ch.sn.assign(pw.begin(), pw.begin() + k);
+    std::vector<BigInt> items{ek.n};
+    items.insert(items.end(), pw.begin(), pw.end());          // n, sn.., rn..
+    ch.e = compute_digest(eng, items);
+    std::vector<BigInt> se = powm_batch(eng, s, {ch.e}, ek.n);
+    for (size_t i = 0; i < k; ++i) ch.z.push_back((r[i] * se[i]) % ek.n);
+    return {ch, VerificationAid{compute_digest(eng, s)}};
+  }
+  // correct_key.rs:109-162
+  static CorrectKeyProof prove(Engine& eng, const DecryptionKey& dk, const Challenge& ch) {
+    const BigInt n = dk.q * dk.p, one(1);
+    for (auto& v : ch.sn)
+      if (BigInt::gcd(n, v) != one) throw CorrectKeyProveError(CorrectKeyProveError::SniNotCoprimeWithN, "`challenge.sn[i]` isn't co-prime with `n`");
+    for (auto& v : ch.z)
+      if (BigInt::gcd(n, v) != one) throw CorrectKeyProveError(CorrectKeyProveError::ZiNotCoprimeWithN, "`challenge.z[i]` isn't co-prime with `n`");
+    const BigInt phi = (dk.q - one) * (dk.p - one);
+    const BigInt phimine = phi - (ch.e % phi);
+    std::vector<BigInt> zn = powm_batch(eng, ch.z, {n}, n), snphi = powm_batch(eng, ch.sn, {phimine}, n), rn;
+    const size_t k = std::min(ch.z.size(), ch.sn.size());     // zip
+    for (size_t i = 0; i < k; ++i) rn.push_back((zn[i] * snphi[i]) % n);
+    for (auto& v : rn)
+      if (BigInt::gcd(n, v) != one) throw CorrectKeyProveError(CorrectKeyProveError::RniNotCoprimeWithN, "`rn[i]` isn't co-prime with `n`");
+    std::vector<BigInt> items{n};
+    items.insert(items.end(), ch.sn.begin(), ch.sn.end());
+    items.insert(items.end(), rn.begin(), rn.end());
+    if (ch.e != compute_digest(eng, items))
+      throw CorrectKeyProveError(CorrectKeyProveError::EWasntComputedCorrectly, "`challenge.e` wasn't computed correctly");
+    return CorrectKeyProof{compute_digest(eng, extract_nroots(eng, dk, ch.sn))};
+  }
+  // correct_key.rs:164-171
+  static void verify(const CorrectKeyProof& proof, const VerificationAid& va) {
+    if (proof.s_digest != va.s_digest) throw IncorrectProof();
+  }
+};
+
 // ----------------------------------------------------------------------------------- sigma protocols
 // Field names and order follow the reference structs; BigInt fields use curv's native serde.
 struct ZeroStatement { EncryptionKey ek; BigInt c; };        // zero_enc_proof.rs:37-41
