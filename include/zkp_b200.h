@@ -226,6 +226,10 @@ int zkp_verlin_verify(zkp_ctx* ctx, int batch, int z_limbs, const uint32_t* c, c
  * carry-chained IMAD.WIDE.U32.X rows the Montgomery loop is made of, 2: 32-bit
  * IMAD.  Returns multiply-adds per second in *mads_per_s. */
 int zkp_imad_peak(zkp_ctx* ctx, int variant, double* mads_per_s);
+/* Which kernel served Paillier::encrypt_with_chosen_randomness so far on this context: launches of K1m (two-digit
+ * Montgomery form, the default), K1 (Montgomery modulo n^2; rows wider than n, keys K1m does not take, or
+ * ZKP_B200_ENC=k1) and K1v2 (ZKP_B200_ENC=k1v2).  Any pointer may be NULL. */
+int zkp_enc_kernel_launches(const zkp_ctx* ctx, long long* k1m, long long* k1, long long* k1v2);
 
 #ifdef __cplusplus
 }

@@ -1,13 +1,14 @@
 import random
 M32=0xffffffff
-def model_montmul(a,b,n,T,L):
+def model_montmul(a,b,n,T,L,init=0):
     S=T*L
     R=1<<(32*S)
     n0inv=(-pow(n,-1,1<<32))&M32
     def limbs(x): return [[(x>>(32*(g*L+j)))&M32 for j in range(L)] for g in range(T)]
     A=limbs(a);B=limbs(b);N=limbs(n)
     # per lane arrays as integers: X = list of L+2 limbs
-    E=[[0]*(L+2) for _ in range(T)]
+    E=[[(init>>(32*(g*L+k)))&M32 if (k<L or g==T-1) else 0 for k in range(L+2)] for g in range(T)]
+    assert init>>(32*(S+2))==0
     O=[[0]*(L+2) for _ in range(T)]
     def val(arr,lo,cnt): # little endian to int
         v=0
@@ -62,18 +63,22 @@ def model_montmul(a,b,n,T,L):
         tot+=val(E[g],0,L+2)<<(32*g*L)
     assert E[0] is not None
     # lane0's O[0] must be zero? (limb -1)
-    exp=(a*b*pow(R,-1,n))%n
+    exp=((init+a*b)*pow(R,-1,n))%n
     assert tot%n==exp,(tot,exp)
-    assert tot<2*n
+    assert tot<2*n+(2 if init else 0)
+    assert tot*R-init-a*b>=0 and (tot*R-init-a*b)%n==0 and (tot*R-init-a*b)//n<R
     # max top limbs
     return tot
-random.seed(1)
-for (T,L) in [(4,8),(8,8),(8,12),(8,16),(16,12),(16,16),(4,2),(32,2)]:
-    S=T*L
-    for it in range(20):
-        n=random.getrandbits(32*S)|1|(1<<(32*S-1)) if it%2==0 else (random.getrandbits(32*S-random.randint(0,40))|1)
-        if it==5: n=(1<<(32*S))-1
-        a=random.randrange(n); b=random.randrange(n)
-        if it==3: a=b=n-1
-        model_montmul(a,b,n,T,L)
-    print(T,L,"ok")
+def model_montmul_init(a,b,n,T,L,init):
+    return model_montmul(a,b,n,T,L,init)
+if __name__=='__main__':
+  random.seed(1)
+  for (T,L) in [(4,8),(8,8),(8,12),(8,16),(16,12),(16,16),(4,2),(32,2)]:
+      S=T*L
+      for it in range(20):
+          n=random.getrandbits(32*S)|1|(1<<(32*S-1)) if it%2==0 else (random.getrandbits(32*S-random.randint(0,40))|1)
+          if it==5: n=(1<<(32*S))-1
+          a=random.randrange(n); b=random.randrange(n)
+          if it==3: a=b=n-1
+          model_montmul(a,b,n,T,L)
+      print(T,L,"ok")

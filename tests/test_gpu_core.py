@@ -155,3 +155,34 @@ def test_two_digit_kernel_matches_montgomery_kernel(monkeypatch):
     assert np.array_equal(outs[0], outs[1])
     for j in (0, 1, 2, 3, 17, batch - 1):
         assert from_limbs(outs[1][j]) == ((m[j] * n + 1) % nn) * pow(r[j], n, nn) % nn
+
+
+@pytest.mark.parametrize("n_bits,nl", [(1024, 32), (2048, 64), (2047, 64), (2041, 64), (3072, 96), (4096, 128), (1536, 48), (2560, 80)])
+def test_two_digit_montgomery_kernel(monkeypatch, n_bits, nl):
+    """K1m (modexp2m.cu, the default encryption kernel) against K1 (ZKP_B200_ENC=k1) and Python pow: moduli that do
+    not fill their top limb, widths that run zero-extended, bases >= n, base 0 / 1, plaintext 0 / n-1 / >= n / none,
+    narrow plaintext rows, more than one persistent wave of a small batch's worth of CTAs and a ragged tail."""
+    rng = random.Random(n_bits)
+    n = rand_odd(rng, n_bits)
+    nn = n * n
+    batch = 333
+    cap = 1 << (32 * nl)
+    r = [rng.getrandbits(32 * nl) for _ in range(batch)]  # about half of them >= n
+    r[0], r[1], r[2], r[3], r[4] = 1, n - 1, 0, min(n + 5, cap - 1), cap - 1
+    m = [rng.getrandbits(32 * nl) if j % 7 == 0 else rng.getrandbits(300) for j in range(batch)]
+    m[0], m[1], m[5] = 0, n - 1, min(n + 1, cap - 1)
+    want = [((mi * n + 1) % nn) * pow(ri, n, nn) % nn for mi, ri in zip(m, r)]
+    outs = {}
+    for mode in ("k1m", "k1"):
+        monkeypatch.setenv("ZKP_B200_ENC", mode)
+        with zk.native.Context(0) as c:
+            c.set_key(to_limbs(n, nl))
+            outs[mode] = c.paillier_enc(ints_to_limbs(m, nl), ints_to_limbs(r, nl))
+            used = c.enc_kernel_launches()
+            assert (used["k1m"] > 0) == (mode == "k1m") and (used["k1"] > 0) == (mode == "k1")
+            if mode == "k1m":
+                narrow = [v & ((1 << 256) - 1) for v in m[:9]]
+                o = rows(c.paillier_enc(ints_to_limbs(narrow, 8), ints_to_limbs(r[:9], nl)))
+                assert o == [((mi * n + 1) % nn) * pow(ri, n, nn) % nn for mi, ri in zip(narrow, r[:9])]
+    assert rows(outs["k1m"]) == want
+    assert np.array_equal(outs["k1m"], outs["k1"])

@@ -58,14 +58,31 @@ cudaError_t ensure_table(zkp_ctx* c, int S, int entries) {
     size_t b2 = enc2d_scratch_limbs(c->num_sms) * sizeof(uint32_t);
     if (b2 > bytes) bytes = b2;
   }
+  if (c->enc2m_key && c->enc2m_enabled) {
+    size_t b3 = enc2m_table_limbs(c->n.S, c->num_sms) * sizeof(uint32_t);
+    if (b3 > bytes) bytes = b3;
+  }
   return c->table.ensure(bytes);
 }
 
 cudaError_t launch_enc(zkp_ctx* c, const uint32_t* bases, int base_limbs, const uint32_t* plain, int plain_limbs, uint32_t* out,
                        int jobs, const unsigned* jobs_dev) {
   if (c->enc2d_key && c->enc2d_enabled && base_limbs == 64 && (!plain || (plain_limbs <= 64 && plain_limbs % 2 == 0)))
-    return launch_enc2d(c->n.h_mod.data(), c->nn.sched.as<uint32_t>(), c->nn.nsteps, bases, plain, plain_limbs, out, jobs,
+    return ++c->enc2d_launches, launch_enc2d(c->n.h_mod.data(), c->nn.sched.as<uint32_t>(), c->nn.nsteps, bases, plain, plain_limbs, out, jobs,
                         c->table.as<uint32_t>(), c->num_sms, c->stream, jobs_dev);
+  if (c->enc2m_key && c->enc2m_enabled && base_limbs <= c->n.S && (!plain || plain_limbs <= c->n.S)) {
+    Enc2mKey k;
+    k.mod = c->n.mod.as<uint32_t>();
+    k.consts = c->enc2m_consts.as<uint32_t>();
+    k.ops = c->enc2m_ops.as<uint32_t>();
+    k.nops = c->enc2m_nops;
+    k.n0inv = c->n.n0inv;
+    k.S = c->n.S;
+    ++c->enc2m_launches;
+    return launch_enc2m(k, bases, base_limbs, plain, plain_limbs, out, c->nn.limbs, jobs, c->table.as<uint32_t>(), c->num_sms,
+                        c->stream, jobs_dev);
+  }
+  ++c->k1_launches;
   return launch_modexp_shared(c->nn.view(), bases, base_limbs, plain, plain_limbs, out, c->nn.limbs, jobs, c->table.as<uint32_t>(),
                               c->num_sms, c->stream, jobs_dev);
 }
@@ -74,7 +91,7 @@ cudaError_t launch_enc(zkp_ctx* c, const uint32_t* bases, int base_limbs, const 
 // significant bit first.  Entry k: low byte = table index of the odd power
 // x^(2*idx+1) to multiply by (0xff = none), upper 24 bits = squarings to do first.
 // Entry 0 only loads the accumulator.
-static std::vector<uint32_t> recode_exponent(const uint32_t* e, int limbs) {
+std::vector<uint32_t> recode_exponent(const uint32_t* e, int limbs) {
   std::vector<uint32_t> out;
   int top = limbs * 32 - 1;
   auto bit = [&](int i) { return (e[i >> 5] >> (i & 31)) & 1u; };
@@ -191,7 +208,7 @@ void zkp_ctx_destroy(zkp_ctx* c) {
   for (auto e : c->ev_pool) cudaEventDestroy(e);
   c->nn.release();
   c->n.release();
-  std::vector<DevBuf*> bufs = {&c->table, &c->in0, &c->in1, &c->in2, &c->in3, &c->out0};
+  std::vector<DevBuf*> bufs = {&c->enc2m_consts, &c->enc2m_ops, &c->table, &c->in0, &c->in1, &c->in2, &c->in3, &c->out0};
   for (DevBuf* b : c->rp.all()) bufs.push_back(b);
   for (DevBuf* b : c->ck.all()) bufs.push_back(b);
   for (DevBuf* b : bufs) b->release();
@@ -275,6 +292,28 @@ int zkp_set_key(zkp_ctx* c, const uint32_t* n, int n_limbs) {
     // (DESIGN.md section 3.7): opt in with ZKP_B200_ENC2D=1.
     const char* env = getenv("ZKP_B200_ENC2D");
     c->enc2d_enabled = env && env[0] == '1';
+  }
+  {
+    // K1m: two-digit Montgomery form (modexp2m.cu), the default encryption kernel
+    const char* env = getenv("ZKP_B200_ENC");
+    if (env && !strcmp(env, "k1v2")) c->enc2d_enabled = true;
+    c->enc2m_enabled = !(env && (!strcmp(env, "k1") || !strcmp(env, "k1v2"))) && !c->enc2d_enabled;
+    c->enc2m_key = false;
+    if (enc2m_supported(c->n.h_mod.data(), c->n.S)) {
+      const int S = c->n.S;
+      std::vector<uint32_t> consts((size_t)3 * S);
+      enc2m_host_constants(c->n.h_mod.data(), S, consts.data());
+      std::vector<uint32_t> sched = recode_exponent(n, n_limbs);
+      std::vector<uint32_t> ops = enc2m_ops(sched.data(), (int)sched.size());
+      c->enc2m_nops = (int)ops.size();
+      ops.resize((ops.size() + 3) & ~size_t(3), 0xffffffu);
+      ZKP_CU(c, c->enc2m_consts.ensure(consts.size() * 4));
+      ZKP_CU(c, c->enc2m_ops.ensure(ops.size() * 4));
+      ZKP_CU(c, cudaMemcpyAsync(c->enc2m_consts.p, consts.data(), consts.size() * 4, cudaMemcpyHostToDevice, c->stream));
+      ZKP_CU(c, cudaMemcpyAsync(c->enc2m_ops.p, ops.data(), ops.size() * 4, cudaMemcpyHostToDevice, c->stream));
+      ZKP_CU(c, cudaStreamSynchronize(c->stream));
+      c->enc2m_key = true;
+    }
   }
   c->rp.prove_staged = c->rp.prove_done = c->rp.verify_staged = c->rp.verify_done = false;
   return ZKP_OK;
@@ -400,6 +439,14 @@ int zkp_modmul(zkp_ctx* c, int which_nn, const uint32_t* a, const uint32_t* b, i
   }
   ZKP_CU(c, cudaMemcpyAsync(out, c->out0.p, (size_t)batch * w * 4, cudaMemcpyDeviceToHost, c->stream));
   ZKP_CU(c, cudaStreamSynchronize(c->stream));
+  return ZKP_OK;
+}
+
+int zkp_enc_kernel_launches(const zkp_ctx* c, long long* k1m, long long* k1, long long* k1v2) {
+  if (!c) return ZKP_E_ARG;
+  if (k1m) *k1m = c->enc2m_launches;
+  if (k1) *k1 = c->k1_launches;
+  if (k1v2) *k1v2 = c->enc2d_launches;
   return ZKP_OK;
 }
 

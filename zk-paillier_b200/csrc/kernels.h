@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <vector>
+
 namespace zkp {
 
 constexpr int kCtaThreads = 128;       // 4 warps per CTA
@@ -51,6 +53,27 @@ int enc2d_resident_groups(int num_sms);
 size_t enc2d_scratch_limbs(int num_sms);  // window tables + cold digit slots
 cudaError_t launch_enc2d(const uint32_t* n_host, const uint32_t* sched_dev, int nsteps, const uint32_t* bases, const uint32_t* plain,
                          int plain_limbs, uint32_t* out, int jobs, uint32_t* table, int num_sms, cudaStream_t st,
+                         const unsigned* jobs_dev = nullptr);
+
+// K1m (modexp2m.cu): the same encryption by Montgomery arithmetic in two-digit base-n form (half the limb products
+// of K1).  S = kernel width of n in limbs (32, 64, 96 or 128); n odd, 1 < n <= 2^(32 S) - 4.
+struct Enc2mKey {
+  const uint32_t* mod;     // n, S limbs
+  const uint32_t* consts;  // K_lo = -W mod n | (W^2 mod n^2) mod n | (W^2 mod n^2) div n, S limbs each (W = 2^(32 S))
+  const uint32_t* ops;     // op list (enc2m_ops)
+  int nops;
+  uint32_t n0inv;          // -n^{-1} mod 2^32
+  int S;
+};
+bool enc2m_supported(const uint32_t* n_host, int S);
+void enc2m_host_constants(const uint32_t* n_host, int S, uint32_t* consts /* [3 S] */);
+std::vector<uint32_t> enc2m_ops(const uint32_t* sched, int nsteps);  // from the K1 schedule of the exponent n
+int enc2m_resident_groups(int S, int num_sms);
+size_t enc2m_table_limbs(int S, int num_sms);
+// bases: [jobs][base_limbs] (any value below 2^(32 base_limbs), base_limbs <= S), plain: [jobs][plain_limbs] or null
+// (plain_limbs <= S), out: [jobs][out_limbs] (out_limbs <= 2 S); base_limbs / plain_limbs multiples of 4.
+cudaError_t launch_enc2m(const Enc2mKey& key, const uint32_t* bases, int base_limbs, const uint32_t* plain, int plain_limbs,
+                         uint32_t* out, int out_limbs, int jobs, uint32_t* table, int num_sms, cudaStream_t st,
                          const unsigned* jobs_dev = nullptr);
 
 // Montgomery setup for per-instance moduli: r2[i] = R^2 mod mods[i] ([count][S]), n0inv[i].

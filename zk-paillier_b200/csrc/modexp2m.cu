@@ -1,0 +1,366 @@
+// K1m: Paillier encryption c = (1 + m n) r^n mod n^2 by MONTGOMERY ARITHMETIC IN TWO-DIGIT BASE-n FORM.
+//
+// Replaces the same reference lines as K1 (Paillier::encrypt_with_chosen_randomness at
+// range_proof.rs:165,179,280,286,330; zero_enc_proof.rs:46,73; correct_ciphertext.rs:45,73;
+// multiplication_proof.rs:63,72,118,125; verlin_proof.rs:157) with half the limb products.
+//
+// K1 already runs the multiplier pipe at its IMAD.WIDE issue limit, so the only way to go faster is to do fewer
+// multiplies.  An element x of Z_{n^2} is held as the pair (X0, X1), x = X0 + X1 n, 0 <= X0, X1 < n.  With
+// W = 2^(32 S) > n, the CIOS Montgomery multiplication of X0 and Y0 modulo n produces, besides Z0 = X0 Y0 / W mod n,
+// the quotient digits q it added, and  X0 Y0 = Z0' W - q n  holds between integers.  Hence modulo n^2
+//     x y / W  =  Z0 + ( (X0 Y1 + X1 Y0 - q_eff) / W  mod n ) n
+// and the second digit is one more Montgomery reduction modulo n whose accumulator starts at a non-negative
+// representative of -q_eff (init = W + K_lo - q, K_lo = -W mod n; or W - q when Z0 = Z0' - n was taken).
+// No true quotient and no Barrett: only half-width CIOS rows of mp_coop.cuh.  A squaring costs 4 S^2 limb products
+// (x^2: X0 X0 and X0 (2 X1)), a multiplication 6 S^2, against 8 S^2 for CIOS modulo n^2 (S = limbs of n):
+// 42.4 M IMAD.WIDE per 2048-bit encryption instead of 79.3 M.  Model and proofs of the bounds:
+// tests/models/mont2d_model.py.
+//
+// Layout: one encryption per group of T lanes, L limbs of each digit per lane (Mp<8,8> for a 2048-bit n), the
+// two digits in separate register arrays; window table of 16 odd powers + x^2 as digit pairs in an L2-resident
+// scratch (each lane re-reads only limbs it wrote); schedule, K_lo and each pass's bases / plaintexts staged by
+// 1-D TMA bulk copies.  The whole exponentiation - entering Montgomery form, the table, the sliding-window
+// ladder, the Paillier factor (1 + m n) = pair (1, m), leaving Montgomery form - is ONE op list run by one loop
+// with a single squaring site and a single multiplication site, so the code stays small.
+#include <vector>
+
+#include "kernels.h"
+#include "mp_coop.cuh"
+#include "tma.cuh"
+
+namespace zkp {
+
+constexpr int kSlots2m = kTableShared + 1;  // odd powers x^1..x^31 and x^2
+constexpr uint32_t OP_NONE = 0xffu, OP_Y_CONST = 0xfeu, OP_Y_PLAIN = 0xfdu;
+
+struct Enc2mParams {
+  Enc2mKey key;
+  const uint32_t* bases;
+  const uint32_t* plain;
+  uint32_t* out;
+  uint32_t* table;
+  int base_limbs, plain_limbs, out_limbs, jobs, ops_pad;
+  const unsigned* jobs_dev;
+};
+
+template <int T, int L>
+struct TwoDigit {
+  using M = Mp<T, L>;
+  static constexpr int S = T * L;
+
+  // init + top 2^(32 S) = W + (delta ? 0 : K_lo) - q   (non-negative, == -q_eff mod n, < W + n)
+  static __device__ __forceinline__ void init_from_q(uint32_t (&init)[L], uint32_t& top, const uint32_t (&q)[L], uint32_t delta,
+                                                     const uint32_t* s_klo, int lane) {
+    const int g = lane & (T - 1);
+    uint32_t m[L];
+    M::load(m, s_klo + g * L);
+#pragma unroll
+    for (int j = 0; j < L; ++j) m[j] = delta ? 0u : m[j];
+    const uint32_t bo = M::sub_full(init, m, q, lane);
+    top = 1u - bo;
+  }
+
+  // (x0, x1) <- (x0, x1)^2 / W
+  static __device__ __forceinline__ void sqr(uint32_t (&x0)[L], uint32_t (&x1)[L], const uint32_t (&n)[L], uint32_t n0inv,
+                                             const uint32_t* s_klo, int lane) {
+    uint32_t q[L], z0[L];
+#pragma unroll
+    for (int j = 0; j < L; ++j) q[j] = 0;
+    const uint32_t delta = M::template mont_mul_x<false, true, 1>(z0, x0, x0, n, n0inv, lane, z0, 0u, q);
+    uint32_t top;
+    init_from_q(q, top, q, delta, s_klo, lane);
+    M::mod_double(x1, n, lane);
+    M::template mont_mul_x<true, false, 2>(x1, x0, x1, n, n0inv, lane, q, top, q);
+#pragma unroll
+    for (int j = 0; j < L; ++j) x0[j] = z0[j];
+  }
+
+  // (x0, x1) <- (x0, x1) (y0, y1) / W
+  static __device__ __forceinline__ void mul(uint32_t (&x0)[L], uint32_t (&x1)[L], const uint32_t (&y0)[L], const uint32_t (&y1)[L],
+                                             const uint32_t (&n)[L], uint32_t n0inv, const uint32_t* s_klo, int lane) {
+    uint32_t q[L], z0[L], t[L];
+#pragma unroll
+    for (int j = 0; j < L; ++j) q[j] = 0;
+    const uint32_t delta = M::template mont_mul_x<false, true, 1>(z0, x0, y0, n, n0inv, lane, z0, 0u, q);
+    uint32_t top;
+    init_from_q(q, top, q, delta, s_klo, lane);
+    M::mont_mul(t, x1, y0, n, n0inv, lane);
+    M::template mont_mul_x<true, false, 2>(x1, x0, y1, n, n0inv, lane, q, top, q);
+    M::add_mod(x1, t, n, lane);
+#pragma unroll
+    for (int j = 0; j < L; ++j) x0[j] = z0[j];
+  }
+};
+
+template <int T, int L>
+__global__ void __launch_bounds__(kCtaThreads, 4) enc2m_kernel(const Enc2mParams p) {
+  using M = Mp<T, L>;
+  using TD = TwoDigit<T, L>;
+  constexpr int S = T * L;
+  constexpr int G = kCtaThreads / T;
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+  uint32_t* s_ops = reinterpret_cast<uint32_t*>(smem_raw + 16);
+  uint32_t* s_klo = s_ops + p.ops_pad;
+  uint32_t* s_bases = s_klo + S;
+  uint32_t* s_plain = s_bases + G * p.base_limbs;
+  uint32_t* s_pair = s_plain + G * p.plain_limbs;
+
+  const int lane = threadIdx.x & 31;
+  const int g = lane & (T - 1);
+  const int grp = threadIdx.x / T;
+  const uint32_t n0inv = p.key.n0inv;
+  uint32_t n[L];
+  M::load(n, p.key.mod + g * L);
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  uint32_t phase = 0;
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(bar, (uint32_t)(p.ops_pad + S) * 4u);
+    bulk_g2s(s_ops, p.key.ops, (uint32_t)p.ops_pad * 4u, bar);
+    bulk_g2s(s_klo, p.key.consts, (uint32_t)S * 4u, bar);
+  }
+  mbar_wait(bar, phase);
+  phase ^= 1;
+
+  uint32_t* tab = p.table + (size_t)(blockIdx.x * G + grp) * kSlots2m * 2 * S + g * L;
+  uint32_t* pair = s_pair + grp * 2 * S;
+  const int jobs = p.jobs_dev ? min((int)*p.jobs_dev, p.jobs) : p.jobs;
+  const int npass = (jobs + G - 1) / G;
+  for (int cj = blockIdx.x; cj < npass; cj += gridDim.x) {
+    const int job0 = cj * G;
+    const int nvalid = min(G, jobs - job0);
+    if (threadIdx.x == 0) {
+      uint32_t bb = (uint32_t)(nvalid * p.base_limbs) * 4u;
+      uint32_t pb = p.plain ? (uint32_t)(nvalid * p.plain_limbs) * 4u : 0u;
+      mbar_expect_tx(bar, bb + pb);
+      bulk_g2s(s_bases, p.bases + (size_t)job0 * p.base_limbs, bb, bar);
+      if (p.plain) bulk_g2s(s_plain, p.plain + (size_t)job0 * p.plain_limbs, pb, bar);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    const bool valid = grp < nvalid;
+    const int src = valid ? grp : 0;
+
+    // the last multiplier: the pair (1, m) = 1 + m n in plain form (it also takes the result out of Montgomery form)
+    uint32_t x0[L], x1[L], y0[L], y1[L];
+    if (p.plain) {
+      M::load_ext(x1, s_plain + src * p.plain_limbs, p.plain_limbs, g);
+    } else {
+#pragma unroll
+      for (int j = 0; j < L; ++j) x1[j] = 0;
+    }
+    M::set_small(x0, 1u, g);
+    M::store(pair + g * L, x0);
+    M::store(pair + S + g * L, x1);
+    __syncwarp();
+
+    M::load_ext(x0, s_bases + src * p.base_limbs, p.base_limbs, g);  // the pair (r, 0); r may exceed n
+#pragma unroll
+    for (int j = 0; j < L; ++j) x1[j] = 0;
+#pragma unroll 1
+    for (int k = 0; k < p.key.nops; ++k) {
+      const uint32_t op = s_ops[k];
+      const uint32_t yk = op & 0xffu, st = (op >> 8) & 0xffu, rl = (op >> 16) & 0xffu;
+      const int nsq = (int)(op >> 24);
+      if (yk != OP_NONE) {  // fetch the multiplier ahead of the squarings
+        const uint32_t* ysrc = yk == OP_Y_CONST ? p.key.consts + S + g * L : (yk == OP_Y_PLAIN ? pair + g * L : tab + (size_t)yk * 2 * S);
+        M::load(y0, ysrc);
+        M::load(y1, ysrc + S);
+      }
+#pragma unroll 1
+      for (int q = 0; q < nsq; ++q) TD::sqr(x0, x1, n, n0inv, s_klo, lane);
+      if (yk != OP_NONE) TD::mul(x0, x1, y0, y1, n, n0inv, s_klo, lane);
+      if (st != OP_NONE) {
+        M::store(tab + (size_t)st * 2 * S, x0);
+        M::store(tab + (size_t)st * 2 * S + S, x1);
+      }
+      if (rl != OP_NONE) {
+        M::load(x0, tab + (size_t)rl * 2 * S);
+        M::load(x1, tab + (size_t)rl * 2 * S + S);
+      }
+    }
+    // c = X0 + X1 n (< n^2): plain product rows with X0 as the initial accumulator; the limb leaving lane 0 at
+    // row i is limb i of c and goes to the lane that owns it
+    {
+      uint32_t E[L + 2], O[L + 2];
+#pragma unroll
+      for (int j = 0; j < L; ++j) {
+        E[j] = x0[j];
+        O[j] = 0;
+      }
+      E[L] = E[L + 1] = O[L] = O[L + 1] = 0;
+#pragma unroll 1
+      for (int owner = 0; owner < T; ++owner) {
+        const bool mine = g == owner;
+#pragma unroll
+        for (int j = 0; j < L; j += 2) {
+          const uint32_t b0 = __shfl_sync(ZKP_FULL, n[j], owner, T);
+          const uint32_t b1 = __shfl_sync(ZKP_FULL, n[j + 1], owner, T);
+          M::mul_step(E, O, x1, b0, g);
+          const uint32_t v0 = __shfl_sync(ZKP_FULL, E[0], 0, T);
+          M::mul_step(O, E, x1, b1, g);
+          const uint32_t v1 = __shfl_sync(ZKP_FULL, O[0], 0, T);
+          y0[j] = mine ? v0 : y0[j];
+          y0[j + 1] = mine ? v1 : y0[j + 1];
+        }
+      }
+      M::mul_finish(y1, E, O, lane);
+    }
+    if (valid) {
+      uint32_t* o = p.out + (size_t)(job0 + grp) * p.out_limbs;
+      M::store_ext(o, y0, p.out_limbs, g);
+      if (p.out_limbs > S) M::store_ext(o + S, y1, p.out_limbs - S, g);
+    }
+    __syncthreads();  // everyone is done with the staged inputs
+    fence_proxy_async();
+  }
+}
+
+// ------------------------------------------------------------------ host side
+namespace {
+using Limbs = std::vector<uint32_t>;
+int cmp(const Limbs& a, const Limbs& b) {
+  for (int i = (int)a.size() - 1; i >= 0; --i)
+    if (a[i] != b[i]) return a[i] < b[i] ? -1 : 1;
+  return 0;
+}
+void sub_in(Limbs& a, const Limbs& b) {
+  uint64_t bo = 0;
+  for (size_t i = 0; i < a.size(); ++i) {
+    uint64_t t = (uint64_t)a[i] - b[i] - bo;
+    a[i] = (uint32_t)t;
+    bo = (t >> 32) & 1u;
+  }
+}
+// x = (2 x + cin) mod n for x < n; returns 1 iff n was subtracted
+uint32_t dbl_mod(Limbs& x, uint32_t cin, const Limbs& n) {
+  uint32_t c = cin;
+  for (size_t i = 0; i < x.size(); ++i) {
+    uint32_t v = x[i];
+    x[i] = (v << 1) | c;
+    c = v >> 31;
+  }
+  if (c || cmp(x, n) >= 0) {
+    sub_in(x, n);
+    return 1;
+  }
+  return 0;
+}
+}  // namespace
+
+static bool pick_shape(int S, int& T, int& L) {
+  switch (S) {
+    case 32: T = 4; L = 8; return true;
+    case 64: T = 8; L = 8; return true;
+    case 96: T = 8; L = 12; return true;
+    case 128: T = 16; L = 8; return true;
+    default: return false;
+  }
+}
+
+bool enc2m_supported(const uint32_t* n_host, int S) {
+  int T, L;
+  if (!pick_shape(S, T, L)) return false;
+  // finish_x<2> needs n <= W - 4; n = 1 is meaningless
+  bool top_ones = true;
+  for (int i = 1; i < S; ++i) top_ones = top_ones && n_host[i] == 0xffffffffu;
+  if (top_ones && n_host[0] >= 0xfffffffcu) return false;
+  bool small = n_host[0] <= 1u;
+  for (int i = 1; i < S; ++i) small = small && n_host[i] == 0u;
+  return !small && (n_host[0] & 1u);
+}
+
+void enc2m_host_constants(const uint32_t* n_host, int S, uint32_t* consts) {
+  Limbs n(n_host, n_host + S), x(S, 0u), x0(S, 0u), x1(S, 0u);
+  x[0] = 1;  // W mod n by 32 S doublings
+  for (int i = 0; i < 32 * S; ++i) dbl_mod(x, 0, n);
+  Limbs klo = n;  // -W mod n (W mod n != 0: n is odd and > 1)
+  sub_in(klo, x);
+  x0[0] = 1;  // W^2 mod n^2 as a digit pair by 64 S pair doublings: (X0, X1) -> (2 X0 - c n, 2 X1 + c mod n)
+  for (int i = 0; i < 64 * S; ++i) {
+    uint32_t c = dbl_mod(x0, 0, n);
+    dbl_mod(x1, c, n);
+  }
+  for (int i = 0; i < S; ++i) {
+    consts[i] = klo[i];
+    consts[S + i] = x0[i];
+    consts[2 * S + i] = x1[i];
+  }
+}
+
+// K1 schedule (api_core.cu: recode_exponent) -> K1m op list.
+// op = nsq << 24 | reload_slot << 16 | store_slot << 8 | multiplier (0xff: none; 0xfe: W^2 pair; 0xfd: (1, m))
+std::vector<uint32_t> enc2m_ops(const uint32_t* sched, int nsteps) {
+  auto mk = [](uint32_t nsq, uint32_t rl, uint32_t st, uint32_t y) { return (nsq << 24) | (rl << 16) | (st << 8) | y; };
+  std::vector<uint32_t> ops;
+  ops.push_back(mk(0, OP_NONE, 0, OP_Y_CONST));                           // x W  -> slot 0
+  ops.push_back(mk(1, 0, kTableShared, OP_NONE));                         // x^2  -> slot 16; back to x
+  for (uint32_t e = 1; e < (uint32_t)kTableShared; ++e) ops.push_back(mk(0, OP_NONE, e, kTableShared));  // x^(2e+1)
+  ops.push_back(mk(0, sched[0] & 0xffu, OP_NONE, OP_NONE));               // accumulator = first window
+  for (int k = 1; k < nsteps; ++k) {
+    uint32_t idx = sched[k] & 0xffu, nsq = sched[k] >> 8;
+    while (nsq > 255u) {
+      ops.push_back(mk(255u, OP_NONE, OP_NONE, OP_NONE));
+      nsq -= 255u;
+    }
+    ops.push_back(mk(nsq, OP_NONE, OP_NONE, idx));
+  }
+  ops.push_back(mk(0, OP_NONE, OP_NONE, OP_Y_PLAIN));
+  return ops;
+}
+
+int enc2m_resident_groups(int S, int num_sms) {
+  int T, L;
+  if (!pick_shape(S, T, L)) return 0;
+  return num_sms * 4 * (kCtaThreads / T);
+}
+size_t enc2m_table_limbs(int S, int num_sms) { return (size_t)enc2m_resident_groups(S, num_sms) * kSlots2m * 2 * S; }
+
+cudaError_t launch_enc2m(const Enc2mKey& key, const uint32_t* bases, int base_limbs, const uint32_t* plain, int plain_limbs,
+                         uint32_t* out, int out_limbs, int jobs, uint32_t* table, int num_sms, cudaStream_t st,
+                         const unsigned* jobs_dev) {
+  if (jobs <= 0) return cudaSuccess;
+  if (base_limbs % 4 || base_limbs > key.S || (plain && (plain_limbs % 4 || plain_limbs > key.S)) || out_limbs % 2 ||
+      out_limbs > 2 * key.S || key.nops <= 0)
+    return cudaErrorInvalidValue;
+  Enc2mParams p;
+  p.key = key;
+  p.bases = bases;
+  p.plain = plain;
+  p.out = out;
+  p.table = table;
+  p.base_limbs = base_limbs;
+  p.plain_limbs = plain ? plain_limbs : 0;
+  p.out_limbs = out_limbs;
+  p.jobs = jobs;
+  p.jobs_dev = jobs_dev;
+  p.ops_pad = (key.nops + 3) & ~3;
+#define CALL(T_, L_)                                                                                                   \
+  {                                                                                                                    \
+    constexpr int G = kCtaThreads / T_;                                                                                \
+    constexpr int S_ = T_ * L_;                                                                                        \
+    size_t smem = 16 + (size_t)(p.ops_pad + S_) * 4 + (size_t)G * (p.base_limbs + p.plain_limbs + 2 * S_) * 4;         \
+    int grid = num_sms * 4;                                                                                            \
+    int npass = (jobs + G - 1) / G;                                                                                    \
+    if (grid > npass) grid = npass;                                                                                    \
+    cudaError_t e = cudaFuncSetAttribute(enc2m_kernel<T_, L_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    if (e != cudaSuccess) return e;                                                                                    \
+    enc2m_kernel<T_, L_><<<grid, kCtaThreads, smem, st>>>(p);                                                          \
+  }
+  switch (key.S) {
+    case 32: CALL(4, 8) break;
+    case 64: CALL(8, 8) break;
+    case 96: CALL(8, 12) break;
+    case 128: CALL(16, 8) break;
+    default: return cudaErrorInvalidValue;
+  }
+#undef CALL
+  return cudaGetLastError();
+}
+
+}  // namespace zkp

@@ -226,6 +226,12 @@ struct Mp {
   // chains read/write 64-bit aligned register pairs only: no MOVs.
   static __device__ __forceinline__ void cios_step(uint32_t (&X)[L + 2], uint32_t (&Y)[L + 2], const uint32_t (&a)[L],
                                                    const uint32_t (&n)[L], uint32_t b, uint32_t n0inv, int g) {
+    uint32_t q;
+    cios_step(X, Y, a, n, b, n0inv, g, q);
+  }
+  // Same step, handing back the quotient digit q it added (uniform across the group).
+  static __device__ __forceinline__ void cios_step(uint32_t (&X)[L + 2], uint32_t (&Y)[L + 2], const uint32_t (&a)[L],
+                                                   const uint32_t (&n)[L], uint32_t b, uint32_t n0inv, int g, uint32_t& q) {
     uint32_t in = __shfl_down_sync(ZKP_FULL, Y[0], 1, T);
     if (g == T - 1) in = 0;
     add_cc(Y[L], in);
@@ -237,7 +243,7 @@ struct Mp {
     Z[L] = addc_out();
     Z[L + 1] = 0;
     mad_even(X, a, b);
-    uint32_t q = __shfl_sync(ZKP_FULL, X[0], 0, T) * n0inv;
+    q = __shfl_sync(ZKP_FULL, X[0], 0, T) * n0inv;
     mad_even(X, n, q);
     mad_odd(Z, n, q);
 #pragma unroll
@@ -272,6 +278,93 @@ struct Mp {
     for (int j = 1; j <= L; ++j) addc_cc(E[j], O[j + 1]);
     addc(E[L + 1], 0);
     finish(r, E, n, lane);
+  }
+
+  // finish() for a value < NSUB*n + 2 (NSUB = 1: the usual < 2n): NSUB conditional subtractions.  Returns 1 iff the
+  // first subtraction was taken (uniform across the group).  Needs n <= 2^(32 S) - 4 when NSUB = 2.
+  template <int NSUB>
+  static __device__ __forceinline__ uint32_t finish_x(uint32_t (&r)[L], uint32_t (&u)[L + 2], const uint32_t (&n)[L], int lane) {
+    const int g = lane & (T - 1);
+    uint32_t ov = __shfl_up_sync(ZKP_FULL, u[L], 1, T);
+    if (g == 0) ov = 0;
+    uint32_t x[L];
+#pragma unroll
+    for (int j = 0; j < L; ++j) x[j] = u[j];
+    add_cc(x[0], ov);
+#pragma unroll
+    for (int j = 1; j < L; ++j) addc_cc(x[j], 0);
+    uint32_t co = addc_out();
+    uint32_t topc;
+    uint32_t cin = resolve(co != 0, all_ones(x), lane, topc);
+    add_small(x, cin);
+    uint32_t hi = __shfl_sync(ZKP_FULL, u[L], T - 1, T) + topc;
+    uint32_t d[L];
+    uint32_t borrow = sub_full(d, x, n, lane);
+    const bool take = (hi != 0) || (borrow == 0);
+#pragma unroll
+    for (int j = 0; j < L; ++j) r[j] = take ? d[j] : x[j];
+    if (NSUB == 2) {
+      borrow = sub_full(d, r, n, lane);
+#pragma unroll
+      for (int j = 0; j < L; ++j) r[j] = borrow ? r[j] : d[j];
+    }
+    return take ? 1u : 0u;
+  }
+
+  // Montgomery multiplication with the two hooks the two-digit base-n form needs (modexp2m.cu):
+  //   INIT : the accumulator starts at init + init_top * 2^(32 S) instead of 0
+  //          (r = (init + a b) / 2^(32 S) mod n; init < 2^(32 S) + n, so r needs NSUB = 2);
+  //   CAPQ : the quotient digits q_i of the reduction are kept, digit i in the lane that owns limb i, so that
+  //          a b = r' 2^(32 S) - q n holds exactly for the unreduced r' (r = r' - n iff the return value is 1).
+  // Only a b < 2^(32 S) n is needed (a may be any S-limb value when b < n).  r may alias a or b.
+  template <bool INIT, bool CAPQ, int NSUB>
+  static __device__ __forceinline__ uint32_t mont_mul_x(uint32_t (&r)[L], const uint32_t (&a)[L], const uint32_t (&b)[L],
+                                                        const uint32_t (&n)[L], uint32_t n0inv, int lane,
+                                                        const uint32_t (&init)[L], uint32_t init_top, uint32_t (&qcap)[L]) {
+    const int g = lane & (T - 1);
+    uint32_t E[L + 2], O[L + 2];
+#pragma unroll
+    for (int j = 0; j < L + 2; ++j) E[j] = O[j] = 0;
+    if (INIT) {
+#pragma unroll
+      for (int j = 0; j < L; ++j) E[j] = init[j];
+      E[L] = (g == T - 1) ? init_top : 0u;
+    }
+#pragma unroll 1
+    for (int owner = 0; owner < T; ++owner) {
+      const bool mine = CAPQ && (g == owner);
+#pragma unroll
+      for (int j = 0; j < L; j += 2) {
+        uint32_t b0 = __shfl_sync(ZKP_FULL, b[j], owner, T);
+        uint32_t b1 = __shfl_sync(ZKP_FULL, b[j + 1], owner, T);
+        uint32_t q0, q1;
+        cios_step(E, O, a, n, b0, n0inv, g, q0);
+        cios_step(O, E, a, n, b1, n0inv, g, q1);
+        if (CAPQ) {
+          qcap[j] = mine ? q0 : qcap[j];
+          qcap[j + 1] = mine ? q1 : qcap[j + 1];
+        }
+      }
+    }
+    uint32_t in = __shfl_down_sync(ZKP_FULL, O[0], 1, T);
+    if (g == T - 1) in = 0;
+    add_cc(O[L], in);
+    addc(O[L + 1], 0);
+    add_cc(E[0], O[1]);
+#pragma unroll
+    for (int j = 1; j <= L; ++j) addc_cc(E[j], O[j + 1]);
+    addc(E[L + 1], 0);
+    return finish_x<NSUB>(r, E, n, lane);
+  }
+
+  // x = (x + y) mod n for x, y < n
+  static __device__ __forceinline__ void add_mod(uint32_t (&x)[L], const uint32_t (&y)[L], const uint32_t (&n)[L], int lane) {
+    const uint32_t ovf = add_full(x, y, lane);
+    uint32_t d[L];
+    const uint32_t borrow = sub_full(d, x, n, lane);
+    const bool take = (ovf != 0u) || (borrow == 0u);
+#pragma unroll
+    for (int j = 0; j < L; ++j) x[j] = take ? d[j] : x[j];
   }
 
   // ---- plain (non-modular) product on the same split accumulator -----------------------------------
