@@ -15,8 +15,9 @@ Numbers printed (one JSON line, rank 0):
   e2e         the same metric through the public C ABI with HOST (pinned) buffers: H2D of the statement and the
               randomness, prove, D2H of the whole proof, H2D of the proof again (the verifier is another party),
               verify, D2H of the verdicts -- all inside the timed region
-  roofline    the dominant kernel K1 (modexp_shared): algorithmic multiply-adds per second
-              of K1 device time against the IMAD.WIDE.U32 issue peak measured in this run; plus its HBM view
+  roofline    the dominant kernel (K1m, the two-digit Montgomery encryption kernel): algorithmic multiply-adds
+               per second of its device time against the IMAD.WIDE.U32 issue peak measured in
+              this run, the multiply-adds it actually executes (executed_frac), and its HBM view
   cpu_baseline  oracle/oracle.c (the reference's loops on the reference's own backend, GMP) on a bounded sample
 """
 import argparse
@@ -254,6 +255,11 @@ def run_b200(args):
     k1_ms, k1_launches, k1_units = prof[KID_MODEXP_SHARED]
     imad_peak = ctx.imad_peak(0)
     achieved = k1_units * ENC_IMADS / (k1_ms * 1e-3)
+    used = ctx.enc_kernel_launches()
+    which = "k1m" if used["k1m"] and not used["k1"] else ("k1" if used["k1"] and not used["k1m"] else "mixed")
+    exec_mads = ctx.enc_executed_mads().get(which, 0.0)
+    executed = k1_units * exec_mads / (k1_ms * 1e-3)
+    kernel_name = {"k1m": "enc2m_kernel<8,8> (K1m, two-digit Montgomery form)", "k1": "modexp_shared_kernel<8,16> (K1)"}.get(which, which)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -262,7 +268,7 @@ def run_b200(args):
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     traffic = None
     try:  # DRAM bytes of K1 from the committed ncu capture, scaled to this run's Enc per launch
-        tr = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json")))
+        tr = json.load(open(os.path.join(ROOT, "profiles", "k1m_traffic.json" if which == "k1m" else "k1_traffic.json")))
         traffic = tr["dram_bytes_per_enc"] * k1_units / max(k1_launches, 1)
     except Exception:
         pass
@@ -296,9 +302,13 @@ def run_b200(args):
                    "sharding": "independent proofs, contiguous shard per rank; NCCL broadcast of n before, all_gather of verdicts after; no collective on the modexp path"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": args.e2e_steps},
         "gpu_launches": launches,
-        "roofline": {"bound": "imad", "kernel": "modexp_shared_kernel<8,16> (K1)", "achieved": achieved / 1e12, "peak": imad_peak / 1e12, "unit": "T IMAD.WIDE.U32/s",
+        "roofline": {"bound": "imad", "kernel": kernel_name, "achieved": achieved / 1e12, "peak": imad_peak / 1e12, "unit": "T IMAD.WIDE.U32/s",
                      "frac": achieved / imad_peak, "traffic": traffic,
-                     "traffic_note": "DRAM bytes per launch = ncu dram_bytes per Enc (profiles/k1_traffic.json) x Enc per launch",
+                     "executed": executed / 1e12, "executed_frac": executed / imad_peak, "executed_imads_per_enc": exec_mads,
+                     "frac_note": "achieved = ALGORITHMIC multiply-adds (SURVEY.md 8d: fixed-window schoolbook CIOS modulo n^2) per second of kernel time; "
+                                  "it exceeds the pipe peak because K1m executes about half of them (two-digit base-n Montgomery form, sliding window): "
+                                  "executed_frac is the share of the measured IMAD.WIDE issue peak the kernel actually runs at",
+                     "traffic_note": "DRAM bytes per launch = ncu dram_bytes per Enc (profiles/k1m_traffic.json or k1_traffic.json) x Enc per launch",
                      "peak_source": "IMAD.WIDE.U32 issue-rate microbenchmark measured in this run (MEASURED_PEAKS.json has no integer entry)",
                      "alg_imads_per_enc": ENC_IMADS, "k1_launches": int(k1_launches), "k1_ms_avg": k1_ms / max(k1_launches, 1),
                      "k1_share_of_step": k1_ms / ms},

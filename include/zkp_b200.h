@@ -227,9 +227,14 @@ int zkp_verlin_verify(zkp_ctx* ctx, int batch, int z_limbs, const uint32_t* c, c
  * IMAD.  Returns multiply-adds per second in *mads_per_s. */
 int zkp_imad_peak(zkp_ctx* ctx, int variant, double* mads_per_s);
 /* Which kernel served Paillier::encrypt_with_chosen_randomness so far on this context: launches of K1m (two-digit
- * Montgomery form, the default), K1 (Montgomery modulo n^2; rows wider than n, keys K1m does not take, or
- * ZKP_B200_ENC=k1) and K1v2 (ZKP_B200_ENC=k1v2).  Any pointer may be NULL. */
-int zkp_enc_kernel_launches(const zkp_ctx* ctx, long long* k1m, long long* k1, long long* k1v2);
+ * Montgomery form, the default) and of K1 (Montgomery modulo n^2: rows wider than n, keys K1m does not take, or
+ * ZKP_B200_ENC=k1 in the environment at zkp_set_key).  Either pointer may be NULL. */
+int zkp_enc_kernel_launches(const zkp_ctx* ctx, long long* k1m, long long* k1);
+/* IMAD.WIDE.U32 (32x32+64 multiply-adds) one encryption EXECUTES under the current key, counted from the kernels'
+ * own op lists: K1m = (4 S^2 per squaring, 5 S^2 per multiplication, S^2 for the final X0 + X1 n, S = limbs of n);
+ * K1 = 2 (2S)^2 per Montgomery multiplication modulo n^2.  The roofline's "executed" view; the algorithmic figure
+ * of SURVEY.md section 8d (fixed 5-bit window, schoolbook CIOS modulo n^2) is larger than either. */
+int zkp_enc_executed_mads(const zkp_ctx* ctx, double* k1m, double* k1);
 
 #ifdef __cplusplus
 }

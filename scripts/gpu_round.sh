@@ -12,8 +12,8 @@ echo "== ncu launch list"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_${TAG}.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu --e2e-steps 1 > gpurun_out/bench_under_ncu_${TAG}.log 2>&1
 tail -3 gpurun_out/launches_${TAG}.csv | cut -c1-300
-echo "== ncu full capture of K1"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:modexp_shared -s 1 -c 2 -f -o gpurun_out/prof_k1_${TAG} \
+echo "== ncu full capture of the encryption kernel (K1m; K1 when ZKP_B200_ENC=k1)"
+timeout 900 ncu --set full --clock-control none --import-source on -k 'regex:enc2m|modexp_shared' -s 1 -c 2 -f -o gpurun_out/prof_enc_${TAG} \
     python bench.py --batch 148 --steps 1 --warmup 1 --no-cpu --e2e-steps 1 > gpurun_out/ncu_full_${TAG}.log 2>&1
 tail -3 gpurun_out/ncu_full_${TAG}.log | cut -c1-300
 ls -la gpurun_out

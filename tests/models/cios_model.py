@@ -1,11 +1,13 @@
 import random
 M32=0xffffffff
-def model_montmul(a,b,n,T,L,init=0):
+def model_montmul(a,b,n,T,L,init=0,a2=None,b2=None):
+    # a2, b2: a second product row per step (cios_step2: acc += a*b_i + a2*b2_i + q*n), as the fused two-digit multiply uses
     S=T*L
     R=1<<(32*S)
     n0inv=(-pow(n,-1,1<<32))&M32
     def limbs(x): return [[(x>>(32*(g*L+j)))&M32 for j in range(L)] for g in range(T)]
     A=limbs(a);B=limbs(b);N=limbs(n)
+    A2=limbs(a2) if a2 is not None else None; B2=limbs(b2) if a2 is not None else None
     # per lane arrays as integers: X = list of L+2 limbs
     E=[[(init>>(32*(g*L+k)))&M32 if (k<L or g==T-1) else 0 for k in range(L+2)] for g in range(T)]
     assert init>>(32*(S+2))==0
@@ -27,7 +29,7 @@ def model_montmul(a,b,n,T,L,init=0):
         v=val(Z,0,L+2)
         for j in range(0,L,2): v+= (a[j+1]*bb)<<(32*j)
         ov=put(Z,0,L+2,v); assert ov==0,"odd overflow"
-    def step(X,Y,bvals):
+    def step(X,Y,bvals,b2v=None):
         # X,Y: per-lane arrays
         ins=[Y[g+1][0] if g<T-1 else 0 for g in range(T)]
         Zs=[]
@@ -40,7 +42,9 @@ def model_montmul(a,b,n,T,L,init=0):
                 t=A[g][j+1]*bvals[g]+val(y,j+2,2)+c
                 Z[j]=t&M32; Z[j+1]=(t>>32)&M32; c=t>>64
             Z[L]=c; Z[L+1]=0
+            if b2v is not None: mad_odd(Z,A2[g],b2v)
             mad_even(x,A[g],bvals[g])
+            if b2v is not None: mad_even(x,A2[g],b2v)
             Zs.append(Z)
         q=(X[0][0]*n0inv)&M32
         for g in range(T):
@@ -50,8 +54,12 @@ def model_montmul(a,b,n,T,L,init=0):
     for owner in range(T):
         for j in range(0,L,2):
             b0=B[owner][j]; b1=B[owner][j+1]
-            step(E,O,[b0]*T)
-            step(O,E,[b1]*T)
+            if a2 is None:
+                step(E,O,[b0]*T)
+                step(O,E,[b1]*T)
+            else:
+                step(E,O,[b0]*T,B2[owner][j])
+                step(O,E,[b1]*T,B2[owner][j+1])
     # merge
     tot=0
     res=[]
@@ -63,14 +71,15 @@ def model_montmul(a,b,n,T,L,init=0):
         tot+=val(E[g],0,L+2)<<(32*g*L)
     assert E[0] is not None
     # lane0's O[0] must be zero? (limb -1)
-    exp=((init+a*b)*pow(R,-1,n))%n
+    ab=a*b+(a2*b2 if a2 is not None else 0)
+    exp=((init+ab)*pow(R,-1,n))%n
     assert tot%n==exp,(tot,exp)
-    assert tot<2*n+(2 if init else 0)
-    assert tot*R-init-a*b>=0 and (tot*R-init-a*b)%n==0 and (tot*R-init-a*b)//n<R
+    assert tot<(3 if a2 is not None else 2)*n+(2 if init else 0)
+    assert tot*R-init-ab>=0 and (tot*R-init-ab)%n==0 and (tot*R-init-ab)//n<R
     # max top limbs
     return tot
-def model_montmul_init(a,b,n,T,L,init):
-    return model_montmul(a,b,n,T,L,init)
+def model_montmul_init(a,b,n,T,L,init,a2=None,b2=None):
+    return model_montmul(a,b,n,T,L,init,a2,b2)
 if __name__=='__main__':
   random.seed(1)
   for (T,L) in [(4,8),(8,8),(8,12),(8,16),(16,12),(16,16),(4,2),(32,2)]:

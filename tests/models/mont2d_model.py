@@ -71,10 +71,16 @@ def phase2(k, a, b, init):
 
 def mul2d(k, X, Y):
     z0, q, d = phase1(k, X[0], Y[0])
-    z1 = phase2(k, X[0], Y[1], init_from_q(k, q, d))
-    if X[1]:
-        t, _, _ = phase1(k, X[1], Y[0])
-        z1 = (z1 + t) % k.n  # add_full + one conditional subtraction
+    # phase 2 is ONE reduction of init + X0 Y1 + X1 Y0 (cios_step2: two product rows and one q n row per step)
+    init = init_from_q(k, q, d)
+    assert X[0] * Y[1] < k.W * k.n and X[1] * Y[0] < k.W * k.n
+    t = init + X[0] * Y[1] + X[1] * Y[0]
+    z1 = (t + ((t * k.nprime) % k.W) * k.n) // k.W
+    assert z1 < 3 * k.n + 2
+    for _ in range(3):
+        if z1 >= k.n:
+            z1 -= k.n
+    assert z1 < k.n
     return (z0, z1)
 
 
@@ -148,6 +154,9 @@ def part2():
             b = random.randrange(n)
             init = random.randrange(W + n) if it else W + n - 1
             model(a, b, n, T, L, init)
+            model(random.randrange(n), b, n, T, L, init, random.randrange(n), random.randrange(n))  # fused multiply: two rows
+            if it == 2:
+                model(n - 1, n - 1, n, T, L, W + n - 1, n - 1, n - 1)
         print("cios rows with initial accumulator", T, L, "ok")
 
 

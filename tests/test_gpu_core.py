@@ -133,30 +133,6 @@ def test_large_batch_all_groups(ctx):
         assert out[j] == ((m[j] * n + 1) % nn) * pow(r[j], n, nn) % nn
 
 
-def test_two_digit_kernel_matches_montgomery_kernel(monkeypatch):
-    """K1v2 (modexp2d.cu, opt-in) and K1 must produce identical ciphertexts, including bases >= n,
-    plaintext 0 / none, and a ragged tail; the switch is read by zkp_set_key."""
-    rng = random.Random(2048)
-    n = rand_odd(rng, 2048)
-    nn = n * n
-    batch = 300
-    r = [rng.getrandbits(2048) for _ in range(batch)]          # some r >= n
-    r[0], r[1], r[2] = 1, n - 1, n + 5 if n + 5 < (1 << 2048) else n - 2
-    m = [rng.getrandbits(300) for _ in range(batch)]
-    m[3] = 0
-    outs = []
-    for flag in ("0", "1"):
-        monkeypatch.setenv("ZKP_B200_ENC2D", flag)
-        with zk.native.Context(0) as c:
-            c.set_key(to_limbs(n, 64))
-            outs.append(c.paillier_enc(ints_to_limbs(m, 64), ints_to_limbs(r, 64)))
-            small = c.paillier_enc(ints_to_limbs(m[:5], 12), ints_to_limbs(r[:5], 64))
-            assert np.array_equal(small, outs[-1][:5]) if all(v < (1 << 384) for v in m[:5]) else True
-    assert np.array_equal(outs[0], outs[1])
-    for j in (0, 1, 2, 3, 17, batch - 1):
-        assert from_limbs(outs[1][j]) == ((m[j] * n + 1) % nn) * pow(r[j], n, nn) % nn
-
-
 @pytest.mark.parametrize("n_bits,nl", [(1024, 32), (2048, 64), (2047, 64), (2041, 64), (3072, 96), (4096, 128), (1536, 48), (2560, 80)])
 def test_two_digit_montgomery_kernel(monkeypatch, n_bits, nl):
     """K1m (modexp2m.cu, the default encryption kernel) against K1 (ZKP_B200_ENC=k1) and Python pow: moduli that do

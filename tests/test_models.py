@@ -2,7 +2,6 @@
 big-int arithmetic.  They were written BEFORE the kernels ran on a GPU and are kept as the specification of
   * the split-accumulator CIOS Montgomery step of mp_coop.cuh (cios_model.py),
   * the plain product on the same rows with the low half captured at lane 0 (mulwide_model.py),
-  * the two-digit base-n arithmetic with truncated Barrett and its error bounds (two_digit_model.py),
   * Montgomery multiplication modulo n^2 in two-digit base-n form, the default encryption kernel (mont2d_model.py)."""
 import os
 import runpy
@@ -12,7 +11,7 @@ import pytest
 HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "models")
 
 
-@pytest.mark.parametrize("name", ["cios_model.py", "mulwide_model.py", "two_digit_model.py", "mont2d_model.py"])
+@pytest.mark.parametrize("name", ["cios_model.py", "mulwide_model.py", "mont2d_model.py"])
 def test_model(name, capsys):
     runpy.run_path(os.path.join(HERE, name), run_name="__main__")
     out = capsys.readouterr().out

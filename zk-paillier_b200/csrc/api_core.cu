@@ -54,10 +54,6 @@ ProfScope::~ProfScope() {
 
 cudaError_t ensure_table(zkp_ctx* c, int S, int entries) {
   size_t bytes = (size_t)resident_groups(S, c->num_sms) * entries * S * sizeof(uint32_t);
-  if (c->enc2d_key && c->enc2d_enabled) {
-    size_t b2 = enc2d_scratch_limbs(c->num_sms) * sizeof(uint32_t);
-    if (b2 > bytes) bytes = b2;
-  }
   if (c->enc2m_key && c->enc2m_enabled) {
     size_t b3 = enc2m_table_limbs(c->n.S, c->num_sms) * sizeof(uint32_t);
     if (b3 > bytes) bytes = b3;
@@ -67,9 +63,6 @@ cudaError_t ensure_table(zkp_ctx* c, int S, int entries) {
 
 cudaError_t launch_enc(zkp_ctx* c, const uint32_t* bases, int base_limbs, const uint32_t* plain, int plain_limbs, uint32_t* out,
                        int jobs, const unsigned* jobs_dev) {
-  if (c->enc2d_key && c->enc2d_enabled && base_limbs == 64 && (!plain || (plain_limbs <= 64 && plain_limbs % 2 == 0)))
-    return ++c->enc2d_launches, launch_enc2d(c->n.h_mod.data(), c->nn.sched.as<uint32_t>(), c->nn.nsteps, bases, plain, plain_limbs, out, jobs,
-                        c->table.as<uint32_t>(), c->num_sms, c->stream, jobs_dev);
   if (c->enc2m_key && c->enc2m_enabled && base_limbs <= c->n.S && (!plain || plain_limbs <= c->n.S)) {
     Enc2mKey k;
     k.mod = c->n.mod.as<uint32_t>();
@@ -286,18 +279,10 @@ int zkp_set_key(zkp_ctx* c, const uint32_t* n, int n_limbs) {
   ZKP_CU(c, cudaStreamSynchronize(c->stream));
   c->n_limbs = n_limbs;
   c->paillier = true;
-  c->enc2d_key = n_limbs == 64 && enc2d_supported(n, n_limbs);
-  {
-    // K1v2 (two-digit base-n, modexp2d.cu) is bit-exact but measured 7 % slower than K1 on B200 in round 1
-    // (DESIGN.md section 3.7): opt in with ZKP_B200_ENC2D=1.
-    const char* env = getenv("ZKP_B200_ENC2D");
-    c->enc2d_enabled = env && env[0] == '1';
-  }
   {
     // K1m: two-digit Montgomery form (modexp2m.cu), the default encryption kernel
     const char* env = getenv("ZKP_B200_ENC");
-    if (env && !strcmp(env, "k1v2")) c->enc2d_enabled = true;
-    c->enc2m_enabled = !(env && (!strcmp(env, "k1") || !strcmp(env, "k1v2"))) && !c->enc2d_enabled;
+    c->enc2m_enabled = !(env && !strcmp(env, "k1"));
     c->enc2m_key = false;
     if (enc2m_supported(c->n.h_mod.data(), c->n.S)) {
       const int S = c->n.S;
@@ -313,6 +298,18 @@ int zkp_set_key(zkp_ctx* c, const uint32_t* n, int n_limbs) {
       ZKP_CU(c, cudaMemcpyAsync(c->enc2m_ops.p, ops.data(), ops.size() * 4, cudaMemcpyHostToDevice, c->stream));
       ZKP_CU(c, cudaStreamSynchronize(c->stream));
       c->enc2m_key = true;
+      double sq = 0, mu = 0;
+      for (int k = 0; k < c->enc2m_nops; ++k) {
+        sq += ops[k] >> 24;
+        mu += (ops[k] & 0xffu) != 0xffu;
+      }
+      c->enc2m_mads = ((double)S * S) * (4.0 * sq + 5.0 * mu + 1.0);
+    }
+    {
+      std::vector<uint32_t> sched = recode_exponent(n, n_limbs);
+      double mm = 2 + (kTableShared - 1) + 2;  // into Montgomery form, x^2, the odd powers, m n and the final product
+      for (size_t k = 1; k < sched.size(); ++k) mm += (sched[k] >> 8) + ((sched[k] & 0xffu) != 0xffu);
+      c->k1_mads = mm * 2.0 * c->nn.S * c->nn.S;
     }
   }
   c->rp.prove_staged = c->rp.prove_done = c->rp.verify_staged = c->rp.verify_done = false;
@@ -442,11 +439,17 @@ int zkp_modmul(zkp_ctx* c, int which_nn, const uint32_t* a, const uint32_t* b, i
   return ZKP_OK;
 }
 
-int zkp_enc_kernel_launches(const zkp_ctx* c, long long* k1m, long long* k1, long long* k1v2) {
+int zkp_enc_kernel_launches(const zkp_ctx* c, long long* k1m, long long* k1) {
   if (!c) return ZKP_E_ARG;
   if (k1m) *k1m = c->enc2m_launches;
   if (k1) *k1 = c->k1_launches;
-  if (k1v2) *k1v2 = c->enc2d_launches;
+  return ZKP_OK;
+}
+
+int zkp_enc_executed_mads(const zkp_ctx* c, double* k1m, double* k1) {
+  if (!c || !c->paillier) return ZKP_E_ARG;
+  if (k1m) *k1m = c->enc2m_key ? c->enc2m_mads : 0.0;
+  if (k1) *k1 = c->k1_mads;
   return ZKP_OK;
 }
 

@@ -117,14 +117,13 @@ struct zkp_ctx {
   zkp::KeySlot n;    // modulus n
   bool paillier = false;
   int n_limbs = 0;   // caller's width of n after zkp_set_key
-  bool enc2d_enabled = false; // ZKP_B200_ENC2D=1 selects the experimental two-digit kernel K1v2 for Paillier encryptions
-  bool enc2d_key = false;     // the current key qualifies for the two-digit kernel (|n| = 2048 exactly)
   // K1m (two-digit Montgomery, modexp2m.cu): the default Paillier encryption kernel when the key qualifies.
-  // ZKP_B200_ENC=k1 forces K1 (Montgomery modulo n^2), ZKP_B200_ENC=k1v2 (or ZKP_B200_ENC2D=1) the Barrett two-digit kernel.
+  // ZKP_B200_ENC=k1 forces K1 (Montgomery modulo n^2).
   bool enc2m_key = false, enc2m_enabled = true;
   zkp::DevBuf enc2m_consts, enc2m_ops;
   int enc2m_nops = 0;
-  long long enc2m_launches = 0, k1_launches = 0, enc2d_launches = 0;
+  long long enc2m_launches = 0, k1_launches = 0;
+  double enc2m_mads = 0, k1_mads = 0;  // IMAD.WIDE one encryption executes (zkp_enc_executed_mads)
   zkp::DevBuf table;                 // window-table scratch
   zkp::DevBuf in0, in1, in2, in3, out0;  // generic staging for the one-shot calls
   bool profiling = false;

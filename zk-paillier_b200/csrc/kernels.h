@@ -45,16 +45,6 @@ cudaError_t launch_modexp_shared(const SharedKey& key, const uint32_t* bases, in
                                  const uint32_t* plain, int plain_limbs, uint32_t* out, int out_limbs, int jobs,
                                  uint32_t* table, int num_sms, cudaStream_t st, const unsigned* jobs_dev = nullptr);
 
-// K1v2 (modexp2d.cu): Enc(m, r) = (1 + m n) r^n mod n^2 in two-digit base-n arithmetic, |n| = 2048 exactly.
-// bases: [jobs][64] (any value < 2^2048), plain: [jobs][plain_limbs] (plain_limbs <= 64) or null, out: [jobs][128].
-// sched_dev / nsteps: the sliding-window schedule of the exponent n (as K1).  scratch: enc2d_scratch_limbs() limbs.
-bool enc2d_supported(const uint32_t* n_host, int n_limbs_exact);
-int enc2d_resident_groups(int num_sms);
-size_t enc2d_scratch_limbs(int num_sms);  // window tables + cold digit slots
-cudaError_t launch_enc2d(const uint32_t* n_host, const uint32_t* sched_dev, int nsteps, const uint32_t* bases, const uint32_t* plain,
-                         int plain_limbs, uint32_t* out, int jobs, uint32_t* table, int num_sms, cudaStream_t st,
-                         const unsigned* jobs_dev = nullptr);
-
 // K1m (modexp2m.cu): the same encryption by Montgomery arithmetic in two-digit base-n form (half the limb products
 // of K1).  S = kernel width of n in limbs (32, 64, 96 or 128); n odd, 1 < n <= 2^(32 S) - 4.
 struct Enc2mKey {

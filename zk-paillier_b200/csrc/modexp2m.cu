@@ -43,7 +43,7 @@ struct Enc2mParams {
   const unsigned* jobs_dev;
 };
 
-template <int T, int L>
+template <int T, int L, int U>
 struct TwoDigit {
   using M = Mp<T, L>;
   static constexpr int S = T * L;
@@ -66,11 +66,11 @@ struct TwoDigit {
     uint32_t q[L], z0[L];
 #pragma unroll
     for (int j = 0; j < L; ++j) q[j] = 0;
-    const uint32_t delta = M::template mont_mul_x<false, true, 1>(z0, x0, x0, n, n0inv, lane, z0, 0u, q);
+    const uint32_t delta = M::template mont_mul_x<false, true, 1, U>(z0, x0, x0, n, n0inv, lane, z0, 0u, q);
     uint32_t top;
     init_from_q(q, top, q, delta, s_klo, lane);
     M::mod_double(x1, n, lane);
-    M::template mont_mul_x<true, false, 2>(x1, x0, x1, n, n0inv, lane, q, top, q);
+    M::template mont_mul_x<true, false, 2, U>(x1, x0, x1, n, n0inv, lane, q, top, q);
 #pragma unroll
     for (int j = 0; j < L; ++j) x0[j] = z0[j];
   }
@@ -78,24 +78,22 @@ struct TwoDigit {
   // (x0, x1) <- (x0, x1) (y0, y1) / W
   static __device__ __forceinline__ void mul(uint32_t (&x0)[L], uint32_t (&x1)[L], const uint32_t (&y0)[L], const uint32_t (&y1)[L],
                                              const uint32_t (&n)[L], uint32_t n0inv, const uint32_t* s_klo, int lane) {
-    uint32_t q[L], z0[L], t[L];
+    uint32_t q[L], z0[L];
 #pragma unroll
     for (int j = 0; j < L; ++j) q[j] = 0;
-    const uint32_t delta = M::template mont_mul_x<false, true, 1>(z0, x0, y0, n, n0inv, lane, z0, 0u, q);
+    const uint32_t delta = M::template mont_mul_x<false, true, 1, U>(z0, x0, y0, n, n0inv, lane, z0, 0u, q);
     uint32_t top;
     init_from_q(q, top, q, delta, s_klo, lane);
-    M::mont_mul(t, x1, y0, n, n0inv, lane);
-    M::template mont_mul_x<true, false, 2>(x1, x0, y1, n, n0inv, lane, q, top, q);
-    M::add_mod(x1, t, n, lane);
+    M::template mont_mul2_x<U>(x1, x0, y1, x1, y0, n, n0inv, lane, q, top);  // X0 Y1 + X1 Y0 under one reduction
 #pragma unroll
     for (int j = 0; j < L; ++j) x0[j] = z0[j];
   }
 };
 
-template <int T, int L>
-__global__ void __launch_bounds__(kCtaThreads, 4) enc2m_kernel(const Enc2mParams p) {
+template <int T, int L, int U, int MINB>
+__global__ void __launch_bounds__(kCtaThreads, MINB) enc2m_kernel(const Enc2mParams p) {
   using M = Mp<T, L>;
-  using TD = TwoDigit<T, L>;
+  using TD = TwoDigit<T, L, U>;
   constexpr int S = T * L;
   constexpr int G = kCtaThreads / T;
   extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -314,12 +312,29 @@ std::vector<uint32_t> enc2m_ops(const uint32_t* sched, int nsteps) {
   return ops;
 }
 
+constexpr int kCtasPerSm2m = 4;  // measured on B200: 5 and 6 resident CTAs (96 / 80 registers) are 2-4 % slower, unrolling the owner loop gains nothing
+
 int enc2m_resident_groups(int S, int num_sms) {
   int T, L;
   if (!pick_shape(S, T, L)) return 0;
-  return num_sms * 4 * (kCtaThreads / T);
+  return num_sms * kCtasPerSm2m * (kCtaThreads / T);
 }
 size_t enc2m_table_limbs(int S, int num_sms) { return (size_t)enc2m_resident_groups(S, num_sms) * kSlots2m * 2 * S; }
+
+template <int T, int L>
+static cudaError_t launch_one(const Enc2mParams& p, int num_sms, cudaStream_t st) {
+  constexpr int G = kCtaThreads / T;
+  constexpr int S = T * L;
+  constexpr int U = 1, MINB = kCtasPerSm2m;
+  size_t smem = 16 + (size_t)(p.ops_pad + S) * 4 + (size_t)G * (p.base_limbs + p.plain_limbs + 2 * S) * 4;
+  int grid = num_sms * MINB;
+  int npass = (p.jobs + G - 1) / G;
+  if (grid > npass) grid = npass;
+  cudaError_t e = cudaFuncSetAttribute(enc2m_kernel<T, L, U, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  enc2m_kernel<T, L, U, MINB><<<grid, kCtaThreads, smem, st>>>(p);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_enc2m(const Enc2mKey& key, const uint32_t* bases, int base_limbs, const uint32_t* plain, int plain_limbs,
                          uint32_t* out, int out_limbs, int jobs, uint32_t* table, int num_sms, cudaStream_t st,
@@ -340,27 +355,13 @@ cudaError_t launch_enc2m(const Enc2mKey& key, const uint32_t* bases, int base_li
   p.jobs = jobs;
   p.jobs_dev = jobs_dev;
   p.ops_pad = (key.nops + 3) & ~3;
-#define CALL(T_, L_)                                                                                                   \
-  {                                                                                                                    \
-    constexpr int G = kCtaThreads / T_;                                                                                \
-    constexpr int S_ = T_ * L_;                                                                                        \
-    size_t smem = 16 + (size_t)(p.ops_pad + S_) * 4 + (size_t)G * (p.base_limbs + p.plain_limbs + 2 * S_) * 4;         \
-    int grid = num_sms * 4;                                                                                            \
-    int npass = (jobs + G - 1) / G;                                                                                    \
-    if (grid > npass) grid = npass;                                                                                    \
-    cudaError_t e = cudaFuncSetAttribute(enc2m_kernel<T_, L_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    if (e != cudaSuccess) return e;                                                                                    \
-    enc2m_kernel<T_, L_><<<grid, kCtaThreads, smem, st>>>(p);                                                          \
-  }
   switch (key.S) {
-    case 32: CALL(4, 8) break;
-    case 64: CALL(8, 8) break;
-    case 96: CALL(8, 12) break;
-    case 128: CALL(16, 8) break;
+    case 32: return launch_one<4, 8>(p, num_sms, st);
+    case 64: return launch_one<8, 8>(p, num_sms, st);
+    case 96: return launch_one<8, 12>(p, num_sms, st);
+    case 128: return launch_one<16, 8>(p, num_sms, st);
     default: return cudaErrorInvalidValue;
   }
-#undef CALL
-  return cudaGetLastError();
 }
 
 }  // namespace zkp

@@ -280,35 +280,35 @@ struct Mp {
     finish(r, E, n, lane);
   }
 
-  // finish() for a value < NSUB*n + 2 (NSUB = 1: the usual < 2n): NSUB conditional subtractions.  Returns 1 iff the
-  // first subtraction was taken (uniform across the group).  Needs n <= 2^(32 S) - 4 when NSUB = 2.
+  // finish() for a value < NSUB*n + 2 (NSUB = 1: the usual < 2n): NSUB conditional subtractions, the overflow above
+  // 2^(32 S) tracked across them.  Returns 1 iff the first subtraction was taken (uniform across the group).
   template <int NSUB>
   static __device__ __forceinline__ uint32_t finish_x(uint32_t (&r)[L], uint32_t (&u)[L + 2], const uint32_t (&n)[L], int lane) {
     const int g = lane & (T - 1);
     uint32_t ov = __shfl_up_sync(ZKP_FULL, u[L], 1, T);
     if (g == 0) ov = 0;
-    uint32_t x[L];
 #pragma unroll
-    for (int j = 0; j < L; ++j) x[j] = u[j];
-    add_cc(x[0], ov);
+    for (int j = 0; j < L; ++j) r[j] = u[j];
+    add_cc(r[0], ov);
 #pragma unroll
-    for (int j = 1; j < L; ++j) addc_cc(x[j], 0);
+    for (int j = 1; j < L; ++j) addc_cc(r[j], 0);
     uint32_t co = addc_out();
     uint32_t topc;
-    uint32_t cin = resolve(co != 0, all_ones(x), lane, topc);
-    add_small(x, cin);
+    uint32_t cin = resolve(co != 0, all_ones(r), lane, topc);
+    add_small(r, cin);
     uint32_t hi = __shfl_sync(ZKP_FULL, u[L], T - 1, T) + topc;
-    uint32_t d[L];
-    uint32_t borrow = sub_full(d, x, n, lane);
-    const bool take = (hi != 0) || (borrow == 0);
+    uint32_t first = 0;
 #pragma unroll
-    for (int j = 0; j < L; ++j) r[j] = take ? d[j] : x[j];
-    if (NSUB == 2) {
-      borrow = sub_full(d, r, n, lane);
+    for (int s = 0; s < NSUB; ++s) {
+      uint32_t d[L];
+      const uint32_t borrow = sub_full(d, r, n, lane);
+      const bool take = (hi != 0) || (borrow == 0);
 #pragma unroll
-      for (int j = 0; j < L; ++j) r[j] = borrow ? r[j] : d[j];
+      for (int j = 0; j < L; ++j) r[j] = take ? d[j] : r[j];
+      hi = take ? hi - borrow : hi;
+      if (s == 0) first = take ? 1u : 0u;
     }
-    return take ? 1u : 0u;
+    return first;
   }
 
   // Montgomery multiplication with the two hooks the two-digit base-n form needs (modexp2m.cu):
@@ -317,7 +317,7 @@ struct Mp {
   //   CAPQ : the quotient digits q_i of the reduction are kept, digit i in the lane that owns limb i, so that
   //          a b = r' 2^(32 S) - q n holds exactly for the unreduced r' (r = r' - n iff the return value is 1).
   // Only a b < 2^(32 S) n is needed (a may be any S-limb value when b < n).  r may alias a or b.
-  template <bool INIT, bool CAPQ, int NSUB>
+  template <bool INIT, bool CAPQ, int NSUB, int U = 1>
   static __device__ __forceinline__ uint32_t mont_mul_x(uint32_t (&r)[L], const uint32_t (&a)[L], const uint32_t (&b)[L],
                                                         const uint32_t (&n)[L], uint32_t n0inv, int lane,
                                                         const uint32_t (&init)[L], uint32_t init_top, uint32_t (&qcap)[L]) {
@@ -330,7 +330,7 @@ struct Mp {
       for (int j = 0; j < L; ++j) E[j] = init[j];
       E[L] = (g == T - 1) ? init_top : 0u;
     }
-#pragma unroll 1
+#pragma unroll U
     for (int owner = 0; owner < T; ++owner) {
       const bool mine = CAPQ && (g == owner);
 #pragma unroll
@@ -355,6 +355,69 @@ struct Mp {
     for (int j = 1; j <= L; ++j) addc_cc(E[j], O[j + 1]);
     addc(E[L + 1], 0);
     return finish_x<NSUB>(r, E, n, lane);
+  }
+
+  // One step of the two-product form  acc = (acc + a1*b1 + a2*b2 + q*n) / 2^32  (the second digit of a two-digit
+  // multiplication needs X0 Y1 + X1 Y0 under ONE reduction).  Same array roles as cios_step.
+  static __device__ __forceinline__ void cios_step2(uint32_t (&X)[L + 2], uint32_t (&Y)[L + 2], const uint32_t (&a1)[L],
+                                                    const uint32_t (&a2)[L], const uint32_t (&n)[L], uint32_t b1, uint32_t b2,
+                                                    uint32_t n0inv, int g) {
+    uint32_t in = __shfl_down_sync(ZKP_FULL, Y[0], 1, T);
+    if (g == T - 1) in = 0;
+    add_cc(Y[L], in);
+    addc(Y[L + 1], 0);
+    uint32_t Z[L + 2];
+    add_cc(X[0], Y[1]);
+#pragma unroll
+    for (int j = 0; j < L; j += 2) madc_wide3_cc(Z[j], Z[j + 1], a1[j + 1], b1, Y[j + 2], Y[j + 3]);
+    Z[L] = addc_out();
+    Z[L + 1] = 0;
+    mad_odd(Z, a2, b2);
+    mad_even(X, a1, b1);
+    mad_even(X, a2, b2);
+    const uint32_t q = __shfl_sync(ZKP_FULL, X[0], 0, T) * n0inv;
+    mad_even(X, n, q);
+    mad_odd(Z, n, q);
+#pragma unroll
+    for (int j = 0; j < L + 2; ++j) Y[j] = Z[j];
+  }
+
+  // r = (init + init_top 2^(32 S) + a1 b1 + a2 b2) / 2^(32 S) mod n   (each product < 2^(32 S) n, init < 2^(32 S) + n:
+  // the unreduced value is < 3n + 2).  r may alias any operand.
+  template <int U = 1>
+  static __device__ __forceinline__ void mont_mul2_x(uint32_t (&r)[L], const uint32_t (&a1)[L], const uint32_t (&b1)[L],
+                                                     const uint32_t (&a2)[L], const uint32_t (&b2)[L], const uint32_t (&n)[L],
+                                                     uint32_t n0inv, int lane, const uint32_t (&init)[L], uint32_t init_top) {
+    const int g = lane & (T - 1);
+    uint32_t E[L + 2], O[L + 2];
+#pragma unroll
+    for (int j = 0; j < L; ++j) {
+      E[j] = init[j];
+      O[j] = 0;
+    }
+    E[L] = (g == T - 1) ? init_top : 0u;
+    E[L + 1] = O[L] = O[L + 1] = 0;
+#pragma unroll U
+    for (int owner = 0; owner < T; ++owner) {
+#pragma unroll
+      for (int j = 0; j < L; j += 2) {
+        const uint32_t p0 = __shfl_sync(ZKP_FULL, b1[j], owner, T);
+        const uint32_t s0 = __shfl_sync(ZKP_FULL, b2[j], owner, T);
+        const uint32_t p1 = __shfl_sync(ZKP_FULL, b1[j + 1], owner, T);
+        const uint32_t s1 = __shfl_sync(ZKP_FULL, b2[j + 1], owner, T);
+        cios_step2(E, O, a1, a2, n, p0, s0, n0inv, g);
+        cios_step2(O, E, a1, a2, n, p1, s1, n0inv, g);
+      }
+    }
+    uint32_t in = __shfl_down_sync(ZKP_FULL, O[0], 1, T);
+    if (g == T - 1) in = 0;
+    add_cc(O[L], in);
+    addc(O[L + 1], 0);
+    add_cc(E[0], O[1]);
+#pragma unroll
+    for (int j = 1; j <= L; ++j) addc_cc(E[j], O[j + 1]);
+    addc(E[L + 1], 0);
+    finish_x<3>(r, E, n, lane);
   }
 
   // x = (x + y) mod n for x, y < n

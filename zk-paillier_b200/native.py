@@ -68,7 +68,8 @@ SIGNATURES = {
     "zkp_verlin_prove": (C.c_int, [C.c_void_p, C.c_int, C.c_int] + [_u32p] * 16),
     "zkp_verlin_verify": (C.c_int, [C.c_void_p, C.c_int, C.c_int] + [_u32p] * 8 + [_u8p]),
     "zkp_imad_peak": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double)]),
-    "zkp_enc_kernel_launches": (C.c_int, [C.c_void_p] + [C.POINTER(C.c_longlong)] * 3),
+    "zkp_enc_kernel_launches": (C.c_int, [C.c_void_p] + [C.POINTER(C.c_longlong)] * 2),
+    "zkp_enc_executed_mads": (C.c_int, [C.c_void_p] + [C.POINTER(C.c_double)] * 2),
 }
 
 _lib = None
@@ -196,10 +197,16 @@ class Context:
         return v.value
 
     def enc_kernel_launches(self):
-        """launch counts of the encryption kernels on this context: {"k1m", "k1", "k1v2"}"""
-        a, b, d = C.c_longlong(), C.c_longlong(), C.c_longlong()
-        self._ck(self._lib.zkp_enc_kernel_launches(self._h, C.byref(a), C.byref(b), C.byref(d)))
-        return {"k1m": a.value, "k1": b.value, "k1v2": d.value}
+        """launch counts of the encryption kernels on this context: {"k1m", "k1"}"""
+        a, b = C.c_longlong(), C.c_longlong()
+        self._ck(self._lib.zkp_enc_kernel_launches(self._h, C.byref(a), C.byref(b)))
+        return {"k1m": a.value, "k1": b.value}
+
+    def enc_executed_mads(self):
+        """IMAD.WIDE one encryption executes under the current key: {"k1m", "k1"} (k1m = 0 when the key does not qualify)"""
+        a, b = C.c_double(), C.c_double()
+        self._ck(self._lib.zkp_enc_executed_mads(self._h, C.byref(a), C.byref(b)))
+        return {"k1m": a.value, "k1": b.value}
 
     # -- key
     def set_key(self, n_limbs_arr):
