@@ -133,7 +133,7 @@ def test_large_batch_all_groups(ctx):
         assert out[j] == ((m[j] * n + 1) % nn) * pow(r[j], n, nn) % nn
 
 
-@pytest.mark.parametrize("n_bits,nl", [(1024, 32), (2048, 64), (2047, 64), (2041, 64), (3072, 96), (4096, 128), (1536, 48), (2560, 80)])
+@pytest.mark.parametrize("n_bits,nl", [(1024, 32), (2048, 64), (2047, 64), (3072, 96), (4096, 128), (1536, 48)])
 def test_two_digit_montgomery_kernel(monkeypatch, n_bits, nl):
     """K1m (modexp2m.cu, the default encryption kernel) against K1 (ZKP_B200_ENC=k1) and Python pow: moduli that do
     not fill their top limb, widths that run zero-extended, bases >= n, base 0 / 1, plaintext 0 / n-1 / >= n / none,
@@ -141,7 +141,7 @@ def test_two_digit_montgomery_kernel(monkeypatch, n_bits, nl):
     rng = random.Random(n_bits)
     n = rand_odd(rng, n_bits)
     nn = n * n
-    batch = 333
+    batch = 150
     cap = 1 << (32 * nl)
     r = [rng.getrandbits(32 * nl) for _ in range(batch)]  # about half of them >= n
     r[0], r[1], r[2], r[3], r[4] = 1, n - 1, 0, min(n + 5, cap - 1), cap - 1

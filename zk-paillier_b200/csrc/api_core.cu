@@ -56,21 +56,40 @@ cudaError_t ensure_table(zkp_ctx* c, int S, int entries) {
   size_t bytes = (size_t)resident_groups(S, c->num_sms) * entries * S * sizeof(uint32_t);
   if (c->enc2m_key && c->enc2m_enabled) {
     size_t b3 = enc2m_table_limbs(c->n.S, c->num_sms) * sizeof(uint32_t);
+    if (entries == kTableVar) b3 = var2m_table_limbs(c->n.S, c->num_sms) * sizeof(uint32_t);
     if (b3 > bytes) bytes = b3;
   }
   return c->table.ensure(bytes);
 }
 
+static Enc2mKey enc2m_view(const zkp_ctx* c) {
+  Enc2mKey k;
+  k.mod = c->n.mod.as<uint32_t>();
+  k.consts = c->enc2m_consts.as<uint32_t>();
+  k.ops = c->enc2m_ops.as<uint32_t>();
+  k.nops = c->enc2m_nops;
+  k.n0inv = c->n.n0inv;
+  k.S = c->n.S;
+  return k;
+}
+
+cudaError_t launch_pow_nn(zkp_ctx* c, const uint32_t* base, int base_limbs, const uint32_t* exp, int exp_limbs, int exp_bits,
+                          int exp_per, uint32_t* out, int jobs) {
+  if (c->enc2m_key && c->enc2m_enabled && base_limbs <= 2 * c->n.S) {
+    ++c->enc2m_launches;
+    return launch_modexp2m_var(enc2m_view(c), base, base_limbs, exp, exp_limbs, exp_bits, exp_per, out, c->nn.limbs, jobs,
+                               c->table.as<uint32_t>(), c->num_sms, c->stream);
+  }
+  ++c->k1_launches;
+  return launch_modexp_var(base, c->nn.mod.as<uint32_t>(), c->nn.limbs, c->nn.r2.as<uint32_t>(), c->nn.n0.as<uint32_t>(), exp,
+                           exp_limbs, exp_bits, exp_per, 0x7fffffff, out, jobs, c->nn.S, c->table.as<uint32_t>(), c->num_sms,
+                           c->stream, base_limbs);
+}
+
 cudaError_t launch_enc(zkp_ctx* c, const uint32_t* bases, int base_limbs, const uint32_t* plain, int plain_limbs, uint32_t* out,
                        int jobs, const unsigned* jobs_dev) {
-  if (c->enc2m_key && c->enc2m_enabled && base_limbs <= c->n.S && (!plain || plain_limbs <= c->n.S)) {
-    Enc2mKey k;
-    k.mod = c->n.mod.as<uint32_t>();
-    k.consts = c->enc2m_consts.as<uint32_t>();
-    k.ops = c->enc2m_ops.as<uint32_t>();
-    k.nops = c->enc2m_nops;
-    k.n0inv = c->n.n0inv;
-    k.S = c->n.S;
+  if (c->enc2m_key && c->enc2m_enabled && base_limbs <= 2 * c->n.S && (!plain || plain_limbs <= 2 * c->n.S)) {
+    const Enc2mKey k = enc2m_view(c);
     ++c->enc2m_launches;
     return launch_enc2m(k, bases, base_limbs, plain, plain_limbs, out, c->nn.limbs, jobs, c->table.as<uint32_t>(), c->num_sms,
                         c->stream, jobs_dev);
@@ -286,7 +305,7 @@ int zkp_set_key(zkp_ctx* c, const uint32_t* n, int n_limbs) {
     c->enc2m_key = false;
     if (enc2m_supported(c->n.h_mod.data(), c->n.S)) {
       const int S = c->n.S;
-      std::vector<uint32_t> consts((size_t)3 * S);
+      std::vector<uint32_t> consts((size_t)5 * S);
       enc2m_host_constants(c->n.h_mod.data(), S, consts.data());
       std::vector<uint32_t> sched = recode_exponent(n, n_limbs);
       std::vector<uint32_t> ops = enc2m_ops(sched.data(), (int)sched.size());

@@ -76,8 +76,7 @@ struct Sig {
     uint32_t* out = rows(nnl);
     if (bad) return out;
     ProfScope ps(c, KID_MODEXP_VAR, batch);
-    ck(launch_modexp_var(base, c->nn.mod.as<uint32_t>(), nnl, c->nn.r2.as<uint32_t>(), c->nn.n0.as<uint32_t>(), exp, exp_limbs,
-                         32 * exp_limbs, 1, 0x7fffffff, out, batch, c->nn.S, c->table.as<uint32_t>(), c->num_sms, st, base_limbs));
+    ck(launch_pow_nn(c, base, base_limbs, exp, exp_limbs, 32 * exp_limbs, 1, out, batch));
     return out;
   }
   // BigInt::mod_mul(a, b, nn) / Paillier::add

@@ -160,6 +160,12 @@ cudaError_t ensure_table(zkp_ctx* c, int S, int entries);
 cudaError_t launch_enc(zkp_ctx* c, const uint32_t* bases, int base_limbs, const uint32_t* plain, int plain_limbs, uint32_t* out,
                        int jobs, const unsigned* jobs_dev = nullptr);
 
+// BigInt::mod_pow(base, exp, nn) / Paillier::mul for `jobs` rows with per-row exponents (row j uses exps[j / exp_per]) under
+// the current key: K2m (two-digit Montgomery form) when the key qualifies, else K2 on the modulus n^2.
+// The table scratch must have been sized with ensure_table(c, c->nn.S, kTableVar).
+cudaError_t launch_pow_nn(zkp_ctx* c, const uint32_t* base, int base_limbs, const uint32_t* exp, int exp_limbs, int exp_bits,
+                          int exp_per, uint32_t* out, int jobs);
+
 // Montgomery/key helpers (api_core.cu)
 int setup_slot(zkp_ctx* c, KeySlot& slot, const uint32_t* mod, int limbs, const uint32_t* exp, int exp_limbs);
 

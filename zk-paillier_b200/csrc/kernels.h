@@ -49,22 +49,30 @@ cudaError_t launch_modexp_shared(const SharedKey& key, const uint32_t* bases, in
 // of K1).  S = kernel width of n in limbs (32, 64, 96 or 128); n odd, 1 < n <= 2^(32 S) - 4.
 struct Enc2mKey {
   const uint32_t* mod;     // n, S limbs
-  const uint32_t* consts;  // K_lo = -W mod n | (W^2 mod n^2) mod n | (W^2 mod n^2) div n, S limbs each (W = 2^(32 S))
+  const uint32_t* consts;  // K_lo = -W mod n | pair(W^2 mod n^2) | pair(W mod n^2): 5 S limbs (W = 2^(32 S); pair(v) = v mod n | v div n)
   const uint32_t* ops;     // op list (enc2m_ops)
   int nops;
   uint32_t n0inv;          // -n^{-1} mod 2^32
   int S;
 };
 bool enc2m_supported(const uint32_t* n_host, int S);
-void enc2m_host_constants(const uint32_t* n_host, int S, uint32_t* consts /* [3 S] */);
+void enc2m_host_constants(const uint32_t* n_host, int S, uint32_t* consts /* [5 S] */);
 std::vector<uint32_t> enc2m_ops(const uint32_t* sched, int nsteps);  // from the K1 schedule of the exponent n
 int enc2m_resident_groups(int S, int num_sms);
 size_t enc2m_table_limbs(int S, int num_sms);
-// bases: [jobs][base_limbs] (any value below 2^(32 base_limbs), base_limbs <= S), plain: [jobs][plain_limbs] or null
-// (plain_limbs <= S), out: [jobs][out_limbs] (out_limbs <= 2 S); base_limbs / plain_limbs multiples of 4.
+// bases: [jobs][base_limbs] (any value below 2^(32 base_limbs), base_limbs <= 2 S), plain: [jobs][plain_limbs] or null
+// (plain_limbs <= 2 S), out: [jobs][out_limbs] (out_limbs <= 2 S); base_limbs / plain_limbs multiples of 4.
 cudaError_t launch_enc2m(const Enc2mKey& key, const uint32_t* bases, int base_limbs, const uint32_t* plain, int plain_limbs,
                          uint32_t* out, int out_limbs, int jobs, uint32_t* table, int num_sms, cudaStream_t st,
                          const unsigned* jobs_dev = nullptr);
+
+// K2m (modexp2m.cu): out[j] = bases[j]^exps[j / exp_per] mod n^2 in the same form, fixed 5-bit window.
+// bases: [jobs][base_limbs] (base_limbs <= 2 S, even), exps: [ceil(jobs/exp_per)][exp_limbs], out: [jobs][out_limbs].
+// table: var2m_table_limbs() limbs of scratch.  key.ops / key.nops are not used.
+size_t var2m_table_limbs(int S, int num_sms);
+cudaError_t launch_modexp2m_var(const Enc2mKey& key, const uint32_t* bases, int base_limbs, const uint32_t* exps, int exp_limbs,
+                                int exp_bits, int exp_per, uint32_t* out, int out_limbs, int jobs, uint32_t* table, int num_sms,
+                                cudaStream_t st);
 
 // Montgomery setup for per-instance moduli: r2[i] = R^2 mod mods[i] ([count][S]), n0inv[i].
 // mods: [count][mod_limbs].

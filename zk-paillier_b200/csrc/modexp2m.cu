@@ -40,6 +40,7 @@ struct Enc2mParams {
   uint32_t* out;
   uint32_t* table;
   int base_limbs, plain_limbs, out_limbs, jobs, ops_pad;
+  uint32_t zero;
   const unsigned* jobs_dev;
 };
 
@@ -62,31 +63,132 @@ struct TwoDigit {
 
   // (x0, x1) <- (x0, x1)^2 / W
   static __device__ __forceinline__ void sqr(uint32_t (&x0)[L], uint32_t (&x1)[L], const uint32_t (&n)[L], uint32_t n0inv,
-                                             const uint32_t* s_klo, int lane) {
+                                             const uint32_t* s_klo, int lane, uint32_t zr) {
     uint32_t q[L], z0[L];
 #pragma unroll
     for (int j = 0; j < L; ++j) q[j] = 0;
-    const uint32_t delta = M::template mont_mul_x<false, true, 1, U>(z0, x0, x0, n, n0inv, lane, z0, 0u, q);
+    const uint32_t delta = M::template mont_mul_x<false, true, 1, U>(z0, x0, x0, n, n0inv, lane, z0, 0u, q, zr);
     uint32_t top;
     init_from_q(q, top, q, delta, s_klo, lane);
     M::mod_double(x1, n, lane);
-    M::template mont_mul_x<true, false, 2, U>(x1, x0, x1, n, n0inv, lane, q, top, q);
+    M::template mont_mul_x<true, false, 2, U>(x1, x0, x1, n, n0inv, lane, q, top, q, zr);
 #pragma unroll
     for (int j = 0; j < L; ++j) x0[j] = z0[j];
   }
 
   // (x0, x1) <- (x0, x1) (y0, y1) / W
   static __device__ __forceinline__ void mul(uint32_t (&x0)[L], uint32_t (&x1)[L], const uint32_t (&y0)[L], const uint32_t (&y1)[L],
-                                             const uint32_t (&n)[L], uint32_t n0inv, const uint32_t* s_klo, int lane) {
+                                             const uint32_t (&n)[L], uint32_t n0inv, const uint32_t* s_klo, int lane, uint32_t zr) {
     uint32_t q[L], z0[L];
 #pragma unroll
     for (int j = 0; j < L; ++j) q[j] = 0;
-    const uint32_t delta = M::template mont_mul_x<false, true, 1, U>(z0, x0, y0, n, n0inv, lane, z0, 0u, q);
+    const uint32_t delta = M::template mont_mul_x<false, true, 1, U>(z0, x0, y0, n, n0inv, lane, z0, 0u, q, zr);
     uint32_t top;
     init_from_q(q, top, q, delta, s_klo, lane);
-    M::template mont_mul2_x<U>(x1, x0, y1, x1, y0, n, n0inv, lane, q, top);  // X0 Y1 + X1 Y0 under one reduction
+    M::template mont_mul2_x<U>(x1, x0, y1, x1, y0, n, n0inv, lane, q, top, zr);  // X0 Y1 + X1 Y0 under one reduction
 #pragma unroll
     for (int j = 0; j < L; ++j) x0[j] = z0[j];
+  }
+
+  // x += c (c in {0,1}, uniform across the group) over the whole digit
+  static __device__ __forceinline__ void add_bit(uint32_t (&x)[L], uint32_t c, int lane) {
+    const int g = lane & (T - 1);
+    add_cc(x[0], g == 0 ? c : 0u);
+#pragma unroll
+    for (int j = 1; j < L; ++j) addc_cc(x[j], 0);
+    uint32_t co = addc_out();
+    uint32_t top;
+    uint32_t cin = M::resolve(co != 0, M::all_ones(x), lane, top);
+    M::add_small(x, cin);
+  }
+
+  // (x0, x1) <- (x0, x1) + (y0, y1) mod n^2, all four digits below n
+  static __device__ __forceinline__ void pair_add(uint32_t (&x0)[L], uint32_t (&x1)[L], const uint32_t (&y0)[L], const uint32_t (&y1)[L],
+                                                  const uint32_t (&n)[L], int lane) {
+    const uint32_t ovf = M::add_full(x0, y0, lane);
+    uint32_t d[L];
+    const uint32_t borrow = M::sub_full(d, x0, n, lane);
+    const bool take = (ovf != 0u) || (borrow == 0u);
+#pragma unroll
+    for (int j = 0; j < L; ++j) x0[j] = take ? d[j] : x0[j];
+    // digit 1: x1 + y1 + take < 2n.  (y1 + take) may reach n; the sum still needs one subtraction at most.
+    const uint32_t ovf1 = M::add_full(x1, y1, lane);
+    add_bit(x1, take ? 1u : 0u, lane);  // cannot overflow past ovf1: x1 + y1 + 1 <= 2n - 1 < 2^(32 S + 1)
+    const uint32_t borrow1 = M::sub_full(d, x1, n, lane);
+    const bool take1 = (ovf1 != 0u) || (borrow1 == 0u);
+#pragma unroll
+    for (int j = 0; j < L; ++j) x1[j] = take1 ? d[j] : x1[j];
+  }
+
+  // The value of a little-endian row of `limbs` <= 2S limbs as a digit pair.  limbs <= S: the pair (row, 0), with
+  // digit 0 possibly above n (fine as the first operand of mul).  Wider rows z = Zlo + Zhi W:
+  //   mul((Zlo, 0), pair(W)) + mul((Zhi, 0), pair(W^2)) = Zlo + Zhi W   (mod n^2), both digits reduced.
+  // consts: K_lo | pair(W^2 mod n^2) | pair(W mod n^2).
+  static __device__ __forceinline__ void entry_pair(uint32_t (&x0)[L], uint32_t (&x1)[L], const uint32_t* row, int limbs,
+                                                    const uint32_t* consts, const uint32_t (&n)[L], uint32_t n0inv,
+                                                    const uint32_t* s_klo, int lane, uint32_t zr) {
+    const int g = lane & (T - 1);
+    if (limbs <= S) {
+      M::load_ext(x0, row, limbs, g);
+#pragma unroll
+      for (int j = 0; j < L; ++j) x1[j] = 0;
+      return;
+    }
+    uint32_t h0[L], h1[L], y0[L], y1[L];
+#pragma unroll 1
+    for (int half = 1; half >= 0; --half) {
+      const uint32_t* cp = consts + S + (half ? 0 : 2 * S) + g * L;
+      M::load(y0, cp);
+      M::load(y1, cp + S);
+      if (half) M::load_ext(x0, row + S, limbs - S, g);
+      else M::load_ext(x0, row, S, g);
+#pragma unroll
+      for (int j = 0; j < L; ++j) x1[j] = 0;
+      mul(x0, x1, y0, y1, n, n0inv, s_klo, lane, zr);
+      if (half) {
+#pragma unroll
+        for (int j = 0; j < L; ++j) {
+          h0[j] = x0[j];
+          h1[j] = x1[j];
+        }
+      }
+    }
+    pair_add(x0, x1, h0, h1, n, lane);
+  }
+
+  // out row = X0 + X1 n (< n^2): plain product rows with X0 as the initial accumulator; the limb leaving lane 0
+  // at row i is limb i of the result and goes to the lane that owns it
+  static __device__ __forceinline__ void assemble_store(uint32_t* o, int out_limbs, bool valid, const uint32_t (&x0)[L],
+                                                        const uint32_t (&x1)[L], const uint32_t (&n)[L], int lane) {
+    const int g = lane & (T - 1);
+    uint32_t E[L + 2], O[L + 2], lo[L], hi[L];
+#pragma unroll
+    for (int j = 0; j < L; ++j) {
+      E[j] = x0[j];
+      O[j] = 0;
+      lo[j] = 0;
+    }
+    E[L] = E[L + 1] = O[L] = O[L + 1] = 0;
+#pragma unroll 1
+    for (int owner = 0; owner < T; ++owner) {
+      const bool mine = g == owner;
+#pragma unroll
+      for (int j = 0; j < L; j += 2) {
+        const uint32_t b0 = __shfl_sync(ZKP_FULL, n[j], owner, T);
+        const uint32_t b1 = __shfl_sync(ZKP_FULL, n[j + 1], owner, T);
+        M::mul_step(E, O, x1, b0, g);
+        const uint32_t v0 = __shfl_sync(ZKP_FULL, E[0], 0, T);
+        M::mul_step(O, E, x1, b1, g);
+        const uint32_t v1 = __shfl_sync(ZKP_FULL, O[0], 0, T);
+        lo[j] = mine ? v0 : lo[j];
+        lo[j + 1] = mine ? v1 : lo[j + 1];
+      }
+    }
+    M::mul_finish(hi, E, O, lane);
+    if (valid) {
+      M::store_ext(o, lo, out_limbs, g);
+      if (out_limbs > S) M::store_ext(o + S, hi, out_limbs - S, g);
+    }
   }
 };
 
@@ -108,6 +210,7 @@ __global__ void __launch_bounds__(kCtaThreads, MINB) enc2m_kernel(const Enc2mPar
   const int g = lane & (T - 1);
   const int grp = threadIdx.x / T;
   const uint32_t n0inv = p.key.n0inv;
+  const uint32_t zr = p.zero;  // always 0, but opaque to ptxas (see cios_step)
   uint32_t n[L];
   M::load(n, p.key.mod + g * L);
 
@@ -146,7 +249,18 @@ __global__ void __launch_bounds__(kCtaThreads, MINB) enc2m_kernel(const Enc2mPar
 
     // the last multiplier: the pair (1, m) = 1 + m n in plain form (it also takes the result out of Montgomery form)
     uint32_t x0[L], x1[L], y0[L], y1[L];
-    if (p.plain) {
+    if (p.plain && p.plain_limbs > S) {
+      // m wider than n (CiphertextProof's unreduced z1): 1 + m n = 1 + (m mod n) n, and
+      // m mod n = Mlo W / W + Mhi W^2 / W  (two Montgomery products by W mod n and W^2 mod n)
+      const uint32_t* mrow = s_plain + src * p.plain_limbs;
+      M::load_ext(x1, mrow, S, g);
+      M::load(y0, p.key.consts + 3 * S + g * L);
+      M::mont_mul(x1, x1, y0, n, n0inv, lane);
+      M::load_ext(y1, mrow + S, p.plain_limbs - S, g);
+      M::load(y0, p.key.consts + S + g * L);
+      M::mont_mul(y1, y1, y0, n, n0inv, lane);
+      M::add_mod(x1, y1, n, lane);
+    } else if (p.plain) {
       M::load_ext(x1, s_plain + src * p.plain_limbs, p.plain_limbs, g);
     } else {
 #pragma unroll
@@ -157,9 +271,8 @@ __global__ void __launch_bounds__(kCtaThreads, MINB) enc2m_kernel(const Enc2mPar
     M::store(pair + S + g * L, x1);
     __syncwarp();
 
-    M::load_ext(x0, s_bases + src * p.base_limbs, p.base_limbs, g);  // the pair (r, 0); r may exceed n
-#pragma unroll
-    for (int j = 0; j < L; ++j) x1[j] = 0;
+    // the pair (r, 0) (r may exceed n), or the reduced pair of a base wider than n
+    TD::entry_pair(x0, x1, s_bases + src * p.base_limbs, p.base_limbs, p.key.consts, n, n0inv, s_klo, lane, zr);
 #pragma unroll 1
     for (int k = 0; k < p.key.nops; ++k) {
       const uint32_t op = s_ops[k];
@@ -171,8 +284,8 @@ __global__ void __launch_bounds__(kCtaThreads, MINB) enc2m_kernel(const Enc2mPar
         M::load(y1, ysrc + S);
       }
 #pragma unroll 1
-      for (int q = 0; q < nsq; ++q) TD::sqr(x0, x1, n, n0inv, s_klo, lane);
-      if (yk != OP_NONE) TD::mul(x0, x1, y0, y1, n, n0inv, s_klo, lane);
+      for (int q = 0; q < nsq; ++q) TD::sqr(x0, x1, n, n0inv, s_klo, lane, zr);
+      if (yk != OP_NONE) TD::mul(x0, x1, y0, y1, n, n0inv, s_klo, lane, zr);
       if (st != OP_NONE) {
         M::store(tab + (size_t)st * 2 * S, x0);
         M::store(tab + (size_t)st * 2 * S + S, x1);
@@ -182,40 +295,107 @@ __global__ void __launch_bounds__(kCtaThreads, MINB) enc2m_kernel(const Enc2mPar
         M::load(x1, tab + (size_t)rl * 2 * S + S);
       }
     }
-    // c = X0 + X1 n (< n^2): plain product rows with X0 as the initial accumulator; the limb leaving lane 0 at
-    // row i is limb i of c and goes to the lane that owns it
-    {
-      uint32_t E[L + 2], O[L + 2];
-#pragma unroll
-      for (int j = 0; j < L; ++j) {
-        E[j] = x0[j];
-        O[j] = 0;
-      }
-      E[L] = E[L + 1] = O[L] = O[L + 1] = 0;
-#pragma unroll 1
-      for (int owner = 0; owner < T; ++owner) {
-        const bool mine = g == owner;
-#pragma unroll
-        for (int j = 0; j < L; j += 2) {
-          const uint32_t b0 = __shfl_sync(ZKP_FULL, n[j], owner, T);
-          const uint32_t b1 = __shfl_sync(ZKP_FULL, n[j + 1], owner, T);
-          M::mul_step(E, O, x1, b0, g);
-          const uint32_t v0 = __shfl_sync(ZKP_FULL, E[0], 0, T);
-          M::mul_step(O, E, x1, b1, g);
-          const uint32_t v1 = __shfl_sync(ZKP_FULL, O[0], 0, T);
-          y0[j] = mine ? v0 : y0[j];
-          y0[j + 1] = mine ? v1 : y0[j + 1];
-        }
-      }
-      M::mul_finish(y1, E, O, lane);
-    }
-    if (valid) {
-      uint32_t* o = p.out + (size_t)(job0 + grp) * p.out_limbs;
-      M::store_ext(o, y0, p.out_limbs, g);
-      if (p.out_limbs > S) M::store_ext(o + S, y1, p.out_limbs - S, g);
-    }
+    TD::assemble_store(p.out + (size_t)(job0 + grp) * p.out_limbs, p.out_limbs, valid, x0, x1, n, lane);
     __syncthreads();  // everyone is done with the staged inputs
     fence_proxy_async();
+  }
+}
+
+// ------------------------------------------------------------------------ K2m
+// out[j] = bases[j]^exps[j / exp_per] mod n^2 in the same two-digit Montgomery form, per-job exponent, fixed 5-bit
+// window (the exponent is data, so every group of a warp scans the same number of windows).  Replaces
+// BigInt::mod_pow(_, _, nn) / Paillier::mul at zero_enc_proof.rs:60,81; correct_ciphertext.rs:62,84;
+// multiplication_proof.rs:91-94,133-138; verlin_proof.rs:89,109,147-155 (bases are ciphertexts: 2 S limbs wide).
+struct Var2mParams {
+  Enc2mKey key;
+  const uint32_t* bases;
+  const uint32_t* exps;
+  uint32_t* out;
+  uint32_t* table;
+  int base_limbs, exp_limbs, exp_bits, exp_per, out_limbs, jobs;
+  uint32_t zero;
+};
+
+__device__ __forceinline__ uint32_t exp_window2m(const uint32_t* e, int exp_limbs, int bit) {
+  int limb = bit >> 5, sh = bit & 31;
+  uint64_t v = e[limb];
+  if (limb + 1 < exp_limbs) v |= (uint64_t)e[limb + 1] << 32;
+  return (uint32_t)(v >> sh) & ((1u << kWindowVar) - 1u);
+}
+
+template <int T, int L, int MINB>
+__global__ void __launch_bounds__(kCtaThreads, MINB) modexp2m_var_kernel(const Var2mParams p) {
+  using M = Mp<T, L>;
+  using TD = TwoDigit<T, L, 1>;
+  constexpr int S = T * L;
+  constexpr int G = kCtaThreads / T;
+  __shared__ __align__(16) uint32_t s_klo[S];
+  const int lane = threadIdx.x & 31;
+  const int g = lane & (T - 1);
+  const int grp = threadIdx.x / T;
+  const uint32_t n0inv = p.key.n0inv;
+  const uint32_t zr = p.zero;
+  uint32_t n[L];
+  M::load(n, p.key.mod + g * L);
+  for (int i = threadIdx.x; i < S; i += kCtaThreads) s_klo[i] = p.key.consts[i];
+  __syncthreads();
+  uint32_t* tab = p.table + (size_t)(blockIdx.x * G + grp) * kTableVar * 2 * S + g * L;
+  const int npass = (p.jobs + G - 1) / G;
+  const int nwin = (p.exp_bits + kWindowVar - 1) / kWindowVar;
+  for (int cj = blockIdx.x; cj < npass; cj += gridDim.x) {
+    const int job = cj * G + grp;
+    const bool valid = job < p.jobs;
+    const int src = valid ? job : 0;
+    const uint32_t* e = p.exps + (size_t)(src / p.exp_per) * p.exp_limbs;
+    uint32_t x0[L], x1[L], y0[L], y1[L];
+    TD::entry_pair(x0, x1, p.bases + (size_t)src * p.base_limbs, p.base_limbs, p.key.consts, n, n0inv, s_klo, lane, zr);
+    M::load(y0, p.key.consts + S + g * L);  // pair(W^2): into Montgomery form
+    M::load(y1, p.key.consts + 2 * S + g * L);
+    TD::mul(x0, x1, y0, y1, n, n0inv, s_klo, lane, zr);
+    M::store(tab + 2 * S, x0);
+    M::store(tab + 2 * S + S, x1);
+#pragma unroll
+    for (int j = 0; j < L; ++j) {
+      y0[j] = x0[j];
+      y1[j] = x1[j];
+    }
+    M::load(x0, p.key.consts + 3 * S + g * L);  // pair(W) = 1 in Montgomery form = x^0
+    M::load(x1, p.key.consts + 4 * S + g * L);
+    M::store(tab, x0);
+    M::store(tab + S, x1);
+#pragma unroll
+    for (int j = 0; j < L; ++j) {
+      x0[j] = y0[j];
+      x1[j] = y1[j];
+    }
+#pragma unroll 1
+    for (int k = 2; k < kTableVar; ++k) {
+      TD::mul(x0, x1, y0, y1, n, n0inv, s_klo, lane, zr);
+      M::store(tab + (size_t)k * 2 * S, x0);
+      M::store(tab + (size_t)k * 2 * S + S, x1);
+    }
+    {
+      const uint32_t* t0 = tab + (size_t)exp_window2m(e, p.exp_limbs, (nwin - 1) * kWindowVar) * 2 * S;
+      M::load(x0, t0);
+      M::load(x1, t0 + S);
+    }
+    // the last pass of the loop multiplies by the plain pair (1, 0): it takes the result out of Montgomery form
+#pragma unroll 1
+    for (int w = nwin - 2; w >= -1; --w) {
+      if (w >= 0) {
+        const uint32_t* t0 = tab + (size_t)exp_window2m(e, p.exp_limbs, w * kWindowVar) * 2 * S;
+        M::load(y0, t0);
+        M::load(y1, t0 + S);
+#pragma unroll 1
+        for (int q = 0; q < kWindowVar; ++q) TD::sqr(x0, x1, n, n0inv, s_klo, lane, zr);
+      } else {
+        M::set_small(y0, 1u, g);
+#pragma unroll
+        for (int j = 0; j < L; ++j) y1[j] = 0;
+      }
+      TD::mul(x0, x1, y0, y1, n, n0inv, s_klo, lane, zr);
+    }
+    TD::assemble_store(p.out + (size_t)job * p.out_limbs, p.out_limbs, valid, x0, x1, n, lane);
   }
 }
 
@@ -279,8 +459,14 @@ void enc2m_host_constants(const uint32_t* n_host, int S, uint32_t* consts) {
   for (int i = 0; i < 32 * S; ++i) dbl_mod(x, 0, n);
   Limbs klo = n;  // -W mod n (W mod n != 0: n is odd and > 1)
   sub_in(klo, x);
-  x0[0] = 1;  // W^2 mod n^2 as a digit pair by 64 S pair doublings: (X0, X1) -> (2 X0 - c n, 2 X1 + c mod n)
+  x0[0] = 1;  // W and W^2 mod n^2 as digit pairs by pair doublings: (X0, X1) -> (2 X0 - c n, 2 X1 + c mod n)
   for (int i = 0; i < 64 * S; ++i) {
+    if (i == 32 * S) {
+      for (int k = 0; k < S; ++k) {
+        consts[3 * S + k] = x0[k];
+        consts[4 * S + k] = x1[k];
+      }
+    }
     uint32_t c = dbl_mod(x0, 0, n);
     dbl_mod(x1, c, n);
   }
@@ -340,7 +526,7 @@ cudaError_t launch_enc2m(const Enc2mKey& key, const uint32_t* bases, int base_li
                          uint32_t* out, int out_limbs, int jobs, uint32_t* table, int num_sms, cudaStream_t st,
                          const unsigned* jobs_dev) {
   if (jobs <= 0) return cudaSuccess;
-  if (base_limbs % 4 || base_limbs > key.S || (plain && (plain_limbs % 4 || plain_limbs > key.S)) || out_limbs % 2 ||
+  if (base_limbs % 4 || base_limbs > 2 * key.S || (plain && (plain_limbs % 4 || plain_limbs > 2 * key.S)) || out_limbs % 2 ||
       out_limbs > 2 * key.S || key.nops <= 0)
     return cudaErrorInvalidValue;
   Enc2mParams p;
@@ -355,11 +541,53 @@ cudaError_t launch_enc2m(const Enc2mKey& key, const uint32_t* bases, int base_li
   p.jobs = jobs;
   p.jobs_dev = jobs_dev;
   p.ops_pad = (key.nops + 3) & ~3;
+  p.zero = 0u;
   switch (key.S) {
     case 32: return launch_one<4, 8>(p, num_sms, st);
     case 64: return launch_one<8, 8>(p, num_sms, st);
     case 96: return launch_one<8, 12>(p, num_sms, st);
     case 128: return launch_one<16, 8>(p, num_sms, st);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+template <int T, int L>
+static cudaError_t launch_var_one(const Var2mParams& p, int num_sms, cudaStream_t st) {
+  constexpr int G = kCtaThreads / T;
+  int grid = num_sms * kCtasPerSm2m;
+  int npass = (p.jobs + G - 1) / G;
+  if (grid > npass) grid = npass;
+  modexp2m_var_kernel<T, L, kCtasPerSm2m><<<grid, kCtaThreads, 0, st>>>(p);
+  return cudaGetLastError();
+}
+
+size_t var2m_table_limbs(int S, int num_sms) { return (size_t)enc2m_resident_groups(S, num_sms) * kTableVar * 2 * S; }
+
+cudaError_t launch_modexp2m_var(const Enc2mKey& key, const uint32_t* bases, int base_limbs, const uint32_t* exps, int exp_limbs,
+                                int exp_bits, int exp_per, uint32_t* out, int out_limbs, int jobs, uint32_t* table, int num_sms,
+                                cudaStream_t st) {
+  if (jobs <= 0) return cudaSuccess;
+  if (base_limbs % 2 || base_limbs <= 0 || base_limbs > 2 * key.S || out_limbs % 2 || out_limbs > 2 * key.S || exp_per <= 0 ||
+      exp_bits <= 0 || exp_bits > 32 * exp_limbs)
+    return cudaErrorInvalidValue;
+  Var2mParams p;
+  p.key = key;
+  p.bases = bases;
+  p.exps = exps;
+  p.out = out;
+  p.table = table;
+  p.base_limbs = base_limbs;
+  p.exp_limbs = exp_limbs;
+  p.exp_bits = exp_bits;
+  p.exp_per = exp_per;
+  p.out_limbs = out_limbs;
+  p.jobs = jobs;
+  p.zero = 0u;
+  switch (key.S) {
+    case 32: return launch_var_one<4, 8>(p, num_sms, st);
+    case 64: return launch_var_one<8, 8>(p, num_sms, st);
+    case 96: return launch_var_one<8, 12>(p, num_sms, st);
+    case 128: return launch_var_one<16, 8>(p, num_sms, st);
     default: return cudaErrorInvalidValue;
   }
 }

@@ -231,11 +231,14 @@ struct Mp {
   }
   // Same step, handing back the quotient digit q it added (uniform across the group).
   static __device__ __forceinline__ void cios_step(uint32_t (&X)[L + 2], uint32_t (&Y)[L + 2], const uint32_t (&a)[L],
-                                                   const uint32_t (&n)[L], uint32_t b, uint32_t n0inv, int g, uint32_t& q) {
+                                                   const uint32_t (&n)[L], uint32_t b, uint32_t n0inv, int g, uint32_t& q,
+                                                   uint32_t zr = 0u) {
+    // zr: a zero the compiler cannot see through.  With a literal 0 ptxas turns the carry add below into IMAD.X,
+    // which competes with the IMAD.WIDE rows for the multiplier pipe; with a register it stays an IADD3.X.
     uint32_t in = __shfl_down_sync(ZKP_FULL, Y[0], 1, T);
     if (g == T - 1) in = 0;
     add_cc(Y[L], in);
-    addc(Y[L + 1], 0);
+    addc(Y[L + 1], zr);
     uint32_t Z[L + 2];
     add_cc(X[0], Y[1]);  // limb 0; the carry enters the odd chain at limb 1
 #pragma unroll
@@ -320,7 +323,8 @@ struct Mp {
   template <bool INIT, bool CAPQ, int NSUB, int U = 1>
   static __device__ __forceinline__ uint32_t mont_mul_x(uint32_t (&r)[L], const uint32_t (&a)[L], const uint32_t (&b)[L],
                                                         const uint32_t (&n)[L], uint32_t n0inv, int lane,
-                                                        const uint32_t (&init)[L], uint32_t init_top, uint32_t (&qcap)[L]) {
+                                                        const uint32_t (&init)[L], uint32_t init_top, uint32_t (&qcap)[L],
+                                                        uint32_t zr = 0u) {
     const int g = lane & (T - 1);
     uint32_t E[L + 2], O[L + 2];
 #pragma unroll
@@ -338,8 +342,8 @@ struct Mp {
         uint32_t b0 = __shfl_sync(ZKP_FULL, b[j], owner, T);
         uint32_t b1 = __shfl_sync(ZKP_FULL, b[j + 1], owner, T);
         uint32_t q0, q1;
-        cios_step(E, O, a, n, b0, n0inv, g, q0);
-        cios_step(O, E, a, n, b1, n0inv, g, q1);
+        cios_step(E, O, a, n, b0, n0inv, g, q0, zr);
+        cios_step(O, E, a, n, b1, n0inv, g, q1, zr);
         if (CAPQ) {
           qcap[j] = mine ? q0 : qcap[j];
           qcap[j + 1] = mine ? q1 : qcap[j + 1];
@@ -361,11 +365,11 @@ struct Mp {
   // multiplication needs X0 Y1 + X1 Y0 under ONE reduction).  Same array roles as cios_step.
   static __device__ __forceinline__ void cios_step2(uint32_t (&X)[L + 2], uint32_t (&Y)[L + 2], const uint32_t (&a1)[L],
                                                     const uint32_t (&a2)[L], const uint32_t (&n)[L], uint32_t b1, uint32_t b2,
-                                                    uint32_t n0inv, int g) {
+                                                    uint32_t n0inv, int g, uint32_t zr = 0u) {
     uint32_t in = __shfl_down_sync(ZKP_FULL, Y[0], 1, T);
     if (g == T - 1) in = 0;
     add_cc(Y[L], in);
-    addc(Y[L + 1], 0);
+    addc(Y[L + 1], zr);
     uint32_t Z[L + 2];
     add_cc(X[0], Y[1]);
 #pragma unroll
@@ -387,7 +391,8 @@ struct Mp {
   template <int U = 1>
   static __device__ __forceinline__ void mont_mul2_x(uint32_t (&r)[L], const uint32_t (&a1)[L], const uint32_t (&b1)[L],
                                                      const uint32_t (&a2)[L], const uint32_t (&b2)[L], const uint32_t (&n)[L],
-                                                     uint32_t n0inv, int lane, const uint32_t (&init)[L], uint32_t init_top) {
+                                                     uint32_t n0inv, int lane, const uint32_t (&init)[L], uint32_t init_top,
+                                                     uint32_t zr = 0u) {
     const int g = lane & (T - 1);
     uint32_t E[L + 2], O[L + 2];
 #pragma unroll
@@ -405,8 +410,8 @@ struct Mp {
         const uint32_t s0 = __shfl_sync(ZKP_FULL, b2[j], owner, T);
         const uint32_t p1 = __shfl_sync(ZKP_FULL, b1[j + 1], owner, T);
         const uint32_t s1 = __shfl_sync(ZKP_FULL, b2[j + 1], owner, T);
-        cios_step2(E, O, a1, a2, n, p0, s0, n0inv, g);
-        cios_step2(O, E, a1, a2, n, p1, s1, n0inv, g);
+        cios_step2(E, O, a1, a2, n, p0, s0, n0inv, g, zr);
+        cios_step2(O, E, a1, a2, n, p1, s1, n0inv, g, zr);
       }
     }
     uint32_t in = __shfl_down_sync(ZKP_FULL, O[0], 1, T);
