@@ -12,8 +12,8 @@
 // and the second digit is one more Montgomery reduction modulo n whose accumulator starts at a non-negative
 // representative of -q_eff (init = W + K_lo - q, K_lo = -W mod n; or W - q when Z0 = Z0' - n was taken).
 // No true quotient and no Barrett: only half-width CIOS rows of mp_coop.cuh.  A squaring costs 4 S^2 limb products
-// (x^2: X0 X0 and X0 (2 X1)), a multiplication 6 S^2, against 8 S^2 for CIOS modulo n^2 (S = limbs of n):
-// 42.4 M IMAD.WIDE per 2048-bit encryption instead of 79.3 M.  Model and proofs of the bounds:
+// (x^2: X0 X0 and X0 (2 X1)), a multiplication 5 S^2 (X0 Y1 + X1 Y0 under one reduction), against 8 S^2 for CIOS
+// modulo n^2 (S = limbs of n): 40.8 M IMAD.WIDE per 2048-bit encryption instead of 79.3 M.  Model and bounds:
 // tests/models/mont2d_model.py.
 //
 // Layout: one encryption per group of T lanes, L limbs of each digit per lane (Mp<8,8> for a 2048-bit n), the
@@ -192,7 +192,9 @@ struct TwoDigit {
   }
 };
 
-template <int T, int L, int U, int MINB>
+// WIDE: rows wider than n (bases up to 2S limbs: ciphertexts as randomness; plaintexts up to 2S limbs: unreduced z1).
+// Kept out of the common instantiation so that its extra live state does not cost the hot loop registers.
+template <int T, int L, int U, int MINB, bool WIDE>
 __global__ void __launch_bounds__(kCtaThreads, MINB) enc2m_kernel(const Enc2mParams p) {
   using M = Mp<T, L>;
   using TD = TwoDigit<T, L, U>;
@@ -249,7 +251,7 @@ __global__ void __launch_bounds__(kCtaThreads, MINB) enc2m_kernel(const Enc2mPar
 
     // the last multiplier: the pair (1, m) = 1 + m n in plain form (it also takes the result out of Montgomery form)
     uint32_t x0[L], x1[L], y0[L], y1[L];
-    if (p.plain && p.plain_limbs > S) {
+    if (WIDE && p.plain && p.plain_limbs > S) {
       // m wider than n (CiphertextProof's unreduced z1): 1 + m n = 1 + (m mod n) n, and
       // m mod n = Mlo W / W + Mhi W^2 / W  (two Montgomery products by W mod n and W^2 mod n)
       const uint32_t* mrow = s_plain + src * p.plain_limbs;
@@ -272,7 +274,13 @@ __global__ void __launch_bounds__(kCtaThreads, MINB) enc2m_kernel(const Enc2mPar
     __syncwarp();
 
     // the pair (r, 0) (r may exceed n), or the reduced pair of a base wider than n
-    TD::entry_pair(x0, x1, s_bases + src * p.base_limbs, p.base_limbs, p.key.consts, n, n0inv, s_klo, lane, zr);
+    if (WIDE) {
+      TD::entry_pair(x0, x1, s_bases + src * p.base_limbs, p.base_limbs, p.key.consts, n, n0inv, s_klo, lane, zr);
+    } else {
+      M::load_ext(x0, s_bases + src * p.base_limbs, p.base_limbs, g);
+#pragma unroll
+      for (int j = 0; j < L; ++j) x1[j] = 0;
+    }
 #pragma unroll 1
     for (int k = 0; k < p.key.nops; ++k) {
       const uint32_t op = s_ops[k];
@@ -516,9 +524,11 @@ static cudaError_t launch_one(const Enc2mParams& p, int num_sms, cudaStream_t st
   int grid = num_sms * MINB;
   int npass = (p.jobs + G - 1) / G;
   if (grid > npass) grid = npass;
-  cudaError_t e = cudaFuncSetAttribute(enc2m_kernel<T, L, U, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const bool wide = p.base_limbs > S || p.plain_limbs > S;
+  auto kern = wide ? enc2m_kernel<T, L, U, MINB, true> : enc2m_kernel<T, L, U, MINB, false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  enc2m_kernel<T, L, U, MINB><<<grid, kCtaThreads, smem, st>>>(p);
+  kern<<<grid, kCtaThreads, smem, st>>>(p);
   return cudaGetLastError();
 }
 
