@@ -103,7 +103,7 @@ cudaError_t launch_enc(zkp_ctx* c, const uint32_t* bases, int base_limbs, const 
 // significant bit first.  Entry k: low byte = table index of the odd power
 // x^(2*idx+1) to multiply by (0xff = none), upper 24 bits = squarings to do first.
 // Entry 0 only loads the accumulator.
-std::vector<uint32_t> recode_exponent(const uint32_t* e, int limbs) {
+std::vector<uint32_t> recode_exponent(const uint32_t* e, int limbs, int window = kWindowShared) {
   std::vector<uint32_t> out;
   int top = limbs * 32 - 1;
   auto bit = [&](int i) { return (e[i >> 5] >> (i & 31)) & 1u; };
@@ -118,7 +118,7 @@ std::vector<uint32_t> recode_exponent(const uint32_t* e, int limbs) {
       --i;
       continue;
     }
-    int l = std::max(i - kWindowShared + 1, 0);
+    int l = std::max(i - window + 1, 0);
     while (!bit(l)) ++l;  // window [i .. l] ends in a one
     uint32_t v = 0;
     for (int k = i; k >= l; --k) v = (v << 1) | bit(k);
@@ -307,7 +307,7 @@ int zkp_set_key(zkp_ctx* c, const uint32_t* n, int n_limbs) {
       const int S = c->n.S;
       std::vector<uint32_t> consts((size_t)5 * S);
       enc2m_host_constants(c->n.h_mod.data(), S, consts.data());
-      std::vector<uint32_t> sched = recode_exponent(n, n_limbs);
+      std::vector<uint32_t> sched = recode_exponent(n, n_limbs, enc2m_window());
       std::vector<uint32_t> ops = enc2m_ops(sched.data(), (int)sched.size());
       c->enc2m_nops = (int)ops.size();
       ops.resize((ops.size() + 3) & ~size_t(3), 0xffffffu);

@@ -10,6 +10,7 @@ namespace zkp {
 constexpr int kCtaThreads = 128;       // 4 warps per CTA
 constexpr int kWindowShared = 5;       // sliding window, shared exponent (K1)
 constexpr int kTableShared = 16;       // odd powers x^1..x^31
+constexpr int kWindow2m = 6;           // sliding window of K1m (32 odd powers + x^2 per encryption in flight)
 constexpr int kWindowVar = 5;          // fixed window, per-instance exponent (K2)
 constexpr int kTableVar = 32;          // x^0..x^31
 constexpr int kMaxSchedSteps = 2048;
@@ -57,7 +58,8 @@ struct Enc2mKey {
 };
 bool enc2m_supported(const uint32_t* n_host, int S);
 void enc2m_host_constants(const uint32_t* n_host, int S, uint32_t* consts /* [5 S] */);
-std::vector<uint32_t> enc2m_ops(const uint32_t* sched, int nsteps);  // from the K1 schedule of the exponent n
+int enc2m_window();  // sliding-window width of K1m (5, or 6 with ZKP_B200_K1M_WINDOW=6)
+std::vector<uint32_t> enc2m_ops(const uint32_t* sched, int nsteps);  // from the schedule of the exponent n recoded with enc2m_window()
 int enc2m_resident_groups(int S, int num_sms);
 size_t enc2m_table_limbs(int S, int num_sms);
 // bases: [jobs][base_limbs] (any value below 2^(32 base_limbs), base_limbs <= 2 S), plain: [jobs][plain_limbs] or null

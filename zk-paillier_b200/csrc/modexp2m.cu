@@ -22,6 +22,8 @@
 // 1-D TMA bulk copies.  The whole exponentiation - entering Montgomery form, the table, the sliding-window
 // ladder, the Paillier factor (1 + m n) = pair (1, m), leaving Montgomery form - is ONE op list run by one loop
 // with a single squaring site and a single multiplication site, so the code stays small.
+#include <stdlib.h>
+
 #include <vector>
 
 #include "kernels.h"
@@ -30,7 +32,6 @@
 
 namespace zkp {
 
-constexpr int kSlots2m = kTableShared + 1;  // odd powers x^1..x^31 and x^2
 constexpr uint32_t OP_NONE = 0xffu, OP_Y_CONST = 0xfeu, OP_Y_PLAIN = 0xfdu;
 
 struct Enc2mParams {
@@ -39,15 +40,20 @@ struct Enc2mParams {
   const uint32_t* plain;
   uint32_t* out;
   uint32_t* table;
-  int base_limbs, plain_limbs, out_limbs, jobs, ops_pad;
+  int base_limbs, plain_limbs, out_limbs, jobs, ops_pad, slots;
   uint32_t zero;
   const unsigned* jobs_dev;
 };
 
-template <int T, int L, int U>
+// MODE 0: the two halves of a squaring / multiplication are separate instances of the row loop (multiplier limbs by SHFL).
+// MODE 1: both halves of a squaring run through one copy of the row loop (multiplier picked by SEL): smaller code.
+// MODE 2: multiplier limbs and quotient digits go through a per-group shared-memory scratch (kSg2m words), the row loop
+//         is rolled U pairs of steps deep: smallest code, no multiplier shuffles.
+template <int T, int L, int U, int MODE = 0>
 struct TwoDigit {
   using M = Mp<T, L>;
   static constexpr int S = T * L;
+  static constexpr int kSg = 3 * S + 4;  // MODE 2 scratch per group: multiplier row | second multiplier row | q row (+4: bank skew)
 
   // init + top 2^(32 S) = W + (delta ? 0 : K_lo) - q   (non-negative, == -q_eff mod n, < W + n)
   static __device__ __forceinline__ void init_from_q(uint32_t (&init)[L], uint32_t& top, const uint32_t (&q)[L], uint32_t delta,
@@ -63,29 +69,76 @@ struct TwoDigit {
 
   // (x0, x1) <- (x0, x1)^2 / W
   static __device__ __forceinline__ void sqr(uint32_t (&x0)[L], uint32_t (&x1)[L], const uint32_t (&n)[L], uint32_t n0inv,
-                                             const uint32_t* s_klo, int lane, uint32_t zr) {
+                                             const uint32_t* s_klo, int lane, uint32_t zr, uint32_t* sg = nullptr) {
     uint32_t q[L], z0[L];
 #pragma unroll
     for (int j = 0; j < L; ++j) q[j] = 0;
-    const uint32_t delta = M::template mont_mul_x<false, true, 1, U>(z0, x0, x0, n, n0inv, lane, z0, 0u, q, zr);
-    uint32_t top;
-    init_from_q(q, top, q, delta, s_klo, lane);
-    M::mod_double(x1, n, lane);
-    M::template mont_mul_x<true, false, 2, U>(x1, x0, x1, n, n0inv, lane, q, top, q, zr);
+    if (MODE == 0) {
+      const uint32_t delta = M::template mont_mul_x<false, true, 1, U>(z0, x0, x0, n, n0inv, lane, z0, 0u, q, zr);
+      uint32_t top;
+      init_from_q(q, top, q, delta, s_klo, lane);
+      M::mod_double(x1, n, lane);
+      M::template mont_mul_x<true, false, 2, U>(x1, x0, x1, n, n0inv, lane, q, top, q, zr);
+    } else {
+      const int g = lane & (T - 1);
+      uint32_t init[L], res[L], top = 0u;
+#pragma unroll
+      for (int j = 0; j < L; ++j) init[j] = 0;
+#pragma unroll 1
+      for (int ph = 0; ph < 2; ++ph) {
+        uint32_t delta;
+        if (MODE == 1) {
+          delta = M::template mont_mul_sel<1>(res, x0, x0, x1, ph != 0, n, n0inv, lane, init, top, q, zr);
+        } else {
+          __syncwarp();
+          if (ph == 0) M::store(sg + g * L, x0);
+          else M::store(sg + g * L, x1);
+          __syncwarp();
+          delta = M::template mont_mul_s<U>(res, x0, sg, sg + 2 * S, n, n0inv, lane, init, top, zr);
+        }
+        if (ph == 0) {
+          if (MODE == 2) {
+            __syncwarp();
+            M::load(q, sg + 2 * S + g * L);
+          }
+#pragma unroll
+          for (int j = 0; j < L; ++j) z0[j] = res[j];
+          init_from_q(init, top, q, delta, s_klo, lane);
+          M::mod_double(x1, n, lane);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < L; ++j) x1[j] = res[j];
+    }
 #pragma unroll
     for (int j = 0; j < L; ++j) x0[j] = z0[j];
   }
 
   // (x0, x1) <- (x0, x1) (y0, y1) / W
   static __device__ __forceinline__ void mul(uint32_t (&x0)[L], uint32_t (&x1)[L], const uint32_t (&y0)[L], const uint32_t (&y1)[L],
-                                             const uint32_t (&n)[L], uint32_t n0inv, const uint32_t* s_klo, int lane, uint32_t zr) {
+                                             const uint32_t (&n)[L], uint32_t n0inv, const uint32_t* s_klo, int lane, uint32_t zr,
+                                             uint32_t* sg = nullptr) {
     uint32_t q[L], z0[L];
 #pragma unroll
     for (int j = 0; j < L; ++j) q[j] = 0;
-    const uint32_t delta = M::template mont_mul_x<false, true, 1, U>(z0, x0, y0, n, n0inv, lane, z0, 0u, q, zr);
-    uint32_t top;
-    init_from_q(q, top, q, delta, s_klo, lane);
-    M::template mont_mul2_x<U>(x1, x0, y1, x1, y0, n, n0inv, lane, q, top, zr);  // X0 Y1 + X1 Y0 under one reduction
+    if (MODE != 2) {
+      const uint32_t delta = M::template mont_mul_x<false, true, 1, U>(z0, x0, y0, n, n0inv, lane, z0, 0u, q, zr);
+      uint32_t top;
+      init_from_q(q, top, q, delta, s_klo, lane);
+      M::template mont_mul2_x<U>(x1, x0, y1, x1, y0, n, n0inv, lane, q, top, zr);  // X0 Y1 + X1 Y0 under one reduction
+    } else {
+      const int g = lane & (T - 1);
+      __syncwarp();
+      M::store(sg + g * L, y0);
+      M::store(sg + S + g * L, y1);
+      __syncwarp();
+      const uint32_t delta = M::template mont_mul_s<U>(z0, x0, sg, sg + 2 * S, n, n0inv, lane, q, 0u, zr);  // q == 0 here
+      __syncwarp();
+      M::load(q, sg + 2 * S + g * L);
+      uint32_t top;
+      init_from_q(q, top, q, delta, s_klo, lane);
+      M::template mont_mul2_s<U>(x1, x0, sg + S, x1, sg, n, n0inv, lane, q, top, zr);
+    }
 #pragma unroll
     for (int j = 0; j < L; ++j) x0[j] = z0[j];
   }
@@ -126,7 +179,7 @@ struct TwoDigit {
   // consts: K_lo | pair(W^2 mod n^2) | pair(W mod n^2).
   static __device__ __forceinline__ void entry_pair(uint32_t (&x0)[L], uint32_t (&x1)[L], const uint32_t* row, int limbs,
                                                     const uint32_t* consts, const uint32_t (&n)[L], uint32_t n0inv,
-                                                    const uint32_t* s_klo, int lane, uint32_t zr) {
+                                                    const uint32_t* s_klo, int lane, uint32_t zr, uint32_t* sg = nullptr) {
     const int g = lane & (T - 1);
     if (limbs <= S) {
       M::load_ext(x0, row, limbs, g);
@@ -144,7 +197,7 @@ struct TwoDigit {
       else M::load_ext(x0, row, S, g);
 #pragma unroll
       for (int j = 0; j < L; ++j) x1[j] = 0;
-      mul(x0, x1, y0, y1, n, n0inv, s_klo, lane, zr);
+      mul(x0, x1, y0, y1, n, n0inv, s_klo, lane, zr, sg);
       if (half) {
 #pragma unroll
         for (int j = 0; j < L; ++j) {
@@ -194,10 +247,10 @@ struct TwoDigit {
 
 // WIDE: rows wider than n (bases up to 2S limbs: ciphertexts as randomness; plaintexts up to 2S limbs: unreduced z1).
 // Kept out of the common instantiation so that its extra live state does not cost the hot loop registers.
-template <int T, int L, int U, int MINB, bool WIDE>
+template <int T, int L, int U, int MINB, bool WIDE, int MODE = 0>
 __global__ void __launch_bounds__(kCtaThreads, MINB) enc2m_kernel(const Enc2mParams p) {
   using M = Mp<T, L>;
-  using TD = TwoDigit<T, L, U>;
+  using TD = TwoDigit<T, L, U, MODE>;
   constexpr int S = T * L;
   constexpr int G = kCtaThreads / T;
   extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -211,6 +264,7 @@ __global__ void __launch_bounds__(kCtaThreads, MINB) enc2m_kernel(const Enc2mPar
   const int lane = threadIdx.x & 31;
   const int g = lane & (T - 1);
   const int grp = threadIdx.x / T;
+  uint32_t* sg = MODE == 2 ? s_pair + G * 2 * S + grp * TD::kSg : nullptr;  // multiplier / quotient rows of this group
   const uint32_t n0inv = p.key.n0inv;
   const uint32_t zr = p.zero;  // always 0, but opaque to ptxas (see cios_step)
   uint32_t n[L];
@@ -230,7 +284,7 @@ __global__ void __launch_bounds__(kCtaThreads, MINB) enc2m_kernel(const Enc2mPar
   mbar_wait(bar, phase);
   phase ^= 1;
 
-  uint32_t* tab = p.table + (size_t)(blockIdx.x * G + grp) * kSlots2m * 2 * S + g * L;
+  uint32_t* tab = p.table + (size_t)(blockIdx.x * G + grp) * p.slots * 2 * S + g * L;
   uint32_t* pair = s_pair + grp * 2 * S;
   const int jobs = p.jobs_dev ? min((int)*p.jobs_dev, p.jobs) : p.jobs;
   const int npass = (jobs + G - 1) / G;
@@ -275,7 +329,7 @@ __global__ void __launch_bounds__(kCtaThreads, MINB) enc2m_kernel(const Enc2mPar
 
     // the pair (r, 0) (r may exceed n), or the reduced pair of a base wider than n
     if (WIDE) {
-      TD::entry_pair(x0, x1, s_bases + src * p.base_limbs, p.base_limbs, p.key.consts, n, n0inv, s_klo, lane, zr);
+      TD::entry_pair(x0, x1, s_bases + src * p.base_limbs, p.base_limbs, p.key.consts, n, n0inv, s_klo, lane, zr, sg);
     } else {
       M::load_ext(x0, s_bases + src * p.base_limbs, p.base_limbs, g);
 #pragma unroll
@@ -292,8 +346,8 @@ __global__ void __launch_bounds__(kCtaThreads, MINB) enc2m_kernel(const Enc2mPar
         M::load(y1, ysrc + S);
       }
 #pragma unroll 1
-      for (int q = 0; q < nsq; ++q) TD::sqr(x0, x1, n, n0inv, s_klo, lane, zr);
-      if (yk != OP_NONE) TD::mul(x0, x1, y0, y1, n, n0inv, s_klo, lane, zr);
+      for (int q = 0; q < nsq; ++q) TD::sqr(x0, x1, n, n0inv, s_klo, lane, zr, sg);
+      if (yk != OP_NONE) TD::mul(x0, x1, y0, y1, n, n0inv, s_klo, lane, zr, sg);
       if (st != OP_NONE) {
         M::store(tab + (size_t)st * 2 * S, x0);
         M::store(tab + (size_t)st * 2 * S + S, x1);
@@ -485,14 +539,49 @@ void enc2m_host_constants(const uint32_t* n_host, int S, uint32_t* consts) {
   }
 }
 
-// K1 schedule (api_core.cu: recode_exponent) -> K1m op list.
+// Tuning variant of K1m, fixed per process.  ZKP_B200_K1M_VARIANT picks the lane layout of a 2048-bit n
+// (default 0 = Mp<8,8>, 4 CTAs per SM), ZKP_B200_K1M_WINDOW the sliding-window width (5 or 6; default kWindow2m).
+// Measured on B200 (profiles/r01_k1m_variants2.jsonl): the <4,16> layouts are 1-12 % slower than <8,8> (3 resident CTAs,
+// or spills at 4; larger loops against the 32 KB instruction cache), the shared-memory rows are within 0.4 %, and a
+// 6-bit window is 1.6 % faster than a 5-bit one (32 odd powers: 17 KB of table per encryption in flight).
+//   variant  layout  CTAs/SM  MODE (TwoDigit)
+//   0        <8,8>   4        0   separate row loops, multiplier by SHFL
+//   1        <4,16>  3        0
+//   2        <4,16>  4        0   (128 registers: a few spills)
+//   3        <4,16>  3        1   one row loop per squaring
+//   4        <8,8>   4        1
+//   5        <4,16>  3        2   multiplier / quotient rows in shared memory, row loop 4 steps deep
+//   6        <4,16>  3        2   ... 8 steps deep
+//   7        <8,8>   4        2   ... 8 steps deep
+//   8        <4,16>  4        2   ... 4 steps deep
+// The other key sizes keep their layout and take only the MODE of the variant.
+struct Enc2mConfig {
+  int variant, window;
+};
+static Enc2mConfig enc2m_config() {
+  static Enc2mConfig cfg = [] {
+    Enc2mConfig c{0, kWindow2m};
+    if (const char* v = getenv("ZKP_B200_K1M_VARIANT")) c.variant = atoi(v);
+    if (const char* w = getenv("ZKP_B200_K1M_WINDOW")) c.window = atoi(w);
+    if (c.variant < 0 || c.variant > 8) c.variant = 0;
+    if (c.window != 5 && c.window != 6) c.window = kWindow2m;
+    return c;
+  }();
+  return cfg;
+}
+int enc2m_window() { return enc2m_config().window; }
+static int enc2m_table() { return 1 << (enc2m_config().window - 1); }  // odd powers kept
+static int enc2m_slots() { return enc2m_table() + 1; }                 // ... and x^2
+
+// Sliding-window schedule of the exponent n (api_core.cu: recode_exponent, same window) -> K1m op list.
 // op = nsq << 24 | reload_slot << 16 | store_slot << 8 | multiplier (0xff: none; 0xfe: W^2 pair; 0xfd: (1, m))
 std::vector<uint32_t> enc2m_ops(const uint32_t* sched, int nsteps) {
   auto mk = [](uint32_t nsq, uint32_t rl, uint32_t st, uint32_t y) { return (nsq << 24) | (rl << 16) | (st << 8) | y; };
+  const uint32_t tbl = (uint32_t)enc2m_table();
   std::vector<uint32_t> ops;
   ops.push_back(mk(0, OP_NONE, 0, OP_Y_CONST));                           // x W  -> slot 0
-  ops.push_back(mk(1, 0, kTableShared, OP_NONE));                         // x^2  -> slot 16; back to x
-  for (uint32_t e = 1; e < (uint32_t)kTableShared; ++e) ops.push_back(mk(0, OP_NONE, e, kTableShared));  // x^(2e+1)
+  ops.push_back(mk(1, 0, tbl, OP_NONE));                                  // x^2  -> last slot; back to x
+  for (uint32_t e = 1; e < tbl; ++e) ops.push_back(mk(0, OP_NONE, e, tbl));  // x^(2e+1)
   ops.push_back(mk(0, sched[0] & 0xffu, OP_NONE, OP_NONE));               // accumulator = first window
   for (int k = 1; k < nsteps; ++k) {
     uint32_t idx = sched[k] & 0xffu, nsq = sched[k] >> 8;
@@ -506,30 +595,54 @@ std::vector<uint32_t> enc2m_ops(const uint32_t* sched, int nsteps) {
   return ops;
 }
 
-constexpr int kCtasPerSm2m = 4;  // measured on B200: 5 and 6 resident CTAs (96 / 80 registers) are 2-4 % slower, unrolling the owner loop gains nothing
+// measured on B200 with <8,8>: 5 and 6 resident CTAs (96 / 80 registers) are 2-4 % slower than 4, unrolling the owner loop gains nothing
+constexpr int kCtasPerSm2m = 4;
+
+static bool pick_shape_v(int S, int& T, int& L, int& minb, int& mode) {
+  if (!pick_shape(S, T, L)) return false;
+  static const int kMinb[9] = {4, 3, 4, 3, 4, 3, 3, 4, 4}, kMode[9] = {0, 0, 0, 1, 1, 2, 2, 2, 2};
+  static const bool kT4[9] = {false, true, true, true, false, true, true, false, true};
+  const int v = enc2m_config().variant;
+  minb = kCtasPerSm2m;
+  mode = kMode[v];
+  if (S == 64) {
+    minb = kMinb[v];
+    if (kT4[v]) { T = 4; L = 16; }
+  }
+  return true;
+}
 
 int enc2m_resident_groups(int S, int num_sms) {
-  int T, L;
-  if (!pick_shape(S, T, L)) return 0;
-  return num_sms * kCtasPerSm2m * (kCtaThreads / T);
+  int T, L, minb, mode;
+  if (!pick_shape_v(S, T, L, minb, mode)) return 0;
+  return num_sms * minb * (kCtaThreads / T);
 }
-size_t enc2m_table_limbs(int S, int num_sms) { return (size_t)enc2m_resident_groups(S, num_sms) * kSlots2m * 2 * S; }
+size_t enc2m_table_limbs(int S, int num_sms) { return (size_t)enc2m_resident_groups(S, num_sms) * enc2m_slots() * 2 * S; }
 
-template <int T, int L>
+template <int T, int L, int U, int MINB, int MODE>
 static cudaError_t launch_one(const Enc2mParams& p, int num_sms, cudaStream_t st) {
   constexpr int G = kCtaThreads / T;
   constexpr int S = T * L;
-  constexpr int U = 1, MINB = kCtasPerSm2m;
   size_t smem = 16 + (size_t)(p.ops_pad + S) * 4 + (size_t)G * (p.base_limbs + p.plain_limbs + 2 * S) * 4;
+  if (MODE == 2) smem += (size_t)G * TwoDigit<T, L, U, MODE>::kSg * 4;
   int grid = num_sms * MINB;
   int npass = (p.jobs + G - 1) / G;
   if (grid > npass) grid = npass;
   const bool wide = p.base_limbs > S || p.plain_limbs > S;
-  auto kern = wide ? enc2m_kernel<T, L, U, MINB, true> : enc2m_kernel<T, L, U, MINB, false>;
+  auto kern = wide ? enc2m_kernel<T, L, U, MINB, true, MODE> : enc2m_kernel<T, L, U, MINB, false, MODE>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   kern<<<grid, kCtaThreads, smem, st>>>(p);
   return cudaGetLastError();
+}
+
+template <int T, int L>
+static cudaError_t launch_mode(const Enc2mParams& p, int mode, int num_sms, cudaStream_t st) {
+  switch (mode) {
+    case 1: return launch_one<T, L, 1, kCtasPerSm2m, 1>(p, num_sms, st);
+    case 2: return launch_one<T, L, 2, kCtasPerSm2m, 2>(p, num_sms, st);
+    default: return launch_one<T, L, 1, kCtasPerSm2m, 0>(p, num_sms, st);
+  }
 }
 
 cudaError_t launch_enc2m(const Enc2mKey& key, const uint32_t* bases, int base_limbs, const uint32_t* plain, int plain_limbs,
@@ -551,12 +664,26 @@ cudaError_t launch_enc2m(const Enc2mKey& key, const uint32_t* bases, int base_li
   p.jobs = jobs;
   p.jobs_dev = jobs_dev;
   p.ops_pad = (key.nops + 3) & ~3;
+  p.slots = enc2m_slots();
   p.zero = 0u;
+  int T, L, minb, mode;
+  if (!pick_shape_v(key.S, T, L, minb, mode)) return cudaErrorInvalidValue;
   switch (key.S) {
-    case 32: return launch_one<4, 8>(p, num_sms, st);
-    case 64: return launch_one<8, 8>(p, num_sms, st);
-    case 96: return launch_one<8, 12>(p, num_sms, st);
-    case 128: return launch_one<16, 8>(p, num_sms, st);
+    case 32: return launch_mode<4, 8>(p, mode, num_sms, st);
+    case 96: return launch_mode<8, 12>(p, mode, num_sms, st);
+    case 128: return launch_mode<16, 8>(p, mode, num_sms, st);
+    case 64:
+      switch (enc2m_config().variant) {
+        case 1: return launch_one<4, 16, 1, 3, 0>(p, num_sms, st);
+        case 2: return launch_one<4, 16, 1, 4, 0>(p, num_sms, st);
+        case 3: return launch_one<4, 16, 1, 3, 1>(p, num_sms, st);
+        case 4: return launch_one<8, 8, 1, 4, 1>(p, num_sms, st);
+        case 5: return launch_one<4, 16, 2, 3, 2>(p, num_sms, st);
+        case 6: return launch_one<4, 16, 4, 3, 2>(p, num_sms, st);
+        case 7: return launch_one<8, 8, 4, 4, 2>(p, num_sms, st);
+        case 8: return launch_one<4, 16, 2, 4, 2>(p, num_sms, st);
+        default: return launch_one<8, 8, 1, 4, 0>(p, num_sms, st);
+      }
     default: return cudaErrorInvalidValue;
   }
 }

@@ -425,6 +425,123 @@ struct Mp {
     finish_x<3>(r, E, n, lane);
   }
 
+  // ---- variants of the two-digit rows with a smaller code footprint (modexp2m.cu, TwoDigit MODE 1 / 2) -------------
+  // mont_mul_x<INIT, CAPQ, 2> with the multiplier picked at run time (b = alt ? b1 : b0), so that both halves of a
+  // two-digit squaring run through ONE copy of the row loop (instruction-cache footprint).
+  template <int U = 1>
+  static __device__ __forceinline__ uint32_t mont_mul_sel(uint32_t (&r)[L], const uint32_t (&a)[L], const uint32_t (&b0)[L],
+                                                          const uint32_t (&b1)[L], bool alt, const uint32_t (&n)[L],
+                                                          uint32_t n0inv, int lane, const uint32_t (&init)[L],
+                                                          uint32_t init_top, uint32_t (&qcap)[L], uint32_t zr = 0u) {
+    const int g = lane & (T - 1);
+    uint32_t E[L + 2], O[L + 2];
+#pragma unroll
+    for (int j = 0; j < L; ++j) {
+      E[j] = init[j];
+      O[j] = 0;
+    }
+    E[L] = (g == T - 1) ? init_top : 0u;
+    E[L + 1] = O[L] = O[L + 1] = 0;
+#pragma unroll U
+    for (int owner = 0; owner < T; ++owner) {
+      const bool mine = g == owner;
+#pragma unroll
+      for (int j = 0; j < L; j += 2) {
+        uint32_t b0v = __shfl_sync(ZKP_FULL, alt ? b1[j] : b0[j], owner, T);
+        uint32_t b1v = __shfl_sync(ZKP_FULL, alt ? b1[j + 1] : b0[j + 1], owner, T);
+        uint32_t q0, q1;
+        cios_step(E, O, a, n, b0v, n0inv, g, q0, zr);
+        cios_step(O, E, a, n, b1v, n0inv, g, q1, zr);
+        qcap[j] = mine ? q0 : qcap[j];
+        qcap[j + 1] = mine ? q1 : qcap[j + 1];
+      }
+    }
+    uint32_t in = __shfl_down_sync(ZKP_FULL, O[0], 1, T);
+    if (g == T - 1) in = 0;
+    add_cc(O[L], in);
+    addc(O[L + 1], 0);
+    add_cc(E[0], O[1]);
+#pragma unroll
+    for (int j = 1; j <= L; ++j) addc_cc(E[j], O[j + 1]);
+    addc(E[L + 1], 0);
+    return finish_x<2>(r, E, n, lane);
+  }
+
+  // The same product with the multiplier limbs read from the group's shared-memory row sb[0..S) (LDS broadcast instead
+  // of SHFL) and the quotient digits written to sq[0..S): the row loop can then be rolled at any depth (UNR pairs of
+  // steps per iteration) because nothing in it indexes registers by the row number.
+  template <int UNR>
+  static __device__ __forceinline__ uint32_t mont_mul_s(uint32_t (&r)[L], const uint32_t (&a)[L], const uint32_t* sb, uint32_t* sq,
+                                                        const uint32_t (&n)[L], uint32_t n0inv, int lane,
+                                                        const uint32_t (&init)[L], uint32_t init_top, uint32_t zr = 0u) {
+    static_assert(S % (2 * UNR) == 0, "row loop depth");
+    const int g = lane & (T - 1);
+    uint32_t E[L + 2], O[L + 2];
+#pragma unroll
+    for (int j = 0; j < L; ++j) {
+      E[j] = init[j];
+      O[j] = 0;
+    }
+    E[L] = (g == T - 1) ? init_top : 0u;
+    E[L + 1] = O[L] = O[L + 1] = 0;
+#pragma unroll 1
+    for (int i = 0; i < S; i += 2 * UNR) {
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const uint2 bb = *reinterpret_cast<const uint2*>(sb + i + 2 * u);
+        uint32_t q0, q1;
+        cios_step(E, O, a, n, bb.x, n0inv, g, q0, zr);
+        cios_step(O, E, a, n, bb.y, n0inv, g, q1, zr);
+        if (g == 0) *reinterpret_cast<uint2*>(sq + i + 2 * u) = make_uint2(q0, q1);
+      }
+    }
+    uint32_t in = __shfl_down_sync(ZKP_FULL, O[0], 1, T);
+    if (g == T - 1) in = 0;
+    add_cc(O[L], in);
+    addc(O[L + 1], 0);
+    add_cc(E[0], O[1]);
+#pragma unroll
+    for (int j = 1; j <= L; ++j) addc_cc(E[j], O[j + 1]);
+    addc(E[L + 1], 0);
+    return finish_x<2>(r, E, n, lane);
+  }
+
+  // mont_mul2_x with both multipliers in shared memory (sb1 pairs with a1, sb2 with a2).
+  template <int UNR>
+  static __device__ __forceinline__ void mont_mul2_s(uint32_t (&r)[L], const uint32_t (&a1)[L], const uint32_t* sb1,
+                                                     const uint32_t (&a2)[L], const uint32_t* sb2, const uint32_t (&n)[L],
+                                                     uint32_t n0inv, int lane, const uint32_t (&init)[L], uint32_t init_top,
+                                                     uint32_t zr = 0u) {
+    const int g = lane & (T - 1);
+    uint32_t E[L + 2], O[L + 2];
+#pragma unroll
+    for (int j = 0; j < L; ++j) {
+      E[j] = init[j];
+      O[j] = 0;
+    }
+    E[L] = (g == T - 1) ? init_top : 0u;
+    E[L + 1] = O[L] = O[L + 1] = 0;
+#pragma unroll 1
+    for (int i = 0; i < S; i += 2 * UNR) {
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const uint2 p = *reinterpret_cast<const uint2*>(sb1 + i + 2 * u);
+        const uint2 s = *reinterpret_cast<const uint2*>(sb2 + i + 2 * u);
+        cios_step2(E, O, a1, a2, n, p.x, s.x, n0inv, g, zr);
+        cios_step2(O, E, a1, a2, n, p.y, s.y, n0inv, g, zr);
+      }
+    }
+    uint32_t in = __shfl_down_sync(ZKP_FULL, O[0], 1, T);
+    if (g == T - 1) in = 0;
+    add_cc(O[L], in);
+    addc(O[L + 1], 0);
+    add_cc(E[0], O[1]);
+#pragma unroll
+    for (int j = 1; j <= L; ++j) addc_cc(E[j], O[j + 1]);
+    addc(E[L + 1], 0);
+    finish_x<3>(r, E, n, lane);
+  }
+
   // x = (x + y) mod n for x, y < n
   static __device__ __forceinline__ void add_mod(uint32_t (&x)[L], const uint32_t (&y)[L], const uint32_t (&n)[L], int lane) {
     const uint32_t ovf = add_full(x, y, lane);
