@@ -220,6 +220,34 @@ int zkp_verlin_verify(zkp_ctx* ctx, int batch, int z_limbs, const uint32_t* c, c
                       const uint32_t* phi_a, const uint32_t* z, const uint32_t* z_prime, const uint32_t* z_dp,
                       const uint32_t* r_z, uint8_t* accept);
 
+/* ---- the remaining public proofs ------------------------------
+ * CorrectOpening::verify_opening (correct_opening.rs:17-30): ok[b] = (c[b] == Enc(m[b], r[b])) under the current key.
+ * m: [batch][m_limbs], r: [batch][n_limbs], c: [batch][nn_limbs]. */
+int zkp_verify_opening(zkp_ctx* ctx, int batch, int m_limbs, const uint32_t* m, const uint32_t* r, const uint32_t* c, uint8_t* ok);
+/* CompositeDLogProof (wi_dlog_proof.rs:46-91): one DLogStatement {N, g, ni} per proof (rows of n_limbs limbs, every N odd;
+ * no zkp_set_key needed).  prove: secret [batch][secret_limbs], the prover's sample r < 2^(K + K' + S) [batch][r_limbs];
+ * out x = g^r mod N [batch][n_limbs], y = r + e * secret (unreduced) [batch][y_limbs], e = H(x, g, N, ni);
+ * fault[b] = 1 if y overflows y_limbs.
+ * verify: fault[b] = 1 where the reference's asserts fire (N <= 2^128, gcd(g, N) != 1, gcd(ni, N) != 1: panics);
+ * accept[b] = (x == g^y * ni^e mod N). */
+int zkp_dlog_prove(zkp_ctx* ctx, int batch, int n_limbs, const uint32_t* N, const uint32_t* g, const uint32_t* ni,
+                   const uint32_t* secret, int secret_limbs, const uint32_t* r, int r_limbs, int y_limbs, uint32_t* x, uint32_t* y,
+                   uint8_t* fault);
+int zkp_dlog_verify(zkp_ctx* ctx, int batch, int n_limbs, const uint32_t* N, const uint32_t* g, const uint32_t* ni, const uint32_t* x,
+                    const uint32_t* y, int y_limbs, uint8_t* accept, uint8_t* fault);
+/* CorrectMessageProof (correct_message.rs:35-162) under the current key: M valid messages per proof.
+ * prove: valid [batch][M][m_limbs], msg [batch][m_limbs], randomness r [batch][n_limbs], e_rand [batch][M-1][8] (B = 256 bits),
+ * z_rand [batch][M-1][n_limbs], w [batch][n_limbs]; out ciphertext [batch][nn_limbs], e_vec [batch][M][8],
+ * z_vec [batch][M][n_limbs], a_vec [batch][M][nn_limbs]; fault[b] = 1 where the reference panics (message not among the
+ * valid ones: index past the random vectors; a non-invertible value under unwrap()).
+ * verify: fault[b] = 1 where assert_eq!(chal, ei_sum) fires; accept[b] = AND_i (u_i^e_i * a_i == z_i^n mod nn). */
+int zkp_correct_message_prove(zkp_ctx* ctx, int batch, int M, int m_limbs, const uint32_t* valid, const uint32_t* msg,
+                              const uint32_t* r, const uint32_t* e_rand, const uint32_t* z_rand, const uint32_t* w,
+                              uint32_t* ciphertext, uint32_t* e_vec, uint32_t* z_vec, uint32_t* a_vec, uint8_t* fault);
+int zkp_correct_message_verify(zkp_ctx* ctx, int batch, int M, int m_limbs, int e_limbs, const uint32_t* ciphertext,
+                               const uint32_t* valid, const uint32_t* e_vec, const uint32_t* z_vec, const uint32_t* a_vec,
+                               uint8_t* accept, uint8_t* fault);
+
 /* ---- measurement ----------------------------------------------------------
  * Register-only multiply-add issue-rate microbenchmark (the roofline denominator
  * for the modexp kernels).  variant 0: independent IMAD.WIDE.U32, 1: the

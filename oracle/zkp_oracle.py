@@ -491,6 +491,112 @@ class VerlinProof:
 
 
 # ----------------------------------------------------------------------------------------------
+# The remaining public proofs
+def verify_opening(n, m, r, c) -> bool:
+    """CorrectOpening::verify_opening, correct_opening.rs:17-30."""
+    return c == paillier_encrypt(n, m, r)
+
+
+DLOG_K, DLOG_K_PRIME, DLOG_SAMPLE_S = 128, 128, 256  # wi_dlog_proof.rs:19-21
+
+
+class CompositeDLogProof:
+    """wi_dlog_proof.rs:28-91.  statement (N, g, ni), secret s with ni = g^-s mod N; r is the prover's sample below
+    2^(K + K' + SAMPLE_S) (explicit here; the reference draws it with sample_below, :52-53)."""
+
+    def __init__(self, x, y):
+        self.x, self.y = x, y
+
+    @staticmethod
+    def prove(N, g, ni, secret, r):
+        x = pow(g, r, N)  # :54
+        e = compute_digest([x, g, N, ni])  # :55-60
+        return CompositeDLogProof(x, r + e * secret)  # :61 (unreduced)
+
+    def verify(self, N, g, ni):
+        import math
+
+        if not N > 2 ** DLOG_K:  # :68 assert!
+            raise ReferencePanic("N <= 2^K")
+        if math.gcd(g, N) != 1 or math.gcd(ni, N) != 1:  # :71-72 assert_eq!
+            raise ReferencePanic("g or ni not in Z_N*")
+        e = compute_digest([self.x, g, N, ni])  # :74-79
+        if self.x != pow(g, self.y, N) * pow(ni, e, N) % N:  # :80-85
+            raise IncorrectProof()
+
+    def to_json(self):
+        """#[derive(Serialize)] with curv's native BigInt serde (RECALLED: hex of to_bytes), wi_dlog_proof.rs:28-32."""
+        return json.dumps({"x": serde_bigint_native(self.x), "y": serde_bigint_native(self.y)}, separators=(",", ":"))
+
+    @staticmethod
+    def from_json(s):
+        d = json.loads(s)
+        return CompositeDLogProof(serde_bigint_native_parse(d["x"]), serde_bigint_native_parse(d["y"]))
+
+
+CM_B = 256  # correct_message.rs:19
+
+
+class CorrectMessageProof:
+    """correct_message.rs:25-162.  Randomness explicit: r (encryption), e_rand / z_rand (the M-1 simulated branches,
+    sample(B) and sample_below(n)), w."""
+
+    def __init__(self, e_vec, z_vec, a_vec, ciphertext, valid_messages, n):
+        self.e_vec, self.z_vec, self.a_vec, self.ciphertext, self.valid_messages, self.n = e_vec, z_vec, a_vec, ciphertext, valid_messages, n
+
+    @staticmethod
+    def _u_vec(n, ciphertext, valid_messages):
+        nn = n * n
+        return [ciphertext * _mod_inv((m * n + 1) % nn, nn) % nn for m in valid_messages]  # :50-56 / :134-142
+
+    @staticmethod
+    def prove(n, valid_messages, message, r, e_rand, z_rand, w):
+        nn, M = n * n, len(valid_messages)
+        ciphertext = paillier_encrypt(n, message, r)  # :43-49
+        u = CorrectMessageProof._u_vec(n, ciphertext, valid_messages)
+
+        def rnd(vec, j):
+            if j >= len(vec):
+                raise ReferencePanic("index out of bounds: the message is not one of the valid messages")
+            return vec[j]
+
+        a_vec, j = [], 0
+        for i in range(M):  # :66-83
+            if valid_messages[i] == message:
+                a_vec.append(pow(w, n, nn))
+            else:
+                zi_n = pow(rnd(z_rand, j), n, nn)
+                ui_ei_inv = _mod_inv(pow(u[i], rnd(e_rand, j), nn), nn)
+                j += 1
+                a_vec.append(zi_n * ui_ei_inv % nn)
+        two_b = 1 << CM_B
+        chal = compute_digest(a_vec) % two_b  # :85-87
+        ei = (chal - sum(e_rand[: M - 1]) % two_b) % two_b  # :88-91
+        zi = w * pow(r, ei, n) % n  # :92-93
+        e_vec, z_vec, j = [], [], 0
+        for i in range(M):  # :95-121
+            if valid_messages[i] == message:
+                e_vec.append(ei)
+                z_vec.append(zi)
+            else:
+                e_vec.append(rnd(e_rand, j))
+                z_vec.append(rnd(z_rand, j))
+                j += 1
+        return CorrectMessageProof(e_vec, z_vec, a_vec, ciphertext, list(valid_messages), n)
+
+    def verify(self):
+        n = self.n
+        nn, two_b = n * n, 1 << CM_B
+        chal = compute_digest(self.a_vec) % two_b  # :128-129
+        if chal != sum(self.e_vec) % two_b:  # :130-133 assert_eq!
+            raise ReferencePanic("chal != ei_sum")
+        u = CorrectMessageProof._u_vec(n, self.ciphertext, self.valid_messages)
+        ok = [pow(u[i], self.e_vec[i], nn) * self.a_vec[i] % nn == pow(self.z_vec[i], n, nn) for i in range(len(u))]  # :143-150
+        if not all(ok):
+            raise IncorrectProof()
+
+
+# ----------------------------------------------------------------------------------------------
 # serde codecs of src/serialize.rs (decimal strings)
 def serialize_bigint(x: int) -> str:
     """serialize.rs:9-11"""

@@ -1,0 +1,89 @@
+"""CPU suite (-m "not gpu") for the oracle restatements of the remaining public proofs:
+CorrectOpening, CompositeDLogProof, CorrectMessageProof -- the accept / reject / panic classes of the reference's own
+tests (correct_opening.rs:47-56, wi_dlog_proof.rs:112-196, correct_message.rs:170-197)."""
+import random
+
+import pytest
+
+from util import keys, po
+
+
+def jacobi_minus_one_base(rng, p, q):
+    """h1 with Jacobi symbol -1, as wi_dlog_proof.rs:121-126 picks it (legendre_symbol :93-105)."""
+    leg = lambda a, pr: 1 if pow(a, (pr - 1) // 2, pr) == 1 else -1
+    n = p * q
+    while True:
+        h1 = rng.randrange(1, n - 1)
+        if leg(h1, p) * leg(h1, q) == -1:
+            return h1
+
+
+def dlog_statement(rng, p, q, kind="good"):
+    n = p * q
+    h1 = jacobi_minus_one_base(rng, p, q)
+    secret = rng.randrange(1 << po.DLOG_SAMPLE_S)
+    if kind == "good":
+        h2 = pow(pow(h1, -1, n), secret, n)        # wi_dlog_proof.rs:128-129
+    elif kind == "plus":
+        h2 = pow(h1, secret, n)                    # test_bad_dlog_proof: +secret instead of -secret
+    else:
+        h2 = rng.randrange(1, n - 1)               # test_bad_dlog_proof_2: random ni
+    return n, h1, h2, secret
+
+
+def test_verify_opening():
+    p, q = keys(2048)[0]
+    n = p * q
+    r = 0x1234567 * 3 + 1
+    c = po.paillier_encrypt(n, 10, r)
+    m2, r2 = po.paillier_open(p, q, c)             # correct_opening.rs:50-55
+    assert (m2, r2 % n) == (10, r % n) and po.verify_opening(n, m2, r2, c)
+    assert not po.verify_opening(n, 11, r2, c) and not po.verify_opening(n, 10, r2 + 1, c)
+
+
+@pytest.mark.parametrize("bits", [1024, 2048])
+def test_dlog_proof_classes(bits):
+    rng = random.Random(bits)
+    p, q = keys(bits)[0]
+    R = 1 << (po.DLOG_K + po.DLOG_K_PRIME + po.DLOG_SAMPLE_S)
+    N, g, ni, s = dlog_statement(rng, p, q, "good")
+    proof = po.CompositeDLogProof.prove(N, g, ni, s, rng.randrange(R))
+    proof.verify(N, g, ni)
+    assert po.CompositeDLogProof.from_json(proof.to_json()).__dict__ == proof.__dict__
+    for kind in ("plus", "random"):
+        N, g, ni, s = dlog_statement(rng, p, q, kind)
+        with pytest.raises(po.IncorrectProof):
+            po.CompositeDLogProof.prove(N, g, ni, s, rng.randrange(R)).verify(N, g, ni)
+    with pytest.raises(po.ReferencePanic):       # g shares a factor with N: assert_eq!(gcd, 1)
+        po.CompositeDLogProof(1, 1).verify(N, p, ni)
+    with pytest.raises(po.ReferencePanic):       # N <= 2^K
+        po.CompositeDLogProof(1, 1).verify((1 << 128) - 159, 3, 5)
+
+
+@pytest.mark.parametrize("bits", [1024, 2048])
+def test_correct_message_proof_classes(bits):
+    rng = random.Random(bits + 1)
+    p, q = keys(bits)[0]
+    n = p * q
+    valid = [3, 4, 5, 6]                           # correct_message.rs:172-179
+    rand = lambda: dict(r=rng.randrange(1, n), e_rand=[rng.getrandbits(256) for _ in valid[1:]],
+                        z_rand=[rng.randrange(1, n) for _ in valid[1:]], w=rng.randrange(1, n))
+    for msg in valid:
+        proof = po.CorrectMessageProof.prove(n, valid, msg, **rand())
+        proof.verify()
+        assert sum(proof.e_vec) % (1 << 256) == po.compute_digest(proof.a_vec)
+    with pytest.raises(po.ReferencePanic):       # test_bad_message_zk_proof: 7 is not a valid message
+        po.CorrectMessageProof.prove(n, valid, 7, **rand())
+    proof = po.CorrectMessageProof.prove(n, valid, 5, **rand())
+    proof.z_vec[1] = (proof.z_vec[1] + 1) % n
+    with pytest.raises(po.IncorrectProof):
+        proof.verify()
+    proof = po.CorrectMessageProof.prove(n, valid, 5, **rand())
+    proof.e_vec[0] ^= 1                            # breaks chal == sum e: assert_eq! panics
+    with pytest.raises(po.ReferencePanic):
+        proof.verify()
+    # a ciphertext of a message outside the list cannot be proven even by a cheating prover who claims slot 0
+    forged = po.CorrectMessageProof.prove(n, valid, 3, **rand())
+    forged.ciphertext = po.paillier_encrypt(n, 7, rng.randrange(1, n))
+    with pytest.raises(po.IncorrectProof):
+        forged.verify()

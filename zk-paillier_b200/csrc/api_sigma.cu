@@ -6,134 +6,9 @@
 // Each call uploads the statement/witness/randomness rows, sequences K1 (Enc), K2 (mod_pow with the
 // per-proof challenge / response exponents), K3 (mod_mul), K4 (the Fiat-Shamir hash) and the
 // per-proof helpers of sigma.cu on the device, and downloads the proof rows or verdicts.
-#include "ctx.h"
+#include "sig.h"
 
 using namespace zkp;
-
-namespace {
-
-// Bump allocator over one device buffer for the temporaries of a call.
-struct Arena {
-  zkp_ctx* c;
-  size_t off = 0, cap = 0;
-  uint8_t* base = nullptr;
-  std::vector<size_t> wants;
-  explicit Arena(zkp_ctx* ctx) : c(ctx) {}
-  cudaError_t reserve(size_t bytes) {
-    cudaError_t e = c->in0.ensure(bytes);
-    base = c->in0.as<uint8_t>();
-    cap = bytes;
-    off = 0;
-    return e;
-  }
-  template <class U>
-  U* get(size_t count) {
-    size_t bytes = (count * sizeof(U) + 255) & ~size_t(255);
-    if (off + bytes > cap) return nullptr;
-    U* p = reinterpret_cast<U*>(base + off);
-    off += bytes;
-    return p;
-  }
-};
-
-struct Sig {
-  zkp_ctx* c;
-  cudaStream_t st;
-  int batch, nl, nnl;
-  Arena ar;
-  bool bad = false;
-  Sig(zkp_ctx* ctx, int b) : c(ctx), st(ctx->stream), batch(b), nl(ctx->n.limbs), nnl(ctx->nn.limbs), ar(ctx) {}
-
-  uint32_t* rows(int limbs) {
-    uint32_t* p = ar.get<uint32_t>((size_t)batch * limbs);
-    if (!p) bad = true;
-    return p;
-  }
-  uint32_t* up(const uint32_t* host, int limbs) {  // upload [batch][limbs]
-    uint32_t* p = rows(limbs);
-    if (p && cudaMemcpyAsync(p, host, (size_t)batch * limbs * 4, cudaMemcpyHostToDevice, st) != cudaSuccess) bad = true;
-    return p;
-  }
-  void down(uint32_t* host, const uint32_t* dev, int limbs) {
-    if (host && cudaMemcpyAsync(host, dev, (size_t)batch * limbs * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) bad = true;
-  }
-  void ck(cudaError_t e) {
-    if (e != cudaSuccess) {
-      bad = true;
-      fail_cuda(c, e, "sigma-protocol launch");
-    }
-  }
-  // Paillier::encrypt_with_chosen_randomness(ek, m, r); m == nullptr means the plaintext 0 (c = r^n mod nn)
-  uint32_t* enc(const uint32_t* m, int m_limbs, const uint32_t* r, int r_limbs) {
-    uint32_t* out = rows(nnl);
-    if (bad) return out;
-    ProfScope ps(c, KID_MODEXP_SHARED, batch);
-    ck(launch_enc(c, r, r_limbs, m, m_limbs, out, batch));
-    return out;
-  }
-  // BigInt::mod_pow(base, exp, nn) / Paillier::mul, per-proof exponent
-  uint32_t* powm(const uint32_t* base, int base_limbs, const uint32_t* exp, int exp_limbs) {
-    uint32_t* out = rows(nnl);
-    if (bad) return out;
-    ProfScope ps(c, KID_MODEXP_VAR, batch);
-    ck(launch_pow_nn(c, base, base_limbs, exp, exp_limbs, 32 * exp_limbs, 1, out, batch));
-    return out;
-  }
-  // BigInt::mod_mul(a, b, nn) / Paillier::add
-  uint32_t* mulm(const uint32_t* a, int a_limbs, const uint32_t* b, int b_limbs) {
-    uint32_t* out = rows(nnl);
-    if (bad) return out;
-    ProfScope ps(c, KID_MODMUL, batch);
-    ck(launch_modmul_shared(c->nn.view(), 0, a, a_limbs, b, b_limbs, 1, out, nnl, batch, st));
-    return out;
-  }
-  // e = compute_digest(n, items...) as 8 limbs
-  uint32_t* challenge(std::initializer_list<const uint32_t*> items) {
-    uint8_t* dig = ar.get<uint8_t>((size_t)batch * 32);
-    uint32_t* e = rows(8);
-    if (!dig || bad) { bad = true; return e; }
-    ShaSegs s;
-    s.nseg = 0;
-    s.seg[s.nseg++] = {c->n.mod.as<uint32_t>(), 0, 1, nl};
-    for (const uint32_t* p : items) s.seg[s.nseg++] = {p, (long long)nnl, 1, nnl};
-    {
-      ProfScope ps(c, KID_SHA, batch);
-      ck(launch_sha256_transcript(s, batch, dig, st));
-    }
-    ProfScope ps(c, KID_OTHER, batch);
-    ck(launch_digest_to_limbs(dig, batch, e, st));
-    return e;
-  }
-  int finish(const char* what) {
-    if (bad) {
-      cudaStreamSynchronize(st);
-      if (c->err.empty()) c->err = what;
-      return ZKP_E_CUDA;
-    }
-    cudaError_t e = cudaStreamSynchronize(st);
-    if (e != cudaSuccess) return fail_cuda(c, e, what);
-    return ZKP_OK;
-  }
-};
-
-int sigma_begin(zkp_ctx* c, int batch, int z_limbs, size_t rows_nnl, size_t rows_other_bytes, Sig& s) {
-  if (!c->paillier) return fail(c, ZKP_E_STATE, "zkp_set_key not called");
-  if (batch <= 0) return fail(c, ZKP_E_ARG, "batch must be positive");
-  if (z_limbs && (z_limbs % 4 || z_limbs < c->n.limbs + 12 || z_limbs > c->nn.S))
-    return fail(c, ZKP_E_ARG, "z_limbs must be a multiple of 4 in [n_limbs + 12, nn_limbs]");
-  cudaError_t e = cudaSetDevice(c->device);
-  if (e != cudaSuccess) return fail_cuda(c, e, "cudaSetDevice");
-  c->err.clear();
-  // generous: every helper result is one [batch][nn_limbs] row array
-  size_t bytes = (size_t)batch * ((rows_nnl + 12) * s.nnl * 4 + rows_other_bytes + 256) + 64 * 256;
-  e = s.ar.reserve(bytes);
-  if (e != cudaSuccess) return fail_cuda(c, e, "arena");
-  e = ensure_table(c, c->nn.S, kTableVar);
-  if (e != cudaSuccess) return fail_cuda(c, e, "table");
-  return ZKP_OK;
-}
-
-}  // namespace
 
 extern "C" {
 

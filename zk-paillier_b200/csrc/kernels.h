@@ -186,8 +186,28 @@ cudaError_t launch_modadd(const uint32_t* a, const uint32_t* c, const uint32_t* 
 cudaError_t launch_rows_equal(const uint32_t* x, const uint32_t* y, int limbs, int batch, int and_in, uint8_t* accept,
                               cudaStream_t st);
 // out[b] = v[b]^-1 mod m (m odd, shared); fault[b] = 1 when not invertible.  scratch: [batch][4*limbs]
+// m_stride = 0: one shared modulus; otherwise row b uses m + b * m_stride (per-statement moduli; gcd(v, m) == 1 checks).
 cudaError_t launch_modinv(const uint32_t* v, const uint32_t* m, int limbs, int batch, uint32_t* scratch, uint32_t* out,
-                          uint8_t* fault, cudaStream_t st);
+                          uint8_t* fault, cudaStream_t st, long long m_stride = 0);
+
+// ---- helpers of the remaining proofs (more.cu): CompositeDLogProof, CorrectMessageProof ----------
+// out[j] = a[j] * b[j] mod mods[j / mod_per] (rows of `limbs` limbs; r2 / n0inv from launch_mont_setup, S = kernel width)
+cudaError_t launch_modmul_var(const uint32_t* a, const uint32_t* b, int limbs, const uint32_t* mods, const uint32_t* r2,
+                              const uint32_t* n0inv, int mod_per, int S, int jobs, uint32_t* out, cudaStream_t st);
+// fault[b] = 1 unless N_b > 2^bits
+cudaError_t launch_gt_pow2(const uint32_t* n, int limbs, int bits, int batch, uint8_t* fault, cudaStream_t st);
+// out[t] = (1 + m_t n)^-1 mod n^2 = 1 + ((n - m_t) mod n) n, m_t < n: [rows][nl] -> [rows][2 nl]
+cudaError_t launch_gm_inv(const uint32_t* m, const uint32_t* n, int nl, int rows, uint32_t* out, cudaStream_t st);
+cudaError_t launch_cm_layout(const uint32_t* valid, const uint32_t* msg, int ml, const uint32_t* e_rand, int el,
+                             const uint32_t* z_rand, const uint32_t* w, int nl, int batch, int M, uint8_t* match, uint32_t* esel,
+                             uint32_t* zsel, uint32_t* esum, uint8_t* fault, cudaStream_t st);
+cudaError_t launch_sub_pow2(const uint32_t* a, const uint32_t* c, int limbs, int batch, uint32_t* out, cudaStream_t st);
+cudaError_t launch_cm_finish(const uint8_t* match, const uint32_t* e, int el, const uint32_t* z, int nl, int batch, int M,
+                             uint32_t* esel, uint32_t* zsel, cudaStream_t st);
+cudaError_t launch_sum_pow2(const uint32_t* e, int el, int ol, int batch, int M, uint32_t* esum, cudaStream_t st);
+// out[b] = AND (mode 0) / OR (mode 1) of rows[b][0..M); merge: combined with the value already in out[b]
+cudaError_t launch_rows_reduce(const uint8_t* rows, int batch, int M, int mode, int merge, uint8_t* out, cudaStream_t st);
+cudaError_t launch_rows_differ_fault(const uint32_t* x, const uint32_t* y, int limbs, int batch, uint8_t* fault, cudaStream_t st);
 
 // IMAD.WIDE.U32 peak microbenchmark (register-only).  variant 0: independent
 // IMAD.WIDE.U32; 1: carry-chained IMAD.WIDE.U32.X rows; 2: plain IMAD (32-bit).

@@ -1,0 +1,150 @@
+// Shared plumbing of the sigma-protocol entry points (api_sigma.cu, api_more.cu): a bump allocator over one device
+// buffer and the handful of batched primitives every proof is sequenced from (Enc, mod_pow, mod_mul, Fiat-Shamir hash).
+#pragma once
+#include <initializer_list>
+
+#include "ctx.h"
+
+namespace zkp {
+// Bump allocator over one device buffer for the temporaries of a call.
+struct Arena {
+  zkp_ctx* c;
+  size_t off = 0, cap = 0;
+  uint8_t* base = nullptr;
+  std::vector<size_t> wants;
+  explicit Arena(zkp_ctx* ctx) : c(ctx) {}
+  cudaError_t reserve(size_t bytes) {
+    cudaError_t e = c->in0.ensure(bytes);
+    base = c->in0.as<uint8_t>();
+    cap = bytes;
+    off = 0;
+    return e;
+  }
+  template <class U>
+  U* get(size_t count) {
+    size_t bytes = (count * sizeof(U) + 255) & ~size_t(255);
+    if (off + bytes > cap) return nullptr;
+    U* p = reinterpret_cast<U*>(base + off);
+    off += bytes;
+    return p;
+  }
+};
+
+struct Sig {
+  zkp_ctx* c;
+  cudaStream_t st;
+  int batch, nl, nnl;
+  Arena ar;
+  bool bad = false;
+  Sig(zkp_ctx* ctx, int b) : c(ctx), st(ctx->stream), batch(b), nl(ctx->n.limbs), nnl(ctx->nn.limbs), ar(ctx) {}
+
+  // `jobs` < 0 means one row per proof (batch rows); the ring proof passes batch * M
+  int nrows(int jobs) const { return jobs < 0 ? batch : jobs; }
+  uint32_t* rows(int limbs, int jobs = -1) {
+    uint32_t* p = ar.get<uint32_t>((size_t)nrows(jobs) * limbs);
+    if (!p) bad = true;
+    return p;
+  }
+  uint8_t* bytes(size_t count, bool zero = false) {
+    uint8_t* p = ar.get<uint8_t>(count);
+    if (!p) { bad = true; return p; }
+    if (zero && cudaMemsetAsync(p, 0, count, st) != cudaSuccess) bad = true;
+    return p;
+  }
+  uint32_t* up(const uint32_t* host, int limbs, int jobs = -1) {  // upload [rows][limbs]
+    uint32_t* p = rows(limbs, jobs);
+    if (p && cudaMemcpyAsync(p, host, (size_t)nrows(jobs) * limbs * 4, cudaMemcpyHostToDevice, st) != cudaSuccess) bad = true;
+    return p;
+  }
+  void down(uint32_t* host, const uint32_t* dev, int limbs, int jobs = -1) {
+    if (host && !bad && cudaMemcpyAsync(host, dev, (size_t)nrows(jobs) * limbs * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) bad = true;
+  }
+  void down8(uint8_t* host, const uint8_t* dev, size_t count) {
+    if (host && !bad && cudaMemcpyAsync(host, dev, count, cudaMemcpyDeviceToHost, st) != cudaSuccess) bad = true;
+  }
+  void ck(cudaError_t e) {
+    if (e != cudaSuccess) {
+      bad = true;
+      fail_cuda(c, e, "sigma-protocol launch");
+    }
+  }
+  // Paillier::encrypt_with_chosen_randomness(ek, m, r); m == nullptr means the plaintext 0 (c = r^n mod nn)
+  uint32_t* enc(const uint32_t* m, int m_limbs, const uint32_t* r, int r_limbs, int jobs = -1) {
+    uint32_t* out = rows(nnl, jobs);
+    if (bad) return out;
+    ProfScope ps(c, KID_MODEXP_SHARED, nrows(jobs));
+    ck(launch_enc(c, r, r_limbs, m, m_limbs, out, nrows(jobs)));
+    return out;
+  }
+  // BigInt::mod_pow(base, exp, nn) / Paillier::mul, per-proof exponent
+  uint32_t* powm(const uint32_t* base, int base_limbs, const uint32_t* exp, int exp_limbs, int jobs = -1) {
+    uint32_t* out = rows(nnl, jobs);
+    if (bad) return out;
+    ProfScope ps(c, KID_MODEXP_VAR, nrows(jobs));
+    ck(launch_pow_nn(c, base, base_limbs, exp, exp_limbs, 32 * exp_limbs, 1, out, nrows(jobs)));
+    return out;
+  }
+  // BigInt::mod_mul(a, b, nn) / Paillier::add
+  // row j of a is multiplied by row j / b_per of b
+  uint32_t* mulm(const uint32_t* a, int a_limbs, const uint32_t* b, int b_limbs, int jobs = -1, int b_per = 1) {
+    uint32_t* out = rows(nnl, jobs);
+    if (bad) return out;
+    ProfScope ps(c, KID_MODMUL, nrows(jobs));
+    ck(launch_modmul_shared(c->nn.view(), 0, a, a_limbs, b, b_limbs, b_per, out, nnl, nrows(jobs), st));
+    return out;
+  }
+  // the same modulo n
+  uint32_t* mulm_n(const uint32_t* a, int a_limbs, const uint32_t* b, int b_limbs, int jobs = -1, int b_per = 1) {
+    uint32_t* out = rows(nl, jobs);
+    if (bad) return out;
+    ProfScope ps(c, KID_MODMUL, nrows(jobs));
+    ck(launch_modmul_shared(c->n.view(), 0, a, a_limbs, b, b_limbs, b_per, out, nl, nrows(jobs), st));
+    return out;
+  }
+  // e = compute_digest(n, items...) as 8 limbs
+  uint32_t* challenge(std::initializer_list<const uint32_t*> items) {
+    uint8_t* dig = ar.get<uint8_t>((size_t)batch * 32);
+    uint32_t* e = rows(8);
+    if (!dig || bad) { bad = true; return e; }
+    ShaSegs s;
+    s.nseg = 0;
+    s.seg[s.nseg++] = {c->n.mod.as<uint32_t>(), 0, 1, nl};
+    for (const uint32_t* p : items) s.seg[s.nseg++] = {p, (long long)nnl, 1, nnl};
+    {
+      ProfScope ps(c, KID_SHA, batch);
+      ck(launch_sha256_transcript(s, batch, dig, st));
+    }
+    ProfScope ps(c, KID_OTHER, batch);
+    ck(launch_digest_to_limbs(dig, batch, e, st));
+    return e;
+  }
+  int finish(const char* what) {
+    if (bad) {
+      cudaStreamSynchronize(st);
+      if (c->err.empty()) c->err = what;
+      return ZKP_E_CUDA;
+    }
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return fail_cuda(c, e, what);
+    return ZKP_OK;
+  }
+};
+
+inline int sigma_begin(zkp_ctx* c, int batch, int z_limbs, size_t rows_nnl, size_t rows_other_bytes, Sig& s) {
+  if (!c->paillier) return fail(c, ZKP_E_STATE, "zkp_set_key not called");
+  if (batch <= 0) return fail(c, ZKP_E_ARG, "batch must be positive");
+  if (z_limbs && (z_limbs % 4 || z_limbs < c->n.limbs + 12 || z_limbs > c->nn.S))
+    return fail(c, ZKP_E_ARG, "z_limbs must be a multiple of 4 in [n_limbs + 12, nn_limbs]");
+  cudaError_t e = cudaSetDevice(c->device);
+  if (e != cudaSuccess) return fail_cuda(c, e, "cudaSetDevice");
+  c->err.clear();
+  // generous: every helper result is one [batch][nn_limbs] row array
+  size_t bytes = (size_t)batch * ((rows_nnl + 12) * s.nnl * 4 + rows_other_bytes + 256) + 64 * 256;
+  e = s.ar.reserve(bytes);
+  if (e != cudaSuccess) return fail_cuda(c, e, "arena");
+  e = ensure_table(c, c->nn.S, kTableVar);
+  if (e != cudaSuccess) return fail_cuda(c, e, "table");
+  return ZKP_OK;
+}
+
+}  // namespace zkp

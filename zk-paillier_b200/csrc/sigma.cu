@@ -131,8 +131,8 @@ struct Inv {
 };
 
 template <int L>
-__global__ void __launch_bounds__(128) modinv_kernel(const uint32_t* v, const uint32_t* m, int limbs, int batch, uint32_t* out,
-                                                     uint8_t* fault) {
+__global__ void __launch_bounds__(128) modinv_kernel(const uint32_t* v, const uint32_t* m, long long m_stride, int limbs, int batch,
+                                                     uint32_t* out, uint8_t* fault) {
   using M = Mp<32, L>;
   using I = Inv<L>;
   const int lane = threadIdx.x & 31;
@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(128) modinv_kernel(const uint32_t* v, const ui
   if (b >= batch) return;
   uint32_t u[L], w[L], x1[L], x2[L], mm[L], d[L];
   M::load_ext(u, v + (size_t)b * limbs, limbs, lane);
-  M::load_ext(mm, m, limbs, lane);
+  M::load_ext(mm, m + (size_t)b * m_stride, limbs, lane);  // m_stride = 0: one shared modulus
 #pragma unroll
   for (int j = 0; j < L; ++j) {
     w[j] = mm[j];
@@ -214,16 +214,16 @@ cudaError_t launch_rows_equal(const uint32_t* x, const uint32_t* y, int limbs, i
   return cudaGetLastError();
 }
 cudaError_t launch_modinv(const uint32_t* v, const uint32_t* m, int limbs, int batch, uint32_t* scratch, uint32_t* out,
-                          uint8_t* fault, cudaStream_t st) {
+                          uint8_t* fault, cudaStream_t st, long long m_stride) {
   (void)scratch;
   if (batch <= 0) return cudaSuccess;
   if (limbs > kMaxLimbs || limbs % 2) return cudaErrorInvalidValue;
   const unsigned grid = blocks_for(batch * 32ll, 128);
   const int per_lane = (limbs + 31) / 32;
-  if (per_lane <= 2) modinv_kernel<2><<<grid, 128, 0, st>>>(v, m, limbs, batch, out, fault);
-  else if (per_lane <= 4) modinv_kernel<4><<<grid, 128, 0, st>>>(v, m, limbs, batch, out, fault);
-  else if (per_lane <= 6) modinv_kernel<6><<<grid, 128, 0, st>>>(v, m, limbs, batch, out, fault);
-  else modinv_kernel<8><<<grid, 128, 0, st>>>(v, m, limbs, batch, out, fault);
+  if (per_lane <= 2) modinv_kernel<2><<<grid, 128, 0, st>>>(v, m, m_stride, limbs, batch, out, fault);
+  else if (per_lane <= 4) modinv_kernel<4><<<grid, 128, 0, st>>>(v, m, m_stride, limbs, batch, out, fault);
+  else if (per_lane <= 6) modinv_kernel<6><<<grid, 128, 0, st>>>(v, m, m_stride, limbs, batch, out, fault);
+  else modinv_kernel<8><<<grid, 128, 0, st>>>(v, m, m_stride, limbs, batch, out, fault);
   return cudaGetLastError();
 }
 

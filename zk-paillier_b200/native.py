@@ -67,6 +67,11 @@ SIGNATURES = {
     "zkp_mul_verify": (C.c_int, [C.c_void_p, C.c_int] + [_u32p] * 8 + [_u8p, _u8p]),
     "zkp_verlin_prove": (C.c_int, [C.c_void_p, C.c_int, C.c_int] + [_u32p] * 16),
     "zkp_verlin_verify": (C.c_int, [C.c_void_p, C.c_int, C.c_int] + [_u32p] * 8 + [_u8p]),
+    "zkp_verify_opening": (C.c_int, [C.c_void_p, C.c_int, C.c_int] + [_u32p] * 3 + [_u8p]),
+    "zkp_dlog_prove": (C.c_int, [C.c_void_p, C.c_int, C.c_int] + [_u32p] * 4 + [C.c_int, _u32p, C.c_int, C.c_int, _u32p, _u32p, _u8p]),
+    "zkp_dlog_verify": (C.c_int, [C.c_void_p, C.c_int, C.c_int] + [_u32p] * 5 + [C.c_int, _u8p, _u8p]),
+    "zkp_correct_message_prove": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int] + [_u32p] * 10 + [_u8p]),
+    "zkp_correct_message_verify": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int] + [_u32p] * 5 + [_u8p, _u8p]),
     "zkp_imad_peak": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double)]),
     "zkp_enc_kernel_launches": (C.c_int, [C.c_void_p] + [C.POINTER(C.c_longlong)] * 2),
     "zkp_enc_executed_mads": (C.c_int, [C.c_void_p] + [C.POINTER(C.c_double)] * 2),
@@ -468,3 +473,63 @@ class Context:
         acc = np.empty(batch, np.uint8)
         self._ck(self._lib.zkp_verlin_verify(self._h, batch, zl, *[_p32(v) for v in ins], _p8(acc)))
         return acc
+
+    # -- the remaining public proofs
+    def verify_opening(self, m, r, c):
+        """CorrectOpening::verify_opening (correct_opening.rs:17-30): ok[b] = (c[b] == Enc(m[b], r[b]))."""
+        m = _c32(m)
+        batch, (m, r, c) = self._rows((m, r, c), (m.shape[1], self.n_limbs, self.nn_limbs))
+        ok = np.empty(batch, np.uint8)
+        self._ck(self._lib.zkp_verify_opening(self._h, batch, m.shape[1], _p32(m), _p32(r), _p32(c), _p8(ok)))
+        return ok
+
+    def dlog_prove(self, N, g, ni, secret, r, y_limbs):
+        """CompositeDLogProof::prove (wi_dlog_proof.rs:46-65) -> (x, y, fault); rows [batch][n_limbs], one N per proof."""
+        N = _c32(N)
+        nl = N.shape[1]
+        secret, r = _c32(secret), _c32(r)
+        batch, (N, g, ni, secret, r) = self._rows((N, g, ni, secret, r), (nl, nl, nl, secret.shape[1], r.shape[1]))
+        x, y, fault = np.empty((batch, nl), np.uint32), np.empty((batch, y_limbs), np.uint32), np.empty(batch, np.uint8)
+        self._ck(self._lib.zkp_dlog_prove(self._h, batch, nl, _p32(N), _p32(g), _p32(ni), _p32(secret), secret.shape[1], _p32(r),
+                                          r.shape[1], y_limbs, _p32(x), _p32(y), _p8(fault)))
+        return x, y, fault
+
+    def dlog_verify(self, N, g, ni, x, y):
+        """CompositeDLogProof::verify (wi_dlog_proof.rs:66-91) -> (accept, fault)."""
+        N, y = _c32(N), _c32(y)
+        nl = N.shape[1]
+        batch, (N, g, ni, x, y) = self._rows((N, g, ni, x, y), (nl, nl, nl, nl, y.shape[1]))
+        acc, fault = np.empty(batch, np.uint8), np.empty(batch, np.uint8)
+        self._ck(self._lib.zkp_dlog_verify(self._h, batch, nl, _p32(N), _p32(g), _p32(ni), _p32(x), _p32(y), y.shape[1], _p8(acc),
+                                           _p8(fault)))
+        return acc, fault
+
+    def correct_message_prove(self, valid, msg, r, e_rand, z_rand, w):
+        """CorrectMessageProof::prove (correct_message.rs:35-125).  valid [batch][M][ml], msg [batch][ml], r / w [batch][nl],
+        e_rand [batch][M-1][8], z_rand [batch][M-1][nl] -> dict(ciphertext, e_vec, z_vec, a_vec, fault)."""
+        valid, msg, r, w = _c32(valid), _c32(msg), _c32(r), _c32(w)
+        batch, M, ml = valid.shape
+        nl, nnl = self.n_limbs, self.nn_limbs
+        e_rand = _c32(e_rand).reshape(batch, max(M - 1, 0), 8)
+        z_rand = _c32(z_rand).reshape(batch, max(M - 1, 0), nl)
+        assert msg.shape == (batch, ml) and r.shape == (batch, nl) and w.shape == (batch, nl)
+        out = {"ciphertext": np.empty((batch, nnl), np.uint32), "e_vec": np.empty((batch, M, 8), np.uint32),
+               "z_vec": np.empty((batch, M, nl), np.uint32), "a_vec": np.empty((batch, M, nnl), np.uint32), "fault": np.empty(batch, np.uint8)}
+        self._ck(self._lib.zkp_correct_message_prove(self._h, batch, M, ml, _p32(valid), _p32(msg), _p32(r),
+                                                     _p32(e_rand) if M > 1 else None, _p32(z_rand) if M > 1 else None, _p32(w),
+                                                     _p32(out["ciphertext"]), _p32(out["e_vec"]), _p32(out["z_vec"]), _p32(out["a_vec"]),
+                                                     _p8(out["fault"])))
+        return out
+
+    def correct_message_verify(self, ciphertext, valid, e_vec, z_vec, a_vec):
+        """CorrectMessageProof::verify (correct_message.rs:126-161) -> (accept, fault)."""
+        valid, e_vec = _c32(valid), _c32(e_vec)
+        batch, M, ml = valid.shape
+        nl, nnl = self.n_limbs, self.nn_limbs
+        el = e_vec.shape[2]
+        ciphertext, z_vec, a_vec = _c32(ciphertext), _c32(z_vec), _c32(a_vec)
+        assert ciphertext.shape == (batch, nnl) and e_vec.shape == (batch, M, el) and z_vec.shape == (batch, M, nl) and a_vec.shape == (batch, M, nnl)
+        acc, fault = np.empty(batch, np.uint8), np.empty(batch, np.uint8)
+        self._ck(self._lib.zkp_correct_message_verify(self._h, batch, M, ml, el, _p32(ciphertext), _p32(valid), _p32(e_vec), _p32(z_vec),
+                                                      _p32(a_vec), _p8(acc), _p8(fault)))
+        return acc, fault
