@@ -251,3 +251,61 @@ def test_interactive_correct_key(bits):
     d["e"] = str(int(d["e"]) ^ 1)
     pr = call("correct_key.prove", p=str(p), q=str(q), challenge=json.dumps(d), s_digest=str(va["s_digest"]))
     assert pr["prove_error"] == "`challenge.e` wasn't computed correctly"
+
+
+def test_remaining_proofs_through_the_host_mirror():
+    """Row f3: CompositeDLogProof (serde wire format, Err vs panic), CorrectMessageProof, CorrectOpening through the
+    reference-shaped C++ interface, on the same random stream as the oracle."""
+    from test_oracle_more import dlog_statement
+
+    rng = random.Random(33)
+    ks = keys(1024)
+    data = rng.randbytes(40000)
+    # --- CompositeDLogProof: statements over three different moduli; 1 = +secret (Err), 2 = random ni (Err)
+    kinds = ["good", "plus", "random", "good"]
+    st = [dlog_statement(rng, *ks[i % len(ks)], kind) for i, kind in enumerate(kinds)]
+    items = [{"N": str(N), "g": str(g), "ni": str(ni), "secret": str(s)} for N, g, ni, s in st]
+    r = call("dlog.prove", items=items, rng_hex=data.hex())
+    assert r["ok"], r
+    stream = Stream(data)
+    R = 1 << (po.DLOG_K + po.DLOG_K_PRIME + po.DLOG_SAMPLE_S)
+    want = [po.CompositeDLogProof.prove(N, g, ni, s, po.sample_below(stream, R)) for N, g, ni, s in st]
+    assert r["proofs"] == [w.to_json() for w in want]                       # byte-identical serde output
+    hexs = lambda **kv: json.dumps({k: po.serde_bigint_native(v) for k, v in kv.items()}, separators=(",", ":"))
+    assert r["statements"] == [hexs(N=N, g=g, ni=ni) for N, g, ni, _ in st]
+    vitems = [dict(it, proof=js) for it, js in zip(items, r["proofs"])]
+    assert call("dlog.verify", items=vitems)["results"] == ["ok", "incorrect", "incorrect", "ok"]
+    vitems[0]["g"] = str(ks[0][0] * 5)                                        # gcd(g, N) != 1: assert_eq! panics
+    vitems[3]["N"] = str((1 << 128) - 159)                                    # N <= 2^K: assert! panics
+    res = call("dlog.verify", items=vitems)["results"]
+    assert res[0].startswith("panic") and res[3].startswith("panic") and res[1:3] == ["incorrect", "incorrect"]
+
+    # --- CorrectMessageProof (correct_message.rs:170-197)
+    p, q = ks[1]
+    n = p * q
+    valid, msgs = [3, 4, 5, 6], [4, 6, 3]
+    r = call("cmsg.prove", n=str(n), valid=[str(v) for v in valid], messages=[str(m) for m in msgs], rng_hex=data.hex())
+    assert r["ok"], r
+    stream = Stream(data)
+    for m, pr in zip(msgs, r["proofs"]):
+        rr = po.sample_below(stream, n)
+        e_rand = [po.sample_bits(stream, 256) for _ in valid[1:]]
+        z_rand = [po.sample_below(stream, n) for _ in valid[1:]]
+        w = po.sample_below(stream, n)
+        wp = po.CorrectMessageProof.prove(n, valid, m, rr, e_rand, z_rand, w)
+        assert [int(v) for v in pr["e_vec"]] == wp.e_vec and [int(v) for v in pr["z_vec"]] == wp.z_vec
+        assert [int(v) for v in pr["a_vec"]] == wp.a_vec and int(pr["ciphertext"]) == wp.ciphertext
+    proofs = r["proofs"]
+    assert call("cmsg.verify", n=str(n), proofs=proofs)["results"] == ["ok", "ok", "ok"]
+    proofs[0]["z_vec"][2] = str(int(proofs[0]["z_vec"][2]) + 1)              # Err(IncorrectProof)
+    proofs[1]["e_vec"][0] = str(int(proofs[1]["e_vec"][0]) ^ 1)              # assert_eq!(chal, ei_sum) panics
+    res = call("cmsg.verify", n=str(n), proofs=proofs)["results"]
+    assert res[0] == "incorrect" and res[1].startswith("panic") and res[2] == "ok"
+    bad = call("cmsg.prove", n=str(n), valid=[str(v) for v in valid], messages=["7"], rng_hex=data.hex())   # test_bad_message_zk_proof
+    assert not bad["ok"] and bad["kind"] == "panic"
+
+    # --- CorrectOpening (correct_opening.rs:47-56): open with the private key, then verify the opening
+    c = po.paillier_encrypt(n, 10, rng.randrange(1, n))
+    m, rr = po.paillier_open(p, q, c)
+    items = [{"m": str(m), "r": str(rr), "c": str(c)}, {"m": str(m + 1), "r": str(rr), "c": str(c)}, {"m": str(m + n), "r": str(rr + n), "c": str(c)}]
+    assert call("opening.verify", n=str(n), items=items)["results"] == [True, False, True]

@@ -200,6 +200,55 @@ Json dispatch(const std::string& op, const Json& req) {
     out.set("results", outcomes(ps.size(), [&](size_t i) { ps[i].verify(eng, eks[i], salt.empty() ? &none : salt.data(), salt.size()); }));
     return out;
   }
+  // CompositeDLogProof: {"items": [{"N","g","ni","secret" | "proof"}]} (decimal strings; no key)
+  if (op == "dlog.prove" || op == "dlog.verify") {
+    const auto& its = req.at("items").arr;
+    std::vector<DLogStatement> st;
+    for (auto& it : its) st.push_back({dec(it, "N"), dec(it, "g"), dec(it, "ni")});
+    if (op == "dlog.prove") {
+      std::vector<BigInt> secret;
+      for (auto& it : its) secret.push_back(dec(it, "secret"));
+      Json arr = Json::array(), sts = Json::array();
+      for (auto& p : CompositeDLogProof::prove_batch(eng, st, secret, rng_from(req))) arr.push(Json::string(p.to_json()));
+      for (auto& s : st) sts.push(Json::string(DLogStatement::from_json(s.to_json()).to_json()));  // serde round trip of the statement
+      out.set("proofs", arr).set("statements", sts);
+    } else {
+      out.set("results", outcomes(its.size(), [&](size_t i) { CompositeDLogProof::from_json(its[i].at("proof").as_str()).verify(eng, st[i]); }));
+    }
+    return out;
+  }
+  // CorrectMessageProof: {"n", "valid": [...], "messages": [...]} -> proofs as plain JSON objects of decimal strings
+  // (the reference derives no serde for it); cmsg.verify takes them back
+  if (op == "cmsg.prove" || op == "cmsg.verify") {
+    EncryptionKey cek(dec(req, "n"));
+    auto decs = [](const Json& a) { std::vector<BigInt> v; for (auto& x : a.arr) v.push_back(BigInt::from_dec(x.as_str())); return v; };
+    auto encs = [](const std::vector<BigInt>& v) { Json a = Json::array(); for (auto& x : v) a.push(Json::string(x.to_dec())); return a; };
+    if (op == "cmsg.prove") {
+      Json arr = Json::array();
+      for (auto& p : CorrectMessageProof::prove_batch(eng, cek, decs(req.at("valid")), decs(req.at("messages")), rng_from(req)))
+        arr.push(Json::object().set("e_vec", encs(p.e_vec)).set("z_vec", encs(p.z_vec)).set("a_vec", encs(p.a_vec))
+                     .set("ciphertext", Json::string(p.ciphertext.to_dec())).set("valid_messages", encs(p.valid_messages)));
+      out.set("proofs", arr);
+    } else {
+      const auto& ps = req.at("proofs").arr;
+      out.set("results", outcomes(ps.size(), [&](size_t i) {
+        CorrectMessageProof p;
+        p.e_vec = decs(ps[i].at("e_vec")); p.z_vec = decs(ps[i].at("z_vec")); p.a_vec = decs(ps[i].at("a_vec"));
+        p.ciphertext = dec(ps[i], "ciphertext"); p.valid_messages = decs(ps[i].at("valid_messages")); p.ek = cek;
+        p.verify(eng);
+      }));
+    }
+    return out;
+  }
+  if (op == "opening.verify") {  // {"n", "items": [{"m","r","c"}]}
+    EncryptionKey oek(dec(req, "n"));
+    std::vector<BigInt> m, r, c;
+    for (auto& it : req.at("items").arr) { m.push_back(dec(it, "m")); r.push_back(dec(it, "r")); c.push_back(dec(it, "c")); }
+    Json arr = Json::array();
+    for (int v : Paillier::verify_opening_batch(eng, oek, m, r, c)) arr.push(Json::boolean(v != 0));
+    out.set("results", arr);
+    return out;
+  }
   // sigma protocols: {"n", "items": [{witness/statement/proof fields as decimal strings}], "rng_hex"}
   EncryptionKey ek(dec(req, "n"));
   const auto& items = req.at("items").arr;

@@ -911,4 +911,228 @@ class VerlinProof {                                                            /
   }
 };
 
+// ------------------------------------------------------------------------------------ CorrectOpening
+// `impl CorrectOpening for Paillier` (correct_opening.rs:17-30): c == encrypt_with_chosen_randomness(ek, m, r)
+struct Paillier {
+  static std::vector<int> verify_opening_batch(Engine& eng, const EncryptionKey& ek, const std::vector<BigInt>& m, const std::vector<BigInt>& r,
+                                               const std::vector<BigInt>& c) {
+    const size_t B = m.size();
+    if (B == 0) return {};
+    eng.use_key(ek);
+    const size_t nl = eng.nl(), nnl = eng.nnl();
+    std::vector<BigInt> mr, rr;
+    for (size_t b = 0; b < B; ++b) {
+      mr.push_back(m[b] % ek.n);  // (m n + 1) % nn only depends on m mod n
+      rr.push_back(r[b] % ek.n);  // r^n mod nn only depends on r mod n
+      if (c[b].d.size() > nnl) throw std::length_error("ciphertext wider than n^2 rows");
+    }
+    std::vector<uint8_t> ok(B);
+    eng.check(zkp_verify_opening(eng.handle(), (int)B, (int)nl, pack(mr, nl).data(), pack(rr, nl).data(), pack(c, nnl).data(), ok.data()));
+    return std::vector<int>(ok.begin(), ok.end());
+  }
+  static bool verify_opening(Engine& eng, const EncryptionKey& ek, const BigInt& m, const BigInt& r, const BigInt& c) {
+    return verify_opening_batch(eng, ek, {m}, {r}, {c})[0] != 0;
+  }
+};
+
+// ------------------------------------------------------------------------------------ CompositeDLogProof
+struct DLogStatement {  // wi_dlog_proof.rs:34-39
+  BigInt N, g, ni;
+  std::string to_json() const { return Json::object().set("N", ser_native(N)).set("g", ser_native(g)).set("ni", ser_native(ni)).dump(); }
+  static DLogStatement from_json(const std::string& s) {
+    Json j = Json::parse(s);
+    return {de_native(j.at("N")), de_native(j.at("g")), de_native(j.at("ni"))};
+  }
+};
+class CompositeDLogProof {  // wi_dlog_proof.rs:28-32
+ public:
+  static constexpr size_t K = 128, K_PRIME = 128, SAMPLE_S = 256;  // :19-21
+  BigInt x, y;
+  static size_t width(const std::vector<DLogStatement>& st) {
+    size_t bits = 0;
+    for (auto& s : st) bits = std::max(bits, std::max(s.N.bit_length(), std::max(s.g.bit_length(), s.ni.bit_length())));
+    return limbs_for_bits(bits);
+  }
+  static std::vector<CompositeDLogProof> prove_batch(Engine& eng, const std::vector<DLogStatement>& st, const std::vector<BigInt>& secret,
+                                                     const ByteSource& rng = os_rng()) {
+    const size_t B = st.size();
+    if (B == 0) return {};
+    const size_t nl = width(st);
+    BigInt R = BigInt(1).shl(K + K_PRIME + SAMPLE_S);                                    // :51
+    std::vector<BigInt> N, g, ni, r;
+    size_t sbits = 1;
+    for (size_t b = 0; b < B; ++b) {
+      N.push_back(st[b].N); g.push_back(st[b].g); ni.push_back(st[b].ni);
+      r.push_back(BigInt::sample_below(rng, R));                                          // :52
+      sbits = std::max(sbits, secret[b].bit_length());
+    }
+    const size_t sl = limbs_for_bits(sbits), rl = limbs_for_bits(K + K_PRIME + SAMPLE_S);
+    const size_t yl = round4(std::max(rl, sl + 8) + 1);                                   // y = r + e * secret, e < 2^256
+    std::vector<uint32_t> x(B * nl), y(B * yl);
+    std::vector<uint8_t> fault(B);
+    eng.check(zkp_dlog_prove(eng.handle(), (int)B, (int)nl, pack(N, nl).data(), pack(g, nl).data(), pack(ni, nl).data(), pack(secret, sl).data(),
+                             (int)sl, pack(r, rl).data(), (int)rl, (int)yl, x.data(), y.data(), fault.data()));
+    std::vector<CompositeDLogProof> out(B);
+    for (size_t b = 0; b < B; ++b) {
+      if (fault[b]) throw std::length_error("y wider than its rows");
+      out[b].x = BigInt::from_limbs(&x[b * nl], nl);
+      out[b].y = BigInt::from_limbs(&y[b * yl], yl);
+    }
+    return out;
+  }
+  static CompositeDLogProof prove(Engine& eng, const DLogStatement& st, const BigInt& secret, const ByteSource& rng = os_rng()) {
+    return prove_batch(eng, {st}, {secret}, rng)[0];
+  }
+  // 1 accept, 0 Err(IncorrectProof), -1 where the reference's assert! / assert_eq! panics (:68-72)
+  static std::vector<int> verify_batch(Engine& eng, const std::vector<const CompositeDLogProof*>& ps, const std::vector<DLogStatement>& st) {
+    const size_t B = ps.size();
+    if (B == 0) return {};
+    const size_t nl = width(st);
+    size_t ybits = 1;
+    std::vector<BigInt> N, g, ni, x, y;
+    std::vector<int> out(B, 0);
+    std::vector<size_t> idx;
+    for (size_t b = 0; b < B; ++b) {
+      if (!st[b].N.is_odd() || ps[b]->x.d.size() > nl) {  // an even N has no Montgomery form: settle these few on the host rules
+        if (!st[b].N.is_odd()) throw std::domain_error("CompositeDLogProof: even modulus is not supported by the engine");
+        out[b] = 0;  // x >= 2^(32 nl) > N can never equal a residue modulo N; the asserts are still checked below
+        if (!(st[b].N > BigInt(1).shl(K)) || BigInt::gcd(st[b].g, st[b].N) != BigInt(1) || BigInt::gcd(st[b].ni, st[b].N) != BigInt(1)) out[b] = -1;
+        continue;
+      }
+      idx.push_back(b);
+      N.push_back(st[b].N); g.push_back(st[b].g); ni.push_back(st[b].ni); x.push_back(ps[b]->x); y.push_back(ps[b]->y);
+      ybits = std::max(ybits, ps[b]->y.bit_length());
+    }
+    if (idx.empty()) return out;
+    const size_t yl = limbs_for_bits(ybits);
+    std::vector<uint8_t> acc(idx.size()), fault(idx.size());
+    eng.check(zkp_dlog_verify(eng.handle(), (int)idx.size(), (int)nl, pack(N, nl).data(), pack(g, nl).data(), pack(ni, nl).data(),
+                              pack(x, nl).data(), pack(y, yl).data(), (int)yl, acc.data(), fault.data()));
+    for (size_t k = 0; k < idx.size(); ++k) out[idx[k]] = fault[k] ? -1 : acc[k];
+    return out;
+  }
+  void verify(Engine& eng, const DLogStatement& st) const {
+    const int v = verify_batch(eng, {this}, {st})[0];
+    if (v < 0) throw ReferencePanic("assertion failed: N > 2^K, gcd(g, N) == 1, gcd(ni, N) == 1");
+    if (!v) throw IncorrectProof();
+  }
+  std::string to_json() const { return Json::object().set("x", ser_native(x)).set("y", ser_native(y)).dump(); }
+  static CompositeDLogProof from_json(const std::string& s) {
+    Json j = Json::parse(s);
+    CompositeDLogProof p;
+    p.x = de_native(j.at("x"));
+    p.y = de_native(j.at("y"));
+    return p;
+  }
+};
+
+// ------------------------------------------------------------------------------------ CorrectMessageProof
+class CorrectMessageProof {  // correct_message.rs:25-32 (no serde derive in the reference)
+ public:
+  static constexpr size_t B_BITS = 256;  // :19
+  std::vector<BigInt> e_vec, z_vec, a_vec;
+  BigInt ciphertext;
+  std::vector<BigInt> valid_messages;
+  EncryptionKey ek;
+  CorrectMessageProof() : ek(BigInt(1)) {}
+  static std::vector<CorrectMessageProof> prove_batch(Engine& eng, const EncryptionKey& ek, const std::vector<BigInt>& valid_messages,
+                                                      const std::vector<BigInt>& messages, const ByteSource& rng = os_rng()) {
+    const size_t B = messages.size(), M = valid_messages.size();
+    if (B == 0) return {};
+    if (M == 0) throw ReferencePanic("attempt to subtract with overflow (no valid messages)");
+    eng.use_key(ek);
+    const size_t nl = eng.nl(), nnl = eng.nnl();
+    std::vector<BigInt> valid, msg, r, er, zr, w;
+    for (size_t b = 0; b < B; ++b) {
+      r.push_back(BigInt::sample_below(rng, ek.n));                                       // :41
+      for (auto& v : valid_messages) valid.push_back(v % ek.n);                            // (m n + 1) % nn depends on m mod n only
+      msg.push_back(messages[b]);
+      for (size_t j = 0; j + 1 < M; ++j) er.push_back(BigInt::sample(rng, B_BITS));        // :58-60
+      for (size_t j = 0; j + 1 < M; ++j) zr.push_back(BigInt::sample_below(rng, ek.n));    // :61-63
+      w.push_back(BigInt::sample_below(rng, ek.n));                                       // :65
+    }
+    // the engine matches slots by comparing rows: compare what the reference compares (the unreduced values)
+    std::vector<uint32_t> valid_rows(B * M * nl), msg_rows(B * nl);
+    for (size_t b = 0; b < B; ++b) {
+      bool any = false;
+      for (size_t i = 0; i < M; ++i) {
+        const bool eq = valid_messages[i] == messages[b];
+        any = any || eq;
+        // a slot that does not match must not compare equal after reduction either: give it the reduced value only when it
+        // differs from the reduced message, otherwise the proof below would take a branch the reference does not take
+        BigInt v = valid_messages[i] % ek.n;
+        if (!eq && v == messages[b] % ek.n) throw std::domain_error("CorrectMessageProof: two distinct messages congruent modulo n");
+        v.to_limbs(&valid_rows[(b * M + i) * nl], nl);
+      }
+      (messages[b] % ek.n).to_limbs(&msg_rows[b * nl], nl);
+      if (!any) throw ReferencePanic("index out of bounds: the message is not one of the valid messages");
+    }
+    std::vector<uint32_t> c(B * nnl), e(B * M * 8), z(B * M * nl), a(B * M * nnl);
+    std::vector<uint8_t> fault(B);
+    eng.check(zkp_correct_message_prove(eng.handle(), (int)B, (int)M, (int)nl, valid_rows.data(), msg_rows.data(), pack(r, nl).data(),
+                                        M > 1 ? pack(er, 8).data() : nullptr, M > 1 ? pack(zr, nl).data() : nullptr, pack(w, nl).data(), c.data(),
+                                        e.data(), z.data(), a.data(), fault.data()));
+    std::vector<CorrectMessageProof> out(B);
+    for (size_t b = 0; b < B; ++b) {
+      if (fault[b]) throw ReferencePanic("called `Option::unwrap()` on a `None` value (mod_inv)");
+      out[b].ciphertext = BigInt::from_limbs(&c[b * nnl], nnl);
+      for (size_t i = 0; i < M; ++i) {
+        out[b].e_vec.push_back(BigInt::from_limbs(&e[(b * M + i) * 8], 8));
+        out[b].z_vec.push_back(BigInt::from_limbs(&z[(b * M + i) * nl], nl));
+        out[b].a_vec.push_back(BigInt::from_limbs(&a[(b * M + i) * nnl], nnl));
+      }
+      out[b].valid_messages = valid_messages;
+      out[b].ek = ek;
+    }
+    return out;
+  }
+  static CorrectMessageProof prove(Engine& eng, const EncryptionKey& ek, const std::vector<BigInt>& valid_messages, const BigInt& message,
+                                   const ByteSource& rng = os_rng()) {
+    return prove_batch(eng, ek, valid_messages, {message}, rng)[0];
+  }
+  // 1 accept, 0 Err(IncorrectProof), -1 where assert_eq!(chal, ei_sum) panics (:133); proofs of one batch share ek and M
+  static std::vector<int> verify_batch(Engine& eng, const std::vector<const CorrectMessageProof*>& ps) {
+    const size_t B = ps.size();
+    if (B == 0) return {};
+    const EncryptionKey& ek = ps[0]->ek;
+    const size_t M = ps[0]->valid_messages.size();
+    eng.use_key(ek);
+    const size_t nl = eng.nl(), nnl = eng.nnl();
+    size_t ebits = 256;
+    for (auto* p : ps) {
+      if (!(p->ek == ek) || p->valid_messages.size() != M) throw std::invalid_argument("verify_batch: proofs must share the key and the number of messages");
+      if (p->e_vec.size() < M || p->z_vec.size() < M || p->a_vec.size() < M) throw ReferencePanic("index out of bounds: short proof vector");
+      for (auto& e : p->e_vec) ebits = std::max(ebits, e.bit_length());
+    }
+    const size_t el = limbs_for_bits(ebits);
+    std::vector<BigInt> c, valid, e, z, a;
+    for (auto* p : ps) {
+      c.push_back(p->ciphertext % ek.nn);
+      for (size_t i = 0; i < M; ++i) {
+        valid.push_back(p->valid_messages[i] % ek.n);
+        e.push_back(p->e_vec[i]);
+        z.push_back(p->z_vec[i] % ek.n);   // z^n mod nn depends on z mod n only
+        a.push_back(p->a_vec[i]);
+      }
+    }
+    // the transcript hashes a_vec as given: rows wider than n^2 cannot be represented -> not supported
+    for (auto& v : a)
+      if (v.d.size() > nnl) throw std::length_error("a_vec entry wider than n^2 rows");
+    // sum over ALL entries of e_vec, as the reference folds the whole vector (:130)
+    std::vector<uint8_t> acc(B), fault(B);
+    eng.check(zkp_correct_message_verify(eng.handle(), (int)B, (int)M, (int)nl, (int)el, pack(c, nnl).data(), pack(valid, nl).data(),
+                                         pack(e, el).data(), pack(z, nl).data(), pack(a, nnl).data(), acc.data(), fault.data()));
+    std::vector<int> out(B);
+    for (size_t b = 0; b < B; ++b) out[b] = fault[b] ? -1 : acc[b];
+    return out;
+  }
+  void verify(Engine& eng) const {
+    if (e_vec.size() != valid_messages.size() || a_vec.size() != valid_messages.size())
+      throw std::invalid_argument("CorrectMessageProof: vectors longer than the message list are not supported");
+    const int v = verify_batch(eng, {this})[0];
+    if (v < 0) throw ReferencePanic("assertion failed: `(left == right)` (chal, ei_sum)");
+    if (!v) throw IncorrectProof();
+  }
+};
+
 }  // namespace zkproofs
