@@ -309,3 +309,22 @@ def test_remaining_proofs_through_the_host_mirror():
     m, rr = po.paillier_open(p, q, c)
     items = [{"m": str(m), "r": str(rr), "c": str(c)}, {"m": str(m + 1), "r": str(rr), "c": str(c)}, {"m": str(m + n), "r": str(rr + n), "c": str(c)}]
     assert call("opening.verify", n=str(n), items=items)["results"] == [True, False, True]
+
+
+def test_paillier_encrypt_open_flow():
+    """Row f4 (the step before the path): Paillier::encrypt -> Paillier::open -> verify_opening, batched; the modexps
+    (K1m for Enc, K2 for the CRT decryption and the n-th root) run on the device (correct_opening.rs:47-56)."""
+    rng = random.Random(44)
+    for bits in (1024, 2048):
+        p, q = keys(bits)[0]
+        n = p * q
+        data = rng.randbytes(8000)
+        m = [10, 0, n - 1, rng.randrange(n), rng.randrange(n)]
+        r = call("paillier.flow", p=str(p), q=str(q), m=[str(v) for v in m], rng_hex=data.hex())
+        assert r["ok"], r
+        stream = Stream(data)
+        rs = [po.sample_below(stream, n) for _ in m]
+        assert [int(c) for c in r["c"]] == [po.paillier_encrypt(n, mi, ri) for mi, ri in zip(m, rs)]
+        assert [int(v) for v in r["m"]] == m and [int(v) for v in r["r"]] == rs
+        assert [po.paillier_open(p, q, int(c)) for c in r["c"]] == list(zip(m, rs))
+        assert r["opening_ok"] == [True] * len(m)

@@ -240,6 +240,22 @@ Json dispatch(const std::string& op, const Json& req) {
     }
     return out;
   }
+  if (op == "paillier.flow") {  // {"p","q","m":[...],"rng_hex"}: encrypt -> open -> verify_opening (correct_opening.rs:47-56), batched
+    DecryptionKey dk{dec(req, "p"), dec(req, "q")};
+    EncryptionKey fek(dk.p * dk.q);
+    std::vector<BigInt> m;
+    for (auto& x : req.at("m").arr) m.push_back(BigInt::from_dec(x.as_str()));
+    auto enc = Paillier::encrypt_batch(eng, fek, m, rng_from(req));
+    auto opened = Paillier::open_batch(eng, dk, enc.first);
+    auto ok = Paillier::verify_opening_batch(eng, fek, opened.first, opened.second, enc.first);
+    Json cs = Json::array(), ms = Json::array(), rs = Json::array(), oks = Json::array();
+    for (size_t i = 0; i < m.size(); ++i) {
+      cs.push(Json::string(enc.first[i].to_dec())); ms.push(Json::string(opened.first[i].to_dec()));
+      rs.push(Json::string(opened.second[i].to_dec())); oks.push(Json::boolean(ok[i] != 0));
+    }
+    out.set("c", cs).set("m", ms).set("r", rs).set("ok", Json::boolean(true)).set("opening_ok", oks);
+    return out;
+  }
   if (op == "opening.verify") {  // {"n", "items": [{"m","r","c"}]}
     EncryptionKey oek(dec(req, "n"));
     std::vector<BigInt> m, r, c;

@@ -914,6 +914,55 @@ class VerlinProof {                                                            /
 // ------------------------------------------------------------------------------------ CorrectOpening
 // `impl CorrectOpening for Paillier` (correct_opening.rs:17-30): c == encrypt_with_chosen_randomness(ek, m, r)
 struct Paillier {
+  // Paillier::encrypt_with_chosen_randomness (kzen-paillier; K1m on the device)
+  static std::vector<BigInt> encrypt_with_chosen_randomness_batch(Engine& eng, const EncryptionKey& ek, const std::vector<BigInt>& m,
+                                                                  const std::vector<BigInt>& r) {
+    const size_t B = m.size();
+    if (B == 0) return {};
+    eng.use_key(ek);
+    const size_t nl = eng.nl(), nnl = eng.nnl();
+    std::vector<BigInt> mr, rr;
+    for (size_t b = 0; b < B; ++b) { mr.push_back(m[b] % ek.n); rr.push_back(r[b] % ek.n); }
+    std::vector<uint32_t> out(B * nnl);
+    eng.check(zkp_paillier_enc(eng.handle(), pack(mr, nl).data(), (int)nl, pack(rr, nl).data(), (int)nl, (int)B, out.data()));
+    return unpack(out, nnl);
+  }
+  // Paillier::encrypt: r = sample_below(n) per plaintext (kzen-paillier RECALLED), then the above.  Returns (c, r).
+  static std::pair<std::vector<BigInt>, std::vector<BigInt>> encrypt_batch(Engine& eng, const EncryptionKey& ek, const std::vector<BigInt>& m,
+                                                                           const ByteSource& rng = os_rng()) {
+    std::vector<BigInt> r;
+    for (size_t b = 0; b < m.size(); ++b) r.push_back(BigInt::sample_below(rng, ek.n));
+    return {encrypt_with_chosen_randomness_batch(eng, ek, m, r), r};
+  }
+  // Paillier::decrypt by CRT (kzen-paillier RECALLED): m_p = L_p(c^(p-1) mod p^2) h_p mod p, likewise q, recombined.
+  // The two half-width modexps per ciphertext run on the device (K2); the plaintext is the unique m in [0, n) either way.
+  static std::vector<BigInt> decrypt_batch(Engine& eng, const DecryptionKey& dk, const std::vector<BigInt>& c) {
+    const size_t B = c.size();
+    if (B == 0) return {};
+    const BigInt &p = dk.p, &q = dk.q, one(1);
+    const BigInt n = p * q, pp = p * p, qq = q * q, pm1 = p - one, qm1 = q - one;
+    auto L = [&](const BigInt& x, const BigInt& pr) { return (x - one) / pr; };
+    auto h = [&](const BigInt& pr, const BigInt& prpr) {  // h_p = L_p((1 + n)^(p-1) mod p^2)^-1 mod p, and (1 + n)^(p-1) = 1 + (p-1) n mod p^2
+      BigInt gp = (one + ((pr - one) * (n % prpr)) % prpr) % prpr, inv;
+      if (!BigInt::mod_inv(L(gp, pr) % pr, pr, inv)) throw ReferencePanic("decrypt: L_p(g^(p-1)) is not invertible mod p");
+      return inv;
+    };
+    const BigInt hp = h(p, pp), hq = h(q, qq);
+    BigInt pinv;
+    if (!BigInt::mod_inv(p % q, q, pinv)) throw ReferencePanic("decrypt: p is not invertible mod q");
+    std::vector<BigInt> cp, cq;
+    for (auto& x : c) { cp.push_back(x % pp); cq.push_back(x % qq); }
+    std::vector<BigInt> dp = powm_batch(eng, cp, {pm1}, pp), dq = powm_batch(eng, cq, {qm1}, qq), out;
+    for (size_t i = 0; i < B; ++i) {
+      const BigInt mp = (L(dp[i], p) * hp) % p, mq = (L(dq[i], q) * hq) % q;
+      const BigInt diff = (mq + q - (mp % q)) % q;
+      out.push_back(mp + p * ((diff * pinv) % q));
+    }
+    return out;
+  }
+  // Paillier::open (kzen-paillier RECALLED): (m, r) with c = Enc(m, r); r = extract_nroot(dk, c (1 + m n)^-1 mod n)
+  // and (1 + m n)^-1 = 1 (mod n), so r is the n-th root of c mod n.  Used at correct_opening.rs:52-53.
+  static std::pair<std::vector<BigInt>, std::vector<BigInt>> open_batch(Engine& eng, const DecryptionKey& dk, const std::vector<BigInt>& c);
   static std::vector<int> verify_opening_batch(Engine& eng, const EncryptionKey& ek, const std::vector<BigInt>& m, const std::vector<BigInt>& r,
                                                const std::vector<BigInt>& c) {
     const size_t B = m.size();
@@ -934,6 +983,13 @@ struct Paillier {
     return verify_opening_batch(eng, ek, {m}, {r}, {c})[0] != 0;
   }
 };
+
+inline std::pair<std::vector<BigInt>, std::vector<BigInt>> Paillier::open_batch(Engine& eng, const DecryptionKey& dk, const std::vector<BigInt>& c) {
+  const BigInt n = dk.p * dk.q;
+  std::vector<BigInt> cn;
+  for (auto& x : c) cn.push_back(x % n);
+  return {decrypt_batch(eng, dk, c), extract_nroots(eng, dk, cn)};
+}
 
 // ------------------------------------------------------------------------------------ CompositeDLogProof
 struct DLogStatement {  // wi_dlog_proof.rs:34-39
