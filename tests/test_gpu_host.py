@@ -328,3 +328,20 @@ def test_paillier_encrypt_open_flow():
         assert [int(v) for v in r["m"]] == m and [int(v) for v in r["r"]] == rs
         assert [po.paillier_open(p, q, int(c)) for c in r["c"]] == list(zip(m, rs))
         assert r["opening_ok"] == [True] * len(m)
+
+
+def test_paillier_keypair_on_device():
+    """Row f4: Paillier::keypair_with_modulus_size with the Miller-Rabin exponentiations of each candidate wave on the device
+    (K2, a distinct modulus per job); the key then proves and verifies its own correctness (NiCorrectKeyProof)."""
+    import sympy
+
+    r = call("paillier.keypair", bits=1024)
+    assert r["ok"], r
+    p, q = int(r["p"]), int(r["q"])
+    assert p != q and p.bit_length() == q.bit_length() == 512 and (p * q).bit_length() == 1024
+    assert sympy.isprime(p) and sympy.isprime(q)
+    pr = call("correct_key_ni.proof", p=str(p), q=str(q), salt_hex=po.SALT_STRING.hex())
+    assert pr["ok"], pr
+    assert pr["proof"] == po.NiCorrectKeyProof.proof(p, q, po.SALT_STRING).to_json()
+    v = call("correct_key_ni.verify", proofs=[pr["proof"]], n=[str(p * q)], salt_hex=po.SALT_STRING.hex())
+    assert v["results"] == ["ok"]

@@ -208,6 +208,17 @@ class BigInt {
     r.trim();
     return r;
   }
+  BigInt operator|(const BigInt& o) const {
+    BigInt r = d.size() >= o.d.size() ? *this : o;
+    const BigInt& s = d.size() >= o.d.size() ? o : *this;
+    for (size_t i = 0; i < s.d.size(); ++i) r.d[i] |= s.d[i];
+    return r;
+  }
+  uint32_t mod_small(uint32_t m) const {  // this mod m for a 32-bit m
+    uint64_t rem = 0;
+    for (size_t i = d.size(); i-- > 0;) rem = ((rem << 32) | d[i]) % m;
+    return (uint32_t)rem;
+  }
   BigInt shl(size_t bits) const {
     if (d.empty()) return *this;
     BigInt r;

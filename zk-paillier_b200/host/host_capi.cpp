@@ -240,6 +240,11 @@ Json dispatch(const std::string& op, const Json& req) {
     }
     return out;
   }
+  if (op == "paillier.keypair") {  // {"bits", "rng_hex"?}
+    DecryptionKey dk = Paillier::keypair_with_modulus_size(eng, (size_t)req.at("bits").as_num(), rng_from(req));
+    out.set("p", Json::string(dk.p.to_dec())).set("q", Json::string(dk.q.to_dec()));
+    return out;
+  }
   if (op == "paillier.flow") {  // {"p","q","m":[...],"rng_hex"}: encrypt -> open -> verify_opening (correct_opening.rs:47-56), batched
     DecryptionKey dk{dec(req, "p"), dec(req, "q")};
     EncryptionKey fek(dk.p * dk.q);

@@ -960,6 +960,69 @@ struct Paillier {
     }
     return out;
   }
+  // Paillier::keypair_with_modulus_size (kzen-paillier RECALLED: two primes of bits/2 bits drawn by rejection sampling with
+  // a probabilistic primality test).  The primality tests are what costs: candidates are drawn a wave at a time, sieved by
+  // small primes on the host, and the Miller-Rabin exponentiations a^d mod candidate of the whole wave (a distinct modulus per
+  // job) run as one K2 launch.  Top two bits of each prime are set so that n has exactly `bits` bits.  `rounds` bases per
+  // candidate, base 2 first.
+  static DecryptionKey keypair_with_modulus_size(Engine& eng, size_t bits, const ByteSource& rng = os_rng(), int rounds = 24, size_t wave = 96) {
+    if (bits < 256 || bits % 64) throw std::invalid_argument("keypair: modulus size must be a multiple of 64, at least 256");
+    const size_t hb = bits / 2;
+    static const std::vector<uint32_t> small = [] {
+      std::vector<uint32_t> v;
+      for (uint32_t x = 3; x < 4000; x += 2) {
+        bool pr = true;
+        for (uint32_t d = 3; d * d <= x; d += 2) if (x % d == 0) { pr = false; break; }
+        if (pr) v.push_back(x);
+      }
+      return v;
+    }();
+    const BigInt one(1), two(2);
+    std::vector<BigInt> primes;
+    while (primes.size() < 2) {
+      std::vector<BigInt> cand;
+      while (cand.size() < wave) {
+        BigInt c = BigInt::sample(rng, hb);
+        c = c | one | one.shl(hb - 1) | one.shl(hb - 2);
+        bool ok = true;
+        for (uint32_t sp : small) if (c.mod_small(sp) == 0) { ok = false; break; }
+        if (ok) cand.push_back(c);
+      }
+      // Miller-Rabin: cand - 1 = d 2^s; a^d on the device, the s - 1 squarings (s is 1 here: the low bits are random) on the host
+      std::vector<BigInt> d, alive = cand;
+      for (int round = 0; round < rounds && !alive.empty(); ++round) {
+        std::vector<BigInt> bases, exps, mods;
+        std::vector<size_t> ss;
+        for (auto& c : alive) {
+          BigInt dd = c - one;
+          size_t sft = 0;
+          while (!dd.is_odd()) { dd = dd.shr(1); ++sft; }
+          ss.push_back(sft);
+          exps.push_back(dd);
+          mods.push_back(c);
+          bases.push_back(round == 0 ? two : two + BigInt::sample_below(rng, c - BigInt(3)));
+        }
+        const size_t nl = limbs_for_bits(hb);
+        std::vector<uint32_t> out(alive.size() * nl);
+        eng.check(zkp_modexp_var(eng.handle(), pack(bases, nl).data(), pack(exps, nl).data(), (int)nl, (int)(32 * nl), 1, pack(mods, nl).data(),
+                                 (int)nl, 1, (int)alive.size(), out.data()));
+        std::vector<BigInt> x = unpack(out, nl), next;
+        for (size_t i = 0; i < alive.size(); ++i) {
+          const BigInt cm1 = alive[i] - one;
+          bool pass = x[i] == one || x[i] == cm1;
+          for (size_t k = 1; !pass && k < ss[i]; ++k) {
+            x[i] = (x[i] * x[i]) % alive[i];
+            pass = x[i] == cm1;
+          }
+          if (pass) next.push_back(alive[i]);
+        }
+        alive.swap(next);
+      }
+      for (auto& c : alive)
+        if (primes.size() < 2 && (primes.empty() || primes[0] != c)) primes.push_back(c);
+    }
+    return DecryptionKey{primes[0], primes[1]};
+  }
   // Paillier::open (kzen-paillier RECALLED): (m, r) with c = Enc(m, r); r = extract_nroot(dk, c (1 + m n)^-1 mod n)
   // and (1 + m n)^-1 = 1 (mod n), so r is the n-th root of c mod n.  Used at correct_opening.rs:52-53.
   static std::pair<std::vector<BigInt>, std::vector<BigInt>> open_batch(Engine& eng, const DecryptionKey& dk, const std::vector<BigInt>& c);
