@@ -54,10 +54,23 @@ ENC_BYTES = N_BITS // 8 + 48 + 2 * N_BITS // 8
 
 
 def test_key():
+    """2048-bit n: the reference's fixed test primes (range_proof_ni.rs:141-145).  --n-bits 3072 / 4096 (secondary lines, the
+    other key sizes BASELINE.json's target names): the first committed fixture key of that size (tests/golden/keys.json)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import zkp_oracle as po  # constants only (the reference's fixed test primes)
 
-    return po.TEST_P * po.TEST_Q
+    if N_BITS == 2048:
+        return po.TEST_P * po.TEST_Q
+    k = json.load(open(os.path.join(ROOT, "tests", "golden", "keys.json")))[str(N_BITS)][0]
+    return int(k["p"]) * int(k["q"])
+
+
+def set_key_size(bits):
+    global N_BITS, METRIC, ENC_IMADS, ENC_BYTES
+    N_BITS = bits
+    METRIC = f"RangeProofNi proofs+verifies/sec at {bits}-bit n"
+    ENC_IMADS = modexp_imads(2 * bits, bits)
+    ENC_BYTES = bits // 8 + 48 + 2 * bits // 8
 
 
 def cpu_sample(n_int, work, cx, sel, threads):
@@ -261,7 +274,8 @@ def run_b200(args):
     which = "k1m" if used["k1m"] and not used["k1"] else ("k1" if used["k1"] and not used["k1m"] else "mixed")
     exec_mads = ctx.enc_executed_mads().get(which, 0.0)
     executed = k1_units * exec_mads / (k1_ms * 1e-3)
-    kernel_name = {"k1m": "enc2m_kernel<8,8> (K1m, two-digit Montgomery form)", "k1": "modexp_shared_kernel<8,16> (K1)"}.get(which, which)
+    shape = {1024: "<4,8>", 2048: "<8,8>", 3072: "<8,12>", 4096: "<16,8>"}.get(N_BITS, "")
+    kernel_name = {"k1m": f"enc2m_kernel{shape} (K1m, two-digit Montgomery form)", "k1": "modexp_shared_kernel (K1)"}.get(which, which)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -271,7 +285,8 @@ def run_b200(args):
     traffic = None
     try:  # DRAM bytes of K1 from the committed ncu capture, scaled to this run's Enc per launch
         tr = json.load(open(os.path.join(ROOT, "profiles", "k1m_traffic.json" if which == "k1m" else "k1_traffic.json")))
-        traffic = tr["dram_bytes_per_enc"] * k1_units / max(k1_launches, 1)
+        if N_BITS == 2048:  # the capture is of the 2048-bit kernel
+            traffic = tr["dram_bytes_per_enc"] * k1_units / max(k1_launches, 1)
     except Exception:
         pass
     hbm_ach = k1_units * ENC_BYTES / (k1_ms * 1e-3) / 1e9
@@ -297,8 +312,8 @@ def run_b200(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (32x32+64 IMAD)",
-        "data": "synthetic (seeded PCG64; reference test key; 1% reject-path statements)",
-        "config": {"workload": f"RangeProofNi prove+verify, batch={batch} per GPU, 2048-bit n (reference test key), error_factor=128, 256-bit range",
+        "data": "synthetic (seeded PCG64; " + ("reference test key" if N_BITS == 2048 else "committed fixture key") + "; 1% reject-path statements)",
+        "config": {"workload": f"RangeProofNi prove+verify, batch={batch} per GPU, {N_BITS}-bit n ({'reference test key' if N_BITS == 2048 else 'committed fixture key'}), error_factor=128, 256-bit range",
                    "batch_per_gpu": batch, "n_bits": N_BITS, "error_factor": EF, "enc_per_step_per_gpu": int(2 * batch * EF + enc_verify),
                    "l2": "working set per step (approx 0.5 GB of bases, ciphertexts and responses) exceeds the 126 MB L2; no explicit flush",
                    "sharding": "independent proofs, contiguous shard per rank; NCCL broadcast of n before, all_gather of verdicts after; no collective on the modexp path"},
@@ -357,8 +372,8 @@ def run_reference(args):
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "GMP mpz (64-bit limbs)",
-        "data": "synthetic (seeded PCG64; reference test key)",
-        "config": {"workload": f"RangeProofNi prove+verify, batch={batch} per GPU, 2048-bit n (reference test key), error_factor=128, 256-bit range",
+        "data": "synthetic (seeded PCG64; " + ("reference test key)" if N_BITS == 2048 else "committed fixture key)"),
+        "config": {"workload": f"RangeProofNi prove+verify, batch={batch} per GPU, {N_BITS}-bit n ({'reference test key' if N_BITS == 2048 else 'committed fixture key'}), error_factor=128, 256-bit range",
                    "note": "the Rust reference cannot be built offline (no cargo; curv-kzen / kzen-paillier un-vendored): this arm is its loops restated in C on its own bigint backend (GMP), parallel over the security parameter like rayon"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -490,7 +505,11 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--ref-seconds", type=float, default=120.0, help="target total time of the --impl reference run")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--n-bits", type=int, default=2048, choices=[1024, 2048, 3072, 4096],
+                    help="key size of the RangeProofNi workload (the headline is 2048; the others are secondary lines)")
     args = ap.parse_args()
+    if args.n_bits != N_BITS:
+        set_key_size(args.n_bits)
     if args.impl == "reference":
         run_reference(args)
     elif args.config != "rangeproof":

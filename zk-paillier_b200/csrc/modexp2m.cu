@@ -73,8 +73,15 @@ struct TwoDigit {
     uint32_t q[L], z0[L];
 #pragma unroll
     for (int j = 0; j < L; ++j) q[j] = 0;
-    if (MODE == 0) {
-      const uint32_t delta = M::template mont_mul_x<false, true, 1, U>(z0, x0, x0, n, n0inv, lane, z0, 0u, q, zr);
+    if (MODE == 0 || MODE == 3) {
+      uint32_t delta;
+      if (MODE == 3) {  // symmetric squaring: every pair of lane blocks multiplied once, then S reduction-only rows
+        uint32_t plo[L], phi[L];
+        M::sqr_product(plo, phi, x0, lane);
+        delta = M::mont_redc_x(z0, plo, phi, n, n0inv, lane, q, zr);
+      } else {
+        delta = M::template mont_mul_x<false, true, 1, U>(z0, x0, x0, n, n0inv, lane, z0, 0u, q, zr);
+      }
       uint32_t top;
       init_from_q(q, top, q, delta, s_klo, lane);
       M::mod_double(x1, n, lane);
@@ -554,6 +561,7 @@ void enc2m_host_constants(const uint32_t* n_host, int S, uint32_t* consts) {
 //   6        <4,16>  3        2   ... 8 steps deep
 //   7        <8,8>   4        2   ... 8 steps deep
 //   8        <4,16>  4        2   ... 4 steps deep
+//   9        <8,8>   4        3   symmetric squaring of the first digit (each pair of lane blocks once) + reduction-only rows
 // The other key sizes keep their layout and take only the MODE of the variant.
 struct Enc2mConfig {
   int variant, window;
@@ -563,7 +571,7 @@ static Enc2mConfig enc2m_config() {
     Enc2mConfig c{0, kWindow2m};
     if (const char* v = getenv("ZKP_B200_K1M_VARIANT")) c.variant = atoi(v);
     if (const char* w = getenv("ZKP_B200_K1M_WINDOW")) c.window = atoi(w);
-    if (c.variant < 0 || c.variant > 8) c.variant = 0;
+    if (c.variant < 0 || c.variant > 9) c.variant = 0;
     if (c.window != 5 && c.window != 6) c.window = kWindow2m;
     return c;
   }();
@@ -600,8 +608,8 @@ constexpr int kCtasPerSm2m = 4;
 
 static bool pick_shape_v(int S, int& T, int& L, int& minb, int& mode) {
   if (!pick_shape(S, T, L)) return false;
-  static const int kMinb[9] = {4, 3, 4, 3, 4, 3, 3, 4, 4}, kMode[9] = {0, 0, 0, 1, 1, 2, 2, 2, 2};
-  static const bool kT4[9] = {false, true, true, true, false, true, true, false, true};
+  static const int kMinb[10] = {4, 3, 4, 3, 4, 3, 3, 4, 4, 4}, kMode[10] = {0, 0, 0, 1, 1, 2, 2, 2, 2, 3};
+  static const bool kT4[10] = {false, true, true, true, false, true, true, false, true, false};
   const int v = enc2m_config().variant;
   minb = kCtasPerSm2m;
   mode = kMode[v];
@@ -641,6 +649,7 @@ static cudaError_t launch_mode(const Enc2mParams& p, int mode, int num_sms, cuda
   switch (mode) {
     case 1: return launch_one<T, L, 1, kCtasPerSm2m, 1>(p, num_sms, st);
     case 2: return launch_one<T, L, 2, kCtasPerSm2m, 2>(p, num_sms, st);
+    case 3: return launch_one<T, L, 1, kCtasPerSm2m, 3>(p, num_sms, st);
     default: return launch_one<T, L, 1, kCtasPerSm2m, 0>(p, num_sms, st);
   }
 }
@@ -682,6 +691,7 @@ cudaError_t launch_enc2m(const Enc2mKey& key, const uint32_t* bases, int base_li
         case 6: return launch_one<4, 16, 4, 3, 2>(p, num_sms, st);
         case 7: return launch_one<8, 8, 4, 4, 2>(p, num_sms, st);
         case 8: return launch_one<4, 16, 2, 4, 2>(p, num_sms, st);
+        case 9: return launch_one<8, 8, 1, 4, 3>(p, num_sms, st);
         default: return launch_one<8, 8, 1, 4, 0>(p, num_sms, st);
       }
     default: return cudaErrorInvalidValue;

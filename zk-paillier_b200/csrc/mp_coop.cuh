@@ -21,6 +21,8 @@
 #pragma once
 #include <stdint.h>
 
+#include "blockmul.cuh"
+
 namespace zkp {
 
 #define ZKP_FULL 0xffffffffu
@@ -474,7 +476,7 @@ struct Mp {
   static __device__ __forceinline__ uint32_t mont_mul_s(uint32_t (&r)[L], const uint32_t (&a)[L], const uint32_t* sb, uint32_t* sq,
                                                         const uint32_t (&n)[L], uint32_t n0inv, int lane,
                                                         const uint32_t (&init)[L], uint32_t init_top, uint32_t zr = 0u) {
-    static_assert(S % (2 * UNR) == 0, "row loop depth");
+    // any depth: the tail runs pair by pair
     const int g = lane & (T - 1);
     uint32_t E[L + 2], O[L + 2];
 #pragma unroll
@@ -484,8 +486,9 @@ struct Mp {
     }
     E[L] = (g == T - 1) ? init_top : 0u;
     E[L + 1] = O[L] = O[L + 1] = 0;
+    constexpr int kMain = S / (2 * UNR) * (2 * UNR);  // rows in whole iterations; the rest runs pair by pair
 #pragma unroll 1
-    for (int i = 0; i < S; i += 2 * UNR) {
+    for (int i = 0; i < kMain; i += 2 * UNR) {
 #pragma unroll
       for (int u = 0; u < UNR; ++u) {
         const uint2 bb = *reinterpret_cast<const uint2*>(sb + i + 2 * u);
@@ -494,6 +497,14 @@ struct Mp {
         cios_step(O, E, a, n, bb.y, n0inv, g, q1, zr);
         if (g == 0) *reinterpret_cast<uint2*>(sq + i + 2 * u) = make_uint2(q0, q1);
       }
+    }
+#pragma unroll 1
+    for (int i = kMain; i < S; i += 2) {
+      const uint2 bb = *reinterpret_cast<const uint2*>(sb + i);
+      uint32_t q0, q1;
+      cios_step(E, O, a, n, bb.x, n0inv, g, q0, zr);
+      cios_step(O, E, a, n, bb.y, n0inv, g, q1, zr);
+      if (g == 0) *reinterpret_cast<uint2*>(sq + i) = make_uint2(q0, q1);
     }
     uint32_t in = __shfl_down_sync(ZKP_FULL, O[0], 1, T);
     if (g == T - 1) in = 0;
@@ -521,8 +532,9 @@ struct Mp {
     }
     E[L] = (g == T - 1) ? init_top : 0u;
     E[L + 1] = O[L] = O[L + 1] = 0;
+    constexpr int kMain = S / (2 * UNR) * (2 * UNR);
 #pragma unroll 1
-    for (int i = 0; i < S; i += 2 * UNR) {
+    for (int i = 0; i < kMain; i += 2 * UNR) {
 #pragma unroll
       for (int u = 0; u < UNR; ++u) {
         const uint2 p = *reinterpret_cast<const uint2*>(sb1 + i + 2 * u);
@@ -530,6 +542,13 @@ struct Mp {
         cios_step2(E, O, a1, a2, n, p.x, s.x, n0inv, g, zr);
         cios_step2(O, E, a1, a2, n, p.y, s.y, n0inv, g, zr);
       }
+    }
+#pragma unroll 1
+    for (int i = kMain; i < S; i += 2) {
+      const uint2 p = *reinterpret_cast<const uint2*>(sb1 + i);
+      const uint2 s = *reinterpret_cast<const uint2*>(sb2 + i);
+      cios_step2(E, O, a1, a2, n, p.x, s.x, n0inv, g, zr);
+      cios_step2(O, E, a1, a2, n, p.y, s.y, n0inv, g, zr);
     }
     uint32_t in = __shfl_down_sync(ZKP_FULL, O[0], 1, T);
     if (g == T - 1) in = 0;
@@ -540,6 +559,177 @@ struct Mp {
     for (int j = 1; j <= L; ++j) addc_cc(E[j], O[j + 1]);
     addc(E[L + 1], 0);
     finish_x<3>(r, E, n, lane);
+  }
+
+  // ---- symmetric squaring (modexp2m.cu, TwoDigit MODE 3; model: tests/models/sqr_sym_model.py) -------------------------
+  // x^2 = sum_g A_g^2 B^(2g) + 2 sum_{g<h} A_g A_h B^(g+h) over the lane blocks A_g (B = 2^(32 L)), each unordered pair of
+  // blocks multiplied ONCE.  Round R = 0 .. T/2: lane g multiplies its block by the block of lane (g + R) mod T, an in-lane
+  // L x L product (blockmul.cuh).  Without wrap-around that is the pair of difference R at block position p = 2g + R, with
+  // wrap-around the pair of difference T - R at p = 2g + R - T; R = T/2 yields every pair twice (weight 1, not 2).
+  // Position p belongs to lane p >> 1, slot p & 1 = R & 1 (static per round), so lane d adds what lanes d - h and
+  // d - h + T/2 (h = R >> 1) made, when those are valid sources.  (T/2 + 1) L^2 limb products per lane instead of T L^2.
+  // one round: acc += weight * (A_src A_(src + R)) for the valid sources of this lane (R, h = R >> 1 and the doubling
+  // flag are run-time values, so that the rounds can run as a rolled loop: the code has to stay inside the instruction cache)
+  static __device__ __forceinline__ void sqr_round(uint32_t (&acc)[2 * L + 1], const uint32_t (&x)[L], int g, int R, int h, uint32_t dbl) {
+    uint32_t b[L], prod[2 * L], pw[2 * L + 1];
+#pragma unroll
+    for (int j = 0; j < L; ++j) b[j] = __shfl_sync(ZKP_FULL, x[j], (g + R) & (T - 1), T);
+    block_mul<L, L, ShapeFull>(prod, x, b);
+    pw[0] = prod[0] << dbl;
+#pragma unroll
+    for (int i = 1; i < 2 * L; ++i) pw[i] = __funnelshift_l(prod[i - 1], prod[i], dbl);
+    pw[2 * L] = dbl ? prod[2 * L - 1] >> 31 : 0u;
+    const int s1 = g - h, s2 = g - h + T / 2;
+    const bool v1 = s1 >= 0 && s1 + R <= T - 1;  // s1's product did not wrap: it sits at 2 s1 + R, owner s1 + h = g
+    const bool v2 = s2 <= T - 1 && s2 + R >= T;  // s2's product wrapped: 2 s2 + R - T, owner s2 + h - T/2 = g
+    {
+      uint32_t t = __shfl_sync(ZKP_FULL, pw[0], s1 & (T - 1), T);
+      add_cc(acc[0], v1 ? t : 0u);
+#pragma unroll
+      for (int i = 1; i < 2 * L; ++i) {
+        t = __shfl_sync(ZKP_FULL, pw[i], s1 & (T - 1), T);
+        addc_cc(acc[i], v1 ? t : 0u);
+      }
+      t = __shfl_sync(ZKP_FULL, pw[2 * L], s1 & (T - 1), T);
+      addc(acc[2 * L], v1 ? t : 0u);
+    }
+    {
+      uint32_t t = __shfl_sync(ZKP_FULL, pw[0], s2 & (T - 1), T);
+      add_cc(acc[0], v2 ? t : 0u);
+#pragma unroll
+      for (int i = 1; i < 2 * L; ++i) {
+        t = __shfl_sync(ZKP_FULL, pw[i], s2 & (T - 1), T);
+        addc_cc(acc[i], v2 ? t : 0u);
+      }
+      t = __shfl_sync(ZKP_FULL, pw[2 * L], s2 & (T - 1), T);
+      addc(acc[2 * L], v2 ? t : 0u);
+    }
+  }
+
+  // plo / phi = block g of the low / high half of x^2 (canonical limbs), x any S-limb value
+  static __device__ __forceinline__ void sqr_product(uint32_t (&plo)[L], uint32_t (&phi)[L], const uint32_t (&x)[L], int lane) {
+    static_assert(T == 4 || T == 8 || T == 16, "symmetric squaring: rounds 1 .. T/2 run in (odd, even) pairs");
+    using M2 = Mp<T, 2 * L>;
+    const int g = lane & (T - 1);
+    uint32_t acc0[2 * L + 1], acc1[2 * L + 1];
+    {
+      uint32_t prod[2 * L];
+      block_mul<L, L, ShapeFull>(prod, x, x);  // round 0: the diagonal block, position 2g: it stays in this lane
+#pragma unroll
+      for (int i = 0; i < 2 * L; ++i) {
+        acc0[i] = prod[i];
+        acc1[i] = 0;
+      }
+      acc0[2 * L] = acc1[2 * L] = 0;
+    }
+#pragma unroll 1
+    for (int k = 0; k < T / 4; ++k) {  // rounds 2k + 1 (odd positions: slot 1) and 2k + 2 (slot 0; weight 1 when it is round T/2)
+      sqr_round(acc1, x, g, 2 * k + 1, k, 1u);
+      sqr_round(acc0, x, g, 2 * k + 2, k + 1, (2 * k + 2 == T / 2) ? 0u : 1u);
+    }
+    // this lane's two positions as one value: limbs [0, 2L) stay here, the L + 1 limbs above go one lane up
+    uint32_t V[2 * L], OV[L + 1];
+#pragma unroll
+    for (int j = 0; j < L; ++j) V[j] = acc0[j];
+    V[L] = acc0[L];
+    add_cc(V[L], acc1[0]);
+#pragma unroll
+    for (int j = 1; j < L; ++j) {
+      V[L + j] = acc0[L + j];
+      addc_cc(V[L + j], acc1[j]);
+    }
+    OV[0] = acc0[2 * L];
+    addc_cc(OV[0], acc1[L]);
+#pragma unroll
+    for (int j = 1; j < L; ++j) {
+      OV[j] = acc1[L + j];
+      addc_cc(OV[j], 0u);
+    }
+    OV[L] = acc1[2 * L];
+    addc(OV[L], 0u);
+    {
+      uint32_t o = __shfl_up_sync(ZKP_FULL, OV[0], 1, T);
+      add_cc(V[0], g == 0 ? 0u : o);
+#pragma unroll
+      for (int j = 1; j <= L; ++j) {
+        o = __shfl_up_sync(ZKP_FULL, OV[j], 1, T);
+        addc_cc(V[j], g == 0 ? 0u : o);
+      }
+#pragma unroll
+      for (int j = L + 1; j < 2 * L; ++j) addc_cc(V[j], 0u);
+      const uint32_t co = addc_out();
+      uint32_t top;
+      const uint32_t cin = M2::resolve(co != 0, M2::all_ones(V), lane, top);
+      M2::add_small(V, cin);
+    }
+    // two blocks per lane -> block g of each half in lane g
+#pragma unroll
+    for (int j = 0; j < L; ++j) {
+      const uint32_t a0 = __shfl_sync(ZKP_FULL, V[j], g >> 1, T), a1 = __shfl_sync(ZKP_FULL, V[L + j], g >> 1, T);
+      const uint32_t c0 = __shfl_sync(ZKP_FULL, V[j], T / 2 + (g >> 1), T), c1 = __shfl_sync(ZKP_FULL, V[L + j], T / 2 + (g >> 1), T);
+      plo[j] = (g & 1) ? a1 : a0;
+      phi[j] = (g & 1) ? c1 : c0;
+    }
+  }
+
+  // One reduction-only row  acc = (acc + q n) / 2^32 + feed 2^(32 (S - 1))  on the split accumulator (cios_step without the
+  // a b products): `feed` is the limb of the high half that must sit at limb S - 1 after the previous row's shift.
+  static __device__ __forceinline__ void redc_step(uint32_t (&X)[L + 2], uint32_t (&Y)[L + 2], const uint32_t (&n)[L], uint32_t feed,
+                                                   uint32_t n0inv, int g, uint32_t& q, uint32_t zr) {
+    uint32_t in = __shfl_down_sync(ZKP_FULL, Y[0], 1, T);
+    if (g == T - 1) in = feed;
+    add_cc(Y[L], in);
+    addc(Y[L + 1], zr);
+    q = __shfl_sync(ZKP_FULL, X[0] + Y[1], 0, T) * n0inv;
+    uint32_t Z[L + 2];
+    add_cc(X[0], Y[1]);  // limb 0; the carry enters the odd chain at limb 1
+#pragma unroll
+    for (int j = 0; j < L; j += 2) madc_wide3_cc(Z[j], Z[j + 1], n[j + 1], q, Y[j + 2], Y[j + 3]);
+    Z[L] = addc_out();
+    Z[L + 1] = 0;
+    mad_even(X, n, q);
+#pragma unroll
+    for (int j = 0; j < L + 2; ++j) Y[j] = Z[j];
+  }
+
+  // r = (plo + phi W) / W mod n for a 2 S-limb value below n W given as its two halves (block g of each in lane g): S
+  // reduction-only rows.  The quotient digits are kept as in mont_mul_x<.., CAPQ = true, ..>; returns 1 iff n was subtracted.
+  static __device__ __forceinline__ uint32_t mont_redc_x(uint32_t (&r)[L], const uint32_t (&plo)[L], const uint32_t (&phi)[L],
+                                                         const uint32_t (&n)[L], uint32_t n0inv, int lane, uint32_t (&qcap)[L],
+                                                         uint32_t zr = 0u) {
+    const int g = lane & (T - 1);
+    uint32_t E[L + 2], O[L + 2];
+#pragma unroll
+    for (int j = 0; j < L; ++j) {
+      E[j] = plo[j];
+      O[j] = 0;
+    }
+    E[L] = E[L + 1] = O[L] = O[L + 1] = 0;
+    uint32_t prev = 0;
+#pragma unroll 1
+    for (int owner = 0; owner < T; ++owner) {
+      const bool mine = g == owner;
+#pragma unroll
+      for (int j = 0; j < L; j += 2) {
+        const uint32_t f0 = __shfl_sync(ZKP_FULL, phi[j], owner, T);
+        const uint32_t f1 = __shfl_sync(ZKP_FULL, phi[j + 1], owner, T);
+        uint32_t q0, q1;
+        redc_step(E, O, n, prev, n0inv, g, q0, zr);
+        redc_step(O, E, n, f0, n0inv, g, q1, zr);
+        prev = f1;
+        qcap[j] = mine ? q0 : qcap[j];
+        qcap[j + 1] = mine ? q1 : qcap[j + 1];
+      }
+    }
+    uint32_t in = __shfl_down_sync(ZKP_FULL, O[0], 1, T);
+    if (g == T - 1) in = prev;
+    add_cc(O[L], in);
+    addc(O[L + 1], 0);
+    add_cc(E[0], O[1]);
+#pragma unroll
+    for (int j = 1; j <= L; ++j) addc_cc(E[j], O[j + 1]);
+    addc(E[L + 1], 0);
+    return finish_x<1>(r, E, n, lane);
   }
 
   // x = (x + y) mod n for x, y < n
