@@ -57,5 +57,17 @@ extern "C" {
                             r_z: *mut u32) -> c_int;
     pub fn zkp_verlin_verify(ctx: *mut zkp_ctx, batch: c_int, z_limbs: c_int, c: *const u32, c_prime: *const u32, phi_x: *const u32,
                              phi_a: *const u32, z: *const u32, z_prime: *const u32, z_dp: *const u32, r_z: *const u32, accept: *mut u8) -> c_int;
+    // the remaining public proofs: CorrectOpening, CompositeDLogProof, CorrectMessageProof
+    pub fn zkp_verify_opening(ctx: *mut zkp_ctx, batch: c_int, m_limbs: c_int, m: *const u32, r: *const u32, c: *const u32, ok: *mut u8) -> c_int;
+    pub fn zkp_dlog_prove(ctx: *mut zkp_ctx, batch: c_int, n_limbs: c_int, n: *const u32, g: *const u32, ni: *const u32, secret: *const u32,
+                          secret_limbs: c_int, r: *const u32, r_limbs: c_int, y_limbs: c_int, x: *mut u32, y: *mut u32, fault: *mut u8) -> c_int;
+    pub fn zkp_dlog_verify(ctx: *mut zkp_ctx, batch: c_int, n_limbs: c_int, n: *const u32, g: *const u32, ni: *const u32, x: *const u32,
+                           y: *const u32, y_limbs: c_int, accept: *mut u8, fault: *mut u8) -> c_int;
+    pub fn zkp_correct_message_prove(ctx: *mut zkp_ctx, batch: c_int, m_count: c_int, m_limbs: c_int, valid: *const u32, msg: *const u32,
+                                     r: *const u32, e_rand: *const u32, z_rand: *const u32, w: *const u32, ciphertext: *mut u32,
+                                     e_vec: *mut u32, z_vec: *mut u32, a_vec: *mut u32, fault: *mut u8) -> c_int;
+    pub fn zkp_correct_message_verify(ctx: *mut zkp_ctx, batch: c_int, m_count: c_int, m_limbs: c_int, e_limbs: c_int, ciphertext: *const u32,
+                                      valid: *const u32, e_vec: *const u32, z_vec: *const u32, a_vec: *const u32, accept: *mut u8,
+                                      fault: *mut u8) -> c_int;
     pub fn zkp_imad_peak(ctx: *mut zkp_ctx, variant: c_int, mads_per_s: *mut c_double) -> c_int;
 }
