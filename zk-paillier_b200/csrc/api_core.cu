@@ -54,12 +54,59 @@ ProfScope::~ProfScope() {
 
 cudaError_t ensure_table(zkp_ctx* c, int S, int entries) {
   size_t bytes = (size_t)resident_groups(S, c->num_sms) * entries * S * sizeof(uint32_t);
-  if (c->enc2m_key && c->enc2m_enabled) {
-    size_t b3 = enc2m_table_limbs(c->n.S, c->num_sms) * sizeof(uint32_t);
-    if (entries == kTableVar) b3 = var2m_table_limbs(c->n.S, c->num_sms) * sizeof(uint32_t);
-    if (b3 > bytes) bytes = b3;
+  if (c->enc2m_key && c->enc2m_enabled) {  // a call may run K1m (Enc) and K2m (mod_pow) back to back: size for both
+    const size_t b1 = enc2m_table_limbs(c->n.S, c->num_sms) * sizeof(uint32_t);
+    const size_t b2 = var2m_table_limbs(c->n.S, c->num_sms) * sizeof(uint32_t);
+    bytes = std::max(bytes, std::max(b1, b2));
   }
-  return c->table.ensure(bytes);
+  bytes = (bytes + 255) & ~size_t(255);
+  // one region per stream that may run a modexp kernel at the same time (fork_stream below)
+  c->table_region_limbs = bytes / sizeof(uint32_t);
+  return c->table.ensure(bytes * (1 + kAuxStreams));
+}
+
+// ---- concurrent modexp launches of one call (the independent modexps of a sigma-protocol proof) -----------------
+// fork_stream(c, k): later launches go to auxiliary stream k (which first waits for everything queued on the main stream
+// so far) and use window-table region k + 1; join_streams(c): back on the main stream, which waits for every auxiliary
+// stream used since the last join.
+cudaError_t fork_stream(zkp_ctx* c, int k) {
+  if (k < 0 || k >= kAuxStreams) return cudaErrorInvalidValue;
+  if (!c->main_stream) c->main_stream = c->stream;
+  if (!c->aux[k]) {
+    cudaError_t e = cudaStreamCreateWithFlags(&c->aux[k], cudaStreamNonBlocking);
+    if (e != cudaSuccess) return e;
+    e = cudaEventCreateWithFlags(&c->aux_ev[k], cudaEventDisableTiming);
+    if (e != cudaSuccess) return e;
+  }
+  if (!c->fork_ev) {
+    cudaError_t e = cudaEventCreateWithFlags(&c->fork_ev, cudaEventDisableTiming);
+    if (e != cudaSuccess) return e;
+  }
+  cudaError_t e = cudaEventRecord(c->fork_ev, c->main_stream);
+  if (e != cudaSuccess) return e;
+  e = cudaStreamWaitEvent(c->aux[k], c->fork_ev, 0);
+  if (e != cudaSuccess) return e;
+  c->stream = c->aux[k];
+  c->table_off = (size_t)(k + 1) * c->table_region_limbs;
+  c->aux_used |= 1u << k;
+  return cudaSuccess;
+}
+cudaError_t main_stream(zkp_ctx* c) {  // back to the main stream without waiting for the auxiliary ones
+  if (c->main_stream) c->stream = c->main_stream;
+  c->table_off = 0;
+  return cudaSuccess;
+}
+cudaError_t join_streams(zkp_ctx* c) {
+  main_stream(c);
+  for (int k = 0; k < kAuxStreams; ++k) {
+    if (!(c->aux_used & (1u << k))) continue;
+    cudaError_t e = cudaEventRecord(c->aux_ev[k], c->aux[k]);
+    if (e != cudaSuccess) return e;
+    e = cudaStreamWaitEvent(c->stream, c->aux_ev[k], 0);
+    if (e != cudaSuccess) return e;
+  }
+  c->aux_used = 0;
+  return cudaSuccess;
 }
 
 static Enc2mKey enc2m_view(const zkp_ctx* c) {
@@ -78,11 +125,11 @@ cudaError_t launch_pow_nn(zkp_ctx* c, const uint32_t* base, int base_limbs, cons
   if (c->enc2m_key && c->enc2m_enabled && base_limbs <= 2 * c->n.S) {
     ++c->enc2m_launches;
     return launch_modexp2m_var(enc2m_view(c), base, base_limbs, exp, exp_limbs, exp_bits, exp_per, out, c->nn.limbs, jobs,
-                               c->table.as<uint32_t>(), c->num_sms, c->stream);
+                               (c->table.as<uint32_t>() + c->table_off), c->num_sms, c->stream);
   }
   ++c->k1_launches;
   return launch_modexp_var(base, c->nn.mod.as<uint32_t>(), c->nn.limbs, c->nn.r2.as<uint32_t>(), c->nn.n0.as<uint32_t>(), exp,
-                           exp_limbs, exp_bits, exp_per, 0x7fffffff, out, jobs, c->nn.S, c->table.as<uint32_t>(), c->num_sms,
+                           exp_limbs, exp_bits, exp_per, 0x7fffffff, out, jobs, c->nn.S, (c->table.as<uint32_t>() + c->table_off), c->num_sms,
                            c->stream, base_limbs);
 }
 
@@ -91,11 +138,11 @@ cudaError_t launch_enc(zkp_ctx* c, const uint32_t* bases, int base_limbs, const 
   if (c->enc2m_key && c->enc2m_enabled && base_limbs <= 2 * c->n.S && (!plain || plain_limbs <= 2 * c->n.S)) {
     const Enc2mKey k = enc2m_view(c);
     ++c->enc2m_launches;
-    return launch_enc2m(k, bases, base_limbs, plain, plain_limbs, out, c->nn.limbs, jobs, c->table.as<uint32_t>(), c->num_sms,
+    return launch_enc2m(k, bases, base_limbs, plain, plain_limbs, out, c->nn.limbs, jobs, (c->table.as<uint32_t>() + c->table_off), c->num_sms,
                         c->stream, jobs_dev);
   }
   ++c->k1_launches;
-  return launch_modexp_shared(c->nn.view(), bases, base_limbs, plain, plain_limbs, out, c->nn.limbs, jobs, c->table.as<uint32_t>(),
+  return launch_modexp_shared(c->nn.view(), bases, base_limbs, plain, plain_limbs, out, c->nn.limbs, jobs, (c->table.as<uint32_t>() + c->table_off),
                               c->num_sms, c->stream, jobs_dev);
 }
 
@@ -224,6 +271,12 @@ void zkp_ctx_destroy(zkp_ctx* c) {
   for (DevBuf* b : c->rp.all()) bufs.push_back(b);
   for (DevBuf* b : c->ck.all()) bufs.push_back(b);
   for (DevBuf* b : bufs) b->release();
+  if (c->main_stream) c->stream = c->main_stream;
+  for (int k = 0; k < zkp::kAuxStreams; ++k) {
+    if (c->aux[k]) cudaStreamDestroy(c->aux[k]);
+    if (c->aux_ev[k]) cudaEventDestroy(c->aux_ev[k]);
+  }
+  if (c->fork_ev) cudaEventDestroy(c->fork_ev);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -361,7 +414,7 @@ int zkp_modexp_shared(zkp_ctx* c, const uint32_t* bases, int base_limbs, int bat
   {
     ProfScope ps(c, KID_MODEXP_SHARED, batch);
     ZKP_CU(c, launch_modexp_shared(c->nn.view(), c->in0.as<uint32_t>(), base_limbs, nullptr, 0, c->out0.as<uint32_t>(), ol,
-                                   batch, c->table.as<uint32_t>(), c->num_sms, c->stream));
+                                   batch, (c->table.as<uint32_t>() + c->table_off), c->num_sms, c->stream));
   }
   ZKP_CU(c, cudaMemcpyAsync(out, c->out0.p, (size_t)batch * ol * 4, cudaMemcpyDeviceToHost, c->stream));
   ZKP_CU(c, cudaStreamSynchronize(c->stream));
@@ -427,7 +480,7 @@ int zkp_modexp_var(zkp_ctx* c, const uint32_t* bases, const uint32_t* exps, int 
     ProfScope ps(c, KID_MODEXP_VAR, batch);
     ZKP_CU(c, launch_modexp_var(c->in0.as<uint32_t>(), c->in2.as<uint32_t>(), mod_limbs, d_r2, d_n0, c->in1.as<uint32_t>(),
                                 exp_limbs, exp_bits, exp_per, mod_per, c->out0.as<uint32_t>(), batch, S,
-                                c->table.as<uint32_t>(), c->num_sms, c->stream));
+                                (c->table.as<uint32_t>() + c->table_off), c->num_sms, c->stream));
   }
   ZKP_CU(c, cudaMemcpyAsync(out, c->out0.p, (size_t)batch * mod_limbs * 4, cudaMemcpyDeviceToHost, c->stream));
   ZKP_CU(c, cudaStreamSynchronize(c->stream));

@@ -250,10 +250,13 @@ int zkp_correct_message_prove(zkp_ctx* c, int batch, int M, int m_limbs, const u
   if (!s.bad) s.ck(launch_cm_layout(d_valid, d_msg, m_limbs, d_er, el, d_zr, d_w, nl, batch, M, d_match, esel, zsel, esum, d_fault, s.st));
   uint32_t* d_c = s.enc(d_msg, m_limbs, d_r, nl);                                   // ciphertext = Enc(message, r)     :43-49
   uint32_t* u = cm_u(s, d_valid, m_limbs, d_c, M);                                  // u_i                              :50-56
+  s.fork(0);
   uint32_t* zn = s.enc(nullptr, 0, zsel, nl, rows);                                 // z_i^n (w^n in the true slot)      :69,71
+  s.on_main();
   uint32_t* ue = s.powm(u, nnl, esel, el, rows);                                    // u_i^e_i (u^0 = 1 in the true slot) :72
   uint32_t* ueinv = s.rows(nnl, rows);
   if (!s.bad) s.ck(launch_modinv(ue, c->nn.mod.as<uint32_t>(), nnl, rows, nullptr, ueinv, d_rowfault, s.st));  // :73 unwrap()
+  s.join();
   uint32_t* d_a = s.mulm(zn, nnl, ueinv, nnl, rows);                                // a_i                              :75
   uint32_t* chal = cm_challenge(s, d_a, M);                                         // :85-87
   uint32_t* ei = s.rows(el);
@@ -301,9 +304,12 @@ int zkp_correct_message_verify(zkp_ctx* c, int batch, int M, int m_limbs, int e_
   if (!s.bad) s.ck(launch_sum_pow2(d_e, e_limbs, 8, batch, M, esum, s.st));         // sum e_i mod 2^256                :130-131
   if (!s.bad) s.ck(launch_rows_differ_fault(chal, esum, 8, batch, d_fault, s.st));  // assert_eq!(chal, ei_sum)         :133
   uint32_t* u = cm_u(s, d_valid, m_limbs, d_c, M);                                  // :134-142
+  s.fork(0);
   uint32_t* zn = s.enc(nullptr, 0, d_z, nl, rows);                                  // z_i^n                            :145
+  s.on_main();
   uint32_t* ue = s.powm(u, nnl, d_e, e_limbs, rows);                                // u_i^e_i                          :146
   uint32_t* lhs = s.mulm(ue, nnl, d_a, nnl, rows);                                  // :147
+  s.join();
   if (!s.bad) s.ck(launch_rows_equal(lhs, zn, nnl, rows, 0, d_rowok, s.st));        // :148
   if (!s.bad) s.ck(launch_rows_reduce(d_rowok, batch, M, 0, 0, d_acc, s.st));       // :151
   s.down8(accept, d_acc, (size_t)batch);

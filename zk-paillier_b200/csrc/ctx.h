@@ -60,6 +60,8 @@ struct KeySlot {
   }
 };
 
+constexpr int kAuxStreams = 4;  // concurrent modexp launches of one call (fork_stream / join_streams)
+
 enum KernelId { KID_MODEXP_SHARED = 0, KID_MODEXP_VAR = 1, KID_MODMUL = 2, KID_SHA = 3, KID_OTHER = 4, KID_COUNT = 5 };
 
 struct ProfEntry {
@@ -124,7 +126,11 @@ struct zkp_ctx {
   int enc2m_nops = 0;
   long long enc2m_launches = 0, k1_launches = 0;
   double enc2m_mads = 0, k1_mads = 0;  // IMAD.WIDE one encryption executes (zkp_enc_executed_mads)
-  zkp::DevBuf table;                 // window-table scratch
+  zkp::DevBuf table;                 // window-table scratch: one region per stream that may run a modexp kernel
+  size_t table_region_limbs = 0, table_off = 0;  // region size; offset of the current stream's region (limbs)
+  cudaStream_t main_stream = nullptr, aux[zkp::kAuxStreams] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t aux_ev[zkp::kAuxStreams] = {nullptr, nullptr, nullptr, nullptr}, fork_ev = nullptr;
+  unsigned aux_used = 0;
   zkp::DevBuf in0, in1, in2, in3, out0;  // generic staging for the one-shot calls
   bool profiling = false;
   std::vector<zkp::ProfEntry> prof;
@@ -165,6 +171,11 @@ cudaError_t launch_enc(zkp_ctx* c, const uint32_t* bases, int base_limbs, const 
 // The table scratch must have been sized with ensure_table(c, c->nn.S, kTableVar).
 cudaError_t launch_pow_nn(zkp_ctx* c, const uint32_t* base, int base_limbs, const uint32_t* exp, int exp_limbs, int exp_bits,
                           int exp_per, uint32_t* out, int jobs);
+
+// Concurrent modexp launches inside one call (api_core.cu)
+cudaError_t fork_stream(zkp_ctx* c, int k);
+cudaError_t main_stream(zkp_ctx* c);
+cudaError_t join_streams(zkp_ctx* c);
 
 // Montgomery/key helpers (api_core.cu)
 int setup_slot(zkp_ctx* c, KeySlot& slot, const uint32_t* mod, int limbs, const uint32_t* exp, int exp_limbs);

@@ -118,7 +118,24 @@ struct Sig {
     ck(launch_digest_to_limbs(dig, batch, e, st));
     return e;
   }
+  // independent modexps of one proof run side by side: fork(k) sends what follows to auxiliary stream k (after everything
+  // queued on the main stream so far), on_main() goes back without waiting, join() makes the main stream wait for all
+  void fork(int k) {
+    if (bad) return;
+    ck(fork_stream(c, k));
+    st = c->stream;
+  }
+  void on_main() {
+    main_stream(c);
+    st = c->stream;
+  }
+  void join() {
+    cudaError_t e = join_streams(c);
+    st = c->stream;
+    if (e != cudaSuccess) ck(e);
+  }
   int finish(const char* what) {
+    join();
     if (bad) {
       cudaStreamSynchronize(st);
       if (c->err.empty()) c->err = what;
