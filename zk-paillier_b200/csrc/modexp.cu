@@ -15,6 +15,8 @@
 //
 // Bases / plaintexts of one CTA's jobs are staged into shared memory with one
 // 1-D TMA bulk copy (cp.async.bulk -> UBLKCP) per array and an mbarrier.
+#include <stdlib.h>
+
 #include "kernels.h"
 #include "mp_coop.cuh"
 #include "blockmul.cuh"
@@ -333,10 +335,23 @@ template <int T, int L>
 static int blocks_per_sm_shared() {
   return Occ<T, L>::kMinBlocks;
 }
-int resident_groups(int S, int num_sms) {
+// Persistent CTAs per SM of K2 (modexp_var_kernel).  Its register count would allow more than the 4 of K1 at the narrow
+// shapes (72 registers at L = 8, 100 at L = 12), but measured on B200 at 3072-bit N (NiCorrectKeyProof verify, batch 4096):
+// 4 -> 9 786/s, 5 -> 9 709/s, 6 -> 9 900/s: within noise, the multiplier pipe is already 81 % busy at 16 warps per SM.
+// ZKP_B200_K2_CTAS overrides (tuning).
+int k2_ctas_per_sm(int L) {
+  static const int env = [] {
+    const char* e = getenv("ZKP_B200_K2_CTAS");
+    return e ? atoi(e) : 0;
+  }();
+  if (env > 0) return env;
+  return (L <= 16) ? 4 : (L <= 24 ? 3 : 2);
+}
+int resident_groups(int S, int num_sms) {  // sized for the larger of K1's and K2's persistent grids
   int T = group_threads(S);
   int L = S / T;
   int mb = (L <= 16) ? 4 : (L <= 24 ? 3 : 2);
+  mb = mb > k2_ctas_per_sm(L) ? mb : k2_ctas_per_sm(L);
   return num_sms * mb * (kCtaThreads / T);
 }
 
@@ -428,7 +443,7 @@ cudaError_t launch_modexp_var(const uint32_t* bases, const uint32_t* mods, int m
 #define CALL(T_, L_)                                                   \
   {                                                                    \
     constexpr int G = kCtaThreads / T_;                                \
-    int grid = num_sms * Occ<T_, L_>::kMinBlocks;                      \
+    int grid = num_sms * k2_ctas_per_sm(L_);                           \
     int npass = (jobs + G - 1) / G;                                    \
     if (grid > npass) grid = npass;                                    \
     modexp_var_kernel<T_, L_><<<grid, kCtaThreads, 0, st>>>(p);        \
