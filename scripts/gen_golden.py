@@ -35,5 +35,30 @@ ck = po.NiCorrectKeyProof.proof(po.TEST_P, po.TEST_Q, salt)
 ck.verify(n, salt)
 g["correct_key_ni"] = {"p": str(po.TEST_P), "q": str(po.TEST_Q), "salt_hex": salt.hex(), "sigma_vec": [str(s) for s in ck.sigma_vec],
                        "rho_vec": [str(s) for s in po.correct_key_rho(n, salt)]}
+# ---- the remaining public proofs (row f3): a second file so that vectors.json stays byte-identical
+rng = random.Random(0xF3)
+R = 1 << (po.DLOG_K + po.DLOG_K_PRIME + po.DLOG_SAMPLE_S)
+leg = lambda a, pr: 1 if pow(a, (pr - 1) // 2, pr) == 1 else -1
+while True:
+    h1 = rng.randrange(1, n - 1)
+    if leg(h1, po.TEST_P) * leg(h1, po.TEST_Q) == -1:
+        break
+secret = rng.randrange(1 << po.DLOG_SAMPLE_S)
+h2 = pow(pow(h1, -1, n), secret, n)
+rr = rng.randrange(R)
+dl = po.CompositeDLogProof.prove(n, h1, h2, secret, rr)
+dl.verify(n, h1, h2)
+valid = [3, 4, 5, 6]
+cm_in = {"message": 5, "r": rng.randrange(1, n), "e_rand": [rng.getrandbits(256) for _ in valid[1:]],
+         "z_rand": [rng.randrange(1, n) for _ in valid[1:]], "w": rng.randrange(1, n)}
+cm = po.CorrectMessageProof.prove(n, valid, **cm_in)
+cm.verify()
+g3 = {"n": str(n),
+      "dlog": {"g": str(h1), "ni": str(h2), "secret": str(secret), "r": str(rr), "x": str(dl.x), "y": str(dl.y), "json": dl.to_json()},
+      "correct_message": {"valid": valid, "message": cm_in["message"], "r": str(cm_in["r"]), "e_rand": [str(v) for v in cm_in["e_rand"]],
+                          "z_rand": [str(v) for v in cm_in["z_rand"]], "w": str(cm_in["w"]), "ciphertext": str(cm.ciphertext),
+                          "e_vec": [str(v) for v in cm.e_vec], "z_vec": [str(v) for v in cm.z_vec],
+                          "a_vec_sha256": hashlib.sha256(",".join(str(v) for v in cm.a_vec).encode()).hexdigest()}}
+json.dump(g3, open(os.path.join(ROOT, "tests", "golden", "vectors_more.json"), "w"), indent=0)
 json.dump(g, open(os.path.join(ROOT, "tests", "golden", "vectors.json"), "w"), indent=0)
-print("wrote vectors.json")
+print("wrote vectors.json, vectors_more.json")

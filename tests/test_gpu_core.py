@@ -7,9 +7,22 @@ import numpy as np
 import pytest
 
 import zk_paillier_b200 as zk
+from util import c_oracle
 from zk_paillier_b200.native import from_limbs, ints_to_limbs, to_limbs
 
 pytestmark = pytest.mark.gpu
+
+SPOT = 6  # rows of every batch also checked against CPython pow(); the rest against GMP (oracle/oracle.c), which the CPU suite
+          # pins against CPython pow and OpenSSL BN_mod_exp (tests/test_oracle.py) -- 8192-bit pow() in Python is ~0.1 s a row
+
+
+def want_enc(n, nl, m, m_limbs, r, r_limbs):
+    """Expected ciphertext rows: GMP for all, CPython for the first SPOT."""
+    nn = n * n
+    out = c_oracle.paillier_enc(to_limbs(n, nl), ints_to_limbs(m, m_limbs), ints_to_limbs(r, r_limbs))
+    for j in range(min(SPOT, len(m))):
+        assert from_limbs(out[j]) == ((m[j] * n + 1) % nn) * pow(r[j], n, nn) % nn
+    return out
 
 
 def rand_odd(rng, bits, full=True):
@@ -35,8 +48,9 @@ def test_modexp_shared_matches_pow(ctx, mod_bits):
     bases = [rng.getrandbits(mod_bits) for _ in range(batch)]   # includes values >= M
     bases[0], bases[1], bases[2], bases[3] = 0, 1, M - 1, M
     out = ctx.modexp_shared(ints_to_limbs(bases, limbs))
-    got = rows(out)
-    for b, g in zip(bases, got):
+    want = c_oracle.modexp(ints_to_limbs(bases, limbs), ints_to_limbs([E], limbs), ints_to_limbs([M], limbs), per=batch)
+    assert np.array_equal(out, want)
+    for b, g in list(zip(bases, rows(out)))[:SPOT]:
         assert g == pow(b, E, M)
 
 
@@ -65,14 +79,12 @@ def test_paillier_enc(ctx, n_bits):
     m[1], r[1] = n - 1, n - 1
     m[2] = 0
     out = ctx.paillier_enc(ints_to_limbs(m, nl), ints_to_limbs(r, nl))
-    for mi, ri, g in zip(m, r, rows(out)):
-        assert g == ((mi * n + 1) % nn) * pow(ri, n, nn) % nn
+    assert np.array_equal(out, want_enc(n, nl, m, nl, r, nl))
     # narrow plaintext rows, full-width randomness rows (ZeroProof: Enc(0, z) with z < n^2)
     z = [rng.randrange(nn) for _ in range(9)]
     mw = [rng.getrandbits(n_bits + 256) for _ in range(9)]   # unreduced plaintext (CiphertextProof z1)
     out = ctx.paillier_enc(ints_to_limbs(mw, nl + 8), ints_to_limbs(z, 2 * nl))
-    for mi, ri, g in zip(mw, z, rows(out)):
-        assert g == ((mi * n + 1) % nn) * pow(ri, n, nn) % nn
+    assert np.array_equal(out, want_enc(n, nl, mw, nl + 8, z, 2 * nl))
 
 
 @pytest.mark.parametrize("mod_bits,per", [(1024, 1), (2048, 11), (3072, 11), (4096, 3), (8192, 1), (2560, 2)])
@@ -87,7 +99,8 @@ def test_modexp_var(ctx, mod_bits, per):
     exps[1] = 1
     bases = [rng.getrandbits(mod_bits) for _ in range(batch)]
     out = ctx.modexp_var(ints_to_limbs(bases, limbs), ints_to_limbs(exps, limbs), ints_to_limbs(mods, limbs), per=per)
-    for j, g in enumerate(rows(out)):
+    assert np.array_equal(out, c_oracle.modexp(ints_to_limbs(bases, limbs), ints_to_limbs(exps, limbs), ints_to_limbs(mods, limbs), per=per))
+    for j, g in list(enumerate(rows(out)))[:SPOT] + [(batch - 1, from_limbs(out[batch - 1]))]:
         assert g == pow(bases[j], exps[j // per], mods[j // per]), j
 
 
@@ -147,7 +160,7 @@ def test_two_digit_montgomery_kernel(monkeypatch, n_bits, nl):
     r[0], r[1], r[2], r[3], r[4] = 1, n - 1, 0, min(n + 5, cap - 1), cap - 1
     m = [rng.getrandbits(32 * nl) if j % 7 == 0 else rng.getrandbits(300) for j in range(batch)]
     m[0], m[1], m[5] = 0, n - 1, min(n + 1, cap - 1)
-    want = [((mi * n + 1) % nn) * pow(ri, n, nn) % nn for mi, ri in zip(m, r)]
+    want = want_enc(n, nl, m, nl, r, nl)
     outs = {}
     for mode in ("k1m", "k1"):
         monkeypatch.setenv("ZKP_B200_ENC", mode)
@@ -158,7 +171,7 @@ def test_two_digit_montgomery_kernel(monkeypatch, n_bits, nl):
             assert (used["k1m"] > 0) == (mode == "k1m") and (used["k1"] > 0) == (mode == "k1")
             if mode == "k1m":
                 narrow = [v & ((1 << 256) - 1) for v in m[:9]]
-                o = rows(c.paillier_enc(ints_to_limbs(narrow, 8), ints_to_limbs(r[:9], nl)))
-                assert o == [((mi * n + 1) % nn) * pow(ri, n, nn) % nn for mi, ri in zip(narrow, r[:9])]
-    assert rows(outs["k1m"]) == want
+                o = c.paillier_enc(ints_to_limbs(narrow, 8), ints_to_limbs(r[:9], nl))
+                assert np.array_equal(o, want_enc(n, nl, narrow, 8, r[:9], nl))
+    assert np.array_equal(outs["k1m"], want)
     assert np.array_equal(outs["k1m"], outs["k1"])

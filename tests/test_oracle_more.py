@@ -87,3 +87,24 @@ def test_correct_message_proof_classes(bits):
     forged.ciphertext = po.paillier_encrypt(n, 7, rng.randrange(1, n))
     with pytest.raises(po.IncorrectProof):
         forged.verify()
+
+
+def test_golden_vectors_more():
+    """Committed vectors of the row-f3 proofs (scripts/gen_golden.py ran the Python oracle): pins it against regressions."""
+    import hashlib
+    import json
+    import os
+
+    from util import GOLDEN
+
+    g = json.load(open(os.path.join(GOLDEN, "vectors_more.json")))
+    n = int(g["n"])
+    d = g["dlog"]
+    pr = po.CompositeDLogProof.prove(n, int(d["g"]), int(d["ni"]), int(d["secret"]), int(d["r"]))
+    assert (pr.x, pr.y, pr.to_json()) == (int(d["x"]), int(d["y"]), d["json"])
+    pr.verify(n, int(d["g"]), int(d["ni"]))
+    c = g["correct_message"]
+    cm = po.CorrectMessageProof.prove(n, c["valid"], c["message"], int(c["r"]), [int(v) for v in c["e_rand"]], [int(v) for v in c["z_rand"]], int(c["w"]))
+    assert cm.ciphertext == int(c["ciphertext"]) and cm.e_vec == [int(v) for v in c["e_vec"]] and cm.z_vec == [int(v) for v in c["z_vec"]]
+    assert hashlib.sha256(",".join(str(v) for v in cm.a_vec).encode()).hexdigest() == c["a_vec_sha256"]
+    cm.verify()
