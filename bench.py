@@ -492,6 +492,17 @@ def run_other(args):
                                            "their summed durations exceed the wall time); the two-digit kernels execute about half of them",
                               "modexp_kernel_ms_summed": k1_ms + k2_ms},
                     cpu_baseline=None)
+        if not args.no_cpu:
+            # CPU baseline for this secondary line: the Python-int oracle (CPython pow, one core) on a few proofs of the batch
+            m = 3
+            ints = lambda a, i: int.from_bytes(np.ascontiguousarray(a[i]).tobytes(), "little")
+            t0 = time.perf_counter()
+            for i in range(m):
+                po.MulProof(ints(f, i), ints(z1, i), ints(z2, i), ints(e_d, i), ints(e_db, i)).verify(n, ints(e_a, i), ints(e_b, i), ints(e_c, i))
+                po.VerlinProof(ints(phi_a, i), ints(z, i), ints(zp, i), ints(zdp, i), ints(r_z, i)).verify(n, ints(cc, i), ints(cp, i), ints(phi_x, i))
+            cpu_s = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": 2 * m / cpu_s, "unit": "verifies/s", "cores": 1, "kind": "port",
+                                    "sample": f"{m} MulProof + {m} VerlinProof verifies of the batch on the Python-int oracle (CPython pow), all accepted as on the GPU"}
     print(json.dumps(line))
 
 

@@ -4,10 +4,11 @@
 TAG=${1:-r01}
 TESTS=${2:-tests}
 mkdir -p gpurun_out
-echo "== pytest -m gpu ($TESTS)"; timeout 900 python -m pytest $TESTS -m gpu -x -q 2>&1 | tail -15
+if [ -z "$SKIP_TESTS" ]; then echo "== pytest -m gpu ($TESTS)"; timeout 900 python -m pytest $TESTS -m gpu -x -q 2>&1 | tail -15; fi
 echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5
 echo "== bench"; timeout 600 python bench.py 2> gpurun_out/bench_${TAG}.err | tee gpurun_out/bench_${TAG}.json | cut -c1-1500
 tail -5 gpurun_out/bench_${TAG}.err
+if [ -n "$BIG_BATCH" ]; then echo "== bench at the per-GPU share of configs[3] (batch $BIG_BATCH)"; timeout 900 python bench.py --batch $BIG_BATCH --steps 1 --warmup 1 --e2e-steps 1 --no-cpu 2> gpurun_out/bench_${TAG}_b${BIG_BATCH}.err | tee gpurun_out/bench_${TAG}_b${BIG_BATCH}.json | cut -c1-400; fi
 echo "== ncu launch list"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_${TAG}.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu --e2e-steps 1 > gpurun_out/bench_under_ncu_${TAG}.log 2>&1
