@@ -442,6 +442,99 @@ def run_other(args):
                               "unit": "T IMAD.WIDE.U32/s", "frac": k2_units * per / (k2_ms * 1e-3) / imad_peak, "traffic": None, "alg_imads_per_modexp": per,
                               "k2_share_of_step": k2_ms / ms},
                     cpu_baseline={"value": m / cpu_s, "unit": "verifies/s", "cores": cores, "kind": "port", "sample": f"{m} of the {batch} proofs, GMP mpz_powm"})
+    elif args.config == "dlog":
+        # CompositeDLogProof prove + verify (wi_dlog_proof.rs:46-91), one modulus N per statement (the fixture keys, cycled)
+        bits, B = 2048, args.batch if args.batch != 1024 else 4096
+        nl = bits // 32
+        rng = __import__("random").Random(11)
+        ks = keys(bits)
+        st = []
+        for i in range(B):
+            pp, qq = ks[i % len(ks)]
+            N = pp * qq
+            g = rng.randrange(2, N - 1)
+            sec = rng.getrandbits(256)
+            st.append((N, g, pow(pow(g, -1, N), sec, N), sec, rng.getrandbits(512)))
+        N_, g_, ni_, s_, r_ = (ints_to_limbs([t[k] for t in st], w) for k, w in enumerate((nl, nl, nl, 8, 16)))
+
+        def step():
+            x, y, flt = ctx.dlog_prove(N_, g_, ni_, s_, r_, 20)
+            acc, flt2 = ctx.dlog_verify(N_, g_, ni_, x, y)
+            assert acc.all() and not flt.any() and not flt2.any()
+            return x, y
+
+        for _ in range(args.warmup):
+            step()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            x, y = step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        alg = B * (modexp_imads(bits, 512) + modexp_imads(bits, 256) + modexp_imads(bits, 513)) * args.steps
+        m = 8
+        t0 = time.perf_counter()
+        for i in range(m):
+            pr = po.CompositeDLogProof.prove(*st[i])
+            assert pr.x == int.from_bytes(x[i].tobytes(), "little") and pr.y == int.from_bytes(y[i].tobytes(), "little")
+            pr.verify(*st[i][:3])
+        cpu_s = time.perf_counter() - t0
+        line.update(metric="CompositeDLogProof proofs+verifies/sec at 2048-bit N", unit="proofs+verifies/s", value=B * args.steps / dt, ms_per_step=dt / args.steps * 1e3,
+                    config={"workload": f"CompositeDLogProof prove + verify x{B}, 2048-bit N, {len(ks)} distinct moduli cycled, 256-bit secrets; through the host-buffer ABI"},
+                    e2e={"value": B * args.steps / dt, "unit": "proofs+verifies/s", "h2d_bytes_per_step": int(2 * (N_.nbytes + g_.nbytes + ni_.nbytes) + s_.nbytes + r_.nbytes + x.nbytes + y.nbytes),
+                         "d2h_bytes_per_step": int(x.nbytes + y.nbytes + 3 * B)},
+                    roofline={"bound": "imad", "kernel": "modexp_var_kernel<8,8> (K2, short exponents)", "achieved": alg / dt / 1e12, "peak": imad_peak / 1e12,
+                              "unit": "T IMAD.WIDE.U32/s", "frac": alg / dt / imad_peak, "traffic": None,
+                              "frac_note": "algorithmic multiply-adds (SURVEY.md 8d formula) per second of the whole step, host copies included"},
+                    cpu_baseline={"value": m / cpu_s, "unit": "proofs+verifies/s", "cores": 1, "kind": "port",
+                                  "sample": f"{m} of the {B} statements on the Python-int oracle (CPython pow); x and y identical to the GPU's"})
+    elif args.config == "correct_message":
+        # CorrectMessageProof prove + verify (correct_message.rs:35-162), M = 4 valid messages as in the reference's test
+        bits, B, M = 2048, args.batch if args.batch != 1024 else 1024, 4
+        nl, nnl = bits // 32, bits // 16
+        n = test_key()
+        ctx.set_key(to_limbs(n, nl))
+        g = np.random.Generator(np.random.PCG64(7))
+        rows = lambda *shape: workload._rand_limbs_below_pow2(g, shape, nl, bits - 1)
+        valid = ints_to_limbs([[3, 4, 5, 6]] * B, 4)
+        msgs = ints_to_limbs([3 + (i % M) for i in range(B)], 4)
+        r, w, z_rand = rows(B) | 1, rows(B) | 1, rows(B, M - 1) | 1
+        e_rand = np.frombuffer(g.bytes(B * (M - 1) * 32), dtype=np.uint32).reshape(B, M - 1, 8).copy()
+
+        def step():
+            out = ctx.correct_message_prove(valid, msgs, r, e_rand, z_rand, w)
+            acc, flt = ctx.correct_message_verify(out["ciphertext"], valid, out["e_vec"], out["z_vec"], out["a_vec"])
+            assert acc.all() and not flt.any() and not out["fault"].any()
+            return out
+
+        for _ in range(args.warmup):
+            step()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            out = step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        slot = modexp_imads(2 * bits, bits) + modexp_imads(2 * bits, 256)
+        alg = B * (2 * M * slot + modexp_imads(2 * bits, bits) + modexp_imads(bits, 256)) * args.steps
+        m = 2
+        L2I = lambda a: [int.from_bytes(np.ascontiguousarray(v).tobytes(), "little") for v in a]
+        t0 = time.perf_counter()
+        for i in range(m):
+            pr = po.CorrectMessageProof.prove(n, [3, 4, 5, 6], 3 + (i % M), L2I(r[i:i + 1])[0], L2I(e_rand[i]), L2I(z_rand[i]), L2I(w[i:i + 1])[0])
+            assert pr.a_vec == L2I(out["a_vec"][i]) and pr.e_vec == L2I(out["e_vec"][i]) and pr.z_vec == L2I(out["z_vec"][i])
+            pr.verify()
+        cpu_s = time.perf_counter() - t0
+        line.update(metric="CorrectMessageProof proofs+verifies/sec at 2048-bit n", unit="proofs+verifies/s", value=B * args.steps / dt, ms_per_step=dt / args.steps * 1e3,
+                    config={"workload": f"CorrectMessageProof prove + verify x{B}, {M} valid messages, 2048-bit n (reference test key); through the host-buffer ABI"},
+                    e2e={"value": B * args.steps / dt, "unit": "proofs+verifies/s",
+                         "h2d_bytes_per_step": int(2 * valid.nbytes + msgs.nbytes + r.nbytes + w.nbytes + z_rand.nbytes + e_rand.nbytes + sum(out[k].nbytes for k in ("ciphertext", "e_vec", "z_vec", "a_vec"))),
+                         "d2h_bytes_per_step": int(sum(out[k].nbytes for k in ("ciphertext", "e_vec", "z_vec", "a_vec")) + 3 * B)},
+                    roofline={"bound": "imad", "kernel": "enc2m_kernel<8,8> (K1m) + modexp2m_var_kernel<8,8> (K2m)", "achieved": alg / dt / 1e12, "peak": imad_peak / 1e12,
+                              "unit": "T IMAD.WIDE.U32/s", "frac": alg / dt / imad_peak, "traffic": None,
+                              "frac_note": "algorithmic multiply-adds (SURVEY.md 8d formula) per second of the whole step, host copies included; the two-digit kernels execute about half of them"},
+                    cpu_baseline={"value": m / cpu_s, "unit": "proofs+verifies/s", "cores": 1, "kind": "port",
+                                  "sample": f"{m} of the {B} proofs on the Python-int oracle (CPython pow); proof fields identical to the GPU's"})
     else:
         bits, B = 4096, args.batch if args.batch != 1024 else 512
         p, q = keys(bits)[0]
@@ -508,7 +601,7 @@ def run_other(args):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--config", default="rangeproof", choices=["rangeproof", "correct_key", "sigma"])
+    ap.add_argument("--config", default="rangeproof", choices=["rangeproof", "correct_key", "sigma", "dlog", "correct_message"])
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
