@@ -13,17 +13,28 @@ namespace zkp {
 // ------------------------------------------------------------------------ K4
 // digest[b] = SHA-256( to_bytes(seg0 items of b) || to_bytes(seg1 items) || ... )
 __global__ void __launch_bounds__(kShaThreads) sha256_transcript_kernel(const ShaSegs segs, int batch, uint8_t* digest) {
-  __shared__ uint32_t wbuf[16 * kShaThreads];
+  __shared__ uint32_t wbuf[32 * kShaThreads];
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= batch) return;
-  Sha256 s;
+  Sha256Ring s;
   s.init(wbuf + threadIdx.x, kShaThreads);
   for (int k = 0; k < segs.nseg; ++k) {
     const ShaSeg sg = segs.seg[k];
     const uint32_t* base = sg.base + (size_t)b * sg.batch_stride;
     for (int it = 0; it < sg.count; ++it) {
       const uint32_t* p = base + (size_t)it * sg.limbs;
-      s.push_bigint(sg.limbs, [&](int i) { return __ldg(p + i); });
+      // BigInt::to_bytes(): minimal big-endian magnitude, zero -> one 0x00 byte.  Every lane walks all limbs of the item
+      // (leading zero limbs contribute 0 bytes), so that the lanes of a warp stay in the same iteration.
+      bool started = false;
+      for (int i = sg.limbs - 1; i >= 0; --i) {
+        const uint32_t v = __ldg(p + i);
+        int nb = 4;
+        if (!started) {
+          nb = v ? 4 - (__clz(v) >> 3) : (i == 0 ? 1 : 0);
+          started = v != 0u;
+        }
+        s.push(v, nb);
+      }
     }
   }
   uint32_t out[8];

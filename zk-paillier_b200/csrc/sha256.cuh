@@ -132,6 +132,92 @@ struct Sha256 {
   }
 };
 
+// The same absorber for the transcript kernel K4, where the 32 lanes of a warp hash 32 transcripts of (almost) the same
+// length side by side.  Items that lost a leading zero byte make the lanes drift a word or two apart; with one 16-word
+// buffer per lane each lane would call the compression function in a different loop iteration and the warp would run it
+// twice per block (ncu: 4 500 warp instructions per block).  Here every lane has a 32-word ring, words are emitted at ONE
+// code site, and the warp compresses when EVERY converged lane holds a full block (or some lane's ring is full), so the
+// 64 rounds run once per block for the whole warp.
+struct Sha256Ring {
+  uint32_t h[8];
+  uint32_t* w;        // this thread's column of the shared ring: word i at w[(i & 31) * stride]
+  int stride;
+  uint32_t wr, rd;    // words written / consumed so far
+  uint32_t pend;      // pending bytes (< 4), right-aligned
+  int npend;
+  unsigned long long total;
+
+  __device__ __forceinline__ void init(uint32_t* col, int stride_) {
+    h[0] = 0x6a09e667; h[1] = 0xbb67ae85; h[2] = 0x3c6ef372; h[3] = 0xa54ff53a;
+    h[4] = 0x510e527f; h[5] = 0x9b05688c; h[6] = 0x1f83d9ab; h[7] = 0x5be0cd19;
+    w = col;
+    stride = stride_;
+    wr = rd = 0;
+    pend = 0;
+    npend = 0;
+    total = 0;
+  }
+  __device__ __noinline__ void compress() {
+    uint32_t m[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) m[i] = w[((rd + i) & 31u) * stride];
+    rd += 16;
+    uint32_t a = h[0], b = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) {
+      uint32_t wi;
+      if (i < 16) {
+        wi = m[i];
+      } else {
+        uint32_t w15 = m[(i + 1) & 15], w2 = m[(i + 14) & 15];
+        uint32_t s0 = rotr32(w15, 7) ^ rotr32(w15, 18) ^ (w15 >> 3);
+        uint32_t s1 = rotr32(w2, 17) ^ rotr32(w2, 19) ^ (w2 >> 10);
+        wi = m[i & 15] + s0 + m[(i + 9) & 15] + s1;
+        m[i & 15] = wi;
+      }
+      uint32_t S1 = rotr32(e, 6) ^ rotr32(e, 11) ^ rotr32(e, 25);
+      uint32_t ch = (e & f) ^ (~e & g);
+      uint32_t t1 = hh + S1 + ch + kSha256K[i] + wi;
+      uint32_t S0 = rotr32(a, 2) ^ rotr32(a, 13) ^ rotr32(a, 22);
+      uint32_t mj = (a & b) ^ (a & c) ^ (b & c);
+      uint32_t t2 = S0 + mj;
+      hh = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+    }
+    h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
+  }
+  // absorb the low nb (0..4) bytes of v, most significant first; emits at most one word.  The only emit site of the
+  // streaming phase: every lane of the warp passes here once per limb, so the compress trigger below is warp-uniform.
+  __device__ __forceinline__ void push(uint32_t v, int nb) {
+    total += (unsigned long long)nb;
+    const unsigned long long acc = ((unsigned long long)pend << (8 * nb)) | (nb == 4 ? v : (v & ((1u << (8 * nb)) - 1u)));
+    int n = npend + nb;
+    const bool out = n >= 4;
+    if (out) {
+      w[(wr & 31u) * stride] = (uint32_t)(acc >> (8 * (n - 4)));
+      ++wr;
+      n -= 4;
+    }
+    pend = (uint32_t)(acc & ((1ull << (8 * n)) - 1ull));
+    npend = n;
+    const unsigned am = __activemask();
+    const bool ready = wr - rd >= 16u;
+    if (__all_sync(am, ready) || __any_sync(am, wr - rd >= 32u)) {
+      if (ready) compress();
+    }
+  }
+  __device__ __forceinline__ void finish(uint32_t (&out)[8]) {
+    const unsigned long long bits = total * 8ull;
+    push(0x80u, 1);
+    while (npend != 0) push(0u, 1);
+    while ((wr & 15u) != 14u) push(0u, 4);
+    push((uint32_t)(bits >> 32), 4);
+    push((uint32_t)bits, 4);
+    while (wr - rd >= 16u) compress();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) out[i] = h[i];
+  }
+};
+
 // Challenge bit i of ChallengeBits(BigInt::to_bytes(digest)) read MSB-first as
 // BitVec::from_bytes does (reference range_proof.rs:221,225,267,273): the
 // digest's leading zero BYTES are stripped before indexing (to_bytes of the
