@@ -1,6 +1,7 @@
 //! RangeProofNi / NiCorrectKeyProof over the C ABI.  Field names, visibility, serde attributes and error
 //! conventions follow the reference (range_proof_ni.rs:35-44, range_proof.rs:31-81, correct_key_ni.rs:34-39,
-//! errors.rs:5-13); the sigma-protocol structs bind zkp_{zero,ciphertext,mul,verlin}_{prove,verify} the same way.
+//! errors.rs:5-13); CompositeDLogProof and verify_opening follow; the sigma-protocol structs and CorrectMessageProof bind
+//! zkp_{zero,ciphertext,mul,verlin,correct_message}_{prove,verify} the same way.
 use std::fmt;
 use std::ptr;
 
@@ -228,6 +229,75 @@ impl NiCorrectKeyProof {
         }
         if accept[0] == 1 { Ok(()) } else { Err(IncorrectProof) }
     }
+}
+
+/// wi_dlog_proof.rs:28-39 — fields keep curv's native BigInt serde (no `with =` attribute in the reference)
+#[derive(Debug, Serialize, Deserialize, Clone)]
+pub struct CompositeDLogProof {
+    pub x: BigInt,
+    pub y: BigInt,
+}
+#[allow(non_snake_case)]
+#[derive(Debug, Serialize, Deserialize, Clone)]
+pub struct DLogStatement {
+    pub N: BigInt,
+    pub g: BigInt,
+    pub ni: BigInt,
+}
+
+impl CompositeDLogProof {
+    const K: usize = 128;
+    const K_PRIME: usize = 128;
+    const SAMPLE_S: usize = 256;
+
+    /// wi_dlog_proof.rs:46-65: r is drawn here, x = g^r mod N, the hash and y = r + e * secret come from the engine
+    pub fn prove(statement: &DLogStatement, secret: &BigInt) -> CompositeDLogProof {
+        let eng = Engine::new(0);
+        let nl = (statement.N.bit_length() + 127) / 128 * 4;
+        let r = BigInt::sample_below(&BigInt::from(2).pow((Self::K + Self::K_PRIME + Self::SAMPLE_S) as u32));
+        let (sl, rl) = ((secret.bit_length() + 127) / 128 * 4, 16usize);
+        let yl = (std::cmp::max(rl, sl + 8) + 4) / 4 * 4;
+        let (mut x, mut y, mut fault) = (vec![0u32; nl], vec![0u32; yl], [0u8; 1]);
+        unsafe {
+            eng.check(ffi::zkp_dlog_prove(
+                eng.0, 1, nl as i32, to_limbs(&statement.N, nl).as_ptr(), to_limbs(&statement.g, nl).as_ptr(),
+                to_limbs(&statement.ni, nl).as_ptr(), to_limbs(secret, sl).as_ptr(), sl as i32, to_limbs(&r, rl).as_ptr(), rl as i32,
+                yl as i32, x.as_mut_ptr(), y.as_mut_ptr(), fault.as_mut_ptr(),
+            ));
+        }
+        assert_eq!(fault[0], 0);
+        CompositeDLogProof { x: from_limbs(&x), y: from_limbs(&y) }
+    }
+
+    /// wi_dlog_proof.rs:66-91: the three asserts of the reference come back as `fault` and panic here as they do there
+    pub fn verify(&self, statement: &DLogStatement) -> Result<(), IncorrectProof> {
+        let eng = Engine::new(0);
+        let nl = (statement.N.bit_length() + 127) / 128 * 4;
+        let yl = (self.y.bit_length() + 127) / 128 * 4;
+        let (mut accept, mut fault) = ([0u8; 1], [0u8; 1]);
+        unsafe {
+            eng.check(ffi::zkp_dlog_verify(
+                eng.0, 1, nl as i32, to_limbs(&statement.N, nl).as_ptr(), to_limbs(&statement.g, nl).as_ptr(),
+                to_limbs(&statement.ni, nl).as_ptr(), to_limbs(&self.x, nl).as_ptr(), to_limbs(&self.y, yl).as_ptr(), yl as i32,
+                accept.as_mut_ptr(), fault.as_mut_ptr(),
+            ));
+        }
+        assert_eq!(fault[0], 0, "assertion failed: N > 2^K, gcd(g, N) == 1, gcd(ni, N) == 1");
+        if accept[0] == 1 { Ok(()) } else { Err(IncorrectProof) }
+    }
+}
+
+/// correct_opening.rs:17-30 — `Paillier::verify_opening(ek, m, r, c)`
+pub fn verify_opening(ek: &EncryptionKey, m: &BigInt, r: &BigInt, c: &BigInt) -> bool {
+    let eng = Engine::new(0);
+    let nl = (ek.n.bit_length() + 127) / 128 * 4;
+    let mut ok = [0u8; 1];
+    unsafe {
+        eng.check(ffi::zkp_set_key(eng.0, to_limbs(&ek.n, nl).as_ptr(), nl as i32));
+        eng.check(ffi::zkp_verify_opening(eng.0, 1, nl as i32, to_limbs(&(m % &ek.n), nl).as_ptr(), to_limbs(&(r % &ek.n), nl).as_ptr(),
+                                          to_limbs(c, 2 * nl).as_ptr(), ok.as_mut_ptr()));
+    }
+    ok[0] == 1
 }
 
 /// serialize.rs:1-31 — decimal-string BigInt codec
