@@ -153,8 +153,7 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's banner / warnings off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     batch = args.batch
     nl = N_BITS // 32
@@ -244,7 +243,12 @@ def run_b200(args):
     g0.record(stream)
     for _ in range(args.e2e_steps):
         step_e2e()
-    if world > 1:  # final gather of the verdicts + challenge hashes over NVLink (33 B per proof)
+    if world > 1:  # final gather over NVLink: the proofs (device to device, 0.2 MB each), then verdicts + challenge hashes (33 B per proof)
+        allproofs = sharding.gather_proof_bytes([out[k] for k in ("c1", "c2", "kind", "resp_w", "resp_r")], dev)
+        torch.cuda.synchronize(dev)
+        assert allproofs.shape[:2] == (world, batch)
+        gathered_bytes = int(allproofs.numel())
+        del allproofs
         allrec = sharding.gather_records(np.concatenate([acc_h[:, None], dig_h], axis=1), dev, counts=[batch] * world)
         assert allrec.shape == (world * batch, 33)
     g1.record(stream)
@@ -316,7 +320,7 @@ def run_b200(args):
         "config": {"workload": f"RangeProofNi prove+verify, batch={batch} per GPU, {N_BITS}-bit n ({'reference test key' if N_BITS == 2048 else 'committed fixture key'}), error_factor=128, 256-bit range",
                    "batch_per_gpu": batch, "n_bits": N_BITS, "error_factor": EF, "enc_per_step_per_gpu": int(2 * batch * EF + enc_verify),
                    "l2": "working set per step (approx 0.5 GB of bases, ciphertexts and responses) exceeds the 126 MB L2; no explicit flush",
-                   "sharding": "independent proofs, contiguous shard per rank; NCCL broadcast of n before, all_gather of verdicts after; no collective on the modexp path"},
+                   "sharding": "independent proofs, contiguous shard per rank; NCCL broadcast of n before; after the last step of the e2e region an all_gather of the proof bytes (device to device) and of the verdicts; no collective on the modexp path"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": args.e2e_steps},
         "gpu_launches": launches,
         "roofline": {"bound": "imad", "kernel": kernel_name, "achieved": achieved / 1e12, "peak": imad_peak / 1e12, "unit": "T IMAD.WIDE.U32/s",

@@ -75,3 +75,44 @@ def test_two_rank_gloo_matches_single_process():
     assert rec.shape == (total, 33)
     assert np.array_equal(rec[:, 0], acc) and np.array_equal(rec[:, 1:], dig)
     assert acc.tolist() == [1, 1, 0, 1, 1, 0, 1]
+
+
+def _worker_proofs(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(100 + rank)
+    local = 3                                           # equal shards (weak scaling)
+    c1 = rng.integers(0, 2**32, (local, 4, 8), dtype=np.uint32)
+    kind = rng.integers(0, 3, (local, 4), dtype=np.uint8)
+    resp = rng.integers(0, 2**32, (local, 4, 2, 3), dtype=np.uint32)
+    out = sharding.gather_proof_bytes([c1, kind, resp], torch.device("cpu"))
+    if rank == 0:
+        q.put(out.numpy().copy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gather_of_proof_bytes_two_ranks():
+    """The final gather of the proofs themselves (bench.py, N > 1): rank-major, one byte record per proof."""
+    world = 2
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_proofs, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert got.shape == (2, 3, 4 * 8 * 4 + 4 + 4 * 2 * 3 * 4)
+    for r in range(world):
+        rng = np.random.default_rng(100 + r)
+        c1 = rng.integers(0, 2**32, (3, 4, 8), dtype=np.uint32)
+        kind = rng.integers(0, 3, (3, 4), dtype=np.uint8)
+        resp = rng.integers(0, 2**32, (3, 4, 2, 3), dtype=np.uint32)
+        want = np.concatenate([c1.view(np.uint8).reshape(3, -1), kind.reshape(3, -1), resp.view(np.uint8).reshape(3, -1)], axis=1)
+        assert np.array_equal(got[r], want)

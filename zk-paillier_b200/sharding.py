@@ -54,3 +54,28 @@ def gather_records(records: np.ndarray, device, counts=None):
     dist.all_gather_into_tensor(out, pad) if device.type == "cuda" else dist.all_gather(list(out.unbind(0)), pad)
     out = out.cpu().numpy()
     return np.concatenate([out[r, : counts[r]] for r in range(world)], axis=0)
+
+
+def gather_proof_bytes(arrays, device):
+    """Final gather of the proofs themselves over NVLink (BASELINE.json north_star): every rank's proof rows -- the host
+    arrays of one shard, each [local, ...] -- are staged into one device record per proof and all-gathered on the device
+    (NCCL has no gather; the root is whoever reads rank-major slice [r]).  Equal shards (weak scaling).  Returns the device
+    tensor [world, local, bytes_per_proof]; nothing is copied back to the host."""
+    local = arrays[0].shape[0]
+    flats = [np.ascontiguousarray(a).view(np.uint8).reshape(local, -1) for a in arrays]
+    width = sum(f.shape[1] for f in flats)
+    rec = torch.empty((local, width), dtype=torch.uint8, device=device)
+    off = 0
+    for f in flats:
+        rec[:, off:off + f.shape[1]].copy_(torch.from_numpy(f), non_blocking=True)
+        off += f.shape[1]
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    if world == 1:
+        return rec.unsqueeze(0)
+    out = torch.empty((world, local, width), dtype=torch.uint8, device=device)
+    if device.type == "cuda":
+        dist.all_gather_into_tensor(out, rec)
+    else:
+        dist.all_gather(list(out.unbind(0)), rec)
+    return out
+
