@@ -153,7 +153,8 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's banner / warnings off stdout: rank 0 prints ONE JSON line
+        # the GPU box exports NCCL_DEBUG=VERSION, so NCCL prints its version banner on stdout before rank 0's JSON line; it is
+        # left alone (it is the launcher's setting, and the evidence that NCCL initialised)
         dist.init_process_group("nccl", device_id=dev)
     batch = args.batch
     nl = N_BITS // 32
