@@ -248,6 +248,14 @@ int zkp_correct_message_verify(zkp_ctx* ctx, int batch, int M, int m_limbs, int 
                                const uint32_t* valid, const uint32_t* e_vec, const uint32_t* z_vec, const uint32_t* a_vec,
                                uint8_t* accept, uint8_t* fault);
 
+/* ---- environment (read once per process; tuning and A/B measurement only, results are bit-identical) ----------
+ *   ZKP_B200_ENC=k1            Paillier encryption by K1 (Montgomery modulo n^2) instead of K1m (two-digit form)
+ *   ZKP_B200_K1M_VARIANT=0..9  lane layout / loop structure of K1m (modexp2m.cu: Enc2mConfig; 0 is the default and the
+ *                              fastest measured on B200, 9 is the symmetric squaring)
+ *   ZKP_B200_K1M_WINDOW=5|6    sliding-window width of K1m (default 6)
+ *   ZKP_B200_K2_CTAS=n         persistent CTAs per SM of K2 (default 4)
+ */
+
 /* ---- measurement ----------------------------------------------------------
  * Register-only multiply-add issue-rate microbenchmark (the roofline denominator
  * for the modexp kernels).  variant 0: independent IMAD.WIDE.U32, 1: the

@@ -375,7 +375,7 @@ int zkp_set_key(zkp_ctx* c, const uint32_t* n, int n_limbs) {
         sq += ops[k] >> 24;
         mu += (ops[k] & 0xffu) != 0xffu;
       }
-      c->enc2m_mads = ((double)S * S) * (4.0 * sq + 5.0 * mu + 1.0);
+      c->enc2m_mads = ((double)S * S) * (enc2m_sqr_products() * sq + 5.0 * mu + 1.0);
     }
     {
       std::vector<uint32_t> sched = recode_exponent(n, n_limbs);

@@ -58,6 +58,7 @@ struct Enc2mKey {
 };
 bool enc2m_supported(const uint32_t* n_host, int S);
 void enc2m_host_constants(const uint32_t* n_host, int S, uint32_t* consts /* [5 S] */);
+double enc2m_sqr_products();  // limb products of one two-digit squaring in units of S^2: 4, or 3 + (T/2 + 1)/T with the symmetric variant
 int enc2m_window();  // sliding-window width of K1m (5, or 6 with ZKP_B200_K1M_WINDOW=6)
 std::vector<uint32_t> enc2m_ops(const uint32_t* sched, int nsteps);  // from the schedule of the exponent n recoded with enc2m_window()
 int enc2m_resident_groups(int S, int num_sms);

@@ -578,6 +578,9 @@ static Enc2mConfig enc2m_config() {
   return cfg;
 }
 int enc2m_window() { return enc2m_config().window; }
+double enc2m_sqr_products() {  // variant 9 multiplies every pair of lane blocks once: (T/2 + 1)/T of the first product, T = 8 or 16 lanes
+  return enc2m_config().variant == 9 ? 3.0 + 5.0 / 8.0 : 4.0;
+}
 static int enc2m_table() { return 1 << (enc2m_config().window - 1); }  // odd powers kept
 static int enc2m_slots() { return enc2m_table() + 1; }                 // ... and x^2
 
