@@ -2,6 +2,7 @@
 sizes in seconds): prove->verify round trips, the Paillier homomorphism, challenge-hash agreement between
 prover and verifier, reject-path statements, and oracle spot checks on sampled rows.
   configs[1]  RangeProofNi batch=1024, 2048-bit n
+  configs[3]  RangeProofNi batch=65536 over 8 GPUs: one GPU's contiguous shard (8192 proofs), sharded as bench.py does
   configs[2]  NiCorrectKeyProof verify batch=4096, 3072-bit n
   configs[4]  MulProof + VerlinProof verify at 4096-bit n (per-GPU share of the 8192 mixed batch: 1024 = 512 + 512)
 """
@@ -52,6 +53,34 @@ def test_config1_rangeproof_batch1024_2048(ctx):
     want[7] = 0
     want[300] = 0
     assert np.array_equal(acc2, want)
+
+
+def test_config3_one_shard_of_65536(ctx):
+    """The per-GPU share of configs[3]: rank 5 of 8 owns proofs [40960, 49152) of the 65 536 (sharding.shard_bounds); its
+    statements come from the rank's own seeded stream, as in bench.py.  3.7 M encryptions: properties, plus whole proofs
+    against the GMP oracle at the shard's ends."""
+    from zk_paillier_b200 import sharding
+
+    n = po.TEST_P * po.TEST_Q
+    nl, ef, world, rank = 64, 128, 8, 5
+    lo, hi = sharding.shard_bounds(65536, world, rank)
+    batch = hi - lo
+    assert (lo, batch) == (40960, 8192)
+    ctx.set_key(to_limbs(n, nl))
+    work = workload.rangeproof_batch(n, batch, ef=ef, seed=workload.DEFAULT_SEED + rank, reject_every=100)
+    cx = ctx.paillier_enc(work["x_n"], work["r"])
+    out = ctx.rangeproof_ni_prove(ef, work["range"], work["x"], work["r"], work["w1"], work["swap"], work["r1"], work["r2"])
+    acc, fault, dig = ctx.rangeproof_ni_verify(ef, work["range"], cx, out["c1"], out["c2"], out["kind"], out["resp_w"], out["resp_r"])
+    assert acc.tolist() == [0 if b % 100 == 99 else 1 for b in range(batch)] and not fault.any()
+    assert np.array_equal(dig, out["digest"])
+    opens = int((out["kind"] == 0).sum())
+    assert ctx.rp_verify_enc_count() == batch * ef + opens and abs(opens / (batch * ef) - 0.5) < 0.005
+    assert len({bytes(d) for d in dig}) == batch                       # 8192 distinct challenges
+    sel = np.array([0, batch // 2, batch - 1])
+    cpu = c_oracle.rangeproof_ni_prove(to_limbs(n, nl), ef, work["range"][sel], work["x"][sel], work["r"][sel], work["w1"][sel],
+                                       work["swap"][sel], work["r1"][sel], work["r2"][sel])
+    for k in ("c1", "c2", "digest", "kind", "resp_w", "resp_r"):
+        assert np.array_equal(out[k][sel], cpu[k]), k
 
 
 def test_config2_correct_key_batch4096_3072(ctx):
