@@ -27,6 +27,7 @@ def test_bigint_against_python_ints():
         else:
             assert "inv" not in r or b == 1
         assert r["hex"] == po.serde_bigint_native(a) and r["bits"] == a.bit_length() and r["roundtrip"] is True
+        assert int(r["or"]) == a | b and int(r["shl"]) == a << 37 and int(r["shr"]) == a >> 37 and r["mod_small"] == a % 4093
 
 
 def test_knuth_division_corner_cases():

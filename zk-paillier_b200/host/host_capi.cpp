@@ -74,6 +74,10 @@ Json dispatch(const std::string& op, const Json& req) {
       if (BigInt::mod_inv(a, b, inv)) out.set("inv", ser_dec(inv));
     }
     out.set("gcd", ser_dec(BigInt::gcd(a, b)));
+    out.set("or", ser_dec(a | b));
+    out.set("shl", ser_dec(a.shl(37)));
+    out.set("shr", ser_dec(a.shr(37)));
+    out.set("mod_small", Json::number((int64_t)a.mod_small(4093u)));
     out.set("hex", ser_native(a));
     out.set("bits", Json::number((int64_t)a.bit_length()));
     BigInt back;
