@@ -2,6 +2,7 @@
 #   make            -> zk-paillier_b200/libzkp_b200.so + oracle/liboracle.so
 #   make lib        -> CUDA library only
 #   make oracle     -> oracle only
+#   make examples   -> examples/range_proof_ni (the reference's range-proof test against the C++ mirror)
 NVCC      ?= nvcc
 ARCH      := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS   := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall -Xptxas -v
@@ -28,11 +29,15 @@ $(BUILD)/%.o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.h) $(wildcard $(CSRC)/*.cuh) inc
 $(LIB): $(OBJ)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJ) -lcudart
 
+examples: examples/range_proof_ni
+examples/range_proof_ni: examples/range_proof_ni.cpp $(wildcard $(HOSTSRC)/*.hpp) include/zkp_b200.h $(LIB)
+	g++ -O2 -std=c++17 -Wall -o $@ $< -Lzk-paillier_b200 -lzkp_b200 -Wl,-rpath,'$$ORIGIN/../zk-paillier_b200'
+
 oracle:
 	$(MAKE) -C oracle
 
 clean:
-	rm -rf $(BUILD) $(LIB) $(HOSTLIB)
+	rm -rf $(BUILD) $(LIB) $(HOSTLIB) examples/range_proof_ni
 	$(MAKE) -C oracle clean
 
-.PHONY: all lib oracle clean
+.PHONY: all lib oracle examples clean

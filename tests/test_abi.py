@@ -49,3 +49,18 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
                 txt = open(os.path.join(base, f), errors="ignore").read()
                 assert "zkp_oracle" not in txt and "c_oracle" not in txt and "liboracle" not in txt, os.path.join(base, f)
+
+
+def test_example_builds_and_fails_loudly_without_a_gpu():
+    """examples/range_proof_ni.cpp (the reference's range-proof test on the C++ mirror) compiles against the shipped headers;
+    without a CUDA device it must stop with an error, never fall back to a CPU path."""
+    import subprocess
+
+    import torch
+
+    subprocess.check_call(["make", "-C", ROOT, "examples"], stdout=subprocess.DEVNULL)
+    exe = os.path.join(ROOT, "examples", "range_proof_ni")
+    assert os.path.exists(exe)
+    if not torch.cuda.is_available():
+        r = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+        assert r.returncode == 2 and "no usable CUDA device" in r.stderr

@@ -345,3 +345,20 @@ def test_paillier_keypair_on_device():
     assert pr["proof"] == po.NiCorrectKeyProof.proof(p, q, po.SALT_STRING).to_json()
     v = call("correct_key_ni.verify", proofs=[pr["proof"]], n=[str(p * q)], salt_hex=po.SALT_STRING.hex())
     assert v["results"] == ["ok"]
+
+
+def test_cpp_example_end_to_end():
+    """examples/range_proof_ni.cpp: the reference's range-proof test (range_proof_ni.rs:130-199) on the C++ mirror, as a user
+    of the crate would write it -- key generation, encryption, prove, serde round trip, verify, and the out-of-range reject."""
+    import os
+    import subprocess
+
+    from util import ROOT
+
+    exe = os.path.join(ROOT, "examples", "range_proof_ni")
+    if not os.path.exists(exe):  # built by `make examples` in the build container; compile it directly if it did not travel
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", exe, exe + ".cpp", "-L" + os.path.join(ROOT, "zk-paillier_b200"), "-lzkp_b200",
+                               "-Wl,-rpath," + os.path.join(ROOT, "zk-paillier_b200")])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert "RangeProofNi:" in r.stdout and "NiCorrectKeyProof: verified" in r.stdout and "rejected: Err(IncorrectProof)" in r.stdout
