@@ -126,3 +126,41 @@ def correct_key_ni_verify(n, sigma, salt: bytes, threads=0):
     s = np.frombuffer(bytes(salt), dtype=np.uint8).copy() if len(salt) else np.zeros(1, np.uint8)
     load().orc_correct_key_ni_verify(batch, nl, _p32(n), _p32(sigma), _p8(s), len(salt), _p8(accept), _p32(rho), threads)
     return accept, rho
+
+
+# ---- sigma-protocol verifiers on GMP (verdict: 1 Ok, 0 Err(IncorrectProof), 2 where the reference panics)
+def mul_verify(n, e_a, e_b, e_c, f, z1, z2, e_d, e_db, threads=0):
+    n = _c32(n)
+    arrs = [_c32(a) for a in (e_a, e_b, e_c, f, z1, z2, e_d, e_db)]
+    batch = arrs[0].shape[0]
+    out = np.empty(batch, np.uint8)
+    load().orc_mul_verify(_p32(n), n.shape[-1], batch, *[_p32(a) for a in arrs], _p8(out), threads)
+    return out
+
+
+def verlin_verify(n, c, c_prime, phi_x, phi_a, z, z_prime, z_dp, r_z, threads=0):
+    n = _c32(n)
+    arrs = [_c32(a) for a in (c, c_prime, phi_x, phi_a, z, z_prime, z_dp, r_z)]
+    batch = arrs[0].shape[0]
+    out = np.empty(batch, np.uint8)
+    load().orc_verlin_verify(_p32(n), n.shape[-1], arrs[4].shape[1], batch, *[_p32(a) for a in arrs], _p8(out), threads)
+    return out
+
+
+def dlog_verify(N, g, ni, x, y, threads=0):
+    arrs = [_c32(a) for a in (N, g, ni, x, y)]
+    batch, nl = arrs[0].shape
+    out = np.empty(batch, np.uint8)
+    load().orc_dlog_verify(nl, arrs[4].shape[1], batch, *[_p32(a) for a in arrs], _p8(out), threads)
+    return out
+
+
+def correct_message_verify(n, ciphertext, valid, e_vec, z_vec, a_vec, threads=0):
+    n = _c32(n)
+    ciphertext, valid, e_vec, z_vec, a_vec = (_c32(a) for a in (ciphertext, valid, e_vec, z_vec, a_vec))
+    batch, M, ml = valid.shape
+    out = np.empty(batch, np.uint8)
+    load().orc_correct_message_verify(_p32(n), n.shape[-1], batch, M, ml, e_vec.shape[2], _p32(ciphertext), _p32(valid), _p32(e_vec),
+                                      _p32(z_vec), _p32(a_vec), _p8(out), threads)
+    return out
+

@@ -570,3 +570,176 @@ void orc_correct_key_ni_verify(int batch, int n_limbs, const uint32_t* n, const 
   free(j.derived);
   mpz_clear(P); mpz_clear(zn); mpz_clear(salt_bn); mpz_clear(seed); mpz_clear(h); mpz_clear(acc); mpz_clear(idx); mpz_clear(g); mpz_clear(want);
 }
+
+/* ======================================================================================================
+ * Sigma-protocol verifiers on GMP (a second restatement next to oracle/zkp_oracle.py; CPU tests compare the two):
+ *   MulProof::verify            multiplication_proof.rs:108-145
+ *   VerlinProof::verify         verlin_proof.rs:101-134, gen_phi :138-165
+ *   CompositeDLogProof::verify  wi_dlog_proof.rs:66-91
+ *   CorrectMessageProof::verify correct_message.rs:126-161
+ * verdict[b]: 1 = Ok(()), 0 = Err(IncorrectProof), 2 = the reference panics (unwrap() on a missing inverse, assert!).
+ * ====================================================================================================== */
+extern int __gmpz_invert(__mpz_struct*, const __mpz_struct*, const __mpz_struct*);
+#define mpz_invert __gmpz_invert
+
+/* e = compute_digest(items...) as a BigInt (utils.rs:9-22) */
+static void digest_of(mpz_t e, const __mpz_struct* const* items, int count, uint8_t* scratch) {
+  SHA256_CTX h;
+  SHA256_Init(&h);
+  for (int i = 0; i < count; ++i) sha_update_mpz(&h, items[i], scratch);
+  uint8_t d[32];
+  SHA256_Final(d, &h);
+  __gmpz_import(e, 32, 1, 1, 0, 0, d);
+}
+
+typedef struct {
+  int nl, zl, M, el, ml;
+  const uint32_t *n, *a0, *a1, *a2, *a3, *a4, *a5, *a6, *a7;
+  uint8_t* verdict;
+} sig_job;
+
+static void mul_verify_task(void* arg, long b) {
+  sig_job* j = (sig_job*)arg;
+  const int nl = j->nl, nnl = 2 * nl;
+  mpz_t n, nn, e_a, e_b, e_c, f, z1, z2, e_d, e_db, e, t, u, v, lhs;
+  __mpz_struct* all[] = {n, nn, e_a, e_b, e_c, f, z1, z2, e_d, e_db, e, t, u, v, lhs};
+  for (size_t k = 0; k < sizeof(all) / sizeof(all[0]); ++k) mpz_init(all[k]);
+  uint8_t* scratch = (uint8_t*)malloc((size_t)nnl * 4 + 64);
+  imp(n, j->n, nl);
+  mpz_mul(nn, n, n);
+  imp(e_a, j->a0 + (size_t)b * nnl, nnl); imp(e_b, j->a1 + (size_t)b * nnl, nnl); imp(e_c, j->a2 + (size_t)b * nnl, nnl);
+  imp(f, j->a3 + (size_t)b * nl, nl); imp(z1, j->a4 + (size_t)b * nnl, nnl); imp(z2, j->a5 + (size_t)b * nnl, nnl);
+  imp(e_d, j->a6 + (size_t)b * nnl, nnl); imp(e_db, j->a7 + (size_t)b * nnl, nnl);
+  const __mpz_struct* items[] = {n, e_a, e_b, e_c, e_d, e_db};
+  digest_of(e, items, 6, scratch);                                       /* :109-116 */
+  uint8_t verdict = 1;
+  enc(u, n, nn, f, z1, t);                                               /* enc_f_z1  :118-124 */
+  mpz_powm(lhs, e_a, e, nn); mpz_mul(lhs, lhs, e_d); mpz_mod(lhs, lhs, nn);  /* :133-134 */
+  if (mpz_cmp(lhs, u) != 0) verdict = 0;
+  mpz_powm(v, e_c, e, nn); mpz_mul(v, v, e_db); mpz_mod(v, v, nn);       /* :135-136 */
+  if (!mpz_invert(v, v, nn)) verdict = 2;                                /* :137 unwrap() */
+  else {
+    mpz_set_ui(t, 0);
+    mpz_powm(u, z2, n, nn);                                              /* enc_0_z2 = z2^n  :125-131 */
+    mpz_powm(lhs, e_b, f, nn); mpz_mul(lhs, lhs, v); mpz_mod(lhs, lhs, nn);  /* :138-139 */
+    if (mpz_cmp(lhs, u) != 0) verdict = 0;
+  }
+  j->verdict[b] = verdict;
+  free(scratch);
+  for (size_t k = 0; k < sizeof(all) / sizeof(all[0]); ++k) mpz_clear(all[k]);
+}
+void orc_mul_verify(const uint32_t* n, int nl, int batch, const uint32_t* e_a, const uint32_t* e_b, const uint32_t* e_c, const uint32_t* f,
+                    const uint32_t* z1, const uint32_t* z2, const uint32_t* e_d, const uint32_t* e_db, uint8_t* verdict, int threads) {
+  sig_job j = {nl, 0, 0, 0, 0, n, e_a, e_b, e_c, f, z1, z2, e_d, e_db, verdict};
+  run_parallel(mul_verify_task, &j, batch, threads);
+}
+
+static void verlin_verify_task(void* arg, long b) {
+  sig_job* j = (sig_job*)arg;
+  const int nl = j->nl, nnl = 2 * nl, zl = j->zl;
+  mpz_t n, nn, c, cp, phi_x, phi_a, z, zp, zdp, r_z, e, t, u, rhs, phi;
+  __mpz_struct* all[] = {n, nn, c, cp, phi_x, phi_a, z, zp, zdp, r_z, e, t, u, rhs, phi};
+  for (size_t k = 0; k < sizeof(all) / sizeof(all[0]); ++k) mpz_init(all[k]);
+  uint8_t* scratch = (uint8_t*)malloc((size_t)nnl * 4 + 64);
+  imp(n, j->n, nl);
+  mpz_mul(nn, n, n);
+  imp(c, j->a0 + (size_t)b * nnl, nnl); imp(cp, j->a1 + (size_t)b * nnl, nnl); imp(phi_x, j->a2 + (size_t)b * nnl, nnl);
+  imp(phi_a, j->a3 + (size_t)b * nnl, nnl); imp(z, j->a4 + (size_t)b * zl, zl); imp(zp, j->a5 + (size_t)b * zl, zl);
+  imp(zdp, j->a6 + (size_t)b * zl, zl); imp(r_z, j->a7 + (size_t)b * nnl, nnl);
+  const __mpz_struct* items[] = {n, c, cp, phi_x, phi_a};
+  digest_of(e, items, 5, scratch);                                       /* :102-108 */
+  mpz_powm(rhs, phi_x, e, nn); mpz_mul(rhs, rhs, phi_a); mpz_mod(rhs, rhs, nn);   /* :109-118 */
+  mpz_powm(phi, c, z, nn);                                               /* gen_phi :147-163 */
+  mpz_powm(u, cp, zp, nn); mpz_mul(phi, phi, u); mpz_mod(phi, phi, nn);
+  enc(u, n, nn, zdp, r_z, t); mpz_mul(phi, phi, u); mpz_mod(phi, phi, nn);
+  j->verdict[b] = mpz_cmp(phi, rhs) == 0 ? 1 : 0;
+  free(scratch);
+  for (size_t k = 0; k < sizeof(all) / sizeof(all[0]); ++k) mpz_clear(all[k]);
+}
+void orc_verlin_verify(const uint32_t* n, int nl, int zl, int batch, const uint32_t* c, const uint32_t* cp, const uint32_t* phi_x,
+                       const uint32_t* phi_a, const uint32_t* z, const uint32_t* zp, const uint32_t* zdp, const uint32_t* r_z,
+                       uint8_t* verdict, int threads) {
+  sig_job j = {nl, zl, 0, 0, 0, n, c, cp, phi_x, phi_a, z, zp, zdp, r_z, verdict};
+  run_parallel(verlin_verify_task, &j, batch, threads);
+}
+
+static void dlog_verify_task(void* arg, long b) {
+  sig_job* j = (sig_job*)arg;
+  const int nl = j->nl, yl = j->zl;
+  mpz_t N, g, ni, x, y, e, t, u;
+  __mpz_struct* all[] = {N, g, ni, x, y, e, t, u};
+  for (size_t k = 0; k < sizeof(all) / sizeof(all[0]); ++k) mpz_init(all[k]);
+  uint8_t* scratch = (uint8_t*)malloc((size_t)nl * 4 + 64);
+  imp(N, j->a0 + (size_t)b * nl, nl); imp(g, j->a1 + (size_t)b * nl, nl); imp(ni, j->a2 + (size_t)b * nl, nl);
+  imp(x, j->a3 + (size_t)b * nl, nl); imp(y, j->a4 + (size_t)b * yl, yl);
+  uint8_t verdict = 1;
+  mpz_set_ui(t, 1); mpz_mul_2exp(t, t, 128);
+  if (mpz_cmp(N, t) <= 0) verdict = 2;                                   /* :68 assert!(N > 2^K) */
+  mpz_gcd(t, g, N); if (mpz_cmp_ui(t, 1) != 0) verdict = 2;              /* :71 */
+  mpz_gcd(t, ni, N); if (mpz_cmp_ui(t, 1) != 0) verdict = 2;             /* :72 */
+  if (verdict == 1) {
+    const __mpz_struct* items[] = {x, g, N, ni};
+    digest_of(e, items, 4, scratch);                                     /* :74-79 */
+    mpz_powm(t, ni, e, N); mpz_powm(u, g, y, N); mpz_mul(u, u, t); mpz_mod(u, u, N);   /* :80-82 */
+    verdict = mpz_cmp(x, u) == 0 ? 1 : 0;                                /* :85 */
+  }
+  j->verdict[b] = verdict;
+  free(scratch);
+  for (size_t k = 0; k < sizeof(all) / sizeof(all[0]); ++k) mpz_clear(all[k]);
+}
+void orc_dlog_verify(int nl, int yl, int batch, const uint32_t* N, const uint32_t* g, const uint32_t* ni, const uint32_t* x, const uint32_t* y,
+                     uint8_t* verdict, int threads) {
+  sig_job j = {nl, yl, 0, 0, 0, NULL, N, g, ni, x, y, NULL, NULL, NULL, verdict};
+  run_parallel(dlog_verify_task, &j, batch, threads);
+}
+
+static void cmsg_verify_task(void* arg, long b) {
+  sig_job* j = (sig_job*)arg;
+  const int nl = j->nl, nnl = 2 * nl, M = j->M, el = j->el, ml = j->ml;
+  mpz_t n, nn, c, chal, esum, two_b, m, e, z, a, gm, u, t, lhs;
+  __mpz_struct* all[] = {n, nn, c, chal, esum, two_b, m, e, z, a, gm, u, t, lhs};
+  for (size_t k = 0; k < sizeof(all) / sizeof(all[0]); ++k) mpz_init(all[k]);
+  uint8_t* scratch = (uint8_t*)malloc((size_t)nnl * 4 + 64);
+  imp(n, j->n, nl);
+  mpz_mul(nn, n, n);
+  imp(c, j->a0 + (size_t)b * nnl, nnl);
+  mpz_set_ui(two_b, 1); mpz_mul_2exp(two_b, two_b, 256);
+  SHA256_CTX h;                                                           /* chal = H(a_vec) mod 2^256  :128-129 */
+  SHA256_Init(&h);
+  for (int i = 0; i < M; ++i) {
+    imp(a, j->a4 + ((size_t)b * M + i) * nnl, nnl);
+    sha_update_mpz(&h, a, scratch);
+  }
+  uint8_t d[32];
+  SHA256_Final(d, &h);
+  __gmpz_import(chal, 32, 1, 1, 0, 0, d);
+  mpz_mod(chal, chal, two_b);
+  mpz_set_ui(esum, 0);
+  for (int i = 0; i < M; ++i) {                                           /* :130-131 */
+    imp(e, j->a2 + ((size_t)b * M + i) * el, el);
+    mpz_add(esum, esum, e);
+  }
+  mpz_mod(esum, esum, two_b);
+  uint8_t verdict = 1;
+  if (mpz_cmp(chal, esum) != 0) verdict = 2;                              /* :133 assert_eq! */
+  for (int i = 0; i < M && verdict != 2; ++i) {  /* u_vec is built for every slot before any comparison (:134-142) */
+    imp(m, j->a1 + ((size_t)b * M + i) * ml, ml);
+    imp(e, j->a2 + ((size_t)b * M + i) * el, el);
+    imp(z, j->a3 + ((size_t)b * M + i) * nl, nl);
+    imp(a, j->a4 + ((size_t)b * M + i) * nnl, nnl);
+    mpz_mul(gm, m, n); mpz_add_ui(gm, gm, 1); mpz_mod(gm, gm, nn);        /* :136-139 */
+    if (!mpz_invert(gm, gm, nn)) { verdict = 2; break; }                  /* unwrap() */
+    mpz_mul(u, c, gm); mpz_mod(u, u, nn);                                 /* u_i  :140 */
+    mpz_powm(t, z, n, nn);                                                /* z_i^n  :145 */
+    mpz_powm(lhs, u, e, nn); mpz_mul(lhs, lhs, a); mpz_mod(lhs, lhs, nn); /* :146-147 */
+    if (mpz_cmp(lhs, t) != 0) verdict = 0;                                /* :148-151 */
+  }
+  j->verdict[b] = verdict;
+  free(scratch);
+  for (size_t k = 0; k < sizeof(all) / sizeof(all[0]); ++k) mpz_clear(all[k]);
+}
+void orc_correct_message_verify(const uint32_t* n, int nl, int batch, int M, int ml, int el, const uint32_t* ciphertext, const uint32_t* valid,
+                                const uint32_t* e_vec, const uint32_t* z_vec, const uint32_t* a_vec, uint8_t* verdict, int threads) {
+  sig_job j = {nl, 0, M, el, ml, n, ciphertext, valid, e_vec, z_vec, a_vec, NULL, NULL, NULL, verdict};
+  run_parallel(cmsg_verify_task, &j, batch, threads);
+}

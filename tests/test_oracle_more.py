@@ -108,3 +108,82 @@ def test_golden_vectors_more():
     assert cm.ciphertext == int(c["ciphertext"]) and cm.e_vec == [int(v) for v in c["e_vec"]] and cm.z_vec == [int(v) for v in c["z_vec"]]
     assert hashlib.sha256(",".join(str(v) for v in cm.a_vec).encode()).hexdigest() == c["a_vec_sha256"]
     cm.verify()
+
+
+def _verdict(fn):
+    try:
+        fn()
+        return 1
+    except po.IncorrectProof:
+        return 0
+    except po.ReferencePanic:
+        return 2
+
+
+def test_gmp_verifiers_agree_with_the_python_oracle():
+    """oracle/oracle.c restates MulProof / VerlinProof / CompositeDLogProof / CorrectMessageProof verify on GMP; the two
+    restatements must give the same Ok / Err / panic verdict on honest, tampered and panicking inputs."""
+    import numpy as np
+
+    from util import c_oracle
+    from zk_paillier_b200.native import ints_to_limbs, to_limbs
+
+    rng = random.Random(77)
+    p, q = keys(1024)[1]
+    n = p * q
+    nn, nl, nnl, zl = n * n, 32, 64, 44
+    L = ints_to_limbs
+    rnd = lambda: rng.randrange(1, n)
+    # MulProof: honest, c != a b, e_db = 0 (no inverse: unwrap panics)
+    proofs, st = [], []
+    for kind in ("ok", "bad", "panic"):
+        a, b = rnd(), rnd()
+        c = a * b % n if kind != "bad" else (a * b + 1) % n
+        r_a, r_b, r_c = rnd(), rnd(), rnd()
+        e_a, e_b, e_c = (po.paillier_encrypt(n, v, r) for v, r in ((a, r_a), (b, r_b), (c, r_c)))
+        pr = po.MulProof.prove(a, b, c, r_a, r_b, r_c, n, e_a, e_b, e_c, rnd(), rnd())
+        if kind == "panic":
+            pr.e_db = 0
+        proofs.append(pr)
+        st.append((e_a, e_b, e_c))
+    want = [_verdict(lambda pr=pr, s=s: pr.verify(n, *s)) for pr, s in zip(proofs, st)]
+    got = c_oracle.mul_verify(to_limbs(n, nl), L([s[0] for s in st], nnl), L([s[1] for s in st], nnl), L([s[2] for s in st], nnl),
+                              L([pr.f for pr in proofs], nl), L([pr.z1 for pr in proofs], nnl), L([pr.z2 for pr in proofs], nnl),
+                              L([pr.e_d for pr in proofs], nnl), L([pr.e_db for pr in proofs], nnl), 2)
+    assert got.tolist() == want == [1, 0, 2]
+    # VerlinProof: honest, wrong x
+    proofs, st = [], []
+    for kind in ("ok", "bad"):
+        x, xp, xdp, r_x = rnd(), rnd(), rnd(), rnd()
+        c, cp = po.paillier_encrypt(n, rnd(), rnd()), po.paillier_encrypt(n, rnd(), rnd())
+        phi_x = po.gen_phi(n, c, cp, x, xp, xdp, r_x)
+        pr = po.VerlinProof.prove(x + (kind == "bad"), xp, xdp, r_x, n, c, cp, phi_x, rnd(), rnd(), rnd(), rnd())
+        proofs.append(pr)
+        st.append((c, cp, phi_x))
+    want = [_verdict(lambda pr=pr, s=s: pr.verify(n, *s)) for pr, s in zip(proofs, st)]
+    got = c_oracle.verlin_verify(to_limbs(n, nl), L([s[0] for s in st], nnl), L([s[1] for s in st], nnl), L([s[2] for s in st], nnl),
+                                 L([pr.phi_a for pr in proofs], nnl), L([pr.z for pr in proofs], zl), L([pr.z_prime for pr in proofs], zl),
+                                 L([pr.z_double_prime for pr in proofs], zl), L([pr.r_z for pr in proofs], nnl), 2)
+    assert got.tolist() == want == [1, 0]
+    # CompositeDLogProof: good, +secret, g | N shares a factor, N <= 2^128
+    R = 1 << 512
+    rows = []
+    for kind in ("good", "plus", "good", "good"):
+        N, g, ni, s = dlog_statement(rng, p, q, kind)
+        pr = po.CompositeDLogProof.prove(N, g, ni, s, rng.randrange(R))
+        rows.append([N, g, ni, pr.x, pr.y])
+    rows[2][1] = p * 7
+    rows[3][0] = (1 << 128) - 159
+    want = [_verdict(lambda r=r: po.CompositeDLogProof(r[3], r[4]).verify(r[0], r[1], r[2])) for r in rows]
+    got = c_oracle.dlog_verify(*(L([r[k] for r in rows], w) for k, w in enumerate((nl, nl, nl, nl, 20))), 2)
+    assert got.tolist() == want == [1, 0, 2, 2]
+    # CorrectMessageProof: honest, tampered z (Err), tampered e (assert_eq! panics)
+    valid = [3, 4, 5, 6]
+    prs = [po.CorrectMessageProof.prove(n, valid, 3 + k, rnd(), [rng.getrandbits(256) for _ in range(3)], [rnd() for _ in range(3)], rnd()) for k in range(3)]
+    prs[1].z_vec[0] = (prs[1].z_vec[0] + 1) % n
+    prs[2].e_vec[3] ^= 2
+    want = [_verdict(pr.verify) for pr in prs]
+    got = c_oracle.correct_message_verify(to_limbs(n, nl), L([pr.ciphertext for pr in prs], nnl), L([valid] * 3, 4), L([pr.e_vec for pr in prs], 8),
+                                          L([pr.z_vec for pr in prs], nl), L([pr.a_vec for pr in prs], nnl), 2)
+    assert got.tolist() == want == [1, 0, 2]
+    assert isinstance(got, np.ndarray)
