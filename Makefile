@@ -16,6 +16,18 @@ HOSTSRC   := zk-paillier_b200/host
 
 all: lib oracle
 
+# lab build: the measured-and-rejected kernel variants, the pipe probes and the ZKP_B200_* environment knobs
+# (scripts/k1m_variants.py, scripts/imad_probes.py with ZKP_B200_LIB=zk-paillier_b200/libzkp_b200_lab.so); not shipped
+LABBUILD  := build/lab
+LABOBJ    := $(patsubst $(CSRC)/%.cu,$(LABBUILD)/%.o,$(CU))
+LABLIB    := zk-paillier_b200/libzkp_b200_lab.so
+lab: $(LABLIB)
+$(LABBUILD)/%.o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.h) $(wildcard $(CSRC)/*.cuh) include/zkp_b200.h
+	@mkdir -p $(LABBUILD)
+	$(NVCC) $(NVFLAGS) -DZKP_B200_LAB -c $< -o $@ 2> $(LABBUILD)/$*.ptxas.log || (cat $(LABBUILD)/$*.ptxas.log; false)
+$(LABLIB): $(LABOBJ)
+	$(NVCC) $(ARCH) -shared -o $@ $(LABOBJ) -lcudart
+
 lib: $(LIB) $(HOSTLIB)
 
 # C++ host mirror of the reference's zkproofs::* interface (JSON C shim for the tests); links the CUDA library
@@ -37,7 +49,7 @@ oracle:
 	$(MAKE) -C oracle
 
 clean:
-	rm -rf $(BUILD) $(LIB) $(HOSTLIB) examples/range_proof_ni
+	rm -rf $(BUILD) $(LIB) $(LABLIB) $(HOSTLIB) examples/range_proof_ni
 	$(MAKE) -C oracle clean
 
-.PHONY: all lib oracle examples clean
+.PHONY: all lib lab oracle examples clean

@@ -405,6 +405,7 @@ def run_other(args):
     torch.cuda.set_stream(stream)
     ctx = zk.native.Context(0, stream=stream.cuda_stream)
     imad_peak = ctx.imad_peak(0)
+    ctx.tune(zk.native.TUNE_JOBS_SHAPE, args.jobs_shape)
     line = {"n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32 limbs (32x32+64 IMAD)", "data": "synthetic"}
     if args.config == "correct_key":
@@ -618,6 +619,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--ref-seconds", type=float, default=120.0, help="target total time of the --impl reference run")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--jobs-shape", type=int, default=0, choices=[0, 1, 2], help="K2h lane layout (zkp_tune ZKP_TUNE_JOBS_SHAPE): 0 = by job count")
     ap.add_argument("--n-bits", type=int, default=2048, choices=[1024, 2048, 3072, 4096],
                     help="key size of the RangeProofNi workload (the headline is 2048; the others are secondary lines)")
     args = ap.parse_args()

@@ -248,13 +248,17 @@ int zkp_correct_message_verify(zkp_ctx* ctx, int batch, int M, int m_limbs, int 
                                const uint32_t* valid, const uint32_t* e_vec, const uint32_t* z_vec, const uint32_t* a_vec,
                                uint8_t* accept, uint8_t* fault);
 
-/* ---- environment (read once per process; tuning and A/B measurement only, results are bit-identical) ----------
- *   ZKP_B200_ENC=k1            Paillier encryption by K1 (Montgomery modulo n^2) instead of K1m (two-digit form)
- *   ZKP_B200_K1M_VARIANT=0..9  lane layout / loop structure of K1m (modexp2m.cu: Enc2mConfig; 0 is the default and the
- *                              fastest measured on B200, 9 is the symmetric squaring)
- *   ZKP_B200_K1M_WINDOW=5|6    sliding-window width of K1m (default 6)
- *   ZKP_B200_K2_CTAS=n         persistent CTAs per SM of K2 (default 4)
- */
+/* ---- A/B hooks (per context; results are bit-identical whatever the setting) --------------------------------
+ * The library reads no environment variables.  (The measured-and-rejected kernel variants of DESIGN.md section 3.7
+ * and their ZKP_B200_* environment knobs exist only in the lab build, `make lab` -> libzkp_b200_lab.so.)
+ *   ZKP_TUNE_ENC_KERNEL  0 = K1m, the two-digit Montgomery form, whenever the key qualifies (default);
+ *                        1 = K1, Montgomery modulo n^2 (the parity tests run both and compare)
+ *   ZKP_TUNE_JOBS_SHAPE  lane layout of K2h, the one-launch heterogeneous modexp list of the sigma protocols:
+ *                        0 = by job count (default), 1 = wide lanes (as K1m / K2m), 2 = narrow lanes (one job over
+ *                        twice the lanes: fills the GPU at a few hundred proofs of 4096-bit n) */
+#define ZKP_TUNE_ENC_KERNEL 0
+#define ZKP_TUNE_JOBS_SHAPE 1
+int zkp_tune(zkp_ctx* ctx, int knob, int value);
 
 /* ---- measurement ----------------------------------------------------------
  * Register-only multiply-add issue-rate microbenchmark (the roofline denominator
@@ -264,7 +268,7 @@ int zkp_correct_message_verify(zkp_ctx* ctx, int batch, int M, int m_limbs, int 
 int zkp_imad_peak(zkp_ctx* ctx, int variant, double* mads_per_s);
 /* Which kernel served Paillier::encrypt_with_chosen_randomness so far on this context: launches of K1m (two-digit
  * Montgomery form, the default) and of K1 (Montgomery modulo n^2: rows wider than n, keys K1m does not take, or
- * ZKP_B200_ENC=k1 in the environment at zkp_set_key).  Either pointer may be NULL. */
+ * zkp_tune(ctx, ZKP_TUNE_ENC_KERNEL, 1)).  Either pointer may be NULL. */
 int zkp_enc_kernel_launches(const zkp_ctx* ctx, long long* k1m, long long* k1);
 /* IMAD.WIDE.U32 (32x32+64 multiply-adds) one encryption EXECUTES under the current key, counted from the kernels'
  * own op lists: K1m = (4 S^2 per squaring, 5 S^2 per multiplication, S^2 for the final X0 + X1 n, S = limbs of n);

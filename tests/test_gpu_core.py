@@ -147,8 +147,8 @@ def test_large_batch_all_groups(ctx):
 
 
 @pytest.mark.parametrize("n_bits,nl", [(1024, 32), (2048, 64), (2047, 64), (3072, 96), (4096, 128), (1536, 48)])
-def test_two_digit_montgomery_kernel(monkeypatch, n_bits, nl):
-    """K1m (modexp2m.cu, the default encryption kernel) against K1 (ZKP_B200_ENC=k1) and Python pow: moduli that do
+def test_two_digit_montgomery_kernel(n_bits, nl):
+    """K1m (modexp2m.cu, the default encryption kernel) against K1 (zkp_tune ZKP_TUNE_ENC_KERNEL = 1) and Python pow: moduli that do
     not fill their top limb, widths that run zero-extended, bases >= n, base 0 / 1, plaintext 0 / n-1 / >= n / none,
     narrow plaintext rows, more than one persistent wave of a small batch's worth of CTAs and a ragged tail."""
     rng = random.Random(n_bits)
@@ -163,8 +163,8 @@ def test_two_digit_montgomery_kernel(monkeypatch, n_bits, nl):
     want = want_enc(n, nl, m, nl, r, nl)
     outs = {}
     for mode in ("k1m", "k1"):
-        monkeypatch.setenv("ZKP_B200_ENC", mode)
         with zk.native.Context(0) as c:
+            c.tune(zk.native.TUNE_ENC_KERNEL, 1 if mode == "k1" else 0)
             c.set_key(to_limbs(n, nl))
             outs[mode] = c.paillier_enc(ints_to_limbs(m, nl), ints_to_limbs(r, nl))
             used = c.enc_kernel_launches()

@@ -21,14 +21,20 @@ def verdict(fn):
         return 0
 
 
-@pytest.fixture(scope="module", params=[1024, 2048])
+# (key size, K2h lane layout: 0 = by job count - narrow lanes at these batch sizes -, 1 = wide lanes, 2 = narrow lanes)
+@pytest.fixture(scope="module", params=[(1024, 0), (1024, 1), (2048, 1), (2048, 2), (3072, 1), (3072, 2), (4096, 1), (4096, 2)],
+                ids=lambda p: f"{p[0]}-shape{p[1]}")
 def keyed(request, ctx):
-    bits = request.param
+    import zk_paillier_b200 as zk
+
+    bits, shape = request.param
     p, q = keys(bits)[0]
     n = p * q
     nl = limbs_for(bits)
     ctx.set_key(to_limbs(n, nl))
-    return ctx, n, nl, random.Random(bits)
+    ctx.tune(zk.native.TUNE_JOBS_SHAPE, shape)
+    yield ctx, n, nl, random.Random(bits)
+    ctx.tune(zk.native.TUNE_JOBS_SHAPE, 0)
 
 
 def test_zero_proof(keyed):

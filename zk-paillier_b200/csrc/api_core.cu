@@ -52,16 +52,20 @@ ProfScope::~ProfScope() {
   if (idx >= 0) cudaEventRecord(c->prof[idx].b, c->stream);
 }
 
-cudaError_t ensure_table(zkp_ctx* c, int S, int entries) {
+cudaError_t ensure_table(zkp_ctx* c, int S, int entries, int pow_jobs) {
   size_t bytes = (size_t)resident_groups(S, c->num_sms) * entries * S * sizeof(uint32_t);
   if (c->enc2m_key && c->enc2m_enabled) {  // a call may run K1m (Enc) and K2m (mod_pow) back to back: size for both
     const size_t b1 = enc2m_table_limbs(c->n.S, c->num_sms) * sizeof(uint32_t);
     const size_t b2 = var2m_table_limbs(c->n.S, c->num_sms) * sizeof(uint32_t);
-    bytes = std::max(bytes, std::max(b1, b2));
+    const size_t b3 = pow_jobs > 0 ? jobs2m_scratch_limbs(c->n.S, c->num_sms, pow_jobs) * sizeof(uint32_t) : 0;
+    bytes = std::max(std::max(bytes, b3), std::max(b1, b2));
   }
   bytes = (bytes + 255) & ~size_t(255);
   // one region per stream that may run a modexp kernel at the same time (fork_stream below)
+  if (bytes / sizeof(uint32_t) < c->table_region_limbs) bytes = c->table_region_limbs * sizeof(uint32_t);  // regions never shrink
   c->table_region_limbs = bytes / sizeof(uint32_t);
+  cudaError_t e = c->cursor.ensure(256 * (1 + kAuxStreams));
+  if (e != cudaSuccess) return e;
   return c->table.ensure(bytes * (1 + kAuxStreams));
 }
 
@@ -131,6 +135,16 @@ cudaError_t launch_pow_nn(zkp_ctx* c, const uint32_t* base, int base_limbs, cons
   return launch_modexp_var(base, c->nn.mod.as<uint32_t>(), c->nn.limbs, c->nn.r2.as<uint32_t>(), c->nn.n0.as<uint32_t>(), exp,
                            exp_limbs, exp_bits, exp_per, 0x7fffffff, out, jobs, c->nn.S, (c->table.as<uint32_t>() + c->table_off), c->num_sms,
                            c->stream, base_limbs);
+}
+
+bool jobs_supported(const zkp_ctx* c) { return c->enc2m_key && c->enc2m_enabled; }
+
+cudaError_t launch_pow_jobs(zkp_ctx* c, const PowJobs& jobs) {
+  if (!jobs_supported(c)) return cudaErrorNotSupported;
+  ++c->enc2m_launches;
+  const size_t region = c->table_region_limbs ? c->table_off / c->table_region_limbs : 0;  // 0 = main stream, k + 1 = auxiliary stream k
+  return launch_modexp2m_jobs(enc2m_view(c), jobs, c->nn.limbs, c->table.as<uint32_t>() + c->table_off, c->table_region_limbs,
+                              reinterpret_cast<unsigned*>(c->cursor.as<uint8_t>() + 256 * region), c->num_sms, c->stream, c->jobs_shape);
 }
 
 cudaError_t launch_enc(zkp_ctx* c, const uint32_t* bases, int base_limbs, const uint32_t* plain, int plain_limbs, uint32_t* out,
@@ -267,7 +281,7 @@ void zkp_ctx_destroy(zkp_ctx* c) {
   for (auto e : c->ev_pool) cudaEventDestroy(e);
   c->nn.release();
   c->n.release();
-  std::vector<DevBuf*> bufs = {&c->enc2m_consts, &c->enc2m_ops, &c->table, &c->in0, &c->in1, &c->in2, &c->in3, &c->out0};
+  std::vector<DevBuf*> bufs = {&c->enc2m_consts, &c->enc2m_ops, &c->table, &c->cursor, &c->in0, &c->in1, &c->in2, &c->in3, &c->out0};
   for (DevBuf* b : c->rp.all()) bufs.push_back(b);
   for (DevBuf* b : c->ck.all()) bufs.push_back(b);
   for (DevBuf* b : bufs) b->release();
@@ -353,8 +367,6 @@ int zkp_set_key(zkp_ctx* c, const uint32_t* n, int n_limbs) {
   c->paillier = true;
   {
     // K1m: two-digit Montgomery form (modexp2m.cu), the default encryption kernel
-    const char* env = getenv("ZKP_B200_ENC");
-    c->enc2m_enabled = !(env && !strcmp(env, "k1"));
     c->enc2m_key = false;
     if (enc2m_supported(c->n.h_mod.data(), c->n.S)) {
       const int S = c->n.S;
@@ -509,6 +521,22 @@ int zkp_modmul(zkp_ctx* c, int which_nn, const uint32_t* a, const uint32_t* b, i
   ZKP_CU(c, cudaMemcpyAsync(out, c->out0.p, (size_t)batch * w * 4, cudaMemcpyDeviceToHost, c->stream));
   ZKP_CU(c, cudaStreamSynchronize(c->stream));
   return ZKP_OK;
+}
+
+int zkp_tune(zkp_ctx* c, int knob, int value) {
+  if (!c) return ZKP_E_ARG;
+  switch (knob) {
+    case ZKP_TUNE_ENC_KERNEL:
+      if (value != 0 && value != 1) return fail(c, ZKP_E_ARG, "ZKP_TUNE_ENC_KERNEL: 0 (K1m when the key qualifies) or 1 (K1)");
+      c->enc2m_enabled = value == 0;
+      return ZKP_OK;
+    case ZKP_TUNE_JOBS_SHAPE:
+      if (value < 0 || value > 2) return fail(c, ZKP_E_ARG, "ZKP_TUNE_JOBS_SHAPE: 0 (by job count), 1 (wide lanes) or 2 (narrow lanes)");
+      c->jobs_shape = value;
+      return ZKP_OK;
+    default:
+      return fail(c, ZKP_E_ARG, "unknown tuning knob");
+  }
 }
 
 int zkp_enc_kernel_launches(const zkp_ctx* c, long long* k1m, long long* k1) {

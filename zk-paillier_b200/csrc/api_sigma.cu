@@ -40,13 +40,12 @@ int zkp_zero_verify(zkp_ctx* c, int batch, const uint32_t* cc, const uint32_t* z
   uint32_t* d_z = s.up(z, s.nnl);
   uint32_t* d_a = s.up(a, s.nnl);
   uint8_t* d_acc = s.ar.get<uint8_t>((size_t)batch);
-  s.fork(0);
-  uint32_t* c_z = s.enc(nullptr, 0, d_z, s.nnl);                 // Enc(0, z)                 :73-79
-  s.on_main();
   uint32_t* e = s.challenge({d_c, d_a});                         // :67-71
-  uint32_t* c_e = s.powm(d_c, s.nnl, e, 8);                      // Paillier::mul(c, e)       :81-85
+  PowBatch pb(s);                                                // both modexps of the proof in one launch
+  uint32_t* c_z = pb.enc(nullptr, 0, d_z, s.nnl);                // Enc(0, z)                 :73-79
+  uint32_t* c_e = pb.powm(d_c, s.nnl, e, 8);                     // Paillier::mul(c, e)       :81-85
+  pb.run();
   uint32_t* c_z_test = s.mulm(c_e, s.nnl, d_a, s.nnl);           // Paillier::add(c_e, a)     :86-88
-  s.join();
   if (!s.bad) s.ck(launch_rows_equal(c_z, c_z_test, s.nnl, batch, 0, d_acc, s.st));
   if (cudaMemcpyAsync(accept, d_acc, (size_t)batch, cudaMemcpyDeviceToHost, s.st) != cudaSuccess) s.bad = true;
   return s.finish("zkp_zero_verify");
@@ -89,13 +88,12 @@ int zkp_ciphertext_verify(zkp_ctx* c, int batch, int z_limbs, const uint32_t* cc
   uint32_t* d_z2 = s.up(z2, s.nnl);
   uint32_t* d_cp = s.up(c_prime, s.nnl);
   uint8_t* d_acc = s.ar.get<uint8_t>((size_t)batch);
-  s.fork(0);
-  uint32_t* c_z = s.enc(d_z1, z_limbs, d_z2, s.nnl);             // Enc(z1, z2)               :73-79
-  s.on_main();
   uint32_t* e = s.challenge({d_c, d_cp});                        // :67-71
-  uint32_t* c_e = s.powm(d_c, s.nnl, e, 8);                      // :81-85
+  PowBatch pb(s);
+  uint32_t* c_z = pb.enc(d_z1, z_limbs, d_z2, s.nnl);            // Enc(z1, z2)               :73-79
+  uint32_t* c_e = pb.powm(d_c, s.nnl, e, 8);                     // :81-85
+  pb.run();
   uint32_t* c_z_test = s.mulm(c_e, s.nnl, d_cp, s.nnl);          // :86-92
-  s.join();
   if (!s.bad) s.ck(launch_rows_equal(c_z, c_z_test, s.nnl, batch, 0, d_acc, s.st));
   if (cudaMemcpyAsync(accept, d_acc, (size_t)batch, cudaMemcpyDeviceToHost, s.st) != cudaSuccess) s.bad = true;
   return s.finish("zkp_ciphertext_verify");
@@ -115,15 +113,14 @@ int zkp_mul_prove(zkp_ctx* c, int batch, const uint32_t* a, const uint32_t* b, c
   uint32_t *d_ea = s.up(e_a, nnl), *d_eb = s.up(e_b, nnl), *d_ec = s.up(e_c, nnl), *d_d = s.up(d, nl), *d_rd = s.up(r_d, nl);
   uint8_t* d_fault = s.ar.get<uint8_t>((size_t)batch);
   cudaMemsetAsync(d_fault, 0, (size_t)batch, s.st);
-  s.fork(0);
-  uint32_t* d_ed = s.enc(d_d, nl, d_rd, nl);                                   // e_d = Enc(d, r_d)             :63-69
-  s.on_main();
   uint32_t* r_db = s.rows(nnl);
   uint32_t* db = s.rows(nnl);
   if (!s.bad) s.ck(launch_muladd(nullptr, 0, d_rd, nl, d_rb, nl, batch, r_db, nnl, d_fault, s.st));  // r_db = r_d * r_b (unreduced) :70
   if (!s.bad) s.ck(launch_muladd(nullptr, 0, d_d, nl, d_b, nl, batch, db, nnl, d_fault, s.st));      // db = d * b (unreduced)       :71
-  uint32_t* d_edb = s.enc(db, nnl, r_db, nnl);                                 // e_db = Enc(db, r_db)          :72-78
-  s.join();
+  PowBatch p1(s);                                                              // the two encryptions in one launch
+  uint32_t* d_ed = p1.enc(d_d, nl, d_rd, nl);                                  // e_d = Enc(d, r_d)             :63-69
+  uint32_t* d_edb = p1.enc(db, nnl, r_db, nnl);                                // e_db = Enc(db, r_db)          :72-78
+  p1.run();
   uint32_t* e = s.challenge({d_ea, d_eb, d_ec, d_ed, d_edb});                  // :80-87
   uint32_t* ea = s.rows(nl);
   {
@@ -132,17 +129,21 @@ int zkp_mul_prove(zkp_ctx* c, int batch, const uint32_t* a, const uint32_t* b, c
   }
   uint32_t* d_f = s.rows(nl);
   if (!s.bad) s.ck(launch_modadd(ea, d_d, c->n.mod.as<uint32_t>(), nl, batch, d_f, s.st));           // f = ea + d mod n     :90
+  // the short-exponent modexps and the inversion that follows them on an auxiliary stream, next to the long one
   s.fork(0);
-  uint32_t* r_a_e = s.powm(d_ra, nl, e, 8);                                    // :91
+  PowBatch p2(s);
+  uint32_t* r_a_e = p2.powm(d_ra, nl, e, 8);                                   // :91
+  uint32_t* r_c_e = p2.powm(d_rc, nl, e, 8);                                   // :94
+  p2.run();
   uint32_t* d_z1 = s.mulm(r_a_e, nnl, d_rd, nl);                               // :92
-  s.fork(1);
-  uint32_t* r_c_e = s.powm(d_rc, nl, e, 8);                                    // :94
   uint32_t* v = s.mulm(r_db, nnl, r_c_e, nnl);                                 // :95
   uint32_t* vinv = s.rows(nnl);
   uint32_t* scratch = s.rows(4 * nnl);
   if (!s.bad) s.ck(launch_modinv(v, c->nn.mod.as<uint32_t>(), nnl, batch, scratch, vinv, d_fault, s.st));  // mod_inv(..).unwrap() :96
   s.on_main();
-  uint32_t* r_b_f = s.powm(d_rb, nl, d_f, nl);                                 // :93
+  PowBatch p3(s);
+  uint32_t* r_b_f = p3.powm(d_rb, nl, d_f, nl);                                // :93
+  p3.run();
   s.join();
   uint32_t* d_z2 = s.mulm(r_b_f, nnl, vinv, nnl);                              // :97
   s.down(f, d_f, nl);
@@ -168,24 +169,25 @@ int zkp_mul_verify(zkp_ctx* c, int batch, const uint32_t* e_a, const uint32_t* e
   uint8_t* d_fault = s.ar.get<uint8_t>((size_t)batch);
   uint8_t* d_acc = s.ar.get<uint8_t>((size_t)batch);
   cudaMemsetAsync(d_fault, 0, (size_t)batch, s.st);
-  // five independent modexps per proof: side by side on the auxiliary streams (at 4096-bit n a batch of 512 is only 64 CTAs)
-  s.fork(0);
-  uint32_t* enc_f_z1 = s.enc(d_f, nl, d_z1, nnl);                              // :118-124
-  s.fork(1);
-  uint32_t* enc_0_z2 = s.enc(nullptr, 0, d_z2, nnl);                           // :125-131
-  s.on_main();
+  // five independent modexps per proof in two K2h launches: the two with the 256-bit challenge as exponent (and the
+  // products and the inversion that consume them) on an auxiliary stream, the three |n|-bit ones on the main stream
   uint32_t* e = s.challenge({d_ea, d_eb, d_ec, d_ed, d_edb});                  // :109-116
-  s.fork(2);
-  uint32_t* e_a_e = s.powm(d_ea, nnl, e, 8);                                   // :133
+  s.fork(0);
+  PowBatch ps(s);
+  uint32_t* e_a_e = ps.powm(d_ea, nnl, e, 8);                                  // :133
+  uint32_t* e_c_e = ps.powm(d_ec, nnl, e, 8);                                  // :135
+  ps.run();
   uint32_t* lhs1 = s.mulm(e_a_e, nnl, d_ed, nnl);                              // :134
-  s.fork(3);
-  uint32_t* e_c_e = s.powm(d_ec, nnl, e, 8);                                   // :135
   uint32_t* v = s.mulm(d_edb, nnl, e_c_e, nnl);                                // :136
   uint32_t* vinv = s.rows(nnl);
   uint32_t* scratch = s.rows(4 * nnl);
   if (!s.bad) s.ck(launch_modinv(v, c->nn.mod.as<uint32_t>(), nnl, batch, scratch, vinv, d_fault, s.st));  // :137 (unwrap -> fault)
   s.on_main();
-  uint32_t* e_b_f = s.powm(d_eb, nnl, d_f, nl);                                // :138
+  PowBatch pl(s);
+  uint32_t* enc_f_z1 = pl.enc(d_f, nl, d_z1, nnl);                             // :118-124
+  uint32_t* enc_0_z2 = pl.enc(nullptr, 0, d_z2, nnl);                          // :125-131
+  uint32_t* e_b_f = pl.powm(d_eb, nnl, d_f, nl);                               // :138
+  pl.run();
   s.join();
   uint32_t* lhs2 = s.mulm(e_b_f, nnl, vinv, nnl);                              // :139
   if (!s.bad) s.ck(launch_rows_equal(lhs1, enc_f_z1, nnl, batch, 0, d_acc, s.st));         // :141
@@ -204,12 +206,11 @@ namespace {
 // gen_phi (verlin_proof.rs:138-165): c^y * c'^y' * Enc(y'', r_y) mod nn
 uint32_t* gen_phi(Sig& s, const uint32_t* cc, const uint32_t* cp, const uint32_t* y, const uint32_t* yp, const uint32_t* ydp,
                   int y_limbs, const uint32_t* r_y, int r_limbs) {
-  s.fork(0);
-  uint32_t* cp_yp = s.powm(cp, s.nnl, yp, y_limbs);
-  s.fork(1);
-  uint32_t* en = s.enc(ydp, y_limbs, r_y, r_limbs);
-  s.on_main();
-  uint32_t* c_y = s.powm(cc, s.nnl, y, y_limbs);
+  PowBatch pb(s);  // the three modexps in one launch
+  uint32_t* cp_yp = pb.powm(cp, s.nnl, yp, y_limbs);
+  uint32_t* en = pb.enc(ydp, y_limbs, r_y, r_limbs);
+  uint32_t* c_y = pb.powm(cc, s.nnl, y, y_limbs);
+  pb.run();
   s.join();
   uint32_t* t = s.mulm(c_y, s.nnl, cp_yp, s.nnl);
   return s.mulm(t, s.nnl, en, s.nnl);
@@ -262,7 +263,9 @@ int zkp_verlin_verify(zkp_ctx* c, int batch, int z_limbs, const uint32_t* cc, co
   uint8_t* d_acc = s.ar.get<uint8_t>((size_t)batch);
   uint32_t* e = s.challenge({d_c, d_cp, d_phix, d_phia});                      // :102-108
   s.fork(2);
-  uint32_t* phi_x_e = s.powm(d_phix, nnl, e, 8);                               // :109-113
+  PowBatch ps(s);
+  uint32_t* phi_x_e = ps.powm(d_phix, nnl, e, 8);                              // :109-113
+  ps.run();
   uint32_t* rhs = s.mulm(phi_x_e, nnl, d_phia, nnl);                           // :114-118
   s.on_main();
   uint32_t* phi_z = gen_phi(s, d_c, d_cp, d_z, d_zp, d_zdp, z_limbs, d_rz, nnl);  // :120-128 (joins)

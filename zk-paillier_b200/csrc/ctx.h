@@ -131,6 +131,8 @@ struct zkp_ctx {
   cudaStream_t main_stream = nullptr, aux[zkp::kAuxStreams] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t aux_ev[zkp::kAuxStreams] = {nullptr, nullptr, nullptr, nullptr}, fork_ev = nullptr;
   unsigned aux_used = 0;
+  zkp::DevBuf cursor;                // K2h work-unit cursors, one 256-byte slot per stream (ensure_table)
+  int jobs_shape = 0;                // K2h lane layout: 0 = by job count, 1 = wide lanes, 2 = narrow lanes (zkp_set_jobs_shape)
   zkp::DevBuf in0, in1, in2, in3, out0;  // generic staging for the one-shot calls
   bool profiling = false;
   std::vector<zkp::ProfEntry> prof;
@@ -159,7 +161,8 @@ struct ProfScope {
 };
 
 // table scratch large enough for K1/K2 at width S
-cudaError_t ensure_table(zkp_ctx* c, int S, int entries);
+// pow_jobs > 0: also room for a K2h launch of that many jobs (launch_pow_jobs)
+cudaError_t ensure_table(zkp_ctx* c, int S, int entries, int pow_jobs = 0);
 // Paillier::encrypt_with_chosen_randomness for `jobs` rows under the current key: picks K1v2 (two-digit base-n)
 // when the key and row widths qualify, else K1 (Montgomery mod n^2).  plain == nullptr encrypts 0.
 // Returns 1 if K1v2 ran, 0 if K1 ran, negative cudaError as -(int)err - 1000 on failure (see enc_failed()).
@@ -171,6 +174,11 @@ cudaError_t launch_enc(zkp_ctx* c, const uint32_t* bases, int base_limbs, const 
 // The table scratch must have been sized with ensure_table(c, c->nn.S, kTableVar).
 cudaError_t launch_pow_nn(zkp_ctx* c, const uint32_t* base, int base_limbs, const uint32_t* exp, int exp_limbs, int exp_bits,
                           int exp_per, uint32_t* out, int jobs);
+
+// K2h: every modexp / Enc of a batch of sigma-protocol proofs in one launch (modexp2m.cu: modexp2m_jobs_kernel).  Needs a key
+// that K1m takes (c->enc2m_key); callers fall back to launch_enc / launch_pow_nn otherwise.
+bool jobs_supported(const zkp_ctx* c);
+cudaError_t launch_pow_jobs(zkp_ctx* c, const PowJobs& jobs);
 
 // Concurrent modexp launches inside one call (api_core.cu)
 cudaError_t fork_stream(zkp_ctx* c, int k);

@@ -77,6 +77,32 @@ cudaError_t launch_modexp2m_var(const Enc2mKey& key, const uint32_t* bases, int 
                                 int exp_bits, int exp_per, uint32_t* out, int out_limbs, int jobs, uint32_t* table, int num_sms,
                                 cudaStream_t st);
 
+// K2h (modexp2m.cu): every modexp of a batch of sigma-protocol proofs in ONE launch.  A job list is up to kMaxPowSegs
+// homogeneous segments; job j of segment s computes
+//     out[j] = (1 + plain[j] n) * base[j]^exp[j] mod n^2      (plain == nullptr: the plain factor is 1)
+// i.e. BigInt::mod_pow / Paillier::mul with a per-job exponent, or Paillier::encrypt_with_chosen_randomness when the
+// exponent is the shared n (exp = n on the device, exp_stride = 0).  Segments should be listed longest exponent first.
+constexpr int kMaxPowSegs = 8;
+struct PowSeg {
+  const uint32_t* base;   // [jobs][base_limbs], base_limbs <= 2 S, even
+  const uint32_t* exp;    // row j at exp + j * exp_stride (limbs); every exponent < 2^exp_bits
+  const uint32_t* plain;  // [jobs][plain_limbs] or nullptr; plain_limbs <= 2 S, even
+  uint32_t* out;          // [jobs][out_limbs]
+  long long exp_stride;
+  int base_limbs, exp_limbs, exp_bits, plain_limbs, jobs, first;  // first: index of the segment's first job in the launch
+};
+struct PowJobs {
+  PowSeg seg[kMaxPowSegs];
+  int nseg = 0, total = 0;
+};
+// shape: 0 = pick by job count, 1 = the wide-lane layout of K2m (few lanes per job), 2 = the narrow-lane layout (one job
+// over twice the lanes, half the limbs per lane: fills the machine at small batches of wide moduli)
+// Scratch: jobs2m_scratch_limbs(S, num_sms, total jobs) limbs at `table` (window tables; for a launch that under-fills
+// the GPU also the per-job accumulators and phase counters of the phased schedule, see modexp2m.cu).
+size_t jobs2m_scratch_limbs(int S, int num_sms, int total_jobs);
+cudaError_t launch_modexp2m_jobs(const Enc2mKey& key, const PowJobs& jobs, int out_limbs, uint32_t* table, size_t table_limbs,
+                                 unsigned* cursor, int num_sms, cudaStream_t st, int shape = 0);
+
 // Montgomery setup for per-instance moduli: r2[i] = R^2 mod mods[i] ([count][S]), n0inv[i].
 // mods: [count][mod_limbs].
 cudaError_t launch_mont_setup(const uint32_t* mods, int mod_limbs, int S, int count, uint32_t* r2, uint32_t* n0inv,

@@ -340,11 +340,13 @@ static int blocks_per_sm_shared() {
 // 4 -> 9 786/s, 5 -> 9 709/s, 6 -> 9 900/s: within noise, the multiplier pipe is already 81 % busy at 16 warps per SM.
 // ZKP_B200_K2_CTAS overrides (tuning).
 int k2_ctas_per_sm(int L) {
+#ifdef ZKP_B200_LAB
   static const int env = [] {
     const char* e = getenv("ZKP_B200_K2_CTAS");
     return e ? atoi(e) : 0;
   }();
   if (env > 0) return env;
+#endif
   return (L <= 16) ? 4 : (L <= 24 ? 3 : 2);
 }
 int resident_groups(int S, int num_sms) {  // sized for the larger of K1's and K2's persistent grids
@@ -523,7 +525,7 @@ __global__ void __launch_bounds__(256) imad_peak_kernel(int iters, uint32_t* sin
   }
   uint32_t b = seed | 1u;
   for (int it = 0; it < iters; ++it) {
-    if (VARIANT == 0) {  // 16 independent 64-bit accumulators: IMAD.WIDE.U32
+    if (VARIANT == 0 || VARIANT == 3) {  // 16 independent 64-bit accumulators: IMAD.WIDE.U32
 #pragma unroll
       for (int j = 0; j < 16; j += 2) {
         uint64_t acc = ((uint64_t)u[j + 1] << 32) | u[j];
@@ -547,6 +549,84 @@ __global__ void __launch_bounds__(256) imad_peak_kernel(int iters, uint32_t* sin
   if (x == 0x12345678u) sink[0] = x;
 }
 
+#ifdef ZKP_B200_LAB
+// Probes of the multiplier pipe (lab build only; scripts/imad_probes.py, profiles/r02_imad_probes.json): why does a
+// register-only IMAD.WIDE.U32 loop stop at 86 % of one warp instruction per 4 cycles per sub-partition?
+//   7  IMAD.HI.U32, independent            8  IMAD.WIDE.U32 with a zero addend (mul.wide)
+//   9  IMAD.WIDE.U32 : IADD3 = 1 : 1       10 IMAD.WIDE.U32 : LOP3 = 1 : 2
+//   11 32 independent accumulators         12 both multiplicands loop-invariant
+//   13 IMAD.WIDE.U32 : IMAD (32-bit) = 1 : 1 on independent registers
+template <int VARIANT>
+__global__ void __launch_bounds__(256) imad_probe_kernel(int iters, uint32_t* sink) {
+  constexpr int NA = VARIANT == 11 ? 32 : 16;
+  uint32_t a[16], u[NA], v[16];
+  uint32_t seed = threadIdx.x * 2654435761u + blockIdx.x;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    a[j] = seed = seed * 1664525u + 1013904223u;
+    v[j] = ~seed;
+  }
+#pragma unroll
+  for (int j = 0; j < NA; ++j) u[j] = seed = seed * 1664525u + 1013904223u;
+  uint32_t b = seed | 1u;
+  for (int it = 0; it < iters; ++it) {
+    if (VARIANT == 7) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) asm volatile("mad.hi.u32 %0, %1, %2, %0;" : "+r"(u[j]) : "r"(a[j]), "r"(b));
+    } else if (VARIANT == 8) {
+#pragma unroll
+      for (int j = 0; j < 16; j += 2) {
+        uint64_t acc;
+        asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(acc) : "r"(a[j] ^ u[j]), "r"(b));
+        uint64_t acc2;
+        asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(acc2) : "r"(a[j + 1] ^ u[j + 1]), "r"(b));
+        u[j] = (uint32_t)acc ^ (uint32_t)(acc2 >> 32);
+        u[j + 1] = (uint32_t)(acc >> 32) ^ (uint32_t)acc2;
+      }
+    } else if (VARIANT == 9 || VARIANT == 10 || VARIANT == 13) {
+#pragma unroll
+      for (int j = 0; j < 16; j += 2) {
+        uint64_t acc = ((uint64_t)u[j + 1] << 32) | u[j];
+        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc) : "r"(a[j]), "r"(b));
+        if (VARIANT == 9) asm volatile("add.u32 %0, %0, %1;" : "+r"(v[j]) : "r"(a[j]));
+        if (VARIANT == 10) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;\n\tlop3.b32 %3, %3, %1, %2, 0x96;" : "+r"(v[j]), "+r"(v[j + 1]) : "r"(a[j]), "r"(b));
+        if (VARIANT == 13) asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(v[j]) : "r"(a[j]), "r"(b));
+        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc) : "r"(a[j + 1]), "r"(b));
+        if (VARIANT == 9) asm volatile("add.u32 %0, %0, %1;" : "+r"(v[j + 1]) : "r"(a[j + 1]));
+        if (VARIANT == 13) asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(v[j + 1]) : "r"(a[j + 1]), "r"(b));
+        u[j] = (uint32_t)acc;
+        u[j + 1] = (uint32_t)(acc >> 32);
+      }
+    } else if (VARIANT == 11) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) {
+        uint64_t acc = ((uint64_t)u[j + 1] << 32) | u[j];
+        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc) : "r"(a[j >> 1]), "r"(b));
+        u[j] = (uint32_t)acc;
+        u[j + 1] = (uint32_t)(acc >> 32);
+      }
+    } else {  // 12
+#pragma unroll
+      for (int j = 0; j < 16; j += 2) {
+        uint64_t acc = ((uint64_t)u[j + 1] << 32) | u[j];
+        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc) : "r"(a[0]), "r"(b));
+        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc) : "r"(a[0]), "r"(b));
+        u[j] = (uint32_t)acc;
+        u[j + 1] = (uint32_t)(acc >> 32);
+      }
+    }
+    b += u[0] & 2u;
+  }
+  uint32_t x = 0;
+#pragma unroll
+  for (int j = 0; j < NA; ++j) x ^= u[j];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) x ^= v[j];
+  if (x == 0x12345678u) sink[0] = x;
+}
+#endif  // ZKP_B200_LAB
+
+#ifdef ZKP_B200_LAB
 // In-lane 32x32 block products by product scanning (blockmul.cuh): the building block of a
 // two-digit base-n engine.  MINB = resident CTAs of 128 threads per SM (register budget).
 template <int MINB, class Shape>
@@ -572,7 +652,30 @@ __global__ void __launch_bounds__(128, MINB) blockmul_peak_kernel(int iters, uin
   if (x == 0x12345678u) sink[0] = x;
 }
 
+#endif  // ZKP_B200_LAB
+
 cudaError_t launch_imad_peak(int variant, int blocks, int iters, uint32_t* sink, double* ops, cudaStream_t st) {
+#ifdef ZKP_B200_LAB
+  if (variant >= 7 && variant <= 13) {
+    switch (variant) {
+      case 7: imad_probe_kernel<7><<<blocks, 256, 0, st>>>(iters, sink); break;
+      case 8: imad_probe_kernel<8><<<blocks, 256, 0, st>>>(iters, sink); break;
+      case 9: imad_probe_kernel<9><<<blocks, 256, 0, st>>>(iters, sink); break;
+      case 10: imad_probe_kernel<10><<<blocks, 256, 0, st>>>(iters, sink); break;
+      case 11: imad_probe_kernel<11><<<blocks, 256, 0, st>>>(iters, sink); break;
+      case 12: imad_probe_kernel<12><<<blocks, 256, 0, st>>>(iters, sink); break;
+      default: imad_probe_kernel<13><<<blocks, 256, 0, st>>>(iters, sink); break;
+    }
+    *ops = (double)blocks * 256.0 * (double)iters * 16.0;  // multiply-adds of the probed kind (the filler instructions are not counted)
+    return cudaGetLastError();
+  }
+  if (variant >= 14 && variant <= 16) {  // variant 0 at 1 / 2 / 4 warps per sub-partition (4 / 8 / 16 warps per SM)
+    const int per_sm = variant == 14 ? 1 : (variant == 15 ? 2 : 4);
+    const int grid = blocks / 8 * per_sm;
+    imad_peak_kernel<3><<<grid, 128, 0, st>>>(iters, sink);
+    *ops = (double)grid * 128.0 * (double)iters * 16.0;
+    return cudaGetLastError();
+  }
   if (variant >= 3 && variant <= 6) {
     // 3: full block, 4 CTAs/SM (16 warps); 4: full, 2 CTAs/SM (8 warps); 5: lower triangle, 4 CTAs/SM; 6: full, 3 CTAs/SM
     const int it2 = iters / 64 > 0 ? iters / 64 : 1;
@@ -585,6 +688,7 @@ cudaError_t launch_imad_peak(int variant, int blocks, int iters, uint32_t* sink,
     *ops = (double)grid * 128.0 * (double)it2 * (variant == 5 ? 528.0 : 1024.0);
     return cudaGetLastError();
   }
+#endif
   switch (variant) {
     case 0: imad_peak_kernel<0><<<blocks, 256, 0, st>>>(iters, sink); break;
     case 1: imad_peak_kernel<1><<<blocks, 256, 0, st>>>(iters, sink); break;

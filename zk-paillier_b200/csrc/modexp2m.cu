@@ -73,9 +73,9 @@ struct TwoDigit {
     uint32_t q[L], z0[L];
 #pragma unroll
     for (int j = 0; j < L; ++j) q[j] = 0;
-    if (MODE == 0 || MODE == 3) {
+    if constexpr (MODE == 0 || MODE == 3) {
       uint32_t delta;
-      if (MODE == 3) {  // symmetric squaring: every pair of lane blocks multiplied once, then S reduction-only rows
+      if constexpr (MODE == 3) {  // symmetric squaring: every pair of lane blocks multiplied once, then S reduction-only rows
         uint32_t plo[L], phi[L];
         M::sqr_product(plo, phi, x0, lane);
         delta = M::mont_redc_x(z0, plo, phi, n, n0inv, lane, q, zr);
@@ -94,7 +94,7 @@ struct TwoDigit {
 #pragma unroll 1
       for (int ph = 0; ph < 2; ++ph) {
         uint32_t delta;
-        if (MODE == 1) {
+        if constexpr (MODE == 1) {
           delta = M::template mont_mul_sel<1>(res, x0, x0, x1, ph != 0, n, n0inv, lane, init, top, q, zr);
         } else {
           __syncwarp();
@@ -128,7 +128,7 @@ struct TwoDigit {
     uint32_t q[L], z0[L];
 #pragma unroll
     for (int j = 0; j < L; ++j) q[j] = 0;
-    if (MODE != 2) {
+    if constexpr (MODE != 2) {
       const uint32_t delta = M::template mont_mul_x<false, true, 1, U>(z0, x0, y0, n, n0inv, lane, z0, 0u, q, zr);
       uint32_t top;
       init_from_q(q, top, q, delta, s_klo, lane);
@@ -187,8 +187,15 @@ struct TwoDigit {
   static __device__ __forceinline__ void entry_pair(uint32_t (&x0)[L], uint32_t (&x1)[L], const uint32_t* row, int limbs,
                                                     const uint32_t* consts, const uint32_t (&n)[L], uint32_t n0inv,
                                                     const uint32_t* s_klo, int lane, uint32_t zr, uint32_t* sg = nullptr) {
+    entry_pair_u(x0, x1, row, limbs, limbs > S, consts, n, n0inv, s_klo, lane, zr, sg);
+  }
+  // The same with the choice of path handed in: `wide` must be uniform across the warp (the wide path shuffles), `limbs`
+  // need not be - a row of at most S limbs taken through the wide path has a zero high half.
+  static __device__ __forceinline__ void entry_pair_u(uint32_t (&x0)[L], uint32_t (&x1)[L], const uint32_t* row, int limbs, bool wide,
+                                                      const uint32_t* consts, const uint32_t (&n)[L], uint32_t n0inv,
+                                                      const uint32_t* s_klo, int lane, uint32_t zr, uint32_t* sg = nullptr) {
     const int g = lane & (T - 1);
-    if (limbs <= S) {
+    if (!wide) {
       M::load_ext(x0, row, limbs, g);
 #pragma unroll
       for (int j = 0; j < L; ++j) x1[j] = 0;
@@ -201,7 +208,7 @@ struct TwoDigit {
       M::load(y0, cp);
       M::load(y1, cp + S);
       if (half) M::load_ext(x0, row + S, limbs - S, g);
-      else M::load_ext(x0, row, S, g);
+      else M::load_ext(x0, row, limbs < S ? limbs : S, g);
 #pragma unroll
       for (int j = 0; j < L; ++j) x1[j] = 0;
       mul(x0, x1, y0, y1, n, n0inv, s_klo, lane, zr, sg);
@@ -375,6 +382,22 @@ __global__ void __launch_bounds__(kCtaThreads, MINB) enc2m_kernel(const Enc2mPar
 // window (the exponent is data, so every group of a warp scans the same number of windows).  Replaces
 // BigInt::mod_pow(_, _, nn) / Paillier::mul at zero_enc_proof.rs:60,81; correct_ciphertext.rs:62,84;
 // multiplication_proof.rs:91-94,133-138; verlin_proof.rs:89,109,147-155 (bases are ciphertexts: 2 S limbs wide).
+constexpr int kMaxPhases = 32;
+struct Jobs2mParams {
+  Enc2mKey key;
+  PowJobs jobs;
+  uint32_t* table;    // phased: [total jobs][kTableVar][2 S]; else one [kTableVar][2 S] block per resident group
+  uint32_t* acc;      // phased: the accumulator pair of every job between phases, [total jobs][2 S]
+  unsigned* done;     // phased: phases completed per work unit, [units] (zeroed by the launcher)
+  unsigned* cursor;   // next phase-unit (zeroed by the launcher on the same stream)
+  int out_limbs;
+  int win_per_phase;  // windows of the exponent scan per phase; >= the longest scan: one phase per unit, nothing migrates
+  int nphase;         // phases of the longest unit
+  unsigned pre[kMaxPhases + 1];  // pre[p] = phase-units before phase p (units are ordered longest scan first, so the
+                                 // units that have a phase p are the first pre[p + 1] - pre[p])
+  uint32_t zero;
+};
+
 struct Var2mParams {
   Enc2mKey key;
   const uint32_t* bases;
@@ -387,6 +410,7 @@ struct Var2mParams {
 
 __device__ __forceinline__ uint32_t exp_window2m(const uint32_t* e, int exp_limbs, int bit) {
   int limb = bit >> 5, sh = bit & 31;
+  if (limb >= exp_limbs) return 0u;  // K2h pads a warp's shorter exponents with leading zero windows
   uint64_t v = e[limb];
   if (limb + 1 < exp_limbs) v |= (uint64_t)e[limb + 1] << 32;
   return (uint32_t)(v >> sh) & ((1u << kWindowVar) - 1u);
@@ -465,6 +489,151 @@ __global__ void __launch_bounds__(kCtaThreads, MINB) modexp2m_var_kernel(const V
       TD::mul(x0, x1, y0, y1, n, n0inv, s_klo, lane, zr);
     }
     TD::assemble_store(p.out + (size_t)job * p.out_limbs, p.out_limbs, valid, x0, x1, n, lane);
+  }
+}
+
+// ------------------------------------------------------------------------ K2h
+// One launch for ALL the modular exponentiations of a batch of sigma-protocol proofs: a heterogeneous job list of up
+// to kMaxPowSegs homogeneous segments (PowSeg: its own base rows, exponent rows / shared exponent, exponent length,
+// optional Paillier plaintext and output rows), longest exponents first.  Replaces the five separate launches behind
+// MulProof::verify (multiplication_proof.rs:118-138: Enc(f, z1), Enc(0, z2), e_a^e, e_c^e, e_b^f) and the four behind
+// VerlinProof::verify (verlin_proof.rs:109,147-163), which at a 512-proof batch were 64 CTAs each.  Same arithmetic as
+// K2m: fixed 5-bit window, two-digit Montgomery form; an Enc job is the modexp with exponent n whose final multiplier
+// is the plain pair (1, m) instead of (1, 0).
+//
+// Scheduling.  A unit is one warp's worth of jobs (32 / T).  A batch of 512 proofs at 4096-bit n is ~5 whole modexps per
+// SM sub-partition: handing out whole modexps leaves most sub-partitions idle while the unlucky ones finish their sixth
+// (measured: 59-66 % of the multiplier pipe, profiles/r02_fill_curve.json).  So the exponent scan of a unit is cut into
+// PHASES of win_per_phase windows, and the persistent warps take phase-units from one device-side cursor, phase-major:
+// every unit's phase 0 (entry, window table, first windows), then every phase 1, ...  Between phases the state of a job
+// lives in global memory - its window table (indexed by job, written once in phase 0) and its accumulator pair - so
+// whichever warp is free next continues it.  done[unit] counts finished phases; the cursor hands phases out in
+// dependency order, so a warp that has to wait for the previous phase of its unit waits on a warp that is already
+// running (no deadlock), and with thousands of phase-units in flight it practically never waits.
+template <int T, int L, int MINB>
+__global__ void __launch_bounds__(kCtaThreads, MINB) modexp2m_jobs_kernel(const __grid_constant__ Jobs2mParams p) {
+  using M = Mp<T, L>;
+  using TD = TwoDigit<T, L, 1>;
+  constexpr int S = T * L;
+  constexpr int G = kCtaThreads / T;
+  constexpr int GW = 32 / T;  // jobs per warp
+  __shared__ __align__(16) uint32_t s_klo[S];
+  const int lane = threadIdx.x & 31;
+  const int g = lane & (T - 1);
+  const int grp = threadIdx.x / T;
+  const uint32_t n0inv = p.key.n0inv;
+  const uint32_t zr = p.zero;
+  uint32_t n[L];
+  M::load(n, p.key.mod + g * L);
+  for (int i = threadIdx.x; i < S; i += kCtaThreads) s_klo[i] = p.key.consts[i];
+  __syncthreads();
+  const bool phased = p.nphase > 1;
+  const int total = p.jobs.total;
+  const unsigned nwork = p.pre[p.nphase];
+  for (;;) {
+    unsigned work = 0;
+    if (lane == 0) work = atomicAdd(p.cursor, 1u);
+    work = __shfl_sync(ZKP_FULL, work, 0);
+    if (work >= nwork) break;
+    int ph = 0;
+    while (work >= p.pre[ph + 1]) ++ph;
+    const unsigned unit = work - p.pre[ph];
+    const int job = (int)unit * GW + (lane / T);
+    const bool valid = job < total;
+    const int src = valid ? job : total - 1;
+    int si = 0;
+#pragma unroll
+    for (int k = 1; k < kMaxPowSegs; ++k)
+      if (k < p.jobs.nseg && src >= p.jobs.seg[k].first) si = k;
+    const PowSeg& sgm = p.jobs.seg[si];
+    const int rel = src - sgm.first;
+    const int exp_limbs = sgm.exp_limbs;
+    const uint32_t* e = sgm.exp + (size_t)rel * sgm.exp_stride;
+    int nwin = (sgm.exp_bits + kWindowVar - 1) / kWindowVar;
+#pragma unroll
+    for (int o = T; o < 32; o <<= 1) nwin = max(nwin, __shfl_xor_sync(ZKP_FULL, nwin, o));  // one trip count per warp
+    // windows hi - 1 .. lo of the scan (most significant first) belong to this phase
+    const int hi = nwin - ph * p.win_per_phase;
+    const int lo = max(hi - p.win_per_phase, 0);
+    uint32_t* tab = (phased ? p.table + (size_t)src * kTableVar * 2 * S : p.table + (size_t)(blockIdx.x * G + grp) * kTableVar * 2 * S) + g * L;
+    uint32_t* accp = p.acc + (size_t)src * 2 * S + g * L;
+
+    uint32_t x0[L], x1[L], y0[L], y1[L];
+    if (ph == 0) {
+      const int base_limbs = sgm.base_limbs;
+      const bool wide_base = __any_sync(ZKP_FULL, base_limbs > S);
+      TD::entry_pair_u(x0, x1, sgm.base + (size_t)rel * base_limbs, base_limbs, wide_base, p.key.consts, n, n0inv, s_klo, lane, zr);
+      M::load(y0, p.key.consts + S + g * L);  // pair(W^2): into Montgomery form
+      M::load(y1, p.key.consts + 2 * S + g * L);
+      TD::mul(x0, x1, y0, y1, n, n0inv, s_klo, lane, zr);
+      M::store(tab + 2 * S, x0);
+      M::store(tab + 2 * S + S, x1);
+#pragma unroll
+      for (int j = 0; j < L; ++j) {
+        y0[j] = x0[j];
+        y1[j] = x1[j];
+      }
+      M::load(x0, p.key.consts + 3 * S + g * L);  // pair(W) = 1 in Montgomery form = x^0
+      M::load(x1, p.key.consts + 4 * S + g * L);
+      M::store(tab, x0);
+      M::store(tab + S, x1);
+#pragma unroll
+      for (int j = 0; j < L; ++j) {
+        x0[j] = y0[j];
+        x1[j] = y1[j];
+      }
+#pragma unroll 1
+      for (int k = 2; k < kTableVar; ++k) {
+        TD::mul(x0, x1, y0, y1, n, n0inv, s_klo, lane, zr);
+        M::store(tab + (size_t)k * 2 * S, x0);
+        M::store(tab + (size_t)k * 2 * S + S, x1);
+      }
+      const uint32_t* t0 = tab + (size_t)exp_window2m(e, exp_limbs, (hi - 1) * kWindowVar) * 2 * S;
+      M::load(x0, t0);
+      M::load(x1, t0 + S);
+    } else {
+      if (lane == 0)
+        while (atomicAdd(p.done + unit, 0u) < (unsigned)ph) __nanosleep(256);
+      __syncwarp();
+      __threadfence();
+      M::load_cg(x0, accp);  // rewritten every phase, possibly by another SM: not through L1
+      M::load_cg(x1, accp + S);
+    }
+#pragma unroll 1
+    for (int w = hi - 1 - (ph == 0 ? 1 : 0); w >= lo; --w) {
+      const uint32_t* t0 = tab + (size_t)exp_window2m(e, exp_limbs, w * kWindowVar) * 2 * S;
+      M::load(y0, t0);
+      M::load(y1, t0 + S);
+#pragma unroll 1
+      for (int q = 0; q < kWindowVar; ++q) TD::sqr(x0, x1, n, n0inv, s_klo, lane, zr);
+      TD::mul(x0, x1, y0, y1, n, n0inv, s_klo, lane, zr);
+    }
+    if (lo > 0) {  // hand the job over to whoever takes its next phase
+      M::store(accp, x0);
+      M::store(accp + S, x1);
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) atomicExch(p.done + unit, (unsigned)ph + 1u);
+      continue;
+    }
+    // the final multiplier (1, m): the Paillier factor 1 + m n (m = 0: it only takes the result out of Montgomery form)
+    const uint32_t* mrow = sgm.plain ? sgm.plain + (size_t)rel * sgm.plain_limbs : nullptr;
+    const int pl = mrow ? sgm.plain_limbs : 0;
+    if (__any_sync(ZKP_FULL, pl > S)) {  // m wider than n: m mod n = Mlo W / W + Mhi W^2 / W (see enc2m_kernel)
+      M::load_ext(y1, mrow, pl < S ? pl : S, g);
+      M::load(y0, p.key.consts + 3 * S + g * L);
+      M::mont_mul(y1, y1, y0, n, n0inv, lane);
+      uint32_t hi1[L];
+      M::load_ext(hi1, mrow ? mrow + S : nullptr, pl - S, g);
+      M::load(y0, p.key.consts + S + g * L);
+      M::mont_mul(hi1, hi1, y0, n, n0inv, lane);
+      M::add_mod(y1, hi1, n, lane);
+    } else {
+      M::load_ext(y1, mrow, pl, g);
+    }
+    M::set_small(y0, 1u, g);
+    TD::mul(x0, x1, y0, y1, n, n0inv, s_klo, lane, zr);
+    TD::assemble_store(sgm.out + (size_t)rel * p.out_limbs, p.out_limbs, valid, x0, x1, n, lane);
   }
 }
 
@@ -563,10 +732,13 @@ void enc2m_host_constants(const uint32_t* n_host, int S, uint32_t* consts) {
 //   8        <4,16>  4        2   ... 4 steps deep
 //   9        <8,8>   4        3   symmetric squaring of the first digit (each pair of lane blocks once) + reduction-only rows
 // The other key sizes keep their layout and take only the MODE of the variant.
+// The variants other than 0 and the environment knobs exist only in the lab build (make lab: -DZKP_B200_LAB ->
+// libzkp_b200_lab.so); the product library holds the dispatched instantiations only and reads no environment.
 struct Enc2mConfig {
   int variant, window;
 };
 static Enc2mConfig enc2m_config() {
+#ifdef ZKP_B200_LAB
   static Enc2mConfig cfg = [] {
     Enc2mConfig c{0, kWindow2m};
     if (const char* v = getenv("ZKP_B200_K1M_VARIANT")) c.variant = atoi(v);
@@ -576,6 +748,9 @@ static Enc2mConfig enc2m_config() {
     return c;
   }();
   return cfg;
+#else
+  return Enc2mConfig{0, kWindow2m};
+#endif
 }
 int enc2m_window() { return enc2m_config().window; }
 double enc2m_sqr_products() {  // variant 9 multiplies every pair of lane blocks once: (T/2 + 1)/T of the first product, T = 8 or 16 lanes
@@ -649,12 +824,16 @@ static cudaError_t launch_one(const Enc2mParams& p, int num_sms, cudaStream_t st
 
 template <int T, int L>
 static cudaError_t launch_mode(const Enc2mParams& p, int mode, int num_sms, cudaStream_t st) {
+#ifdef ZKP_B200_LAB
   switch (mode) {
     case 1: return launch_one<T, L, 1, kCtasPerSm2m, 1>(p, num_sms, st);
     case 2: return launch_one<T, L, 2, kCtasPerSm2m, 2>(p, num_sms, st);
     case 3: return launch_one<T, L, 1, kCtasPerSm2m, 3>(p, num_sms, st);
-    default: return launch_one<T, L, 1, kCtasPerSm2m, 0>(p, num_sms, st);
+    default: break;
   }
+#endif
+  (void)mode;
+  return launch_one<T, L, 1, kCtasPerSm2m, 0>(p, num_sms, st);
 }
 
 cudaError_t launch_enc2m(const Enc2mKey& key, const uint32_t* bases, int base_limbs, const uint32_t* plain, int plain_limbs,
@@ -686,6 +865,7 @@ cudaError_t launch_enc2m(const Enc2mKey& key, const uint32_t* bases, int base_li
     case 128: return launch_mode<16, 8>(p, mode, num_sms, st);
     case 64:
       switch (enc2m_config().variant) {
+#ifdef ZKP_B200_LAB
         case 1: return launch_one<4, 16, 1, 3, 0>(p, num_sms, st);
         case 2: return launch_one<4, 16, 1, 4, 0>(p, num_sms, st);
         case 3: return launch_one<4, 16, 1, 3, 1>(p, num_sms, st);
@@ -695,6 +875,7 @@ cudaError_t launch_enc2m(const Enc2mKey& key, const uint32_t* bases, int base_li
         case 7: return launch_one<8, 8, 4, 4, 2>(p, num_sms, st);
         case 8: return launch_one<4, 16, 2, 4, 2>(p, num_sms, st);
         case 9: return launch_one<8, 8, 1, 4, 3>(p, num_sms, st);
+#endif
         default: return launch_one<8, 8, 1, 4, 0>(p, num_sms, st);
       }
     default: return cudaErrorInvalidValue;
@@ -738,6 +919,147 @@ cudaError_t launch_modexp2m_var(const Enc2mKey& key, const uint32_t* bases, int 
     case 64: return launch_var_one<8, 8>(p, num_sms, st);
     case 96: return launch_var_one<8, 12>(p, num_sms, st);
     case 128: return launch_var_one<16, 8>(p, num_sms, st);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+// ---- K2h launcher -------------------------------------------------------------------------------------------------
+// Narrow-lane layouts: the same integer over twice the lanes (S = 128: one job per warp).  A batch of 512 MulProofs at
+// 4096-bit n is 1 536 long jobs: 768 warps in <16,8>, 1.3 per SM sub-partition, against 1 536 warps in <32,4>.
+constexpr int kCtasPerSmNarrow = 5;  // the narrow-lane layouts hold half the limbs per lane: more resident warps
+constexpr int kPhasedUnitsPerSmsp = 12;   // phased scheduling while the launch has fewer units than this per sub-partition ...
+constexpr int kPhaseTargetPerSmsp = 24;   // ... cut so that every sub-partition sees about this many phase-units
+constexpr int kMinWinPerPhase = 8;
+
+static int jobs_shape_T(int S, int shape) {
+  int T, L;
+  if (!pick_shape(S, T, L)) return 0;
+  return shape == 2 ? 2 * T : T;
+}
+static int scan_windows(int exp_bits) { return (exp_bits + kWindowVar - 1) / kWindowVar; }
+
+// limbs of scratch one launch needs: the window tables (by job when phased, else by resident group), the accumulators
+// of a phased launch and its done[] counters
+size_t jobs2m_scratch_limbs(int S, int num_sms, int total_jobs) {
+  int T, L;
+  if (!pick_shape(S, T, L)) return 0;
+  const size_t wide = (size_t)num_sms * kCtasPerSm2m * (kCtaThreads / T);
+  const size_t narrow = (size_t)num_sms * kCtasPerSmNarrow * (kCtaThreads / (2 * T));
+  const size_t resident = (wide > narrow ? wide : narrow) * kTableVar * 2 * S;
+  // a phased launch has fewer than kPhasedUnitsPerSmsp long units per sub-partition, 32 / T jobs each; twice that leaves
+  // room for the short jobs of the same launch (a launch that still does not fit runs unphased)
+  size_t jobs = (size_t)num_sms * 4 * kPhasedUnitsPerSmsp * (32 / T) * 2;
+  if ((size_t)total_jobs < jobs) jobs = (size_t)total_jobs;
+  const size_t phased = jobs * (kTableVar + 1) * 2 * S + jobs + 64;
+  return resident > phased ? resident : phased;
+}
+
+template <int T, int L, int MINB>
+static cudaError_t launch_jobs_one(Jobs2mParams& p, size_t table_limbs, int num_sms, cudaStream_t st) {
+  constexpr int GW = 32 / T;
+  constexpr int S = T * L;
+  const int nunits = (p.jobs.total + GW - 1) / GW;
+  // windows scanned by unit u = those of its first job (segments are listed longest first)
+  auto unit_windows = [&](int u) {
+    const int job = u * GW;
+    int si = 0;
+    for (int k = 1; k < p.jobs.nseg; ++k)
+      if (job >= p.jobs.seg[k].first) si = k;
+    return scan_windows(p.jobs.seg[si].exp_bits);
+  };
+  const int max_win = unit_windows(0);
+  int long_units = 0;  // units within a factor 2 of the longest: they decide how full the machine is
+  for (int k = 0; k < p.jobs.nseg; ++k)
+    if (2 * scan_windows(p.jobs.seg[k].exp_bits) >= max_win) long_units = (p.jobs.seg[k].first + p.jobs.seg[k].jobs + GW - 1) / GW;
+  const int smsp = num_sms * 4;
+  int nphase = 1;
+  const size_t phased_limbs = (size_t)nunits * GW * (kTableVar + 1) * 2 * S + (size_t)nunits + 64;
+  if (long_units < kPhasedUnitsPerSmsp * smsp && phased_limbs <= table_limbs) {
+    nphase = (kPhaseTargetPerSmsp * smsp + long_units - 1) / long_units;
+    if (nphase > kMaxPhases) nphase = kMaxPhases;
+    if (nphase > max_win / kMinWinPerPhase) nphase = max_win / kMinWinPerPhase;
+    if (nphase < 1) nphase = 1;
+  }
+  p.win_per_phase = (max_win + nphase - 1) / nphase;
+  p.nphase = (max_win + p.win_per_phase - 1) / p.win_per_phase;
+  // pre[]: the units that have a phase ph are the first cnt(ph) (binary search over the non-increasing unit_windows)
+  p.pre[0] = 0;
+  for (int ph = 0; ph < p.nphase; ++ph) {
+    int lo = 0, hi = nunits;  // first unit with unit_windows <= ph * win_per_phase
+    while (lo < hi) {
+      const int mid = (lo + hi) / 2;
+      if (unit_windows(mid) > ph * p.win_per_phase) lo = mid + 1;
+      else hi = mid;
+    }
+    p.pre[ph + 1] = p.pre[ph] + (unsigned)lo;
+  }
+  for (int ph = p.nphase; ph < kMaxPhases; ++ph) p.pre[ph + 1] = p.pre[p.nphase];
+  if (p.nphase > 1) {
+    p.acc = p.table + (size_t)p.jobs.total * kTableVar * 2 * S;
+    p.done = reinterpret_cast<unsigned*>(p.acc + (size_t)nunits * GW * 2 * S);
+    cudaError_t e = cudaMemsetAsync(p.done, 0, sizeof(unsigned) * (size_t)nunits, st);
+    if (e != cudaSuccess) return e;
+  } else {
+    p.acc = p.table;  // never touched
+    p.done = p.cursor;
+  }
+  int grid = num_sms * MINB;
+  const int need = (nunits + kCtaThreads / 32 - 1) / (kCtaThreads / 32);
+  if (grid > need) grid = need;
+  cudaError_t e = cudaMemsetAsync(p.cursor, 0, sizeof(unsigned), st);
+  if (e != cudaSuccess) return e;
+  modexp2m_jobs_kernel<T, L, MINB><<<grid, kCtaThreads, 0, st>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_modexp2m_jobs(const Enc2mKey& key, const PowJobs& jobs, int out_limbs, uint32_t* table, size_t table_limbs,
+                                 unsigned* cursor, int num_sms, cudaStream_t st, int shape) {
+  if (jobs.total <= 0) return cudaSuccess;
+  if (jobs.nseg <= 0 || jobs.nseg > kMaxPowSegs || out_limbs % 2 || out_limbs > 2 * key.S) return cudaErrorInvalidValue;
+  int first = 0;
+  long long long_jobs = 0;
+  int max_bits = 0;
+  for (int k = 0; k < jobs.nseg; ++k) max_bits = jobs.seg[k].exp_bits > max_bits ? jobs.seg[k].exp_bits : max_bits;
+  for (int k = 0; k < jobs.nseg; ++k) {
+    const PowSeg& s = jobs.seg[k];
+    if (s.first != first || s.jobs <= 0 || s.base_limbs % 2 || s.base_limbs <= 0 || s.base_limbs > 2 * key.S || s.exp_bits <= 0 ||
+        s.exp_bits > 32 * s.exp_limbs || (s.plain && (s.plain_limbs % 2 || s.plain_limbs <= 0 || s.plain_limbs > 2 * key.S)) ||
+        (k > 0 && s.exp_bits > jobs.seg[k - 1].exp_bits))
+      return cudaErrorInvalidValue;
+    first += s.jobs;
+    if (2 * s.exp_bits >= max_bits) long_jobs += s.jobs;
+  }
+  if (first != jobs.total || table_limbs < jobs2m_scratch_limbs(key.S, num_sms, jobs.total)) return cudaErrorInvalidValue;
+  Jobs2mParams p;
+  p.key = key;
+  p.jobs = jobs;
+  p.table = table;
+  p.cursor = cursor;
+  p.out_limbs = out_limbs;
+  p.zero = 0u;
+  int T, L;
+  if (!pick_shape(key.S, T, L)) return cudaErrorInvalidValue;
+  if (shape == 0) {
+    // narrow lanes while the long jobs in the wide layout would be fewer than ~4 warps per sub-partition: only whole
+    // units run side by side, and the multiplier pipe needs 3-4 resident warps to fill
+    const long long warps_wide = (long_jobs * T + 31) / 32;
+    shape = warps_wide < (long long)num_sms * 4 * 4 ? 2 : 1;
+  }
+  (void)jobs_shape_T;
+  if (shape == 2) {
+    switch (key.S) {
+      case 32: return launch_jobs_one<8, 4, kCtasPerSmNarrow>(p, table_limbs, num_sms, st);
+      case 64: return launch_jobs_one<16, 4, kCtasPerSmNarrow>(p, table_limbs, num_sms, st);
+      case 96: return launch_jobs_one<16, 6, kCtasPerSmNarrow>(p, table_limbs, num_sms, st);
+      case 128: return launch_jobs_one<32, 4, kCtasPerSmNarrow>(p, table_limbs, num_sms, st);
+      default: return cudaErrorInvalidValue;
+    }
+  }
+  switch (key.S) {
+    case 32: return launch_jobs_one<4, 8, kCtasPerSm2m>(p, table_limbs, num_sms, st);
+    case 64: return launch_jobs_one<8, 8, kCtasPerSm2m>(p, table_limbs, num_sms, st);
+    case 96: return launch_jobs_one<8, 12, kCtasPerSm2m>(p, table_limbs, num_sms, st);
+    case 128: return launch_jobs_one<16, 8, kCtasPerSm2m>(p, table_limbs, num_sms, st);
     default: return cudaErrorInvalidValue;
   }
 }

@@ -89,7 +89,7 @@ struct Mp {
     uint32_t pb = __ballot_sync(ZKP_FULL, prop);
     int base = lane & ~(T - 1);
     int g = lane & (T - 1);
-    if (T == 32) {
+    if constexpr (T == 32) {
       uint64_t a = (uint64_t)(gb | pb), b = (uint64_t)gb;
       uint64_t s = a + b;
       uint64_t cin = s ^ a ^ b;
@@ -824,6 +824,15 @@ struct Mp {
         uint2 v = q[j];
         x[2 * j] = v.x; x[2 * j + 1] = v.y;
       }
+    }
+  }
+  // the same through L2 only (ld.global.cg): for rows another SM may have rewritten since this SM last read them
+  static __device__ __forceinline__ void load_cg(uint32_t (&x)[L], const uint32_t* p) {
+    const uint2* q = reinterpret_cast<const uint2*>(p);
+#pragma unroll
+    for (int j = 0; j < L / 2; ++j) {
+      uint2 v = __ldcg(q + j);
+      x[2 * j] = v.x; x[2 * j + 1] = v.y;
     }
   }
   static __device__ __forceinline__ void store(uint32_t* p, const uint32_t (&x)[L]) {

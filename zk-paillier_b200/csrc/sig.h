@@ -1,6 +1,7 @@
 // Shared plumbing of the sigma-protocol entry points (api_sigma.cu, api_more.cu): a bump allocator over one device
 // buffer and the handful of batched primitives every proof is sequenced from (Enc, mod_pow, mod_mul, Fiat-Shamir hash).
 #pragma once
+#include <algorithm>
 #include <initializer_list>
 
 #include "ctx.h"
@@ -147,6 +148,70 @@ struct Sig {
   }
 };
 
+// The modular exponentiations of one proof phase, queued and then launched as ONE K2h kernel over a heterogeneous job
+// list (longest exponents first).  With a key the two-digit kernels do not take, run() issues them one after the other
+// through launch_enc / launch_pow_nn instead - same results.
+struct PowBatch {
+  Sig& s;
+  struct Item {
+    const uint32_t* base;
+    const uint32_t* exp;    // nullptr: Paillier encryption (exponent n)
+    const uint32_t* plain;
+    uint32_t* out;
+    int base_limbs, exp_limbs, plain_limbs, jobs;
+  };
+  std::vector<Item> items;
+  explicit PowBatch(Sig& sig) : s(sig) {}
+  // Paillier::encrypt_with_chosen_randomness(ek, m, r); m == nullptr: the plaintext 0
+  uint32_t* enc(const uint32_t* m, int m_limbs, const uint32_t* r, int r_limbs, int jobs = -1) {
+    uint32_t* out = s.rows(s.nnl, jobs);
+    items.push_back({r, nullptr, m, out, r_limbs, 0, m ? m_limbs : 0, s.nrows(jobs)});
+    return out;
+  }
+  // BigInt::mod_pow(base, exp, nn) / Paillier::mul with a per-proof exponent
+  uint32_t* powm(const uint32_t* base, int base_limbs, const uint32_t* exp, int exp_limbs, int jobs = -1) {
+    uint32_t* out = s.rows(s.nnl, jobs);
+    items.push_back({base, exp, nullptr, out, base_limbs, exp_limbs, 0, s.nrows(jobs)});
+    return out;
+  }
+  void run() {
+    if (s.bad || items.empty()) return;
+    zkp_ctx* c = s.c;
+    if (!jobs_supported(c) || (int)items.size() > kMaxPowSegs) {
+      for (const Item& it : items) {
+        ProfScope ps(c, it.exp ? KID_MODEXP_VAR : KID_MODEXP_SHARED, it.jobs);
+        if (it.exp) s.ck(launch_pow_nn(c, it.base, it.base_limbs, it.exp, it.exp_limbs, 32 * it.exp_limbs, 1, it.out, it.jobs));
+        else s.ck(launch_enc(c, it.base, it.base_limbs, it.plain, it.plain_limbs, it.out, it.jobs));
+      }
+      items.clear();
+      return;
+    }
+    int n_bits = 32 * c->n.S;  // bit length of the shared exponent n
+    while (n_bits > 1 && !((c->n.h_mod[(n_bits - 1) >> 5] >> ((n_bits - 1) & 31)) & 1u)) --n_bits;
+    auto bits = [&](const Item& it) { return it.exp ? 32 * it.exp_limbs : n_bits; };
+    std::stable_sort(items.begin(), items.end(), [&](const Item& a, const Item& b) { return bits(a) > bits(b); });
+    PowJobs pj;
+    for (const Item& it : items) {
+      PowSeg& g = pj.seg[pj.nseg++];
+      g.base = it.base;
+      g.base_limbs = it.base_limbs;
+      g.exp = it.exp ? it.exp : c->n.mod.as<uint32_t>();
+      g.exp_limbs = it.exp ? it.exp_limbs : c->n.S;
+      g.exp_stride = it.exp ? it.exp_limbs : 0;
+      g.exp_bits = bits(it);
+      g.plain = it.plain;
+      g.plain_limbs = it.plain_limbs;
+      g.out = it.out;
+      g.jobs = it.jobs;
+      g.first = pj.total;
+      pj.total += it.jobs;
+    }
+    items.clear();
+    ProfScope ps(c, KID_MODEXP_VAR, pj.total);
+    s.ck(launch_pow_jobs(c, pj));
+  }
+};
+
 inline int sigma_begin(zkp_ctx* c, int batch, int z_limbs, size_t rows_nnl, size_t rows_other_bytes, Sig& s) {
   if (!c->paillier) return fail(c, ZKP_E_STATE, "zkp_set_key not called");
   if (batch <= 0) return fail(c, ZKP_E_ARG, "batch must be positive");
@@ -159,7 +224,7 @@ inline int sigma_begin(zkp_ctx* c, int batch, int z_limbs, size_t rows_nnl, size
   size_t bytes = (size_t)batch * ((rows_nnl + 12) * s.nnl * 4 + rows_other_bytes + 256) + 64 * 256;
   e = s.ar.reserve(bytes);
   if (e != cudaSuccess) return fail_cuda(c, e, "arena");
-  e = ensure_table(c, c->nn.S, kTableVar);
+  e = ensure_table(c, c->nn.S, kTableVar, 4 * batch);  // a K2h launch holds at most 3 modexps per proof (PowBatch)
   if (e != cudaSuccess) return fail_cuda(c, e, "table");
   return ZKP_OK;
 }

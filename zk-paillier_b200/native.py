@@ -11,6 +11,10 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libzkp_b200.so")
+# measurement scripts may point at the lab build (make lab); the product path is always the in-tree library
+if os.environ.get("ZKP_B200_LIB"):
+    LIB_PATH = os.path.abspath(os.environ["ZKP_B200_LIB"])
+TUNE_ENC_KERNEL, TUNE_JOBS_SHAPE = 0, 1
 
 ZKP_OK = 0
 RP_OPEN, RP_MASK1, RP_MASK2 = 0, 1, 2
@@ -72,6 +76,7 @@ SIGNATURES = {
     "zkp_dlog_verify": (C.c_int, [C.c_void_p, C.c_int, C.c_int] + [_u32p] * 5 + [C.c_int, _u8p, _u8p]),
     "zkp_correct_message_prove": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int] + [_u32p] * 10 + [_u8p]),
     "zkp_correct_message_verify": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int] + [_u32p] * 5 + [_u8p, _u8p]),
+    "zkp_tune": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "zkp_imad_peak": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double)]),
     "zkp_enc_kernel_launches": (C.c_int, [C.c_void_p] + [C.POINTER(C.c_longlong)] * 2),
     "zkp_enc_executed_mads": (C.c_int, [C.c_void_p] + [C.POINTER(C.c_double)] * 2),
@@ -195,6 +200,10 @@ class Context:
         ms, n, u = C.c_double(), C.c_longlong(), C.c_double()
         self._ck(self._lib.zkp_profile_get(self._h, kernel, C.byref(ms), C.byref(n), C.byref(u)))
         return ms.value, n.value, u.value
+
+    def tune(self, knob, value):
+        """zkp_tune: TUNE_ENC_KERNEL (0 = K1m when the key qualifies, 1 = K1) / TUNE_JOBS_SHAPE (0 auto, 1 wide, 2 narrow lanes)"""
+        self._ck(self._lib.zkp_tune(self._h, int(knob), int(value)))
 
     def imad_peak(self, variant=0):
         v = C.c_double()
