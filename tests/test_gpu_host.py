@@ -362,3 +362,92 @@ def test_cpp_example_end_to_end():
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr
     assert "RangeProofNi:" in r.stdout and "NiCorrectKeyProof: verified" in r.stdout and "rejected: Err(IncorrectProof)" in r.stdout
+
+
+def _verdict(fn):
+    try:
+        fn()
+        return 1
+    except po.IncorrectProof:
+        return 0
+    except po.ReferencePanic:
+        return -1
+
+
+def test_verify_batches_with_mixed_keys_and_malformed_proofs():
+    """A verification batch is untrusted input: statements under different keys are verified under their own key, and one
+    malformed proof (over-wide fields, a non-invertible value) decides only itself.  Verdicts against the Python oracle, which
+    verifies every proof alone under its own key as the reference does."""
+    (p1, q1), (p2, q2) = keys(1024)[0], keys(1024)[1]
+    nA, nB = p1 * q1, p2 * q2
+    rng = random.Random(77)
+    hexs = lambda **vals: json.dumps({k: po.serde_bigint_native(v) for k, v in vals.items()}, separators=(",", ":"))
+
+    # ---- ZeroProof: keys A, B, A, B; then A's proof under B's key; z + nn (reduced by mod_pow: still Ok); a + nn (hashed: Err)
+    items, want = [], []
+    for n in (nA, nB, nA, nB):
+        r = rng.randrange(1, n)
+        c = po.paillier_encrypt(n, 0, r)
+        pr = po.ZeroProof.prove(r, n, c, rng.randrange(1, n))
+        items.append({"n": str(n), "c": str(c), "proof": hexs(z=pr.z, a=pr.a)})
+        want.append(_verdict(lambda: pr.verify(n, c)))
+    first = json.loads(items[0]["proof"])
+    items.append({"n": str(nB), "c": items[0]["c"], "proof": items[0]["proof"]})
+    want.append(_verdict(lambda: po.ZeroProof(po.serde_bigint_native_parse(first["z"]), po.serde_bigint_native_parse(first["a"])).verify(nB, int(items[0]["c"]))))
+    z0, a0 = po.serde_bigint_native_parse(first["z"]), po.serde_bigint_native_parse(first["a"])
+    for z, a in ((z0 + 5 * nA * nA, a0), (z0, a0 + (nA * nA << 64))):
+        items.append({"n": str(nA), "c": items[0]["c"], "proof": hexs(z=z, a=a)})
+        want.append(_verdict(lambda: po.ZeroProof(z, a).verify(nA, int(items[0]["c"]))))
+    res = call("zero.verify_batch", n=str(nA), items=items)
+    assert res["ok"], res
+    assert res["results"] == want == [1, 1, 1, 1, 0, 1, 0]
+
+    # ---- MulProof: an honest proof per key, a wrong product, and e_db = 0 (mod_inv(..).unwrap() panics in the reference)
+    items, want = [], []
+    for n, bad in ((nA, 0), (nB, 0), (nA, 1)):
+        a, b = rng.randrange(1, n), rng.randrange(1, n)
+        c = (a * b + bad) % n
+        r_a, r_b, r_c = (rng.randrange(1, n) for _ in range(3))
+        e_a, e_b, e_c = po.paillier_encrypt(n, a, r_a), po.paillier_encrypt(n, b, r_b), po.paillier_encrypt(n, c, r_c)
+        pr = po.MulProof.prove(a, b, c, r_a, r_b, r_c, n, e_a, e_b, e_c, rng.randrange(1, n), rng.randrange(1, n))
+        items.append({"n": str(n), "e_a": str(e_a), "e_b": str(e_b), "e_c": str(e_c),
+                      "proof": hexs(f=pr.f, z1=pr.z1, z2=pr.z2, e_d=pr.e_d, e_db=pr.e_db)})
+        want.append(_verdict(lambda: pr.verify(n, e_a, e_b, e_c)))
+    d = json.loads(items[0]["proof"])
+    d["e_db"] = po.serde_bigint_native(0)
+    items.insert(1, dict(items[0], proof=json.dumps(d, separators=(",", ":"))))
+    g = {k: po.serde_bigint_native_parse(v) for k, v in d.items()}
+    want.insert(1, _verdict(lambda: po.MulProof(g["f"], g["z1"], g["z2"], g["e_d"], g["e_db"]).verify(nA, int(items[0]["e_a"]), int(items[0]["e_b"]), int(items[0]["e_c"]))))
+    res = call("mul.verify_batch", n=str(nA), items=items)
+    assert res["ok"], res
+    assert res["results"] == want == [1, -1, 1, 0]
+    # the single-proof verify re-raises the panic
+    single = call("mul.verify", n=str(nA), items=[items[1]])
+    assert single["results"][0].startswith("panic")
+
+    # ---- prove_batch is the prover's own batch: mixed keys are a usage error, not silently proved under the first key
+    # (the JSON shim takes one n per request, so this goes through verify only; the C++ check is require_one_key)
+
+    # ---- RangeProofNi: an over-wide w1 / masked_x rejects ITS proof only; r1 + n is the same randomness (Enc uses r mod n)
+    n, ef = nA, 24
+    st = _range_statements(rng, n, 3)
+    data = rng.randbytes(3 * ef * (64 + 1 + 2 * 3 * 128) + 4096)
+    r = call("rangeproof_ni.prove", n=str(n), error_factor=ef, rng_hex=data.hex(), statements=[{k: str(v) for k, v in s.items()} for s in st])
+    assert r["ok"], r
+    proofs = [json.loads(js) for js in r["proofs"]]
+    k = next(i for i, o in enumerate(proofs[1]["proof"]) if "Open" in o)
+    proofs[1]["proof"][k]["Open"]["w1"] = str(int(proofs[1]["proof"][k]["Open"]["w1"]) + (1 << 2300))   # wider than any device row
+    k = next(i for i, o in enumerate(proofs[2]["proof"]) if "Open" in o)
+    proofs[2]["proof"][k]["Open"]["r1"] = str(int(proofs[2]["proof"][k]["Open"]["r1"]) + n)
+    k = next(i for i, o in enumerate(proofs[2]["proof"]) if "Mask" in o)
+    proofs[2]["proof"][k]["Mask"]["masked_r"] = str(int(proofs[2]["proof"][k]["Mask"]["masked_r"]) + 3 * n)
+    js = [json.dumps(pj, separators=(",", ":")) for pj in proofs]
+    want = [_verdict(lambda j=j: po.RangeProofNi.from_json(j).verify_self()) for j in js]
+    res = call("rangeproof_ni.verify_batch", proofs=js)
+    assert res["ok"], res
+    assert res["accept"] == want == [1, 0, 1]
+
+
+def test_json_nesting_limit():
+    r = call("zero.verify", n="15", items=[{"c": "1", "proof": "[" * 100000}])
+    assert not r["ok"] and "nested" in r["error"]

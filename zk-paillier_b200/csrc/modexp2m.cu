@@ -510,10 +510,10 @@ __global__ void __launch_bounds__(kCtaThreads, MINB) modexp2m_var_kernel(const V
 // whichever warp is free next continues it.  done[unit] counts finished phases; the cursor hands phases out in
 // dependency order, so a warp that has to wait for the previous phase of its unit waits on a warp that is already
 // running (no deadlock), and with thousands of phase-units in flight it practically never waits.
-template <int T, int L, int MINB>
+template <int T, int L, int MINB, int U>
 __global__ void __launch_bounds__(kCtaThreads, MINB) modexp2m_jobs_kernel(const __grid_constant__ Jobs2mParams p) {
   using M = Mp<T, L>;
-  using TD = TwoDigit<T, L, 1>;
+  using TD = TwoDigit<T, L, U>;  // U: lane-owner iterations of a row loop unrolled together (L rows each)
   constexpr int S = T * L;
   constexpr int G = kCtaThreads / T;
   constexpr int GW = 32 / T;  // jobs per warp
@@ -954,7 +954,7 @@ size_t jobs2m_scratch_limbs(int S, int num_sms, int total_jobs) {
   return resident > phased ? resident : phased;
 }
 
-template <int T, int L, int MINB>
+template <int T, int L, int MINB, int U = 1>
 static cudaError_t launch_jobs_one(Jobs2mParams& p, size_t table_limbs, int num_sms, cudaStream_t st) {
   constexpr int GW = 32 / T;
   constexpr int S = T * L;
@@ -1008,7 +1008,7 @@ static cudaError_t launch_jobs_one(Jobs2mParams& p, size_t table_limbs, int num_
   if (grid > need) grid = need;
   cudaError_t e = cudaMemsetAsync(p.cursor, 0, sizeof(unsigned), st);
   if (e != cudaSuccess) return e;
-  modexp2m_jobs_kernel<T, L, MINB><<<grid, kCtaThreads, 0, st>>>(p);
+  modexp2m_jobs_kernel<T, L, MINB, U><<<grid, kCtaThreads, 0, st>>>(p);
   return cudaGetLastError();
 }
 
@@ -1046,6 +1046,13 @@ cudaError_t launch_modexp2m_jobs(const Enc2mKey& key, const PowJobs& jobs, int o
     shape = warps_wide < (long long)num_sms * 4 * 4 ? 2 : 1;
   }
   (void)jobs_shape_T;
+#ifdef ZKP_B200_LAB
+  if (shape == 2 && key.S == 128) {  // lab: row-loop unrolling of the narrow layout (ZKP_B200_K2H_UNROLL = 1 | 2 | 4)
+    static const int u = [] { const char* e = getenv("ZKP_B200_K2H_UNROLL"); return e ? atoi(e) : 1; }();
+    if (u == 2) return launch_jobs_one<32, 4, kCtasPerSmNarrow, 2>(p, table_limbs, num_sms, st);
+    if (u == 4) return launch_jobs_one<32, 4, kCtasPerSmNarrow, 4>(p, table_limbs, num_sms, st);
+  }
+#endif
   if (shape == 2) {
     switch (key.S) {
       case 32: return launch_jobs_one<8, 4, kCtasPerSmNarrow>(p, table_limbs, num_sms, st);

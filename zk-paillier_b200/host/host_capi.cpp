@@ -319,6 +319,44 @@ Json dispatch(const std::string& op, const Json& req) {
     out.set("results", outcomes(items.size(), [&](size_t i) {
       VerlinProof::from_json(items[i].at("proof").as_str()).verify(eng, {ek, dec(items[i], "c"), dec(items[i], "c_prime"), dec(items[i], "phi_x")});
     }));
+  } else if (op == "zero.verify_batch" || op == "ciphertext.verify_batch" || op == "mul.verify_batch" || op == "verlin.verify_batch") {
+    // one call over the whole list; an item may carry its own "n" (mixed-key batches).  results: 1 / 0 / -1 (panic)
+    auto key_of = [&](const Json& it) { return it.find("n") ? EncryptionKey(dec(it, "n")) : ek; };
+    std::vector<int> res;
+    if (op == "zero.verify_batch") {
+      std::vector<ZeroProof> pr; std::vector<ZeroStatement> st;
+      for (auto& it : items) { pr.push_back(ZeroProof::from_json(it.at("proof").as_str())); st.push_back({key_of(it), dec(it, "c")}); }
+      std::vector<const ZeroProof*> ps;
+      for (auto& p : pr) ps.push_back(&p);
+      res = ZeroProof::verify_batch(eng, ps, st);
+    } else if (op == "ciphertext.verify_batch") {
+      std::vector<CiphertextProof> pr; std::vector<CiphertextStatement> st;
+      for (auto& it : items) { pr.push_back(CiphertextProof::from_json(it.at("proof").as_str())); st.push_back({key_of(it), dec(it, "c")}); }
+      std::vector<const CiphertextProof*> ps;
+      for (auto& p : pr) ps.push_back(&p);
+      res = CiphertextProof::verify_batch(eng, ps, st);
+    } else if (op == "mul.verify_batch") {
+      std::vector<MulProof> pr; std::vector<MulStatement> st;
+      for (auto& it : items) {
+        pr.push_back(MulProof::from_json(it.at("proof").as_str()));
+        st.push_back({key_of(it), dec(it, "e_a"), dec(it, "e_b"), dec(it, "e_c")});
+      }
+      std::vector<const MulProof*> ps;
+      for (auto& p : pr) ps.push_back(&p);
+      res = MulProof::verify_batch(eng, ps, st);
+    } else {
+      std::vector<VerlinProof> pr; std::vector<VerlinStatement> st;
+      for (auto& it : items) {
+        pr.push_back(VerlinProof::from_json(it.at("proof").as_str()));
+        st.push_back({key_of(it), dec(it, "c"), dec(it, "c_prime"), dec(it, "phi_x")});
+      }
+      std::vector<const VerlinProof*> ps;
+      for (auto& p : pr) ps.push_back(&p);
+      res = VerlinProof::verify_batch(eng, ps, st);
+    }
+    Json arr = Json::array();
+    for (int v : res) arr.push(Json::number(v));
+    out.set("results", arr);
   } else {
     throw std::runtime_error("unknown op " + op);
   }

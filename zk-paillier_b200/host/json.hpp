@@ -73,7 +73,7 @@ struct Json {
 
   static Json parse(const std::string& s) {
     size_t i = 0;
-    Json j = parse_value(s, i);
+    Json j = parse_value(s, i, 0);
     skip(s, i);
     if (i != s.size()) throw std::runtime_error("trailing characters after JSON value");
     return j;
@@ -81,7 +81,9 @@ struct Json {
 
  private:
   static void skip(const std::string& s, size_t& i) { while (i < s.size() && (s[i] == ' ' || s[i] == '\n' || s[i] == '\t' || s[i] == '\r')) ++i; }
-  static Json parse_value(const std::string& s, size_t& i) {
+  static constexpr int kMaxDepth = 64;  // proofs nest four levels deep; untrusted input must not recurse the stack away
+  static Json parse_value(const std::string& s, size_t& i, int depth) {
+    if (depth > kMaxDepth) throw std::runtime_error("JSON nested deeper than 64 levels");
     skip(s, i);
     if (i >= s.size()) throw std::runtime_error("unexpected end of JSON");
     char c = s[i];
@@ -91,12 +93,12 @@ struct Json {
       if (i < s.size() && s[i] == '}') { ++i; return j; }
       for (;;) {
         skip(s, i);
-        Json k = parse_value(s, i);
+        Json k = parse_value(s, i, depth + 1);
         if (k.kind != Str) throw std::runtime_error("object key must be a string");
         skip(s, i);
         if (i >= s.size() || s[i] != ':') throw std::runtime_error("expected ':'");
         ++i;
-        j.obj.emplace_back(k.str, parse_value(s, i));
+        j.obj.emplace_back(k.str, parse_value(s, i, depth + 1));
         skip(s, i);
         if (i < s.size() && s[i] == ',') { ++i; continue; }
         if (i < s.size() && s[i] == '}') { ++i; return j; }
@@ -108,7 +110,7 @@ struct Json {
       ++i; skip(s, i);
       if (i < s.size() && s[i] == ']') { ++i; return j; }
       for (;;) {
-        j.arr.push_back(parse_value(s, i));
+        j.arr.push_back(parse_value(s, i, depth + 1));
         skip(s, i);
         if (i < s.size() && s[i] == ',') { ++i; continue; }
         if (i < s.size() && s[i] == ']') { ++i; return j; }

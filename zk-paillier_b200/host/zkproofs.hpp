@@ -44,8 +44,9 @@ static const uint8_t SALT_STRING[4] = {75, 90, 101, 110};  // correct_key_ni.rs:
 inline ByteSource os_rng() {  // OsRng
   return [](uint8_t* p, size_t n) {
     FILE* f = fopen("/dev/urandom", "rb");
-    if (!f || fread(p, 1, n, f) != n) throw std::runtime_error("cannot read /dev/urandom");
-    fclose(f);
+    const size_t got = f ? fread(p, 1, n, f) : 0;
+    if (f) fclose(f);
+    if (got != n) throw std::runtime_error("cannot read /dev/urandom");
   };
 }
 
@@ -235,19 +236,22 @@ class RangeProofNi {  // range_proof_ni.rs:36-44
     if (B == 0) return {};
     const EncryptionKey& ek = ps[0]->ek;
     const size_t ef = ps[0]->error_factor;
+    for (auto* p : ps)
+      if (!(p->ek == ek) || p->error_factor != ef) throw std::invalid_argument("verify_batch: proofs must share key and error factor");
+    if (ef == 0) return std::vector<int>(B, 1);  // (0..0).all(..) is true: the reference returns Ok(()) (range_proof.rs:350-354)
     eng.use_key(ek);
     const size_t nl = eng.nl(), nnl = eng.nnl();
-    size_t wbits = 0;
+    // Row width of range / w1 / w2 / masked_x: from the RANGES only (the statement side).  A response value wider than its
+    // proof's range can never pass the interval predicates (w < 2 * third, masked_x <= 2 * third; range_proof.rs:301-307,341),
+    // so it rejects that one proof and does not widen - or poison - the batch.  Ranges beyond 2047 bits are outside what the
+    // device rows hold (documented limit): such a proof is rejected on its own as well.
+    constexpr size_t kMaxRangeBits = 64 * 32 - 1;
+    size_t wbits = 1;
     for (auto* p : ps) {
-      if (!(p->ek == ek) || p->error_factor != ef) throw std::invalid_argument("verify_batch: proofs must share key and error factor");
       // bits_of_e[i] / responses[i] index out of range in the reference (range_proof.rs:273-274)
       if (p->proof.responses.size() < ef || p->encrypted_pairs.c1.size() < ef || p->encrypted_pairs.c2.size() < ef || ef > 256)
         throw ReferencePanic("index out of bounds: proof shorter than error_factor");
-      wbits = std::max(wbits, p->range.bit_length() + 1);
-      for (size_t i = 0; i < ef; ++i) {
-        const Response& r = p->proof.responses[i];
-        wbits = std::max({wbits, r.w1.bit_length(), r.w2.bit_length(), r.masked_x.bit_length()});
-      }
+      if (p->range.bit_length() <= kMaxRangeBits) wbits = std::max(wbits, p->range.bit_length() + 1);
     }
     const size_t wl = limbs_for_bits(wbits);
     std::vector<uint32_t> range(B * wl), cx(B * nnl), c1(B * ef * nnl), c2(B * ef * nnl), resp_w(B * ef * 2 * wl, 0), resp_r(B * ef * 2 * nl, 0);
@@ -256,13 +260,13 @@ class RangeProofNi {  // range_proof_ni.rs:36-44
     auto fits = [](const BigInt& v, size_t limbs) { return v.d.size() <= limbs; };
     for (size_t b = 0; b < B; ++b) {
       const RangeProofNi& p = *ps[b];
-      bool representable = wl <= 64 && fits(p.ciphertext, nnl);
+      bool representable = p.range.bit_length() <= kMaxRangeBits && fits(p.ciphertext, nnl);
       for (size_t i = 0; i < ef && representable; ++i) {
         const Response& r = p.proof.responses[i];
-        representable = fits(p.encrypted_pairs.c1[i], nnl) && fits(p.encrypted_pairs.c2[i], nnl) && fits(r.r1, nl) && fits(r.r2, nl) &&
-                        fits(r.masked_r, nl);
+        representable = fits(p.encrypted_pairs.c1[i], nnl) && fits(p.encrypted_pairs.c2[i], nnl) &&
+                        (r.open ? fits(r.w1, wl) && fits(r.w2, wl) : fits(r.masked_x, wl));
       }
-      if (!representable) {  // a value >= 2^(row width) can never equal a canonical residue: Err(IncorrectProof)
+      if (!representable) {  // wider than its row: never equal to a canonical ciphertext / never inside the interval: Err(IncorrectProof)
         out[b] = 0;
         continue;
       }
@@ -277,12 +281,13 @@ class RangeProofNi {  // range_proof_ni.rs:36-44
           kind[t] = ZKP_RP_OPEN;
           r.w1.to_limbs(&resp_w[t * 2 * wl], wl);
           r.w2.to_limbs(&resp_w[t * 2 * wl + wl], wl);
-          r.r1.to_limbs(&resp_r[t * 2 * nl], nl);
-          r.r2.to_limbs(&resp_r[t * 2 * nl + nl], nl);
+          // randomness enters only as r^n mod nn, which depends on r mod n: reduced as the reference's mod_pow does
+          (fits(r.r1, nl) ? r.r1 : r.r1 % ek.n).to_limbs(&resp_r[t * 2 * nl], nl);
+          (fits(r.r2, nl) ? r.r2 : r.r2 % ek.n).to_limbs(&resp_r[t * 2 * nl + nl], nl);
         } else {
           kind[t] = r.j == 1 ? ZKP_RP_MASK1 : ZKP_RP_MASK2;  // `if *j == 1 { c1 } else { c2 }` (range_proof.rs:321-325)
           r.masked_x.to_limbs(&resp_w[t * 2 * wl], wl);
-          r.masked_r.to_limbs(&resp_r[t * 2 * nl], nl);
+          (fits(r.masked_r, nl) ? r.masked_r : r.masked_r % ek.n).to_limbs(&resp_r[t * 2 * nl], nl);
         }
       }
     }
@@ -643,6 +648,53 @@ class CorrectKey {
 
 // ----------------------------------------------------------------------------------- sigma protocols
 // Field names and order follow the reference structs; BigInt fields use curv's native serde.
+//
+// Batches.  The device verifies one key per launch (zkp_set_key), but every Statement carries its own ek, and a batch
+// handed to verify_batch is untrusted input.  So verify_batch groups the statements by key and runs one device call
+// per key; a proof whose fields cannot be laid out in the device rows is decided on its own (rows the reference only
+// uses under a reduction are reduced here; rows that enter the transcript hash or an exponent wider than their device
+// row make THAT proof 0) and a proof on which the reference would panic is reported as -1 - nothing one proof carries
+// can change the verdict of another.  verify_batch returns 1 = Ok(()), 0 = Err(IncorrectProof), -1 = the reference
+// panics; the single-proof verify() turns those into IncorrectProof / ReferencePanic.  prove_batch is the prover's own
+// batch: it requires one key and throws std::invalid_argument otherwise.
+template <class St>
+inline std::vector<std::vector<size_t>> group_by_key(const std::vector<St>& st) {
+  std::vector<std::vector<size_t>> groups;
+  for (size_t b = 0; b < st.size(); ++b) {
+    size_t k = 0;
+    while (k < groups.size() && !(st[groups[k][0]].ek == st[b].ek)) ++k;
+    if (k == groups.size()) groups.emplace_back();
+    groups[k].push_back(b);
+  }
+  return groups;
+}
+template <class St>
+inline void require_one_key(const std::vector<St>& st, const char* who) {
+  for (auto& s : st)
+    if (!(s.ek == st[0].ek)) throw std::invalid_argument(std::string(who) + ": the statements of one proving batch must share the key");
+}
+inline bool fits_limbs(const BigInt& v, size_t limbs) { return v.d.size() <= limbs; }
+// verify_batch over mixed keys: `one_key(ps, st)` verifies a sub-batch whose statements share st[0].ek
+template <class Proof, class St, class F>
+inline std::vector<int> verify_by_key(const std::vector<const Proof*>& ps, const std::vector<St>& st, F one_key) {
+  if (ps.size() != st.size()) throw std::invalid_argument("verify_batch: one statement per proof");
+  std::vector<int> out(ps.size(), 0);
+  for (auto& idx : group_by_key(st)) {
+    std::vector<const Proof*> p2;
+    std::vector<St> s2;
+    for (size_t b : idx) {
+      p2.push_back(ps[b]);
+      s2.push_back(st[b]);
+    }
+    const std::vector<int> r = one_key(p2, s2);
+    for (size_t k = 0; k < idx.size(); ++k) out[idx[k]] = r[k];
+  }
+  return out;
+}
+inline void throw_for_verdict(int v, const char* panic_text) {
+  if (v < 0) throw ReferencePanic(panic_text);
+  if (!v) throw IncorrectProof();
+}
 struct ZeroStatement { EncryptionKey ek; BigInt c; };        // zero_enc_proof.rs:37-41
 struct ZeroWitness { BigInt r; };                            // :32-35
 class ZeroProof {                                            // :26-30
@@ -652,6 +704,7 @@ class ZeroProof {                                            // :26-30
                                             const ByteSource& rng = os_rng()) {
     const size_t B = st.size();
     if (B == 0) return {};
+    require_one_key(st, "ZeroProof::prove_batch");
     eng.use_key(st[0].ek);
     const size_t nl = eng.nl(), nnl = eng.nnl();
     std::vector<BigInt> r, c, rp;
@@ -673,27 +726,34 @@ class ZeroProof {                                            // :26-30
     return prove_batch(eng, {w}, {st}, rng)[0];
   }
   static std::vector<int> verify_batch(Engine& eng, const std::vector<const ZeroProof*>& ps, const std::vector<ZeroStatement>& st) {
+    return verify_by_key(ps, st, [&](const std::vector<const ZeroProof*>& p, const std::vector<ZeroStatement>& s) { return verify_one_key(eng, p, s); });
+  }
+  void verify(Engine& eng, const ZeroStatement& st) const { throw_for_verdict(verify_batch(eng, {this}, {st})[0], "unreachable"); }
+
+ private:
+  static std::vector<int> verify_one_key(Engine& eng, const std::vector<const ZeroProof*>& ps, const std::vector<ZeroStatement>& st) {
     const size_t B = ps.size();
-    if (B == 0) return {};
     eng.use_key(st[0].ek);
     const size_t nnl = eng.nnl();
+    const BigInt& nn = st[0].ek.nn;
     std::vector<BigInt> c, z, a;
+    std::vector<int> out(B, 1);
     for (size_t b = 0; b < B; ++b) {
-      c.push_back(st[b].c);   // rows are hashed and exponentiated as given (mod_pow reduces its base itself)
-      z.push_back(ps[b]->z);
-      a.push_back(ps[b]->a);
+      // c and a enter the transcript hash as given (and mod_pow / mod_mul reduce them): they must fit their rows
+      const bool ok = fits_limbs(st[b].c, nnl) && fits_limbs(ps[b]->a, nnl);
+      if (!ok) out[b] = 0;
+      c.push_back(ok ? st[b].c : BigInt(0));
+      a.push_back(ok ? ps[b]->a : BigInt(0));
+      z.push_back(ps[b]->z % nn);  // Enc(0, z) = z^n mod nn (zero_enc_proof.rs:73-79): reduced by mod_pow
     }
     std::vector<uint8_t> acc(B);
-    std::vector<int> out(B);
-    for (size_t b = 0; b < B; ++b)
-      if (st[b].c.d.size() > nnl || ps[b]->a.d.size() > nnl || ps[b]->z.d.size() > nnl) throw std::length_error("operand wider than n^2 rows");
     eng.check(zkp_zero_verify(eng.handle(), (int)B, pack(c, nnl).data(), pack(z, nnl).data(), pack(a, nnl).data(), acc.data()));
-    for (size_t b = 0; b < B; ++b) out[b] = acc[b];
+    for (size_t b = 0; b < B; ++b)
+      if (out[b]) out[b] = acc[b];
     return out;
   }
-  void verify(Engine& eng, const ZeroStatement& st) const {
-    if (!verify_batch(eng, {this}, {st})[0]) throw IncorrectProof();
-  }
+
+ public:
   std::string to_json() const { return Json::object().set("z", ser_native(z)).set("a", ser_native(a)).dump(); }
   static ZeroProof from_json(const std::string& s) {
     Json j = Json::parse(s);
@@ -713,6 +773,7 @@ class CiphertextProof {                                      // :22-27
                                                   const std::vector<CiphertextStatement>& st, const ByteSource& rng = os_rng()) {
     const size_t B = st.size();
     if (B == 0) return {};
+    require_one_key(st, "CiphertextProof::prove_batch");
     eng.use_key(st[0].ek);
     const size_t nl = eng.nl(), nnl = eng.nnl(), zl = eng.zl();
     std::vector<BigInt> x, r, c, xp, rp;
@@ -736,25 +797,35 @@ class CiphertextProof {                                      // :22-27
     return prove_batch(eng, {w}, {st}, rng)[0];
   }
   static std::vector<int> verify_batch(Engine& eng, const std::vector<const CiphertextProof*>& ps, const std::vector<CiphertextStatement>& st) {
+    return verify_by_key(ps, st, [&](const std::vector<const CiphertextProof*>& p, const std::vector<CiphertextStatement>& s) { return verify_one_key(eng, p, s); });
+  }
+  void verify(Engine& eng, const CiphertextStatement& st) const { throw_for_verdict(verify_batch(eng, {this}, {st})[0], "unreachable"); }
+
+ private:
+  static std::vector<int> verify_one_key(Engine& eng, const std::vector<const CiphertextProof*>& ps, const std::vector<CiphertextStatement>& st) {
     const size_t B = ps.size();
-    if (B == 0) return {};
     eng.use_key(st[0].ek);
     const size_t nnl = eng.nnl(), zl = eng.zl();
+    const EncryptionKey& ek = st[0].ek;
     std::vector<BigInt> c, z1, z2, cp;
+    std::vector<int> out(B, 1);
     for (size_t b = 0; b < B; ++b) {
-      c.push_back(st[b].c);
-      z1.push_back(ps[b]->z1.d.size() > zl ? ps[b]->z1 % st[b].ek.n : ps[b]->z1);  // (m*n + 1) % nn depends on m mod n only
-      z2.push_back(ps[b]->z2);
-      cp.push_back(ps[b]->c_prime);
+      const bool ok = fits_limbs(st[b].c, nnl) && fits_limbs(ps[b]->c_prime, nnl);  // hashed as given
+      if (!ok) out[b] = 0;
+      c.push_back(ok ? st[b].c : BigInt(0));
+      cp.push_back(ok ? ps[b]->c_prime : BigInt(0));
+      z1.push_back(fits_limbs(ps[b]->z1, zl) ? ps[b]->z1 : ps[b]->z1 % ek.n);  // (m*n + 1) % nn depends on m mod n only
+      z2.push_back(ps[b]->z2 % ek.nn);                                            // randomness: reduced by mod_pow
     }
     std::vector<uint8_t> acc(B);
     eng.check(zkp_ciphertext_verify(eng.handle(), (int)B, (int)zl, pack(c, nnl).data(), pack(z1, zl).data(), pack(z2, nnl).data(),
                                     pack(cp, nnl).data(), acc.data()));
-    return std::vector<int>(acc.begin(), acc.end());
+    for (size_t b = 0; b < B; ++b)
+      if (out[b]) out[b] = acc[b];
+    return out;
   }
-  void verify(Engine& eng, const CiphertextStatement& st) const {
-    if (!verify_batch(eng, {this}, {st})[0]) throw IncorrectProof();
-  }
+
+ public:
   std::string to_json() const {
     return Json::object().set("z1", ser_native(z1)).set("z2", ser_native(z2)).set("c_prime", ser_native(c_prime)).dump();
   }
@@ -781,6 +852,7 @@ class MulProof {                                                        // :32-3
                                            const ByteSource& rng = os_rng()) {
     const size_t B = st.size();
     if (B == 0) return {};
+    require_one_key(st, "MulProof::prove_batch");
     eng.use_key(st[0].ek);
     const size_t nl = eng.nl(), nnl = eng.nnl();
     std::vector<BigInt> a, b, ra, rb, rc, ea, eb, ec, d, rd;
@@ -809,26 +881,42 @@ class MulProof {                                                        // :32-3
   static MulProof prove(Engine& eng, const MulWitness& w, const MulStatement& st, const ByteSource& rng = os_rng()) {
     return prove_batch(eng, {w}, {st}, rng)[0];
   }
+  // -1: BigInt::mod_inv(..).unwrap() panics for that proof (multiplication_proof.rs:137)
   static std::vector<int> verify_batch(Engine& eng, const std::vector<const MulProof*>& ps, const std::vector<MulStatement>& st) {
+    return verify_by_key(ps, st, [&](const std::vector<const MulProof*>& p, const std::vector<MulStatement>& s) { return verify_one_key(eng, p, s); });
+  }
+  void verify(Engine& eng, const MulStatement& st) const {
+    throw_for_verdict(verify_batch(eng, {this}, {st})[0], "called `Option::unwrap()` on a `None` value (mod_inv, multiplication_proof.rs:137)");
+  }
+
+ private:
+  static std::vector<int> verify_one_key(Engine& eng, const std::vector<const MulProof*>& ps, const std::vector<MulStatement>& st) {
     const size_t B = ps.size();
-    if (B == 0) return {};
     eng.use_key(st[0].ek);
     const size_t nl = eng.nl(), nnl = eng.nnl();
+    const BigInt& nn = st[0].ek.nn;
     std::vector<BigInt> ea, eb, ec, f, z1, z2, ed, edb;
+    std::vector<int> out(B, 1);
+    const BigInt zero(0);
     for (size_t i = 0; i < B; ++i) {
-      ea.push_back(st[i].e_a); eb.push_back(st[i].e_b); ec.push_back(st[i].e_c);
-      f.push_back(ps[i]->f); z1.push_back(ps[i]->z1); z2.push_back(ps[i]->z2); ed.push_back(ps[i]->e_d); edb.push_back(ps[i]->e_db);
+      // e_a, e_b, e_c, e_d, e_db are hashed as given; f is the exponent of e_b^f (:138): they must fit their rows
+      const bool ok = fits_limbs(st[i].e_a, nnl) && fits_limbs(st[i].e_b, nnl) && fits_limbs(st[i].e_c, nnl) && fits_limbs(ps[i]->e_d, nnl) &&
+                      fits_limbs(ps[i]->e_db, nnl) && fits_limbs(ps[i]->f, nl);
+      if (!ok) out[i] = 0;
+      ea.push_back(ok ? st[i].e_a : zero); eb.push_back(ok ? st[i].e_b : zero); ec.push_back(ok ? st[i].e_c : zero);
+      f.push_back(ok ? ps[i]->f : zero); ed.push_back(ok ? ps[i]->e_d : zero); edb.push_back(ok ? ps[i]->e_db : zero);
+      z1.push_back(ps[i]->z1 % nn);  // randomness of Enc(f, z1) / Enc(0, z2) (:118-131): reduced by mod_pow
+      z2.push_back(ps[i]->z2 % nn);
     }
     std::vector<uint8_t> acc(B), fault(B);
     eng.check(zkp_mul_verify(eng.handle(), (int)B, pack(ea, nnl).data(), pack(eb, nnl).data(), pack(ec, nnl).data(), pack(f, nl).data(),
                              pack(z1, nnl).data(), pack(z2, nnl).data(), pack(ed, nnl).data(), pack(edb, nnl).data(), acc.data(), fault.data()));
     for (size_t i = 0; i < B; ++i)
-      if (fault[i]) throw ReferencePanic("called `Option::unwrap()` on a `None` value (mod_inv, multiplication_proof.rs:137)");
-    return std::vector<int>(acc.begin(), acc.end());
+      if (out[i]) out[i] = fault[i] ? -1 : acc[i];
+    return out;
   }
-  void verify(Engine& eng, const MulStatement& st) const {
-    if (!verify_batch(eng, {this}, {st})[0]) throw IncorrectProof();
-  }
+
+ public:
   std::string to_json() const {
     return Json::object().set("f", ser_native(f)).set("z1", ser_native(z1)).set("z2", ser_native(z2)).set("e_d", ser_native(e_d)).set("e_db", ser_native(e_db)).dump();
   }
@@ -849,6 +937,7 @@ class VerlinProof {                                                            /
                                               const ByteSource& rng = os_rng()) {
     const size_t B = st.size();
     if (B == 0) return {};
+    require_one_key(st, "VerlinProof::prove_batch");
     eng.use_key(st[0].ek);
     const size_t nl = eng.nl(), nnl = eng.nnl(), zl = eng.zl();
     std::vector<BigInt> x, xp, xdp, rx, c, cp, phix, a, ap, adp, ra;
@@ -879,25 +968,40 @@ class VerlinProof {                                                            /
     return prove_batch(eng, {w}, {st}, rng)[0];
   }
   static std::vector<int> verify_batch(Engine& eng, const std::vector<const VerlinProof*>& ps, const std::vector<VerlinStatement>& st) {
+    return verify_by_key(ps, st, [&](const std::vector<const VerlinProof*>& p, const std::vector<VerlinStatement>& s) { return verify_one_key(eng, p, s); });
+  }
+  void verify(Engine& eng, const VerlinStatement& st) const { throw_for_verdict(verify_batch(eng, {this}, {st})[0], "unreachable"); }
+
+ private:
+  static std::vector<int> verify_one_key(Engine& eng, const std::vector<const VerlinProof*>& ps, const std::vector<VerlinStatement>& st) {
     const size_t B = ps.size();
-    if (B == 0) return {};
     eng.use_key(st[0].ek);
     const size_t nnl = eng.nnl(), zl = eng.zl();
+    const EncryptionKey& ek = st[0].ek;
     std::vector<BigInt> c, cp, phix, phia, z, zp, zdp, rz;
+    std::vector<int> out(B, 1);
+    const BigInt zero(0);
     for (size_t i = 0; i < B; ++i) {
-      c.push_back(st[i].c); cp.push_back(st[i].c_prime); phix.push_back(st[i].phi_x);
-      phia.push_back(ps[i]->phi_a); z.push_back(ps[i]->z); zp.push_back(ps[i]->z_prime); zdp.push_back(ps[i]->z_double_prime);
-      rz.push_back(ps[i]->r_z);
+      // c, c', phi_x, phi_a are hashed as given; z, z' are the exponents of gen_phi (:147-155): they must fit their rows
+      const bool ok = fits_limbs(st[i].c, nnl) && fits_limbs(st[i].c_prime, nnl) && fits_limbs(st[i].phi_x, nnl) && fits_limbs(ps[i]->phi_a, nnl) &&
+                      fits_limbs(ps[i]->z, zl) && fits_limbs(ps[i]->z_prime, zl);
+      if (!ok) out[i] = 0;
+      c.push_back(ok ? st[i].c : zero); cp.push_back(ok ? st[i].c_prime : zero); phix.push_back(ok ? st[i].phi_x : zero);
+      phia.push_back(ok ? ps[i]->phi_a : zero); z.push_back(ok ? ps[i]->z : zero); zp.push_back(ok ? ps[i]->z_prime : zero);
+      const BigInt& zdd = ps[i]->z_double_prime;
+      zdp.push_back(fits_limbs(zdd, zl) ? zdd : zdd % ek.n);  // plaintext of Enc(z'', r_z) (:157-163): only z'' mod n matters
+      rz.push_back(ps[i]->r_z % ek.nn);                        // its randomness: reduced by mod_pow
     }
     std::vector<uint8_t> acc(B);
     eng.check(zkp_verlin_verify(eng.handle(), (int)B, (int)zl, pack(c, nnl).data(), pack(cp, nnl).data(), pack(phix, nnl).data(),
                                 pack(phia, nnl).data(), pack(z, zl).data(), pack(zp, zl).data(), pack(zdp, zl).data(), pack(rz, nnl).data(),
                                 acc.data()));
-    return std::vector<int>(acc.begin(), acc.end());
+    for (size_t i = 0; i < B; ++i)
+      if (out[i]) out[i] = acc[i];
+    return out;
   }
-  void verify(Engine& eng, const VerlinStatement& st) const {
-    if (!verify_batch(eng, {this}, {st})[0]) throw IncorrectProof();
-  }
+
+ public:
   std::string to_json() const {
     return Json::object().set("phi_a", ser_native(phi_a)).set("z", ser_native(z)).set("z_prime", ser_native(z_prime))
         .set("z_double_prime", ser_native(z_double_prime)).set("r_z", ser_native(r_z)).dump();
@@ -1032,15 +1136,19 @@ struct Paillier {
     if (B == 0) return {};
     eng.use_key(ek);
     const size_t nl = eng.nl(), nnl = eng.nnl();
-    std::vector<BigInt> mr, rr;
+    std::vector<BigInt> mr, rr, cc;
+    std::vector<int> out(B, 1);
     for (size_t b = 0; b < B; ++b) {
       mr.push_back(m[b] % ek.n);  // (m n + 1) % nn only depends on m mod n
       rr.push_back(r[b] % ek.n);  // r^n mod nn only depends on r mod n
-      if (c[b].d.size() > nnl) throw std::length_error("ciphertext wider than n^2 rows");
+      if (!fits_limbs(c[b], nnl)) out[b] = 0;  // wider than n^2: never equal to a canonical ciphertext
+      cc.push_back(out[b] ? c[b] : BigInt(0));
     }
     std::vector<uint8_t> ok(B);
-    eng.check(zkp_verify_opening(eng.handle(), (int)B, (int)nl, pack(mr, nl).data(), pack(rr, nl).data(), pack(c, nnl).data(), ok.data()));
-    return std::vector<int>(ok.begin(), ok.end());
+    eng.check(zkp_verify_opening(eng.handle(), (int)B, (int)nl, pack(mr, nl).data(), pack(rr, nl).data(), pack(cc, nnl).data(), ok.data()));
+    for (size_t b = 0; b < B; ++b)
+      if (out[b]) out[b] = ok[b];
+    return out;
   }
   static bool verify_opening(Engine& eng, const EncryptionKey& ek, const BigInt& m, const BigInt& r, const BigInt& c) {
     return verify_opening_batch(eng, ek, {m}, {r}, {c})[0] != 0;
@@ -1221,6 +1329,9 @@ class CorrectMessageProof {  // correct_message.rs:25-32 (no serde derive in the
     for (auto* p : ps) {
       if (!(p->ek == ek) || p->valid_messages.size() != M) throw std::invalid_argument("verify_batch: proofs must share the key and the number of messages");
       if (p->e_vec.size() < M || p->z_vec.size() < M || p->a_vec.size() < M) throw ReferencePanic("index out of bounds: short proof vector");
+      // the reference hashes ALL of a_vec and folds ALL of e_vec (correct_message.rs:128-131); the device rows hold M of each
+      if (p->e_vec.size() != M || p->a_vec.size() != M)
+        throw std::invalid_argument("CorrectMessageProof::verify_batch: e_vec / a_vec longer than the message list are not supported");
       for (auto& e : p->e_vec) ebits = std::max(ebits, e.bit_length());
     }
     const size_t el = limbs_for_bits(ebits);
@@ -1234,20 +1345,22 @@ class CorrectMessageProof {  // correct_message.rs:25-32 (no serde derive in the
         a.push_back(p->a_vec[i]);
       }
     }
-    // the transcript hashes a_vec as given: rows wider than n^2 cannot be represented -> not supported
-    for (auto& v : a)
-      if (v.d.size() > nnl) throw std::length_error("a_vec entry wider than n^2 rows");
-    // sum over ALL entries of e_vec, as the reference folds the whole vector (:130)
+    // the transcript hashes a_vec as given: a proof with a row wider than n^2 cannot be laid out and is rejected on its own
+    std::vector<int> wide(B, 0);
+    for (size_t b = 0; b < B; ++b)
+      for (size_t i = 0; i < M; ++i)
+        if (a[b * M + i].d.size() > nnl) {
+          wide[b] = 1;
+          a[b * M + i] = BigInt(0);
+        }
     std::vector<uint8_t> acc(B), fault(B);
     eng.check(zkp_correct_message_verify(eng.handle(), (int)B, (int)M, (int)nl, (int)el, pack(c, nnl).data(), pack(valid, nl).data(),
                                          pack(e, el).data(), pack(z, nl).data(), pack(a, nnl).data(), acc.data(), fault.data()));
     std::vector<int> out(B);
-    for (size_t b = 0; b < B; ++b) out[b] = fault[b] ? -1 : acc[b];
+    for (size_t b = 0; b < B; ++b) out[b] = wide[b] ? 0 : (fault[b] ? -1 : acc[b]);
     return out;
   }
   void verify(Engine& eng) const {
-    if (e_vec.size() != valid_messages.size() || a_vec.size() != valid_messages.size())
-      throw std::invalid_argument("CorrectMessageProof: vectors longer than the message list are not supported");
     const int v = verify_batch(eng, {this})[0];
     if (v < 0) throw ReferencePanic("assertion failed: `(left == right)` (chal, ei_sum)");
     if (!v) throw IncorrectProof();
