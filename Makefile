@@ -18,13 +18,16 @@ all: lib oracle
 
 # lab build: the measured-and-rejected kernel variants, the pipe probes and the ZKP_B200_* environment knobs
 # (scripts/k1m_variants.py, scripts/imad_probes.py with ZKP_B200_LIB=zk-paillier_b200/libzkp_b200_lab.so); not shipped
-LABBUILD  := build/lab
+# variants of the lab build:  make lab LABTAG=_nosub LABFLAGS=-DZKP_B200_LAB_NOSUB  (timing probe with wrong results, see mp_coop.cuh)
+LABTAG    ?=
+LABFLAGS  ?=
+LABBUILD  := build/lab$(LABTAG)
 LABOBJ    := $(patsubst $(CSRC)/%.cu,$(LABBUILD)/%.o,$(CU))
-LABLIB    := zk-paillier_b200/libzkp_b200_lab.so
+LABLIB    := zk-paillier_b200/libzkp_b200_lab$(LABTAG).so
 lab: $(LABLIB)
 $(LABBUILD)/%.o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.h) $(wildcard $(CSRC)/*.cuh) include/zkp_b200.h
 	@mkdir -p $(LABBUILD)
-	$(NVCC) $(NVFLAGS) -DZKP_B200_LAB -c $< -o $@ 2> $(LABBUILD)/$*.ptxas.log || (cat $(LABBUILD)/$*.ptxas.log; false)
+	$(NVCC) $(NVFLAGS) -DZKP_B200_LAB $(LABFLAGS) -c $< -o $@ 2> $(LABBUILD)/$*.ptxas.log || (cat $(LABBUILD)/$*.ptxas.log; false)
 $(LABLIB): $(LABOBJ)
 	$(NVCC) $(ARCH) -shared -o $@ $(LABOBJ) -lcudart
 

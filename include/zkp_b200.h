@@ -65,8 +65,9 @@ int zkp_sm_count(const zkp_ctx* ctx);
 int zkp_sync(zkp_ctx* ctx);
 
 /* Per-kernel device-time accounting (CUDA events on the launch stream).
- * kernel ids: 0 = modexp_shared (K1), 1 = modexp_var (K2), 2 = modmul (K3),
- * 3 = sha256_transcript (K4), 4 = everything else. */
+ * kernel ids: 0 = modexp_shared (K1 / K1m), 1 = modexp_var (K2 / K2m / K2h), 2 = modmul (K3),
+ * 3 = sha256_transcript (K4), 4 = everything else, 5 = the device span of whole zkp_mul_verify /
+ * zkp_verlin_verify calls (first kernel to last kernel; the host<->device copies excluded). */
 int zkp_profile_enable(zkp_ctx* ctx, int on);
 int zkp_profile_reset(zkp_ctx* ctx);
 int zkp_profile_get(zkp_ctx* ctx, int kernel, double* ms_total, long long* launches, double* units);

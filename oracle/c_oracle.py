@@ -164,3 +164,40 @@ def correct_message_verify(n, ciphertext, valid, e_vec, z_vec, a_vec, threads=0)
                                       _p32(z_vec), _p32(a_vec), _p8(out), threads)
     return out
 
+
+
+# ---- provers on GMP (bench.py baselines; compared with the Python oracle in tests/test_oracle_more.py)
+def zero_prove(n, r, c, r_prime, threads=0):
+    n, r, c, r_prime = _c32(n), _c32(r), _c32(c), _c32(r_prime)
+    batch, nl = r.shape
+    z, a = np.empty((batch, 2 * nl), np.uint32), np.empty((batch, 2 * nl), np.uint32)
+    load().orc_zero_prove(_p32(n), nl, batch, _p32(r), _p32(c), _p32(r_prime), _p32(z), _p32(a), threads)
+    return z, a
+
+
+def zero_verify(n, c, z, a, threads=0):
+    n, c, z, a = _c32(n), _c32(c), _c32(z), _c32(a)
+    batch = c.shape[0]
+    out = np.empty(batch, np.uint8)
+    load().orc_zero_verify(_p32(n), n.shape[-1], batch, _p32(c), _p32(z), _p32(a), _p8(out), threads)
+    return out
+
+
+def dlog_prove(N, g, ni, secret, r, y_limbs, threads=0):
+    N, g, ni, secret, r = (_c32(a) for a in (N, g, ni, secret, r))
+    batch, nl = N.shape
+    x, y = np.empty((batch, nl), np.uint32), np.empty((batch, y_limbs), np.uint32)
+    load().orc_dlog_prove(nl, secret.shape[1], r.shape[1], y_limbs, batch, _p32(N), _p32(g), _p32(ni), _p32(secret), _p32(r), _p32(x), _p32(y), threads)
+    return x, y
+
+
+def correct_message_prove(n, valid, msg, r, e_rand, z_rand, w, threads=0):
+    n, valid, msg, r, e_rand, z_rand, w = (_c32(a) for a in (n, valid, msg, r, e_rand, z_rand, w))
+    batch, M, ml = valid.shape
+    nl = n.shape[-1]
+    assert e_rand.shape == (batch, M - 1, 8) and z_rand.shape == (batch, M - 1, nl)
+    out = {"ciphertext": np.empty((batch, 2 * nl), np.uint32), "e_vec": np.empty((batch, M, 8), np.uint32),
+           "z_vec": np.empty((batch, M, nl), np.uint32), "a_vec": np.empty((batch, M, 2 * nl), np.uint32)}
+    load().orc_correct_message_prove(_p32(n), nl, batch, M, ml, _p32(valid), _p32(msg), _p32(r), _p32(e_rand), _p32(z_rand), _p32(w),
+                                     _p32(out["ciphertext"]), _p32(out["e_vec"]), _p32(out["z_vec"]), _p32(out["a_vec"]), threads)
+    return out

@@ -743,3 +743,157 @@ void orc_correct_message_verify(const uint32_t* n, int nl, int batch, int M, int
   sig_job j = {nl, 0, M, el, ml, n, ciphertext, valid, e_vec, z_vec, a_vec, NULL, NULL, NULL, verdict};
   run_parallel(cmsg_verify_task, &j, batch, threads);
 }
+
+/* ======================================================================================================
+ * Provers and the ZeroProof verifier on GMP: the CPU baselines of bench.py's secondary lines (configs[0] is
+ * ZeroProof prove + verify on the CPU; the dlog / correct_message lines measure prove + verify).
+ * Randomness is an input, as everywhere.  Compared with the Python restatement in tests/test_oracle_more.py.
+ * ====================================================================================================== */
+/* ZeroProof::prove (zero_enc_proof.rs:44-64): a = r'^n mod nn, e = H(n, c, a), z = r' r^e mod nn */
+static void zero_prove_task(void* arg, long b) {
+  sig_job* j = (sig_job*)arg;
+  const int nl = j->nl, nnl = 2 * nl;
+  mpz_t n, nn, r, c, rp, a, e, z, t;
+  __mpz_struct* all[] = {n, nn, r, c, rp, a, e, z, t};
+  for (size_t k = 0; k < sizeof(all) / sizeof(all[0]); ++k) mpz_init(all[k]);
+  uint8_t* scratch = (uint8_t*)malloc((size_t)nnl * 4 + 64);
+  imp(n, j->n, nl);
+  mpz_mul(nn, n, n);
+  imp(r, j->a0 + (size_t)b * nl, nl); imp(c, j->a1 + (size_t)b * nnl, nnl); imp(rp, j->a2 + (size_t)b * nl, nl);
+  mpz_powm(a, rp, n, nn);                                                 /* :46-52 */
+  const __mpz_struct* items[] = {n, c, a};
+  digest_of(e, items, 3, scratch);                                        /* :54-58 */
+  mpz_powm(z, r, e, nn); mpz_mul(z, z, rp); mpz_mod(z, z, nn);            /* :60-61 */
+  expo((uint32_t*)j->a3 + (size_t)b * nnl, nnl, z);
+  expo((uint32_t*)j->a4 + (size_t)b * nnl, nnl, a);
+  free(scratch);
+  for (size_t k = 0; k < sizeof(all) / sizeof(all[0]); ++k) mpz_clear(all[k]);
+}
+void orc_zero_prove(const uint32_t* n, int nl, int batch, const uint32_t* r, const uint32_t* c, const uint32_t* r_prime, uint32_t* z, uint32_t* a,
+                    int threads) {
+  sig_job j = {nl, 0, 0, 0, 0, n, r, c, r_prime, z, a, NULL, NULL, NULL, NULL};
+  run_parallel(zero_prove_task, &j, batch, threads);
+}
+/* ZeroProof::verify (zero_enc_proof.rs:66-94): z^n == c^e a mod nn */
+static void zero_verify_task(void* arg, long b) {
+  sig_job* j = (sig_job*)arg;
+  const int nl = j->nl, nnl = 2 * nl;
+  mpz_t n, nn, c, z, a, e, t, u;
+  __mpz_struct* all[] = {n, nn, c, z, a, e, t, u};
+  for (size_t k = 0; k < sizeof(all) / sizeof(all[0]); ++k) mpz_init(all[k]);
+  uint8_t* scratch = (uint8_t*)malloc((size_t)nnl * 4 + 64);
+  imp(n, j->n, nl);
+  mpz_mul(nn, n, n);
+  imp(c, j->a0 + (size_t)b * nnl, nnl); imp(z, j->a1 + (size_t)b * nnl, nnl); imp(a, j->a2 + (size_t)b * nnl, nnl);
+  const __mpz_struct* items[] = {n, c, a};
+  digest_of(e, items, 3, scratch);                                        /* :67-71 */
+  mpz_powm(t, z, n, nn);                                                  /* Enc(0, z) :73-79 */
+  mpz_powm(u, c, e, nn); mpz_mul(u, u, a); mpz_mod(u, u, nn);             /* :81-88 */
+  j->verdict[b] = mpz_cmp(t, u) == 0 ? 1 : 0;
+  free(scratch);
+  for (size_t k = 0; k < sizeof(all) / sizeof(all[0]); ++k) mpz_clear(all[k]);
+}
+void orc_zero_verify(const uint32_t* n, int nl, int batch, const uint32_t* c, const uint32_t* z, const uint32_t* a, uint8_t* verdict, int threads) {
+  sig_job j = {nl, 0, 0, 0, 0, n, c, z, a, NULL, NULL, NULL, NULL, NULL, verdict};
+  run_parallel(zero_verify_task, &j, batch, threads);
+}
+
+/* CompositeDLogProof::prove (wi_dlog_proof.rs:46-65): x = g^r mod N, e = H(x, g, N, ni), y = r + e * secret (unreduced) */
+static void dlog_prove_task(void* arg, long b) {
+  sig_job* j = (sig_job*)arg;
+  const int nl = j->nl, yl = j->zl, sl = j->el, rl = j->ml;
+  mpz_t N, g, ni, s, r, x, e, y;
+  __mpz_struct* all[] = {N, g, ni, s, r, x, e, y};
+  for (size_t k = 0; k < sizeof(all) / sizeof(all[0]); ++k) mpz_init(all[k]);
+  uint8_t* scratch = (uint8_t*)malloc((size_t)nl * 4 + 64);
+  imp(N, j->a0 + (size_t)b * nl, nl); imp(g, j->a1 + (size_t)b * nl, nl); imp(ni, j->a2 + (size_t)b * nl, nl);
+  imp(s, j->a3 + (size_t)b * sl, sl); imp(r, j->a4 + (size_t)b * rl, rl);
+  mpz_powm(x, g, r, N);                                                   /* :54 */
+  const __mpz_struct* items[] = {x, g, N, ni};
+  digest_of(e, items, 4, scratch);                                        /* :55-60 */
+  mpz_mul(y, e, s); mpz_add(y, y, r);                                     /* :61 */
+  expo((uint32_t*)j->a5 + (size_t)b * nl, nl, x);
+  expo((uint32_t*)j->a6 + (size_t)b * yl, yl, y);
+  free(scratch);
+  for (size_t k = 0; k < sizeof(all) / sizeof(all[0]); ++k) mpz_clear(all[k]);
+}
+void orc_dlog_prove(int nl, int sl, int rl, int yl, int batch, const uint32_t* N, const uint32_t* g, const uint32_t* ni, const uint32_t* secret,
+                    const uint32_t* r, uint32_t* x, uint32_t* y, int threads) {
+  sig_job j = {nl, yl, 0, sl, rl, NULL, N, g, ni, secret, r, x, y, NULL, NULL};
+  run_parallel(dlog_prove_task, &j, batch, threads);
+}
+
+/* CorrectMessageProof::prove (correct_message.rs:35-128); the message must be one of the valid ones (the caller's workload
+ * guarantees it: the reference indexes out of bounds otherwise).  e_rand / z_rand: [batch][M-1] rows. */
+typedef struct {
+  int nl, M, ml, el;
+  const uint32_t *n, *valid, *msg, *r, *e_rand, *z_rand, *w;
+  uint32_t *ciphertext, *e_vec, *z_vec, *a_vec;
+} cmsg_prove_job;
+static void cmsg_prove_task(void* arg, long b) {
+  cmsg_prove_job* j = (cmsg_prove_job*)arg;
+  const int nl = j->nl, nnl = 2 * nl, M = j->M, ml = j->ml, el = j->el;
+  mpz_t n, nn, msg, r, w, c, m, gm, u, e, z, a, t, chal, esum, two_b, ei, zi;
+  __mpz_struct* all[] = {n, nn, msg, r, w, c, m, gm, u, e, z, a, t, chal, esum, two_b, ei, zi};
+  for (size_t k = 0; k < sizeof(all) / sizeof(all[0]); ++k) mpz_init(all[k]);
+  uint8_t* scratch = (uint8_t*)malloc((size_t)nnl * 4 + 64);
+  imp(n, j->n, nl);
+  mpz_mul(nn, n, n);
+  imp(msg, j->msg + (size_t)b * ml, ml); imp(r, j->r + (size_t)b * nl, nl); imp(w, j->w + (size_t)b * nl, nl);
+  enc(c, n, nn, msg, r, t);                                               /* :41-49 */
+  mpz_set_ui(two_b, 1); mpz_mul_2exp(two_b, two_b, 256);
+  mpz_set_ui(esum, 0);
+  SHA256_CTX h;
+  SHA256_Init(&h);
+  int k = 0;
+  uint8_t* hit = (uint8_t*)calloc((size_t)M, 1);                          /* slots whose valid message equals the message (:70,:98,:110) */
+  for (int i = 0; i < M; ++i) {                                           /* a_vec :68-83 */
+    imp(m, j->valid + ((size_t)b * M + i) * ml, ml);
+    if (mpz_cmp(m, msg) == 0) {
+      hit[i] = 1;
+      mpz_powm(a, w, n, nn);
+    } else {
+      mpz_mul(gm, m, n); mpz_add_ui(gm, gm, 1); mpz_mod(gm, gm, nn);      /* u_i :51-57 */
+      mpz_invert(gm, gm, nn);
+      mpz_mul(u, c, gm); mpz_mod(u, u, nn);
+      imp(e, j->e_rand + ((size_t)b * (M - 1) + k) * el, el);
+      imp(z, j->z_rand + ((size_t)b * (M - 1) + k) * nl, nl);
+      ++k;
+      mpz_add(esum, esum, e);
+      mpz_powm(t, z, n, nn);
+      mpz_powm(u, u, e, nn);
+      mpz_invert(u, u, nn);
+      mpz_mul(a, t, u); mpz_mod(a, a, nn);
+    }
+    sha_update_mpz(&h, a, scratch);
+    expo(j->a_vec + ((size_t)b * M + i) * nnl, nnl, a);
+  }
+  uint8_t d[32];
+  SHA256_Final(d, &h);
+  __gmpz_import(chal, 32, 1, 1, 0, 0, d);
+  mpz_mod(chal, chal, two_b);                                             /* :85-88 */
+  mpz_mod(esum, esum, two_b);
+  mpz_sub(ei, chal, esum); mpz_mod(ei, ei, two_b);                        /* :93 */
+  mpz_powm(zi, r, ei, n); mpz_mul(zi, zi, w); mpz_mod(zi, zi, n);         /* :94-95 */
+  k = 0;
+  for (int i = 0; i < M; ++i) {                                           /* :97-121 */
+    if (hit[i]) {
+      expo(j->e_vec + ((size_t)b * M + i) * 8, 8, ei);
+      expo(j->z_vec + ((size_t)b * M + i) * nl, nl, zi);
+    } else {
+      memcpy(j->e_vec + ((size_t)b * M + i) * 8, j->e_rand + ((size_t)b * (M - 1) + k) * el, 32);
+      memcpy(j->z_vec + ((size_t)b * M + i) * nl, j->z_rand + ((size_t)b * (M - 1) + k) * nl, (size_t)nl * 4);
+      ++k;
+    }
+  }
+  expo(j->ciphertext + (size_t)b * nnl, nnl, c);
+  free(hit);
+  free(scratch);
+  for (size_t q = 0; q < sizeof(all) / sizeof(all[0]); ++q) mpz_clear(all[q]);
+}
+void orc_correct_message_prove(const uint32_t* n, int nl, int batch, int M, int ml, const uint32_t* valid, const uint32_t* msg, const uint32_t* r,
+                               const uint32_t* e_rand, const uint32_t* z_rand, const uint32_t* w, uint32_t* ciphertext, uint32_t* e_vec,
+                               uint32_t* z_vec, uint32_t* a_vec, int threads) {
+  cmsg_prove_job j = {nl, M, ml, 8, n, valid, msg, r, e_rand, z_rand, w, ciphertext, e_vec, z_vec, a_vec};
+  run_parallel(cmsg_prove_task, &j, batch, threads);
+}

@@ -84,15 +84,34 @@ def test_config3_one_shard_of_65536(ctx):
 
 
 def test_config2_correct_key_batch4096_3072(ctx):
-    ks = keys(3072)
+    """BASELINE configs[2] as stated: 4096 proofs, 3072-bit n, a DISTINCT modulus per proof.  The keys come from the device
+    keygen (Paillier::keypairs_batch: Miller-Rabin waves on K2) and the honest proofs from NiCorrectKeyProof::proof_batch
+    (C++ mirror); verdicts and rho against the GMP oracle on a sample, primality of sampled p, q against sympy."""
+    import sympy
+
     nl, batch, salt = 96, 4096, b"Zen Go X"
-    work = workload.correct_key_batch(ks, batch, salt, lambda p, q, s: po.NiCorrectKeyProof.proof(p, q, s).sigma_vec, nl, bad_every=64)
+    work = workload.correct_key_distinct(3072, batch, salt, seed=20261017, bad_every=64, with_primes=True)
+    assert len({r.tobytes() for r in work["n"]}) == batch                    # 4096 distinct moduli
     acc, rho = ctx.correct_key_ni_verify(work["n"], work["sigma"], salt, want_rho=True)
     assert acc.tolist() == [0 if b % 64 == 63 else 1 for b in range(batch)]
-    assert limbs_to_ints(rho[17]) == po.correct_key_rho(work["n_int"][17], salt)
-    assert np.array_equal(rho[: len(ks)], rho[len(ks): 2 * len(ks)])      # same key -> same rho
+    sel = np.array([0, 1, 62, 63, 64, 1000, 2047, 4031, 4095])
+    acc_c, rho_c = c_oracle.correct_key_ni_verify(work["n"][sel], work["sigma"][sel], salt)
+    assert np.array_equal(acc[sel], acc_c) and np.array_equal(rho[sel], rho_c)
+    for b in (0, 1777, 4095):
+        pp, qq = from_limbs(work["pq"][b, 0]), from_limbs(work["pq"][b, 1])
+        assert pp != qq and pp.bit_length() == qq.bit_length() == 1536 and pp % 4 == 3 and qq % 4 == 3
+        assert sympy.isprime(pp) and sympy.isprime(qq) and pp * qq == from_limbs(work["n"][b])
+        assert limbs_to_ints(rho[b]) == po.correct_key_rho(pp * qq, salt)
+        # the device-built proof is the oracle's proof (NiCorrectKeyProof::proof is deterministic)
+        want = po.NiCorrectKeyProof.proof(pp, qq, salt).sigma_vec
+        if b % 64 != 63:
+            assert limbs_to_ints(work["sigma"][b]) == want
     # the prover-side derivation agrees with the verifier's
     assert np.array_equal(ctx.correct_key_ni_rho(work["n"][:32], salt), rho[:32])
+    # the same seed and count give the same keys (the byte stream behind every sample is SHA-256(seed || counter))
+    small = workload.correct_key_distinct(1024, 6, salt, seed=7)
+    assert np.array_equal(small["n"], workload.correct_key_distinct(1024, 6, salt, seed=7)["n"])
+    assert not np.array_equal(small["n"], workload.correct_key_distinct(1024, 6, salt, seed=8)["n"])
 
 
 def test_config5_mul_and_verlin_4096(ctx):

@@ -21,8 +21,9 @@ def verdict(fn):
         return 0
 
 
-# (key size, K2h lane layout: 0 = by job count - narrow lanes at these batch sizes -, 1 = wide lanes, 2 = narrow lanes)
-@pytest.fixture(scope="module", params=[(1024, 0), (1024, 1), (2048, 1), (2048, 2), (3072, 1), (3072, 2), (4096, 1), (4096, 2)],
+# (key size, K2h lane layout: 0 = by job count - narrow lanes at these batch sizes -, 1 = wide lanes, 2 = narrow lanes,
+#  "k1" = the two-digit kernels switched off: every modexp by the single-purpose K1 / K2 launches, products by K3)
+@pytest.fixture(scope="module", params=[(1024, 0), (1024, 1), (1024, "k1"), (2048, 1), (2048, 2), (3072, 1), (3072, 2), (4096, 1), (4096, 2)],
                 ids=lambda p: f"{p[0]}-shape{p[1]}")
 def keyed(request, ctx):
     import zk_paillier_b200 as zk
@@ -31,10 +32,12 @@ def keyed(request, ctx):
     p, q = keys(bits)[0]
     n = p * q
     nl = limbs_for(bits)
+    ctx.tune(zk.native.TUNE_ENC_KERNEL, 1 if shape == "k1" else 0)
     ctx.set_key(to_limbs(n, nl))
-    ctx.tune(zk.native.TUNE_JOBS_SHAPE, shape)
+    ctx.tune(zk.native.TUNE_JOBS_SHAPE, 0 if shape == "k1" else shape)
     yield ctx, n, nl, random.Random(bits)
     ctx.tune(zk.native.TUNE_JOBS_SHAPE, 0)
+    ctx.tune(zk.native.TUNE_ENC_KERNEL, 0)
 
 
 def test_zero_proof(keyed):

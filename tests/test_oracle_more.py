@@ -187,3 +187,49 @@ def test_gmp_verifiers_agree_with_the_python_oracle():
                                           L([pr.z_vec for pr in prs], nl), L([pr.a_vec for pr in prs], nnl), 2)
     assert got.tolist() == want == [1, 0, 2]
     assert isinstance(got, np.ndarray)
+
+
+def test_c_oracle_provers_match_the_python_oracle():
+    """The GMP provers behind bench.py's CPU baselines (ZeroProof prove / verify, CompositeDLogProof::prove,
+    CorrectMessageProof::prove) against the Python-int restatement, field for field on identical randomness."""
+    import numpy as np
+
+    import c_oracle
+    from zk_paillier_b200.native import ints_to_limbs, limbs_to_ints, to_limbs
+
+    p, q = keys(1024)[1]
+    n = p * q
+    nl = 32
+    rng = random.Random(5)
+    B = 5
+    # ZeroProof; statement 3 encrypts 1
+    r = [rng.randrange(1, n) for _ in range(B)]
+    c = [po.paillier_encrypt(n, 1 if i == 3 else 0, ri) for i, ri in enumerate(r)]
+    rp = [rng.randrange(1, n) for _ in range(B)]
+    z, a = c_oracle.zero_prove(to_limbs(n, nl), ints_to_limbs(r, nl), ints_to_limbs(c, 2 * nl), ints_to_limbs(rp, nl))
+    want = [po.ZeroProof.prove(ri, n, ci, rpi) for ri, ci, rpi in zip(r, c, rp)]
+    assert limbs_to_ints(z) == [w.z for w in want] and limbs_to_ints(a) == [w.a for w in want]
+    assert c_oracle.zero_verify(to_limbs(n, nl), ints_to_limbs(c, 2 * nl), z, a).tolist() == [1, 1, 1, 0, 1]
+    # CompositeDLogProof::prove
+    st = [dlog_statement(rng, p, q) for _ in range(B)]
+    rr = [rng.getrandbits(512) for _ in range(B)]
+    x, y = c_oracle.dlog_prove(ints_to_limbs([s[0] for s in st], nl), ints_to_limbs([s[1] for s in st], nl), ints_to_limbs([s[2] for s in st], nl),
+                               ints_to_limbs([s[3] for s in st], 8), ints_to_limbs(rr, 16), 20)
+    want = [po.CompositeDLogProof.prove(s[0], s[1], s[2], s[3], ri) for s, ri in zip(st, rr)]
+    assert limbs_to_ints(x) == [w.x for w in want] and limbs_to_ints(y) == [w.y for w in want]
+    # CorrectMessageProof::prove, the message in every position of the ring
+    M = 4
+    valid = [3, 4, 5, 6]
+    msgs = [valid[i % M] for i in range(B)]
+    r = [rng.randrange(1, n) for _ in range(B)]
+    w = [rng.randrange(1, n) for _ in range(B)]
+    e_rand = [[rng.getrandbits(256) for _ in range(M - 1)] for _ in range(B)]
+    z_rand = [[rng.randrange(1, n) for _ in range(M - 1)] for _ in range(B)]
+    out = c_oracle.correct_message_prove(to_limbs(n, nl), ints_to_limbs([valid] * B, 4), ints_to_limbs(msgs, 4), ints_to_limbs(r, nl),
+                                         ints_to_limbs(e_rand, 8), ints_to_limbs(z_rand, nl), ints_to_limbs(w, nl))
+    for i in range(B):
+        pr = po.CorrectMessageProof.prove(n, valid, msgs[i], r[i], e_rand[i], z_rand[i], w[i])
+        assert limbs_to_ints(out["a_vec"][i]) == pr.a_vec and limbs_to_ints(out["e_vec"][i]) == pr.e_vec
+        assert limbs_to_ints(out["z_vec"][i]) == pr.z_vec and limbs_to_ints(out["ciphertext"][i:i + 1])[0] == pr.ciphertext
+    v = c_oracle.correct_message_verify(to_limbs(n, nl), out["ciphertext"], ints_to_limbs([valid] * B, 4), out["e_vec"], out["z_vec"], out["a_vec"])
+    assert (np.asarray(v) == 1).all()

@@ -52,12 +52,12 @@ ProfScope::~ProfScope() {
   if (idx >= 0) cudaEventRecord(c->prof[idx].b, c->stream);
 }
 
-cudaError_t ensure_table(zkp_ctx* c, int S, int entries, int pow_jobs) {
+cudaError_t ensure_table(zkp_ctx* c, int S, int entries, int pow_jobs, int pow_bases) {
   size_t bytes = (size_t)resident_groups(S, c->num_sms) * entries * S * sizeof(uint32_t);
   if (c->enc2m_key && c->enc2m_enabled) {  // a call may run K1m (Enc) and K2m (mod_pow) back to back: size for both
     const size_t b1 = enc2m_table_limbs(c->n.S, c->num_sms) * sizeof(uint32_t);
     const size_t b2 = var2m_table_limbs(c->n.S, c->num_sms) * sizeof(uint32_t);
-    const size_t b3 = pow_jobs > 0 ? jobs2m_scratch_limbs(c->n.S, c->num_sms, pow_jobs) * sizeof(uint32_t) : 0;
+    const size_t b3 = pow_jobs > 0 ? jobs2m_scratch_limbs(c->n.S, c->num_sms, pow_jobs, pow_bases) * sizeof(uint32_t) : 0;
     bytes = std::max(std::max(bytes, b3), std::max(b1, b2));
   }
   bytes = (bytes + 255) & ~size_t(255);

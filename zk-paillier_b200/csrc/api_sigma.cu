@@ -169,6 +169,7 @@ int zkp_mul_verify(zkp_ctx* c, int batch, const uint32_t* e_a, const uint32_t* e
   uint8_t* d_fault = s.ar.get<uint8_t>((size_t)batch);
   uint8_t* d_acc = s.ar.get<uint8_t>((size_t)batch);
   cudaMemsetAsync(d_fault, 0, (size_t)batch, s.st);
+  s.compute_begin();
   // five independent modexps per proof in two K2h launches: the two with the 256-bit challenge as exponent (and the
   // products and the inversion that consume them) on an auxiliary stream, the three |n|-bit ones on the main stream
   uint32_t* e = s.challenge({d_ea, d_eb, d_ec, d_ed, d_edb});                  // :109-116
@@ -192,6 +193,7 @@ int zkp_mul_verify(zkp_ctx* c, int batch, const uint32_t* e_a, const uint32_t* e
   uint32_t* lhs2 = s.mulm(e_b_f, nnl, vinv, nnl);                              // :139
   if (!s.bad) s.ck(launch_rows_equal(lhs1, enc_f_z1, nnl, batch, 0, d_acc, s.st));         // :141
   if (!s.bad) s.ck(launch_rows_equal(lhs2, enc_0_z2, nnl, batch, 1, d_acc, s.st));
+  s.compute_end();
   if (cudaMemcpyAsync(accept, d_acc, (size_t)batch, cudaMemcpyDeviceToHost, s.st) != cudaSuccess) s.bad = true;
   if (cudaMemcpyAsync(fault, d_fault, (size_t)batch, cudaMemcpyDeviceToHost, s.st) != cudaSuccess) s.bad = true;
   rc = s.finish("zkp_mul_verify");
@@ -203,17 +205,16 @@ int zkp_mul_verify(zkp_ctx* c, int batch, const uint32_t* e_a, const uint32_t* e
 
 // ----------------------------------------------------------------- VerlinProof
 namespace {
-// gen_phi (verlin_proof.rs:138-165): c^y * c'^y' * Enc(y'', r_y) mod nn
+// gen_phi (verlin_proof.rs:138-165): c^y * c'^y' * Enc(y'', r_y) mod nn.  Only the product is ever used (it is phi_a in the
+// proof, and the left side of the verifier's comparison), so the three powers are ONE simultaneous exponentiation job:
+// one squaring chain for all three bases, the factor (1 + y'' n) as the job's final multiplier.
 uint32_t* gen_phi(Sig& s, const uint32_t* cc, const uint32_t* cp, const uint32_t* y, const uint32_t* yp, const uint32_t* ydp,
                   int y_limbs, const uint32_t* r_y, int r_limbs) {
-  PowBatch pb(s);  // the three modexps in one launch
-  uint32_t* cp_yp = pb.powm(cp, s.nnl, yp, y_limbs);
-  uint32_t* en = pb.enc(ydp, y_limbs, r_y, r_limbs);
-  uint32_t* c_y = pb.powm(cc, s.nnl, y, y_limbs);
+  PowBatch pb(s);
+  uint32_t* phi = pb.product({PowTerm{cc, s.nnl, y, y_limbs}, PowTerm{cp, s.nnl, yp, y_limbs}, PowTerm{r_y, r_limbs, nullptr, 0}}, ydp, y_limbs);
   pb.run();
   s.join();
-  uint32_t* t = s.mulm(c_y, s.nnl, cp_yp, s.nnl);
-  return s.mulm(t, s.nnl, en, s.nnl);
+  return phi;
 }
 }  // namespace
 
@@ -225,7 +226,7 @@ int zkp_verlin_prove(zkp_ctx* c, int batch, int z_limbs, const uint32_t* x, cons
       !z_prime || !z_dp || !r_z)
     return c ? fail(c, ZKP_E_ARG, "null buffer") : ZKP_E_ARG;
   Sig s(c, batch);
-  int rc = sigma_begin(c, batch, z_limbs, 12, 4 * (8 * (size_t)s.nl + 3 * (size_t)z_limbs) + 128, s);
+  int rc = sigma_begin(c, batch, z_limbs, 12, 4 * (8 * (size_t)s.nl + 3 * (size_t)z_limbs) + 128, s, 3);
   if (rc) return rc;
   const int nl = s.nl, nnl = s.nnl;
   uint32_t *d_x = s.up(x, nl), *d_xp = s.up(x_prime, nl), *d_xdp = s.up(x_dp, nl), *d_rx = s.up(r_x, nl);
@@ -255,12 +256,13 @@ int zkp_verlin_verify(zkp_ctx* c, int batch, int z_limbs, const uint32_t* cc, co
   if (!c || !cc || !c_prime || !phi_x || !phi_a || !z || !z_prime || !z_dp || !r_z || !accept)
     return c ? fail(c, ZKP_E_ARG, "null buffer") : ZKP_E_ARG;
   Sig s(c, batch);
-  int rc = sigma_begin(c, batch, z_limbs, 13, 4 * 3 * (size_t)z_limbs + 128, s);
+  int rc = sigma_begin(c, batch, z_limbs, 13, 4 * 3 * (size_t)z_limbs + 128, s, 3);
   if (rc) return rc;
   const int nnl = s.nnl;
   uint32_t *d_c = s.up(cc, nnl), *d_cp = s.up(c_prime, nnl), *d_phix = s.up(phi_x, nnl), *d_phia = s.up(phi_a, nnl);
   uint32_t *d_z = s.up(z, z_limbs), *d_zp = s.up(z_prime, z_limbs), *d_zdp = s.up(z_dp, z_limbs), *d_rz = s.up(r_z, nnl);
   uint8_t* d_acc = s.ar.get<uint8_t>((size_t)batch);
+  s.compute_begin();
   uint32_t* e = s.challenge({d_c, d_cp, d_phix, d_phia});                      // :102-108
   s.fork(2);
   PowBatch ps(s);
@@ -270,6 +272,7 @@ int zkp_verlin_verify(zkp_ctx* c, int batch, int z_limbs, const uint32_t* cc, co
   s.on_main();
   uint32_t* phi_z = gen_phi(s, d_c, d_cp, d_z, d_zp, d_zdp, z_limbs, d_rz, nnl);  // :120-128 (joins)
   if (!s.bad) s.ck(launch_rows_equal(phi_z, rhs, nnl, batch, 0, d_acc, s.st));
+  s.compute_end();
   if (cudaMemcpyAsync(accept, d_acc, (size_t)batch, cudaMemcpyDeviceToHost, s.st) != cudaSuccess) s.bad = true;
   return s.finish("zkp_verlin_verify");
 }

@@ -62,7 +62,8 @@ struct KeySlot {
 
 constexpr int kAuxStreams = 4;  // concurrent modexp launches of one call (fork_stream / join_streams)
 
-enum KernelId { KID_MODEXP_SHARED = 0, KID_MODEXP_VAR = 1, KID_MODMUL = 2, KID_SHA = 3, KID_OTHER = 4, KID_COUNT = 5 };
+// KID_CALL: the device span of a whole sigma-protocol call - first kernel to last kernel on the main stream, copies excluded
+enum KernelId { KID_MODEXP_SHARED = 0, KID_MODEXP_VAR = 1, KID_MODMUL = 2, KID_SHA = 3, KID_OTHER = 4, KID_CALL = 5, KID_COUNT = 6 };
 
 struct ProfEntry {
   int kid;
@@ -161,8 +162,8 @@ struct ProfScope {
 };
 
 // table scratch large enough for K1/K2 at width S
-// pow_jobs > 0: also room for a K2h launch of that many jobs (launch_pow_jobs)
-cudaError_t ensure_table(zkp_ctx* c, int S, int entries, int pow_jobs = 0);
+// pow_jobs > 0: also room for a K2h launch of that many jobs of up to pow_bases bases each (launch_pow_jobs)
+cudaError_t ensure_table(zkp_ctx* c, int S, int entries, int pow_jobs = 0, int pow_bases = 1);
 // Paillier::encrypt_with_chosen_randomness for `jobs` rows under the current key: picks K1v2 (two-digit base-n)
 // when the key and row widths qualify, else K1 (Montgomery mod n^2).  plain == nullptr encrypts 0.
 // Returns 1 if K1v2 ran, 0 if K1 ran, negative cudaError as -(int)err - 1000 on failure (see enc_failed()).

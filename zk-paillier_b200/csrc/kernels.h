@@ -79,17 +79,23 @@ cudaError_t launch_modexp2m_var(const Enc2mKey& key, const uint32_t* bases, int 
 
 // K2h (modexp2m.cu): every modexp of a batch of sigma-protocol proofs in ONE launch.  A job list is up to kMaxPowSegs
 // homogeneous segments; job j of segment s computes
-//     out[j] = (1 + plain[j] n) * base[j]^exp[j] mod n^2      (plain == nullptr: the plain factor is 1)
-// i.e. BigInt::mod_pow / Paillier::mul with a per-job exponent, or Paillier::encrypt_with_chosen_randomness when the
-// exponent is the shared n (exp = n on the device, exp_stride = 0).  Segments should be listed longest exponent first.
+//     out[j] = (1 + plain[j] n) * PROD_k base_k[j]^exp_k[j] mod n^2      (k < nbase <= 3; plain == nullptr: the factor is 1)
+// i.e. BigInt::mod_pow / Paillier::mul with a per-job exponent (nbase = 1), Paillier::encrypt_with_chosen_randomness when the
+// exponent is the shared n (exp = n on the device, exp_stride = 0), or a whole product of powers by simultaneous (Straus)
+// exponentiation - one squaring chain for all bases - where the reference multiplies the powers together anyway:
+// gen_phi = c^y c'^y' Enc(y'', r_y) (verlin_proof.rs:138-165) is one job of three bases.
+// Segments must be listed longest exponent scan first.
 constexpr int kMaxPowSegs = 8;
+constexpr int kMaxPowBases = 3;
 struct PowSeg {
-  const uint32_t* base;   // [jobs][base_limbs], base_limbs <= 2 S, even
-  const uint32_t* exp;    // row j at exp + j * exp_stride (limbs); every exponent < 2^exp_bits
+  const uint32_t* base[kMaxPowBases];   // [jobs][base_limbs[k]], base_limbs <= 2 S, even
+  const uint32_t* exp[kMaxPowBases];    // row j at exp[k] + j * exp_stride[k] (limbs); every exponent < 2^exp_bits
+  long long exp_stride[kMaxPowBases];
+  int base_limbs[kMaxPowBases], exp_limbs[kMaxPowBases];
+  int nbase;
   const uint32_t* plain;  // [jobs][plain_limbs] or nullptr; plain_limbs <= 2 S, even
   uint32_t* out;          // [jobs][out_limbs]
-  long long exp_stride;
-  int base_limbs, exp_limbs, exp_bits, plain_limbs, jobs, first;  // first: index of the segment's first job in the launch
+  int exp_bits, plain_limbs, jobs, first;  // exp_bits: bits scanned (all bases); first: index of the segment's first job in the launch
 };
 struct PowJobs {
   PowSeg seg[kMaxPowSegs];
@@ -99,7 +105,7 @@ struct PowJobs {
 // over twice the lanes, half the limbs per lane: fills the machine at small batches of wide moduli)
 // Scratch: jobs2m_scratch_limbs(S, num_sms, total jobs) limbs at `table` (window tables; for a launch that under-fills
 // the GPU also the per-job accumulators and phase counters of the phased schedule, see modexp2m.cu).
-size_t jobs2m_scratch_limbs(int S, int num_sms, int total_jobs);
+size_t jobs2m_scratch_limbs(int S, int num_sms, int total_jobs, int max_bases = 1);
 cudaError_t launch_modexp2m_jobs(const Enc2mKey& key, const PowJobs& jobs, int out_limbs, uint32_t* table, size_t table_limbs,
                                  unsigned* cursor, int num_sms, cudaStream_t st, int shape = 0);
 

@@ -391,6 +391,7 @@ struct Jobs2mParams {
   unsigned* done;     // phased: phases completed per work unit, [units] (zeroed by the launcher)
   unsigned* cursor;   // next phase-unit (zeroed by the launcher on the same stream)
   int out_limbs;
+  int tab_bases;      // window tables per job (the largest nbase of the launch)
   int win_per_phase;  // windows of the exponent scan per phase; >= the longest scan: one phase per unit, nothing migrates
   int nphase;         // phases of the longest unit
   unsigned pre[kMaxPhases + 1];  // pre[p] = phase-units before phase p (units are ordered longest scan first, so the
@@ -547,50 +548,76 @@ __global__ void __launch_bounds__(kCtaThreads, MINB) modexp2m_jobs_kernel(const 
       if (k < p.jobs.nseg && src >= p.jobs.seg[k].first) si = k;
     const PowSeg& sgm = p.jobs.seg[si];
     const int rel = src - sgm.first;
-    const int exp_limbs = sgm.exp_limbs;
-    const uint32_t* e = sgm.exp + (size_t)rel * sgm.exp_stride;
-    int nwin = (sgm.exp_bits + kWindowVar - 1) / kWindowVar;
+    int nwin = (sgm.exp_bits + kWindowVar - 1) / kWindowVar, nb = sgm.nbase;
 #pragma unroll
-    for (int o = T; o < 32; o <<= 1) nwin = max(nwin, __shfl_xor_sync(ZKP_FULL, nwin, o));  // one trip count per warp
+    for (int o = T; o < 32; o <<= 1) {  // one trip count and one number of bases per warp
+      nwin = max(nwin, __shfl_xor_sync(ZKP_FULL, nwin, o));
+      nb = max(nb, __shfl_xor_sync(ZKP_FULL, nb, o));
+    }
+    // exponent rows of this job; a base the job does not have scans as zero (its windows pick table entry 0 = 1)
+    const uint32_t* e[kMaxPowBases];
+    int el[kMaxPowBases];
+#pragma unroll
+    for (int k = 0; k < kMaxPowBases; ++k) {
+      const bool has = k < sgm.nbase;
+      e[k] = has ? sgm.exp[k] + (size_t)rel * sgm.exp_stride[k] : nullptr;
+      el[k] = has ? sgm.exp_limbs[k] : 0;
+    }
+    const size_t tab_base_stride = (size_t)kTableVar * 2 * S;
     // windows hi - 1 .. lo of the scan (most significant first) belong to this phase
     const int hi = nwin - ph * p.win_per_phase;
     const int lo = max(hi - p.win_per_phase, 0);
-    uint32_t* tab = (phased ? p.table + (size_t)src * kTableVar * 2 * S : p.table + (size_t)(blockIdx.x * G + grp) * kTableVar * 2 * S) + g * L;
+    uint32_t* tab = (phased ? p.table + (size_t)src * p.tab_bases * tab_base_stride : p.table + (size_t)(blockIdx.x * G + grp) * p.tab_bases * tab_base_stride) + g * L;
     uint32_t* accp = p.acc + (size_t)src * 2 * S + g * L;
 
     uint32_t x0[L], x1[L], y0[L], y1[L];
     if (ph == 0) {
-      const int base_limbs = sgm.base_limbs;
-      const bool wide_base = __any_sync(ZKP_FULL, base_limbs > S);
-      TD::entry_pair_u(x0, x1, sgm.base + (size_t)rel * base_limbs, base_limbs, wide_base, p.key.consts, n, n0inv, s_klo, lane, zr);
-      M::load(y0, p.key.consts + S + g * L);  // pair(W^2): into Montgomery form
-      M::load(y1, p.key.consts + 2 * S + g * L);
-      TD::mul(x0, x1, y0, y1, n, n0inv, s_klo, lane, zr);
-      M::store(tab + 2 * S, x0);
-      M::store(tab + 2 * S + S, x1);
+#pragma unroll 1
+      for (int k = 0; k < nb; ++k) {  // the window table of every base: x^0 .. x^31 in Montgomery form
+        const int kk = k < sgm.nbase ? k : 0;  // (a base this job lacks: uniform work, the table is never read past entry 0)
+        const int base_limbs = sgm.base_limbs[kk];
+        const bool wide_base = __any_sync(ZKP_FULL, base_limbs > S);
+        uint32_t* tk = tab + (size_t)k * tab_base_stride;
+        TD::entry_pair_u(x0, x1, sgm.base[kk] + (size_t)rel * base_limbs, base_limbs, wide_base, p.key.consts, n, n0inv, s_klo, lane, zr);
+        M::load(y0, p.key.consts + S + g * L);  // pair(W^2): into Montgomery form
+        M::load(y1, p.key.consts + 2 * S + g * L);
+        TD::mul(x0, x1, y0, y1, n, n0inv, s_klo, lane, zr);
+        M::store(tk + 2 * S, x0);
+        M::store(tk + 2 * S + S, x1);
 #pragma unroll
-      for (int j = 0; j < L; ++j) {
-        y0[j] = x0[j];
-        y1[j] = x1[j];
+        for (int j = 0; j < L; ++j) {
+          y0[j] = x0[j];
+          y1[j] = x1[j];
+        }
+        M::load(x0, p.key.consts + 3 * S + g * L);  // pair(W) = 1 in Montgomery form = x^0
+        M::load(x1, p.key.consts + 4 * S + g * L);
+        M::store(tk, x0);
+        M::store(tk + S, x1);
+#pragma unroll
+        for (int j = 0; j < L; ++j) {
+          x0[j] = y0[j];
+          x1[j] = y1[j];
+        }
+#pragma unroll 1
+        for (int t = 2; t < kTableVar; ++t) {
+          TD::mul(x0, x1, y0, y1, n, n0inv, s_klo, lane, zr);
+          M::store(tk + (size_t)t * 2 * S, x0);
+          M::store(tk + (size_t)t * 2 * S + S, x1);
+        }
       }
-      M::load(x0, p.key.consts + 3 * S + g * L);  // pair(W) = 1 in Montgomery form = x^0
-      M::load(x1, p.key.consts + 4 * S + g * L);
-      M::store(tab, x0);
-      M::store(tab + S, x1);
-#pragma unroll
-      for (int j = 0; j < L; ++j) {
-        x0[j] = y0[j];
-        x1[j] = y1[j];
+      // the top window: the accumulator starts at the product of the bases' table entries
+      {
+        const uint32_t* t0 = tab + (size_t)exp_window2m(e[0], el[0], (hi - 1) * kWindowVar) * 2 * S;
+        M::load(x0, t0);
+        M::load(x1, t0 + S);
       }
 #pragma unroll 1
-      for (int k = 2; k < kTableVar; ++k) {
+      for (int k = 1; k < nb; ++k) {
+        const uint32_t* t0 = tab + (size_t)k * tab_base_stride + (size_t)exp_window2m(k == 1 ? e[1] : e[2], k == 1 ? el[1] : el[2], (hi - 1) * kWindowVar) * 2 * S;
+        M::load(y0, t0);
+        M::load(y1, t0 + S);
         TD::mul(x0, x1, y0, y1, n, n0inv, s_klo, lane, zr);
-        M::store(tab + (size_t)k * 2 * S, x0);
-        M::store(tab + (size_t)k * 2 * S + S, x1);
       }
-      const uint32_t* t0 = tab + (size_t)exp_window2m(e, exp_limbs, (hi - 1) * kWindowVar) * 2 * S;
-      M::load(x0, t0);
-      M::load(x1, t0 + S);
     } else {
       if (lane == 0)
         while (atomicAdd(p.done + unit, 0u) < (unsigned)ph) __nanosleep(256);
@@ -600,13 +627,18 @@ __global__ void __launch_bounds__(kCtaThreads, MINB) modexp2m_jobs_kernel(const 
       M::load_cg(x1, accp + S);
     }
 #pragma unroll 1
-    for (int w = hi - 1 - (ph == 0 ? 1 : 0); w >= lo; --w) {
-      const uint32_t* t0 = tab + (size_t)exp_window2m(e, exp_limbs, w * kWindowVar) * 2 * S;
-      M::load(y0, t0);
-      M::load(y1, t0 + S);
+    for (int w = hi - 1 - (ph == 0 ? 1 : 0); w >= lo; --w) {  // one squaring chain for all bases (Straus)
 #pragma unroll 1
       for (int q = 0; q < kWindowVar; ++q) TD::sqr(x0, x1, n, n0inv, s_klo, lane, zr);
-      TD::mul(x0, x1, y0, y1, n, n0inv, s_klo, lane, zr);
+#pragma unroll 1
+      for (int k = 0; k < nb; ++k) {
+        const uint32_t* ek = k == 0 ? e[0] : (k == 1 ? e[1] : e[2]);
+        const int elk = k == 0 ? el[0] : (k == 1 ? el[1] : el[2]);
+        const uint32_t* t0 = tab + (size_t)k * tab_base_stride + (size_t)exp_window2m(ek, elk, w * kWindowVar) * 2 * S;
+        M::load(y0, t0);
+        M::load(y1, t0 + S);
+        TD::mul(x0, x1, y0, y1, n, n0inv, s_klo, lane, zr);
+      }
     }
     if (lo > 0) {  // hand the job over to whoever takes its next phase
       M::store(accp, x0);
@@ -940,17 +972,18 @@ static int scan_windows(int exp_bits) { return (exp_bits + kWindowVar - 1) / kWi
 
 // limbs of scratch one launch needs: the window tables (by job when phased, else by resident group), the accumulators
 // of a phased launch and its done[] counters
-size_t jobs2m_scratch_limbs(int S, int num_sms, int total_jobs) {
+size_t jobs2m_scratch_limbs(int S, int num_sms, int total_jobs, int max_bases) {
   int T, L;
   if (!pick_shape(S, T, L)) return 0;
   const size_t wide = (size_t)num_sms * kCtasPerSm2m * (kCtaThreads / T);
   const size_t narrow = (size_t)num_sms * kCtasPerSmNarrow * (kCtaThreads / (2 * T));
-  const size_t resident = (wide > narrow ? wide : narrow) * kTableVar * 2 * S;
+  if (max_bases < 1) max_bases = 1;
+  const size_t resident = (wide > narrow ? wide : narrow) * max_bases * kTableVar * 2 * S;
   // a phased launch has fewer than kPhasedUnitsPerSmsp long units per sub-partition, 32 / T jobs each; twice that leaves
   // room for the short jobs of the same launch (a launch that still does not fit runs unphased)
   size_t jobs = (size_t)num_sms * 4 * kPhasedUnitsPerSmsp * (32 / T) * 2;
   if ((size_t)total_jobs < jobs) jobs = (size_t)total_jobs;
-  const size_t phased = jobs * (kTableVar + 1) * 2 * S + jobs + 64;
+  const size_t phased = jobs * ((size_t)max_bases * kTableVar + 1) * 2 * S + jobs + 64;
   return resident > phased ? resident : phased;
 }
 
@@ -973,7 +1006,8 @@ static cudaError_t launch_jobs_one(Jobs2mParams& p, size_t table_limbs, int num_
     if (2 * scan_windows(p.jobs.seg[k].exp_bits) >= max_win) long_units = (p.jobs.seg[k].first + p.jobs.seg[k].jobs + GW - 1) / GW;
   const int smsp = num_sms * 4;
   int nphase = 1;
-  const size_t phased_limbs = (size_t)nunits * GW * (kTableVar + 1) * 2 * S + (size_t)nunits + 64;
+  const size_t phased_limbs = (size_t)nunits * GW * ((size_t)p.tab_bases * kTableVar + 1) * 2 * S + (size_t)nunits + 64;
+  if ((size_t)num_sms * MINB * (kCtaThreads / T) * p.tab_bases * kTableVar * 2 * S > table_limbs) return cudaErrorInvalidValue;
   if (long_units < kPhasedUnitsPerSmsp * smsp && phased_limbs <= table_limbs) {
     nphase = (kPhaseTargetPerSmsp * smsp + long_units - 1) / long_units;
     if (nphase > kMaxPhases) nphase = kMaxPhases;
@@ -995,7 +1029,7 @@ static cudaError_t launch_jobs_one(Jobs2mParams& p, size_t table_limbs, int num_
   }
   for (int ph = p.nphase; ph < kMaxPhases; ++ph) p.pre[ph + 1] = p.pre[p.nphase];
   if (p.nphase > 1) {
-    p.acc = p.table + (size_t)p.jobs.total * kTableVar * 2 * S;
+    p.acc = p.table + (size_t)nunits * GW * p.tab_bases * kTableVar * 2 * S;
     p.done = reinterpret_cast<unsigned*>(p.acc + (size_t)nunits * GW * 2 * S);
     cudaError_t e = cudaMemsetAsync(p.done, 0, sizeof(unsigned) * (size_t)nunits, st);
     if (e != cudaSuccess) return e;
@@ -1020,22 +1054,27 @@ cudaError_t launch_modexp2m_jobs(const Enc2mKey& key, const PowJobs& jobs, int o
   long long long_jobs = 0;
   int max_bits = 0;
   for (int k = 0; k < jobs.nseg; ++k) max_bits = jobs.seg[k].exp_bits > max_bits ? jobs.seg[k].exp_bits : max_bits;
+  int tab_bases = 1;
   for (int k = 0; k < jobs.nseg; ++k) {
     const PowSeg& s = jobs.seg[k];
-    if (s.first != first || s.jobs <= 0 || s.base_limbs % 2 || s.base_limbs <= 0 || s.base_limbs > 2 * key.S || s.exp_bits <= 0 ||
-        s.exp_bits > 32 * s.exp_limbs || (s.plain && (s.plain_limbs % 2 || s.plain_limbs <= 0 || s.plain_limbs > 2 * key.S)) ||
-        (k > 0 && s.exp_bits > jobs.seg[k - 1].exp_bits))
+    if (s.first != first || s.jobs <= 0 || s.nbase < 1 || s.nbase > kMaxPowBases || s.exp_bits <= 0 ||
+        (s.plain && (s.plain_limbs % 2 || s.plain_limbs <= 0 || s.plain_limbs > 2 * key.S)) || (k > 0 && s.exp_bits > jobs.seg[k - 1].exp_bits))
       return cudaErrorInvalidValue;
+    for (int b = 0; b < s.nbase; ++b)
+      if (!s.base[b] || !s.exp[b] || s.base_limbs[b] % 2 || s.base_limbs[b] <= 0 || s.base_limbs[b] > 2 * key.S || s.exp_limbs[b] <= 0)
+        return cudaErrorInvalidValue;
+    tab_bases = s.nbase > tab_bases ? s.nbase : tab_bases;
     first += s.jobs;
     if (2 * s.exp_bits >= max_bits) long_jobs += s.jobs;
   }
-  if (first != jobs.total || table_limbs < jobs2m_scratch_limbs(key.S, num_sms, jobs.total)) return cudaErrorInvalidValue;
+  if (first != jobs.total) return cudaErrorInvalidValue;
   Jobs2mParams p;
   p.key = key;
   p.jobs = jobs;
   p.table = table;
   p.cursor = cursor;
   p.out_limbs = out_limbs;
+  p.tab_bases = tab_bases;
   p.zero = 0u;
   int T, L;
   if (!pick_shape(key.S, T, L)) return cudaErrorInvalidValue;
@@ -1048,17 +1087,17 @@ cudaError_t launch_modexp2m_jobs(const Enc2mKey& key, const PowJobs& jobs, int o
   (void)jobs_shape_T;
 #ifdef ZKP_B200_LAB
   if (shape == 2 && key.S == 128) {  // lab: row-loop unrolling of the narrow layout (ZKP_B200_K2H_UNROLL = 1 | 2 | 4)
-    static const int u = [] { const char* e = getenv("ZKP_B200_K2H_UNROLL"); return e ? atoi(e) : 1; }();
-    if (u == 2) return launch_jobs_one<32, 4, kCtasPerSmNarrow, 2>(p, table_limbs, num_sms, st);
+    static const int u = [] { const char* e = getenv("ZKP_B200_K2H_UNROLL"); return e ? atoi(e) : 2; }();
+    if (u == 1) return launch_jobs_one<32, 4, kCtasPerSmNarrow, 1>(p, table_limbs, num_sms, st);
     if (u == 4) return launch_jobs_one<32, 4, kCtasPerSmNarrow, 4>(p, table_limbs, num_sms, st);
   }
 #endif
   if (shape == 2) {
     switch (key.S) {
-      case 32: return launch_jobs_one<8, 4, kCtasPerSmNarrow>(p, table_limbs, num_sms, st);
-      case 64: return launch_jobs_one<16, 4, kCtasPerSmNarrow>(p, table_limbs, num_sms, st);
-      case 96: return launch_jobs_one<16, 6, kCtasPerSmNarrow>(p, table_limbs, num_sms, st);
-      case 128: return launch_jobs_one<32, 4, kCtasPerSmNarrow>(p, table_limbs, num_sms, st);
+      case 32: return launch_jobs_one<8, 4, kCtasPerSmNarrow, 2>(p, table_limbs, num_sms, st);
+      case 64: return launch_jobs_one<16, 4, kCtasPerSmNarrow, 2>(p, table_limbs, num_sms, st);
+      case 96: return launch_jobs_one<16, 6, kCtasPerSmNarrow, 2>(p, table_limbs, num_sms, st);
+      case 128: return launch_jobs_one<32, 4, kCtasPerSmNarrow, 2>(p, table_limbs, num_sms, st);
       default: return cudaErrorInvalidValue;
     }
   }

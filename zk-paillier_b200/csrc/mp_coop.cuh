@@ -303,6 +303,12 @@ struct Mp {
     add_small(r, cin);
     uint32_t hi = __shfl_sync(ZKP_FULL, u[L], T - 1, T) + topc;
     uint32_t first = 0;
+#ifdef ZKP_B200_LAB_NOSUB
+    // lab probe only (make lab LABTAG=_nosub LABFLAGS=-DZKP_B200_LAB_NOSUB): WRONG RESULTS - no conditional subtraction at
+    // all, to time the upper bound of what a lazy (redundant-residue) reduction could save
+    (void)hi;
+    return first;
+#endif
 #pragma unroll
     for (int s = 0; s < NSUB; ++s) {
       uint32_t d[L];

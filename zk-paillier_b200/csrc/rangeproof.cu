@@ -49,8 +49,159 @@ __global__ void __launch_bounds__(kShaThreads) sha256_transcript_kernel(const Sh
   }
 }
 
+// ------------------------------------------------------------------------ K4w
+// The same digest with ONE WARP per transcript, for batches too small to fill the GPU with one thread each (a batch of 1024
+// RangeProofNi transcripts is 32 warps of K4: 3 % of the SMs busy for 10 ms; one proof alone waits the same 10 ms twice).
+// The byte stream of a transcript is laid out first - every lane measures items (minimal big-endian length of to_bytes(),
+// zero -> 1 byte) and a warp scan turns the lengths into byte offsets in shared memory - after which any message word can
+// be fetched independently: lanes 0-15 assemble the 16 words of one block and lanes 16-31 those of the next (binary search
+// of the item, then its limbs), the words are broadcast by shuffle and every lane runs the 64 rounds on registers.  What is
+// left per block is the serial round chain itself.
+constexpr int kShaWarpThreads = 128;
+__device__ __forceinline__ const uint32_t* sha_item(const ShaSegs& segs, int b, int item, int& limbs) {
+  int k = 0, first = 0;
+  while (k + 1 < segs.nseg && item >= first + segs.seg[k].count) {
+    first += segs.seg[k].count;
+    ++k;
+  }
+  limbs = segs.seg[k].limbs;
+  return segs.seg[k].base + (size_t)b * segs.seg[k].batch_stride + (size_t)(item - first) * limbs;
+}
+__global__ void __launch_bounds__(kShaWarpThreads) sha256_transcript_warp_kernel(const __grid_constant__ ShaSegs segs, int nitems, int batch,
+                                                                                uint8_t* digest) {
+  extern __shared__ uint32_t s_off_all[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.x * (kShaWarpThreads / 32) + warp;
+  if (b >= batch) return;
+  uint32_t* off = s_off_all + (size_t)warp * (nitems + 1);  // off[i] = first byte of item i in the message; off[nitems] = length
+  // ---- lengths and offsets
+  uint32_t run = 0;
+  for (int base = 0; base < nitems; base += 32) {
+    const int it = base + lane;
+    uint32_t len = 0;
+    if (it < nitems) {
+      int limbs;
+      const uint32_t* p = sha_item(segs, b, it, limbs);
+      int top = limbs - 1;
+      uint32_t v = 0;
+      while (top >= 0 && (v = __ldg(p + top)) == 0u) --top;
+      len = top < 0 ? 1u : (uint32_t)(4 * top + 4 - (__clz(v) >> 3));
+    }
+    uint32_t inc = len;  // inclusive scan over the warp
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (it < nitems) off[it] = run + inc - len;
+    run += __shfl_sync(0xffffffffu, inc, 31);
+  }
+  if (lane == 0) off[nitems] = run;
+  __syncwarp();
+  const uint32_t total = run;
+  const uint32_t nblocks = (total + 9 + 63) / 64;
+  const unsigned long long bits = (unsigned long long)total * 8ull;
+  uint32_t h[8] = {0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a, 0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19};
+  for (uint32_t blk0 = 0; blk0 < nblocks; blk0 += 2) {
+    // ---- this lane's word: word (lane & 15) of block blk0 + (lane >> 4)
+    const uint32_t blk = blk0 + (uint32_t)(lane >> 4);
+    const uint32_t p0 = blk * 64u + 4u * (uint32_t)(lane & 15);
+    uint32_t word = 0;
+    if (blk < nblocks) {
+      if (p0 < total) {
+        int lo = 0, hi = nitems - 1;  // the item that holds byte p0: largest i with off[i] <= p0
+        while (lo < hi) {
+          const int mid = (lo + hi + 1) >> 1;
+          if (off[mid] <= p0) lo = mid;
+          else hi = mid - 1;
+        }
+        int it = lo, limbs;
+        const uint32_t* ptr = sha_item(segs, b, it, limbs);
+        uint32_t start = off[it], end = off[it + 1];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t pos = p0 + (uint32_t)k;
+          uint32_t byte;
+          if (pos < total) {
+            while (pos >= end) {  // next item (an item is at least one byte long)
+              ++it;
+              ptr = sha_item(segs, b, it, limbs);
+              start = end;
+              end = off[it + 1];
+            }
+            const uint32_t le = (end - start) - 1u - (pos - start);  // position from the least significant byte
+            byte = (__ldg(ptr + (le >> 2)) >> (8u * (le & 3u))) & 0xffu;
+          } else {
+            byte = pos == total ? 0x80u : 0u;
+          }
+          word = (word << 8) | byte;
+        }
+      } else if (p0 == total) {
+        word = 0x80000000u;
+      }
+      if (blk == nblocks - 1) {
+        if ((lane & 15) == 14) word = (uint32_t)(bits >> 32);
+        if ((lane & 15) == 15) word = (uint32_t)bits;
+      }
+    }
+    // ---- compress the two blocks, one after the other; every lane runs the rounds on its own registers
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+      if (blk0 + (uint32_t)half >= nblocks) break;
+      uint32_t m[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) m[i] = __shfl_sync(0xffffffffu, word, half * 16 + i);
+      uint32_t a = h[0], bb = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7];
+#pragma unroll
+      for (int i = 0; i < 64; ++i) {
+        uint32_t wi;
+        if (i < 16) {
+          wi = m[i];
+        } else {
+          const uint32_t w15 = m[(i + 1) & 15], w2 = m[(i + 14) & 15];
+          const uint32_t s0 = rotr32(w15, 7) ^ rotr32(w15, 18) ^ (w15 >> 3);
+          const uint32_t s1 = rotr32(w2, 17) ^ rotr32(w2, 19) ^ (w2 >> 10);
+          wi = m[i & 15] + s0 + m[(i + 9) & 15] + s1;
+          m[i & 15] = wi;
+        }
+        const uint32_t S1 = rotr32(e, 6) ^ rotr32(e, 11) ^ rotr32(e, 25);
+        const uint32_t ch = (e & f) ^ (~e & g);
+        const uint32_t t1 = hh + S1 + ch + kSha256K[i] + wi;
+        const uint32_t S0 = rotr32(a, 2) ^ rotr32(a, 13) ^ rotr32(a, 22);
+        const uint32_t mj = (a & bb) ^ (a & c) ^ (bb & c);
+        const uint32_t t2 = S0 + mj;
+        hh = g; g = f; f = e; e = d + t1; d = c; c = bb; bb = a; a = t1 + t2;
+      }
+      h[0] += a; h[1] += bb; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
+    }
+  }
+  if (lane < 8) {
+    const uint32_t v = h[lane];  // h is the same in every lane; lane i writes word i
+    uint8_t* o = digest + (size_t)b * 32 + 4 * lane;
+    o[0] = (uint8_t)(v >> 24);
+    o[1] = (uint8_t)(v >> 16);
+    o[2] = (uint8_t)(v >> 8);
+    o[3] = (uint8_t)v;
+  }
+}
+
+// below this many transcripts one warp each (K4w), above it one thread each (K4): 148 SMs x 64 resident warps
+constexpr int kShaWarpBatchMax = 148 * 64;
+
 cudaError_t launch_sha256_transcript(const ShaSegs& segs, int batch, uint8_t* digest, cudaStream_t st) {
   if (batch <= 0) return cudaSuccess;
+  int nitems = 0;
+  for (int k = 0; k < segs.nseg; ++k) nitems += segs.seg[k].count;
+  const size_t smem = (size_t)(kShaWarpThreads / 32) * (nitems + 1) * sizeof(uint32_t);
+  if (batch < kShaWarpBatchMax && nitems > 0 && smem <= 200 * 1024) {
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(sha256_transcript_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+    }
+    const int per = kShaWarpThreads / 32;
+    sha256_transcript_warp_kernel<<<(batch + per - 1) / per, kShaWarpThreads, smem, st>>>(segs, nitems, batch, digest);
+    return cudaGetLastError();
+  }
   sha256_transcript_kernel<<<(batch + kShaThreads - 1) / kShaThreads, kShaThreads, 0, st>>>(segs, batch, digest);
   return cudaGetLastError();
 }

@@ -135,8 +135,21 @@ struct Sig {
     st = c->stream;
     if (e != cudaSuccess) ck(e);
   }
+  // device span of the call for zkp_profile_get(5): from here (inputs uploaded) ...
+  ProfScope* span = nullptr;
+  void compute_begin() {
+    if (!span) span = new ProfScope(c, KID_CALL, batch);
+  }
+  // ... to here (every kernel queued, streams joined; the downloads follow)
+  void compute_end() {
+    join();
+    delete span;
+    span = nullptr;
+  }
+  ~Sig() { delete span; }
   int finish(const char* what) {
     join();
+    compute_end();
     if (bad) {
       cudaStreamSynchronize(st);
       if (c->err.empty()) c->err = what;
@@ -151,53 +164,75 @@ struct Sig {
 // The modular exponentiations of one proof phase, queued and then launched as ONE K2h kernel over a heterogeneous job
 // list (longest exponents first).  With a key the two-digit kernels do not take, run() issues them one after the other
 // through launch_enc / launch_pow_nn instead - same results.
+struct PowTerm {
+  const uint32_t* base;
+  int base_limbs;
+  const uint32_t* exp;  // nullptr: the shared exponent n (a Paillier encryption's r^n)
+  int exp_limbs;
+};
 struct PowBatch {
   Sig& s;
   struct Item {
-    const uint32_t* base;
-    const uint32_t* exp;    // nullptr: Paillier encryption (exponent n)
+    PowTerm term[kMaxPowBases];
+    int nterm;
     const uint32_t* plain;
     uint32_t* out;
-    int base_limbs, exp_limbs, plain_limbs, jobs;
+    int plain_limbs, jobs;
   };
   std::vector<Item> items;
   explicit PowBatch(Sig& sig) : s(sig) {}
   // Paillier::encrypt_with_chosen_randomness(ek, m, r); m == nullptr: the plaintext 0
   uint32_t* enc(const uint32_t* m, int m_limbs, const uint32_t* r, int r_limbs, int jobs = -1) {
-    uint32_t* out = s.rows(s.nnl, jobs);
-    items.push_back({r, nullptr, m, out, r_limbs, 0, m ? m_limbs : 0, s.nrows(jobs)});
-    return out;
+    return product({PowTerm{r, r_limbs, nullptr, 0}}, m, m_limbs, jobs);
   }
   // BigInt::mod_pow(base, exp, nn) / Paillier::mul with a per-proof exponent
   uint32_t* powm(const uint32_t* base, int base_limbs, const uint32_t* exp, int exp_limbs, int jobs = -1) {
+    return product({PowTerm{base, base_limbs, exp, exp_limbs}}, nullptr, 0, jobs);
+  }
+  // (1 + m n) * PROD base_k^exp_k mod nn as ONE job (simultaneous exponentiation): where the reference multiplies powers
+  // together and only the product is used - gen_phi (verlin_proof.rs:138-165)
+  uint32_t* product(std::initializer_list<PowTerm> terms, const uint32_t* m, int m_limbs, int jobs = -1) {
     uint32_t* out = s.rows(s.nnl, jobs);
-    items.push_back({base, exp, nullptr, out, base_limbs, exp_limbs, 0, s.nrows(jobs)});
+    Item it{};
+    it.nterm = 0;
+    for (const PowTerm& t : terms)
+      if (it.nterm < kMaxPowBases) it.term[it.nterm++] = t;
+    if ((size_t)it.nterm != terms.size()) s.bad = true;
+    it.plain = m;
+    it.plain_limbs = m ? m_limbs : 0;
+    it.out = out;
+    it.jobs = s.nrows(jobs);
+    items.push_back(it);
     return out;
   }
   void run() {
     if (s.bad || items.empty()) return;
     zkp_ctx* c = s.c;
     if (!jobs_supported(c) || (int)items.size() > kMaxPowSegs) {
-      for (const Item& it : items) {
-        ProfScope ps(c, it.exp ? KID_MODEXP_VAR : KID_MODEXP_SHARED, it.jobs);
-        if (it.exp) s.ck(launch_pow_nn(c, it.base, it.base_limbs, it.exp, it.exp_limbs, 32 * it.exp_limbs, 1, it.out, it.jobs));
-        else s.ck(launch_enc(c, it.base, it.base_limbs, it.plain, it.plain_limbs, it.out, it.jobs));
-      }
+      for (const Item& it : items) run_separately(it);
       items.clear();
       return;
     }
     int n_bits = 32 * c->n.S;  // bit length of the shared exponent n
     while (n_bits > 1 && !((c->n.h_mod[(n_bits - 1) >> 5] >> ((n_bits - 1) & 31)) & 1u)) --n_bits;
-    auto bits = [&](const Item& it) { return it.exp ? 32 * it.exp_limbs : n_bits; };
+    auto bits = [&](const Item& it) {
+      int b = 0;
+      for (int k = 0; k < it.nterm; ++k) b = std::max(b, it.term[k].exp ? 32 * it.term[k].exp_limbs : n_bits);
+      return b;
+    };
     std::stable_sort(items.begin(), items.end(), [&](const Item& a, const Item& b) { return bits(a) > bits(b); });
     PowJobs pj;
     for (const Item& it : items) {
       PowSeg& g = pj.seg[pj.nseg++];
-      g.base = it.base;
-      g.base_limbs = it.base_limbs;
-      g.exp = it.exp ? it.exp : c->n.mod.as<uint32_t>();
-      g.exp_limbs = it.exp ? it.exp_limbs : c->n.S;
-      g.exp_stride = it.exp ? it.exp_limbs : 0;
+      g.nbase = it.nterm;
+      for (int k = 0; k < kMaxPowBases; ++k) {
+        const PowTerm& t = it.term[k < it.nterm ? k : 0];
+        g.base[k] = t.base;
+        g.base_limbs[k] = t.base_limbs;
+        g.exp[k] = t.exp ? t.exp : c->n.mod.as<uint32_t>();
+        g.exp_limbs[k] = t.exp ? t.exp_limbs : c->n.S;
+        g.exp_stride[k] = t.exp ? t.exp_limbs : 0;
+      }
       g.exp_bits = bits(it);
       g.plain = it.plain;
       g.plain_limbs = it.plain_limbs;
@@ -210,9 +245,41 @@ struct PowBatch {
     ProfScope ps(c, KID_MODEXP_VAR, pj.total);
     s.ck(launch_pow_jobs(c, pj));
   }
+
+ private:
+  // the same values by the single-purpose kernels: each power by launch_enc / launch_pow_nn, then the products
+  void run_separately(const Item& it) {
+    zkp_ctx* c = s.c;
+    uint32_t* acc = nullptr;
+    for (int k = 0; k < it.nterm; ++k) {
+      const PowTerm& t = it.term[k];
+      const bool last = k == it.nterm - 1;
+      uint32_t* dst = (it.nterm == 1) ? it.out : s.rows(s.nnl, it.jobs);
+      if (s.bad) return;
+      {
+        ProfScope ps(c, t.exp ? KID_MODEXP_VAR : KID_MODEXP_SHARED, it.jobs);
+        // the plaintext factor rides on an encryption term when there is one, else on a separate Enc(m, 1)-free product below
+        if (t.exp) s.ck(launch_pow_nn(c, t.base, t.base_limbs, t.exp, t.exp_limbs, 32 * t.exp_limbs, 1, dst, it.jobs));
+        else s.ck(launch_enc(c, t.base, t.base_limbs, it.plain, it.plain_limbs, dst, it.jobs));
+      }
+      if (acc) {
+        uint32_t* prod = last ? it.out : s.rows(s.nnl, it.jobs);
+        if (s.bad) return;
+        ProfScope ps(c, KID_MODMUL, it.jobs);
+        s.ck(launch_modmul_shared(c->nn.view(), 0, acc, s.nnl, dst, s.nnl, 1, prod, s.nnl, it.jobs, s.st));
+        acc = prod;
+      } else {
+        acc = dst;
+      }
+    }
+    // a plaintext without an encryption term would need a separate (1 + m n) factor: no caller builds one
+    bool has_enc = false;
+    for (int k = 0; k < it.nterm; ++k) has_enc = has_enc || !it.term[k].exp;
+    if (it.plain && !has_enc) s.bad = true;
+  }
 };
 
-inline int sigma_begin(zkp_ctx* c, int batch, int z_limbs, size_t rows_nnl, size_t rows_other_bytes, Sig& s) {
+inline int sigma_begin(zkp_ctx* c, int batch, int z_limbs, size_t rows_nnl, size_t rows_other_bytes, Sig& s, int pow_bases = 1) {
   if (!c->paillier) return fail(c, ZKP_E_STATE, "zkp_set_key not called");
   if (batch <= 0) return fail(c, ZKP_E_ARG, "batch must be positive");
   if (z_limbs && (z_limbs % 4 || z_limbs < c->n.limbs + 12 || z_limbs > c->nn.S))
@@ -224,7 +291,7 @@ inline int sigma_begin(zkp_ctx* c, int batch, int z_limbs, size_t rows_nnl, size
   size_t bytes = (size_t)batch * ((rows_nnl + 12) * s.nnl * 4 + rows_other_bytes + 256) + 64 * 256;
   e = s.ar.reserve(bytes);
   if (e != cudaSuccess) return fail_cuda(c, e, "arena");
-  e = ensure_table(c, c->nn.S, kTableVar, 4 * batch);  // a K2h launch holds at most 3 modexps per proof (PowBatch)
+  e = ensure_table(c, c->nn.S, kTableVar, 4 * batch, pow_bases);  // a K2h launch holds at most 3 modexps per proof (PowBatch)
   if (e != cudaSuccess) return fail_cuda(c, e, "table");
   return ZKP_OK;
 }

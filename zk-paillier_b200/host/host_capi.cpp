@@ -385,4 +385,54 @@ char* zkh_call(const char* op, const char* request_json) {
 
 void zkh_free(char* p) { free(p); }
 
+// Synthetic NiCorrectKeyProof workload with a DISTINCT modulus per proof (BASELINE configs[2]: 4096 proofs at 3072 bits),
+// built on the device: `count` key pairs by Paillier::keypairs_batch (Miller-Rabin waves on K2), one honest proof per key
+// by NiCorrectKeyProof::proof_batch; every `bad_every`-th proof gets sigma_0 + 1 (rejected).  Binary rows out, no JSON:
+//   n_out [count][bits/32], sigma_out [count][11][bits/32], pq_out (optional) [count][2][bits/64].
+// The byte stream behind every sample is SHA-256(seed || counter): the same seed gives the same keys.  Returns 0, or -1
+// with the message in err (at most err_len bytes).
+int zkh_correct_key_workload(int device, int bits, int count, const uint8_t* seed, int seed_len, const uint8_t* salt, int salt_len,
+                             int bad_every, uint32_t* n_out, uint32_t* sigma_out, uint32_t* pq_out, char* err, int err_len) {
+  try {
+    Engine& eng = engine(device);
+    std::vector<uint8_t> key(seed, seed + seed_len);
+    auto ctr = std::make_shared<uint64_t>(0);
+    auto pool = std::make_shared<std::vector<uint8_t>>();
+    ByteSource rng = [key, ctr, pool](uint8_t* p, size_t n) {
+      while (pool->size() < n) {
+        std::vector<uint8_t> msg(key);
+        for (int i = 0; i < 8; ++i) msg.push_back((uint8_t)(*ctr >> (8 * i)));
+        ++*ctr;
+        const std::vector<uint8_t> h = zkhost::sha256(msg.data(), msg.size());
+        pool->insert(pool->end(), h.begin(), h.end());
+      }
+      memcpy(p, pool->data(), n);
+      pool->erase(pool->begin(), pool->begin() + n);
+    };
+    const std::vector<DecryptionKey> dks = Paillier::keypairs_batch(eng, (size_t)bits, (size_t)count, rng);
+    const std::vector<NiCorrectKeyProof> proofs = NiCorrectKeyProof::proof_batch(eng, dks, salt, (size_t)salt_len);
+    const size_t nl = (size_t)bits / 32, hl = (size_t)bits / 64;
+    for (size_t b = 0; b < (size_t)count; ++b) {
+      const BigInt n = dks[b].p * dks[b].q;
+      n.to_limbs(n_out + b * nl, nl);
+      for (size_t i = 0; i < M2; ++i) {
+        BigInt sgm = proofs[b].sigma_vec[i];
+        if (i == 0 && bad_every > 0 && (int)(b % (size_t)bad_every) == bad_every - 1) sgm = (sgm + BigInt(1)) % n;
+        sgm.to_limbs(sigma_out + (b * M2 + i) * nl, nl);
+      }
+      if (pq_out) {
+        dks[b].p.to_limbs(pq_out + (2 * b) * hl, hl);
+        dks[b].q.to_limbs(pq_out + (2 * b + 1) * hl, hl);
+      }
+    }
+    return 0;
+  } catch (const std::exception& e) {
+    if (err && err_len > 0) {
+      strncpy(err, e.what(), (size_t)err_len - 1);
+      err[err_len - 1] = 0;
+    }
+    return -1;
+  }
+}
+
 }  // extern "C"

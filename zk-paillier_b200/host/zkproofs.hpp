@@ -16,7 +16,9 @@
 #include <exception>
 #include <memory>
 #include <stdexcept>
+#include <atomic>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/zkp_b200.h"
@@ -61,6 +63,24 @@ struct EncryptionKey {  // kzen-paillier EncryptionKey {n, nn}
 struct DecryptionKey {
   BigInt p, q;
 };
+
+// fn(i) for i in [0, count) on up to `threads` host threads (0 = hardware concurrency): per-item host BigInt work around a device call
+template <class F>
+inline void parallel_for(size_t count, unsigned threads, F fn) {
+  if (threads == 0) threads = std::max(1u, std::thread::hardware_concurrency());
+  threads = (unsigned)std::min<size_t>(threads, std::max<size_t>(count, 1));
+  if (threads <= 1) {
+    for (size_t i = 0; i < count; ++i) fn(i);
+    return;
+  }
+  std::vector<std::thread> pool;
+  std::atomic<size_t> next(0);
+  for (unsigned t = 0; t < threads; ++t)
+    pool.emplace_back([&] {
+      for (size_t i = next.fetch_add(1); i < count; i = next.fetch_add(1)) fn(i);
+    });
+  for (auto& th : pool) th.join();
+}
 
 inline size_t round4(size_t limbs) { return (limbs + 3) / 4 * 4; }
 inline size_t limbs_for_bits(size_t bits) { return round4((bits + 31) / 32); }
@@ -499,6 +519,60 @@ class NiCorrectKeyProof {  // correct_key_ni.rs:34-39
       pr.sigma_vec.push_back(sp + dk.p * h);
     }
     return pr;
+  }
+
+  // The same for many keys in three device calls (rho of every key; the half-width roots mod every p; mod every q).
+  // The per-key host work (three modular inversions and the CRT recombinations) is spread over host threads.
+  static std::vector<NiCorrectKeyProof> proof_batch(Engine& eng, const std::vector<DecryptionKey>& dks, const uint8_t* salt = nullptr,
+                                                    size_t salt_len = 0, unsigned host_threads = 0) {
+    if (!salt) { salt = SALT_STRING; salt_len = sizeof(SALT_STRING); }
+    const size_t B = dks.size();
+    if (B == 0) return {};
+    std::vector<BigInt> n(B);
+    size_t nbits = 0, hbits = 0;
+    for (size_t b = 0; b < B; ++b) {
+      n[b] = dks[b].p * dks[b].q;
+      nbits = std::max(nbits, n[b].bit_length());
+      hbits = std::max({hbits, dks[b].p.bit_length(), dks[b].q.bit_length()});
+    }
+    const size_t nl = limbs_for_bits(nbits), hl = limbs_for_bits(hbits);
+    std::vector<uint32_t> rho(B * M2 * nl);
+    eng.check(zkp_correct_key_ni_rho(eng.handle(), (int)B, (int)nl, pack(n, nl).data(), salt, (int)salt_len, rho.data()));
+    std::vector<BigInt> dp(B), dq(B), pinv(B);
+    std::vector<uint32_t> base_p(B * M2 * hl), base_q(B * M2 * hl);
+    std::vector<int> bad(B, 0);
+    auto per_key = [&](size_t b) {
+      const BigInt one(1), pm1 = dks[b].p - one, qm1 = dks[b].q - one;
+      if (!BigInt::mod_inv(n[b] % pm1, pm1, dp[b]) || !BigInt::mod_inv(n[b] % qm1, qm1, dq[b]) || !BigInt::mod_inv(dks[b].p % dks[b].q, dks[b].q, pinv[b])) {
+        bad[b] = 1;
+        return;
+      }
+      for (size_t i = 0; i < M2; ++i) {
+        const BigInt r = BigInt::from_limbs(&rho[(b * M2 + i) * nl], nl);
+        (r % dks[b].p).to_limbs(&base_p[(b * M2 + i) * hl], hl);
+        (r % dks[b].q).to_limbs(&base_q[(b * M2 + i) * hl], hl);
+      }
+    };
+    parallel_for(B, host_threads, per_key);
+    for (size_t b = 0; b < B; ++b)
+      if (bad[b]) throw ReferencePanic("extract_nroot: n is not invertible mod phi(n)");
+    std::vector<BigInt> ps, qs;
+    for (auto& dk : dks) { ps.push_back(dk.p); qs.push_back(dk.q); }
+    std::vector<uint32_t> sp(B * M2 * hl), sq(B * M2 * hl);
+    eng.check(zkp_modexp_var(eng.handle(), base_p.data(), pack(dp, hl).data(), (int)hl, (int)(32 * hl), (int)M2, pack(ps, hl).data(), (int)hl, (int)M2,
+                             (int)(B * M2), sp.data()));
+    eng.check(zkp_modexp_var(eng.handle(), base_q.data(), pack(dq, hl).data(), (int)hl, (int)(32 * hl), (int)M2, pack(qs, hl).data(), (int)hl, (int)M2,
+                             (int)(B * M2), sq.data()));
+    std::vector<NiCorrectKeyProof> out(B);
+    parallel_for(B, host_threads, [&](size_t b) {
+      const BigInt &p = dks[b].p, &q = dks[b].q;
+      for (size_t i = 0; i < M2; ++i) {
+        const BigInt a = BigInt::from_limbs(&sp[(b * M2 + i) * hl], hl), c = BigInt::from_limbs(&sq[(b * M2 + i) * hl], hl);
+        const BigInt diff = (c + q - (a % q)) % q;
+        out[b].sigma_vec.push_back(a + p * ((diff * pinv[b]) % q));
+      }
+    });
+    return out;
   }
 
   // correct_key_ni.rs:73-100 for many (proof, key) pairs with one salt; every modulus padded to a common width.
@@ -1126,6 +1200,119 @@ struct Paillier {
         if (primes.size() < 2 && (primes.empty() || primes[0] != c)) primes.push_back(c);
     }
     return DecryptionKey{primes[0], primes[1]};
+  }
+  // `count` key pairs of `bits`-bit moduli at once (synthetic workloads with a distinct modulus per proof: BASELINE configs[2]).
+  // One search window per prime: a random start (top two bits set, = 3 mod 4, so that c - 1 = 2 d with d odd and one
+  // Miller-Rabin exponentiation a^d decides a round), the window c = start + 4 k sieved by the primes below 4000 on the host,
+  // and the surviving candidates of ALL unresolved windows tested together, base 2 first, as one zkp_modexp_var launch per wave
+  // (a distinct modulus per job; ~70 candidates per prime at 1536 bits).  The first candidate of a window that passes is then
+  // confirmed with `rounds - 1` random bases, again one launch per round over every window.
+  static std::vector<DecryptionKey> keypairs_batch(Engine& eng, size_t bits, size_t count, const ByteSource& rng = os_rng(), int rounds = 8,
+                                                   size_t wave_jobs = 131072) {
+    if (bits < 256 || bits % 64) throw std::invalid_argument("keypairs_batch: modulus size must be a multiple of 64, at least 256");
+    const size_t hb = bits / 2, nl = limbs_for_bits(hb), P = 2 * count;
+    constexpr size_t W = 4096;  // candidates per window
+    static const std::vector<uint32_t> small = [] {
+      std::vector<uint32_t> v;
+      for (uint32_t x = 3; x < 4000; x += 2) {
+        bool pr = true;
+        for (uint32_t d = 3; d * d <= x; d += 2) if (x % d == 0) { pr = false; break; }
+        if (pr) v.push_back(x);
+      }
+      return v;
+    }();
+    struct Window {
+      BigInt start;
+      std::vector<uint16_t> alive;  // surviving k, ascending
+      size_t next = 0;              // first untested survivor
+      int confirmed = 0;            // Miller-Rabin rounds the current candidate has passed
+      BigInt cand;
+    };
+    const BigInt one(1), two(2), four(4);
+    auto fresh = [&](Window& w) {
+      BigInt c = BigInt::sample(rng, hb);
+      c = c | one | two | one.shl(hb - 1) | one.shl(hb - 2);  // = 3 mod 4
+      w.start = c;
+      std::vector<uint8_t> dead(W, 0);
+      for (uint32_t sp : small) {
+        const uint32_t r = c.mod_small(sp);
+        // smallest k with r + 4 k = 0 mod sp
+        uint32_t inv4 = 1;
+        while ((4ull * inv4) % sp != 1) ++inv4;
+        for (size_t k = (size_t)(((uint64_t)(sp - r) % sp) * inv4 % sp); k < W; k += sp) dead[k] = 1;
+      }
+      w.alive.clear();
+      for (size_t k = 0; k < W; ++k) if (!dead[k]) w.alive.push_back((uint16_t)k);
+      w.next = 0;
+      w.confirmed = 0;
+    };
+    std::vector<Window> win(P);
+    for (auto& w : win) fresh(w);
+    auto candidate = [&](const Window& w, size_t j) { return w.start + BigInt((uint64_t)4 * w.alive[j]); };
+    for (;;) {
+      // ---- wave: base-2 tests for the windows without a candidate
+      std::vector<size_t> open;
+      for (size_t i = 0; i < P; ++i) if (win[i].confirmed == 0) open.push_back(i);
+      if (!open.empty()) {
+        const size_t per = std::max<size_t>(1, std::min<size_t>(64, wave_jobs / open.size()));
+        std::vector<uint32_t> bases, exps, mods;
+        std::vector<std::pair<size_t, size_t>> job;  // (window, survivor index)
+        for (size_t i : open) {
+          Window& w = win[i];
+          if (w.next >= w.alive.size()) fresh(w);
+          for (size_t j = w.next; j < std::min(w.next + per, w.alive.size()); ++j) job.emplace_back(i, j);
+        }
+        bases.assign(job.size() * nl, 0u);
+        exps.resize(job.size() * nl);
+        mods.resize(job.size() * nl);
+        parallel_for(job.size(), 0, [&](size_t t) {
+          const BigInt c = candidate(win[job[t].first], job[t].second);
+          c.to_limbs(&mods[t * nl], nl);
+          (c - one).shr(1).to_limbs(&exps[t * nl], nl);
+          bases[t * nl] = 2u;
+        });
+        std::vector<uint32_t> out(job.size() * nl);
+        eng.check(zkp_modexp_var(eng.handle(), bases.data(), exps.data(), (int)nl, (int)hb, 1, mods.data(), (int)nl, 1, (int)job.size(), out.data()));
+        for (size_t t = 0; t < job.size(); ++t) {
+          Window& w = win[job[t].first];
+          if (w.confirmed) continue;  // an earlier candidate of this window already passed
+          const BigInt x = BigInt::from_limbs(&out[t * nl], nl), c = candidate(w, job[t].second);
+          w.next = job[t].second + 1;
+          if (x == one || x == c - one) {
+            w.confirmed = 1;
+            w.cand = c;
+          }
+        }
+      }
+      // ---- confirmation rounds with random bases for every window that holds a candidate short of `rounds`
+      std::vector<size_t> todo;
+      for (size_t i = 0; i < P; ++i) if (win[i].confirmed > 0 && win[i].confirmed < rounds) todo.push_back(i);
+      if (todo.empty() && open.empty()) break;
+      if (!todo.empty()) {
+        std::vector<BigInt> bases, exps, mods;
+        for (size_t i : todo) {
+          const BigInt& c = win[i].cand;
+          bases.push_back(two + BigInt::sample_below(rng, c - BigInt(3)));
+          exps.push_back((c - one).shr(1));
+          mods.push_back(c);
+        }
+        std::vector<uint32_t> out(todo.size() * nl);
+        eng.check(zkp_modexp_var(eng.handle(), pack(bases, nl).data(), pack(exps, nl).data(), (int)nl, (int)hb, 1, pack(mods, nl).data(), (int)nl, 1,
+                                 (int)todo.size(), out.data()));
+        for (size_t t = 0; t < todo.size(); ++t) {
+          Window& w = win[todo[t]];
+          const BigInt x = BigInt::from_limbs(&out[t * nl], nl);
+          if (x == one || x == w.cand - one) ++w.confirmed;
+          else w.confirmed = 0;  // a base-2 pseudoprime: the window goes on from the next survivor
+        }
+      }
+    }
+    std::vector<DecryptionKey> keys(count);
+    for (size_t k = 0; k < count; ++k) {
+      keys[k] = DecryptionKey{win[2 * k].cand, win[2 * k + 1].cand};
+      if (keys[k].p == keys[k].q) throw std::runtime_error("keypairs_batch: equal primes (broken randomness source)");
+    }
+    return keys;
   }
   // Paillier::open (kzen-paillier RECALLED): (m, r) with c = Enc(m, r); r = extract_nroot(dk, c (1 + m n)^-1 mod n)
   // and (1 + m n)^-1 = 1 (mod n), so r is the n-th root of c mod n.  Used at correct_opening.rs:52-53.

@@ -19,7 +19,7 @@ TUNE_ENC_KERNEL, TUNE_JOBS_SHAPE = 0, 1
 ZKP_OK = 0
 RP_OPEN, RP_MASK1, RP_MASK2 = 0, 1, 2
 CK_M2 = 11
-KID_MODEXP_SHARED, KID_MODEXP_VAR, KID_MODMUL, KID_SHA, KID_OTHER = range(5)
+KID_MODEXP_SHARED, KID_MODEXP_VAR, KID_MODMUL, KID_SHA, KID_OTHER, KID_CALL = range(6)
 
 _u32p = C.POINTER(C.c_uint32)
 _u8p = C.POINTER(C.c_uint8)

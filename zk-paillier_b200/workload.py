@@ -90,3 +90,32 @@ def correct_key_batch(keys, batch: int, salt: bytes, make_sigma, n_limbs: int, b
         ns.append(n)
         sig.append(s)
     return {"n_int": ns, "sigma_int": sig, "n": ints_to_limbs(ns, n_limbs), "sigma": ints_to_limbs(sig, n_limbs)}
+
+
+def correct_key_distinct(bits: int, batch: int, salt: bytes, seed: int = DEFAULT_SEED, bad_every: int = 0, device: int = 0, with_primes: bool = False):
+    """Inputs of NiCorrectKeyProof::verify for `batch` proofs with a DISTINCT `bits`-bit modulus each (BASELINE.json configs[2]).
+
+    Built on the GPU by the C++ host mirror (libzkp_host.so: Paillier::keypairs_batch - Miller-Rabin waves on the device - and
+    NiCorrectKeyProof::proof_batch), reproducibly from `seed`; every `bad_every`-th proof has sigma_0 + 1.  Statement
+    generation is not on the measured path.  Raises without a GPU, like everything else here."""
+    import ctypes as C
+    import os
+
+    lib = C.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "libzkp_host.so"))
+    fn = lib.zkh_correct_key_workload
+    fn.restype = C.c_int
+    nl = bits // 32
+    n = np.zeros((batch, nl), np.uint32)
+    sigma = np.zeros((batch, 11, nl), np.uint32)
+    pq = np.zeros((batch, 2, bits // 64), np.uint32) if with_primes else None
+    err = C.create_string_buffer(512)
+    sd = int(seed).to_bytes(8, "little") + b"correct_key_distinct"
+    u32p = C.POINTER(C.c_uint32)
+    rc = fn(C.c_int(device), C.c_int(bits), C.c_int(batch), sd, C.c_int(len(sd)), salt, C.c_int(len(salt)), C.c_int(bad_every),
+            n.ctypes.data_as(u32p), sigma.ctypes.data_as(u32p), pq.ctypes.data_as(u32p) if with_primes else None, err, C.c_int(512))
+    if rc != 0:
+        raise RuntimeError("zkh_correct_key_workload: " + err.value.decode(errors="replace"))
+    out = {"n": n, "sigma": sigma}
+    if with_primes:
+        out["pq"] = pq
+    return out
