@@ -47,6 +47,28 @@ def test_sha256_transcript_matches_hashlib(ctx):
     # FIPS 180-4 "abc"
     dig = ctx.sha256_transcript(ints_to_limbs([[int.from_bytes(b"abc", "big")]], 4))
     assert bytes(dig[0]).hex() == "ba7816bf8f01cfea414140de5dae2223b00361a396177a9cb410ff61f20015ad"
+    # message lengths around the padding boundaries (55 / 56 / 63 / 64 / 119 / 120 bytes) and the empty-ish cases
+    for nbytes in (1, 54, 55, 56, 57, 63, 64, 65, 119, 120, 127, 128, 129):
+        v = int.from_bytes(b"\x01" + bytes(range(1, nbytes)), "big")
+        dig = ctx.sha256_transcript(ints_to_limbs([[v]], 36))
+        assert bytes(dig[0]) == hashlib.sha256(po.transcript_bytes([v])).digest(), nbytes
+    # many tiny items: words that span up to four items
+    tiny = [[(b * 7 + k) % 3 * (1 << (8 * ((b + k) % 3))) for k in range(300)] for b in range(5)]
+    dig = ctx.sha256_transcript(ints_to_limbs(tiny, 4))
+    for items, d in zip(tiny, dig):
+        assert bytes(d) == hashlib.sha256(po.transcript_bytes(items)).digest()
+
+
+def test_sha256_transcript_large_batch_takes_the_thread_per_transcript_kernel(ctx):
+    """Below 148 * 64 transcripts K4w hashes one transcript per warp; from there on K4 hashes one per thread.  Same digests."""
+    rng = random.Random(4)
+    B = 148 * 64 + 37
+    rows = [[rng.getrandbits(rng.randrange(1, 256)) if (b + k) % 5 else 0 for k in range(3)] for b in range(B)]
+    dig = ctx.sha256_transcript(ints_to_limbs(rows, 8))
+    for b in (0, 1, 31, 32, 4097, B - 1):
+        assert bytes(dig[b]) == hashlib.sha256(po.transcript_bytes(rows[b])).digest()
+    small = ctx.sha256_transcript(ints_to_limbs(rows[:100], 8))         # the same rows through K4w
+    assert np.array_equal(small, dig[:100])
 
 
 def _prove_both(ctx, n, nl, work):
