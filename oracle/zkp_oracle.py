@@ -17,6 +17,9 @@ vectors (28 randomized prove->verify round trips).  Therefo
   * UNPINNED ("parity unpinned"): the four rules recalled from the dependency crates' public source, each
                isolated in ONE function below so a single edit fixes parity if they are ever checked against
                a real cargo build: bigint_to_bytes, sample_bits, serde_bigint_native, serde_encryption_key.
+               The check exists and waits for its input: rust/gen_vectors links the UNMODIFIED crate and writes
+               tests/golden/reference_vectors.json; tests/test_reference_vectors.py compares this oracle (and the
+               CUDA path) with that file and reports xfail "parity unpinned" while it is absent (no cargo here).
 
 Citations are file:line into /root/reference/src.
 """
