@@ -252,8 +252,10 @@ int zkp_correct_message_verify(zkp_ctx* ctx, int batch, int M, int m_limbs, int 
 /* ---- A/B hooks (per context; results are bit-identical whatever the setting) --------------------------------
  * The library reads no environment variables.  (The measured-and-rejected kernel variants of DESIGN.md section 3.7
  * and their ZKP_B200_* environment knobs exist only in the lab build, `make lab` -> libzkp_b200_lab.so.)
- *   ZKP_TUNE_ENC_KERNEL  0 = K1m, the two-digit Montgomery form, whenever the key qualifies (default);
- *                        1 = K1, Montgomery modulo n^2 (the parity tests run both and compare)
+ *   ZKP_TUNE_ENC_KERNEL  0 = by launch size (default): K1m, the two-digit Montgomery form, whenever the key qualifies, and
+ *                            K2h's one-job-per-warp layout for launches of a few hundred encryptions (one proof's latency);
+ *                        1 = K1, Montgomery modulo n^2;   2 = K1m whatever the launch size
+ *                        (the parity tests run all three and compare)
  *   ZKP_TUNE_JOBS_SHAPE  lane layout of K2h, the one-launch heterogeneous modexp list of the sigma protocols:
  *                        0 = by job count (default), 1 = wide lanes (as K1m / K2m), 2 = narrow lanes (one job over
  *                        twice the lanes: fills the GPU at a few hundred proofs of 4096-bit n) */

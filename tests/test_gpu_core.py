@@ -162,16 +162,17 @@ def test_two_digit_montgomery_kernel(n_bits, nl):
     m[0], m[1], m[5] = 0, n - 1, min(n + 1, cap - 1)
     want = want_enc(n, nl, m, nl, r, nl)
     outs = {}
-    for mode in ("k1m", "k1"):
+    for mode in ("k1m", "k1", "auto"):   # auto: a 150-job launch takes K2h's one-job-per-warp layout
         with zk.native.Context(0) as c:
-            c.tune(zk.native.TUNE_ENC_KERNEL, 1 if mode == "k1" else 0)
+            c.tune(zk.native.TUNE_ENC_KERNEL, {"k1m": 2, "k1": 1, "auto": 0}[mode])
             c.set_key(to_limbs(n, nl))
             outs[mode] = c.paillier_enc(ints_to_limbs(m, nl), ints_to_limbs(r, nl))
             used = c.enc_kernel_launches()
-            assert (used["k1m"] > 0) == (mode == "k1m") and (used["k1"] > 0) == (mode == "k1")
+            assert (used["k1m"] > 0) == (mode != "k1") and (used["k1"] > 0) == (mode == "k1")
             if mode == "k1m":
                 narrow = [v & ((1 << 256) - 1) for v in m[:9]]
                 o = c.paillier_enc(ints_to_limbs(narrow, 8), ints_to_limbs(r[:9], nl))
                 assert np.array_equal(o, want_enc(n, nl, narrow, 8, r[:9], nl))
     assert np.array_equal(outs["k1m"], want)
     assert np.array_equal(outs["k1m"], outs["k1"])
+    assert np.array_equal(outs["auto"], want)

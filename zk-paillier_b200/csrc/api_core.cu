@@ -139,16 +139,47 @@ cudaError_t launch_pow_nn(zkp_ctx* c, const uint32_t* base, int base_limbs, cons
 
 bool jobs_supported(const zkp_ctx* c) { return c->enc2m_key && c->enc2m_enabled; }
 
-cudaError_t launch_pow_jobs(zkp_ctx* c, const PowJobs& jobs) {
+cudaError_t launch_pow_jobs(zkp_ctx* c, const PowJobs& jobs, const unsigned* jobs_dev) {
   if (!jobs_supported(c)) return cudaErrorNotSupported;
   ++c->enc2m_launches;
   const size_t region = c->table_region_limbs ? c->table_off / c->table_region_limbs : 0;  // 0 = main stream, k + 1 = auxiliary stream k
   return launch_modexp2m_jobs(enc2m_view(c), jobs, c->nn.limbs, c->table.as<uint32_t>() + c->table_off, c->table_region_limbs,
-                              reinterpret_cast<unsigned*>(c->cursor.as<uint8_t>() + 256 * region), c->num_sms, c->stream, c->jobs_shape);
+                              reinterpret_cast<unsigned*>(c->cursor.as<uint8_t>() + 256 * region), c->num_sms, c->stream, c->jobs_shape, jobs_dev);
+}
+
+// A launch of so few encryptions that K1m's layout would leave sub-partitions with less than two warps (one proof: 256
+// encryptions are 64 warps of Mp<8,8> on 592 sub-partitions) is latency-bound: K2h spreads every job over more lanes.
+static bool enc_is_small(const zkp_ctx* c, int jobs) {
+  const int T = c->n.S <= 32 ? 4 : (c->n.S <= 96 ? 8 : 16);  // lanes per job of K1m (modexp2m.cu: pick_shape)
+  return (long long)jobs * T / 32 < 2ll * 4 * c->num_sms;
 }
 
 cudaError_t launch_enc(zkp_ctx* c, const uint32_t* bases, int base_limbs, const uint32_t* plain, int plain_limbs, uint32_t* out,
                        int jobs, const unsigned* jobs_dev) {
+  if (c->enc2m_key && c->enc2m_enabled && base_limbs <= 2 * c->n.S && (!plain || plain_limbs <= 2 * c->n.S) && c->enc_small_k2h && enc_is_small(c, jobs) &&
+      c->cursor.p && jobs2m_scratch_limbs(c->n.S, c->num_sms, jobs) <= c->table_region_limbs) {
+    PowJobs pj;
+    PowSeg& g = pj.seg[0];
+    int n_bits = 32 * c->n.S;
+    while (n_bits > 1 && !((c->n.h_mod[(n_bits - 1) >> 5] >> ((n_bits - 1) & 31)) & 1u)) --n_bits;
+    for (int k = 0; k < kMaxPowBases; ++k) {
+      g.base[k] = bases;
+      g.base_limbs[k] = base_limbs;
+      g.exp[k] = c->n.mod.as<uint32_t>();
+      g.exp_limbs[k] = c->n.S;
+      g.exp_stride[k] = 0;
+    }
+    g.nbase = 1;
+    g.exp_bits = n_bits;
+    g.plain = plain;
+    g.plain_limbs = plain ? plain_limbs : 0;
+    g.out = out;
+    g.jobs = jobs;
+    g.first = 0;
+    pj.nseg = 1;
+    pj.total = jobs;
+    return launch_pow_jobs(c, pj, jobs_dev);
+  }
   if (c->enc2m_key && c->enc2m_enabled && base_limbs <= 2 * c->n.S && (!plain || plain_limbs <= 2 * c->n.S)) {
     const Enc2mKey k = enc2m_view(c);
     ++c->enc2m_launches;
@@ -527,8 +558,9 @@ int zkp_tune(zkp_ctx* c, int knob, int value) {
   if (!c) return ZKP_E_ARG;
   switch (knob) {
     case ZKP_TUNE_ENC_KERNEL:
-      if (value != 0 && value != 1) return fail(c, ZKP_E_ARG, "ZKP_TUNE_ENC_KERNEL: 0 (K1m when the key qualifies) or 1 (K1)");
-      c->enc2m_enabled = value == 0;
+      if (value < 0 || value > 2) return fail(c, ZKP_E_ARG, "ZKP_TUNE_ENC_KERNEL: 0 (by launch size: K1m, K2h for a few hundred jobs), 1 (K1) or 2 (K1m)");
+      c->enc2m_enabled = value != 1;
+      c->enc_small_k2h = value == 0;
       return ZKP_OK;
     case ZKP_TUNE_JOBS_SHAPE:
       if (value < 0 || value > 2) return fail(c, ZKP_E_ARG, "ZKP_TUNE_JOBS_SHAPE: 0 (by job count), 1 (wide lanes) or 2 (narrow lanes)");

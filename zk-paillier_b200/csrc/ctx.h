@@ -123,6 +123,7 @@ struct zkp_ctx {
   // K1m (two-digit Montgomery, modexp2m.cu): the default Paillier encryption kernel when the key qualifies.
   // ZKP_B200_ENC=k1 forces K1 (Montgomery modulo n^2).
   bool enc2m_key = false, enc2m_enabled = true;
+  bool enc_small_k2h = true;  // launches of a few hundred encryptions go to K2h's latency layout (zkp_tune ZKP_TUNE_ENC_KERNEL)
   zkp::DevBuf enc2m_consts, enc2m_ops;
   int enc2m_nops = 0;
   long long enc2m_launches = 0, k1_launches = 0;
@@ -179,7 +180,7 @@ cudaError_t launch_pow_nn(zkp_ctx* c, const uint32_t* base, int base_limbs, cons
 // K2h: every modexp / Enc of a batch of sigma-protocol proofs in one launch (modexp2m.cu: modexp2m_jobs_kernel).  Needs a key
 // that K1m takes (c->enc2m_key); callers fall back to launch_enc / launch_pow_nn otherwise.
 bool jobs_supported(const zkp_ctx* c);
-cudaError_t launch_pow_jobs(zkp_ctx* c, const PowJobs& jobs);
+cudaError_t launch_pow_jobs(zkp_ctx* c, const PowJobs& jobs, const unsigned* jobs_dev = nullptr);
 
 // Concurrent modexp launches inside one call (api_core.cu)
 cudaError_t fork_stream(zkp_ctx* c, int k);

@@ -106,8 +106,10 @@ struct PowJobs {
 // Scratch: jobs2m_scratch_limbs(S, num_sms, total jobs) limbs at `table` (window tables; for a launch that under-fills
 // the GPU also the per-job accumulators and phase counters of the phased schedule, see modexp2m.cu).
 size_t jobs2m_scratch_limbs(int S, int num_sms, int total_jobs, int max_bases = 1);
+// shape 3 = one job per warp (the latency layout, chosen when a launch has at most one long job per SM sub-partition).
+// jobs_dev (optional, single-segment launches): device pointer to the actual job count (<= jobs.total).
 cudaError_t launch_modexp2m_jobs(const Enc2mKey& key, const PowJobs& jobs, int out_limbs, uint32_t* table, size_t table_limbs,
-                                 unsigned* cursor, int num_sms, cudaStream_t st, int shape = 0);
+                                 unsigned* cursor, int num_sms, cudaStream_t st, int shape = 0, const unsigned* jobs_dev = nullptr);
 
 // Montgomery setup for per-instance moduli: r2[i] = R^2 mod mods[i] ([count][S]), n0inv[i].
 // mods: [count][mod_limbs].

@@ -390,6 +390,7 @@ struct Jobs2mParams {
   uint32_t* acc;      // phased: the accumulator pair of every job between phases, [total jobs][2 S]
   unsigned* done;     // phased: phases completed per work unit, [units] (zeroed by the launcher)
   unsigned* cursor;   // next phase-unit (zeroed by the launcher on the same stream)
+  const unsigned* jobs_dev;  // optional: the actual job count on the device (<= jobs.total; single-segment, unphased launches)
   int out_limbs;
   int tab_bases;      // window tables per job (the largest nbase of the launch)
   int win_per_phase;  // windows of the exponent scan per phase; >= the longest scan: one phase per unit, nothing migrates
@@ -529,7 +530,7 @@ __global__ void __launch_bounds__(kCtaThreads, MINB) modexp2m_jobs_kernel(const 
   for (int i = threadIdx.x; i < S; i += kCtaThreads) s_klo[i] = p.key.consts[i];
   __syncthreads();
   const bool phased = p.nphase > 1;
-  const int total = p.jobs.total;
+  const int total = p.jobs_dev ? min((int)*p.jobs_dev, p.jobs.total) : p.jobs.total;
   const unsigned nwork = p.pre[p.nphase];
   for (;;) {
     unsigned work = 0;
@@ -539,6 +540,7 @@ __global__ void __launch_bounds__(kCtaThreads, MINB) modexp2m_jobs_kernel(const 
     int ph = 0;
     while (work >= p.pre[ph + 1]) ++ph;
     const unsigned unit = work - p.pre[ph];
+    if ((int)unit * GW >= total) continue;  // (a device-side job count below the host's upper bound)
     const int job = (int)unit * GW + (lane / T);
     const bool valid = job < total;
     const int src = valid ? job : total - 1;
@@ -1008,7 +1010,8 @@ static cudaError_t launch_jobs_one(Jobs2mParams& p, size_t table_limbs, int num_
   int nphase = 1;
   const size_t phased_limbs = (size_t)nunits * GW * ((size_t)p.tab_bases * kTableVar + 1) * 2 * S + (size_t)nunits + 64;
   if ((size_t)num_sms * MINB * (kCtaThreads / T) * p.tab_bases * kTableVar * 2 * S > table_limbs) return cudaErrorInvalidValue;
-  if (long_units < kPhasedUnitsPerSmsp * smsp && phased_limbs <= table_limbs) {
+  // phases balance a launch of a few units per sub-partition; with at most one unit each there is nothing to balance
+  if (long_units > smsp && long_units < kPhasedUnitsPerSmsp * smsp && phased_limbs <= table_limbs && !p.jobs_dev) {
     nphase = (kPhaseTargetPerSmsp * smsp + long_units - 1) / long_units;
     if (nphase > kMaxPhases) nphase = kMaxPhases;
     if (nphase > max_win / kMinWinPerPhase) nphase = max_win / kMinWinPerPhase;
@@ -1047,7 +1050,8 @@ static cudaError_t launch_jobs_one(Jobs2mParams& p, size_t table_limbs, int num_
 }
 
 cudaError_t launch_modexp2m_jobs(const Enc2mKey& key, const PowJobs& jobs, int out_limbs, uint32_t* table, size_t table_limbs,
-                                 unsigned* cursor, int num_sms, cudaStream_t st, int shape) {
+                                 unsigned* cursor, int num_sms, cudaStream_t st, int shape, const unsigned* jobs_dev) {
+  if (jobs_dev && jobs.nseg != 1) return cudaErrorInvalidValue;
   if (jobs.total <= 0) return cudaSuccess;
   if (jobs.nseg <= 0 || jobs.nseg > kMaxPowSegs || out_limbs % 2 || out_limbs > 2 * key.S) return cudaErrorInvalidValue;
   int first = 0;
@@ -1073,6 +1077,7 @@ cudaError_t launch_modexp2m_jobs(const Enc2mKey& key, const PowJobs& jobs, int o
   p.jobs = jobs;
   p.table = table;
   p.cursor = cursor;
+  p.jobs_dev = jobs_dev;
   p.out_limbs = out_limbs;
   p.tab_bases = tab_bases;
   p.zero = 0u;
@@ -1083,6 +1088,16 @@ cudaError_t launch_modexp2m_jobs(const Enc2mKey& key, const PowJobs& jobs, int o
     // units run side by side, and the multiplier pipe needs 3-4 resident warps to fill
     const long long warps_wide = (long_jobs * T + 31) / 32;
     shape = warps_wide < (long long)num_sms * 4 * 4 ? 2 : 1;
+    // at most one job per sub-partition: nothing shares the pipe, the time is ONE modexp's latency - spread every job over a
+    // whole warp (the latency of a single proof: RangeProofNi::prove alone is 256 encryptions)
+    if (long_jobs <= (long long)num_sms * 4) shape = 3;
+  }
+  if (shape == 3) {
+    switch (key.S) {
+      case 32: return launch_jobs_one<16, 2, kCtasPerSmNarrow, 2>(p, table_limbs, num_sms, st);
+      case 64: return launch_jobs_one<32, 2, kCtasPerSmNarrow, 2>(p, table_limbs, num_sms, st);
+      default: shape = 2; break;  // 3072 / 4096-bit n: the narrow layouts are already one job per (half-)warp
+    }
   }
   (void)jobs_shape_T;
 #ifdef ZKP_B200_LAB
