@@ -208,18 +208,33 @@ class Env:
         torch.cuda.set_stream(self.stream)
         self.ctx = zk.native.Context(self.local, stream=self.stream.cuda_stream)
         self._imad_peak = None
+        # solo: measure this rank alone, no collectives (the secondary entries: a failure on one rank must neither hang the others
+        # nor cost the headline line; their per-rank rates are combined afterwards by ONE reduction, combine_ranks)
+        self.solo = False
+
+    @property
+    def nranks(self):
+        return 1 if self.solo else self.world
 
     def barrier(self):
         self.torch.cuda.synchronize(self.dev)
-        if self.world > 1:
+        if self.world > 1 and not self.solo:
             self.dist.barrier()
             self.torch.cuda.synchronize(self.dev)
 
     def max_over_ranks(self, vals):
         t = self.torch.tensor(list(vals), dtype=self.torch.float64, device=self.dev)
-        if self.world > 1:
+        if self.world > 1 and not self.solo:
             self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return t.tolist()
+
+    def combine_ranks(self, rates):
+        """Per-rank rates of identical shards (weak scaling) -> whole-job rates: world x the slowest rank's (NaN if any rank failed)."""
+        t = self.torch.tensor([r if r is not None else float("nan") for r in rates], dtype=self.torch.float64, device=self.dev)
+        t = self.torch.where(self.torch.isnan(t), self.torch.full_like(t, -1.0), t)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN)
+        return [None if v < 0 else v * self.world for v in t.tolist()]
 
     def imad_peak(self):
         if self._imad_peak is None:
@@ -505,11 +520,11 @@ def measure_correct_key(E, batch=4096, bits=3072, steps=5, warmup=3, e2e_rounds=
     clocks = sampler.stop() if sampler else None
     ms, e2e_s = E.max_over_ranks([ms, e2e_s])
     per = modexp_imads(bits, bits)
-    out = {"metric": f"NiCorrectKeyProof verifies/sec at {bits}-bit n", "unit": "verifies/s", "value": E.world * batch * steps / (ms * 1e-3),
-           "ms_per_step": ms / steps, "steps": steps, "warmup": warmup, "n_gpus": E.world, "higher_is_better": True, "scaling": "weak", "dtype": DTYPE,
+    out = {"metric": f"NiCorrectKeyProof verifies/sec at {bits}-bit n", "unit": "verifies/s", "value": E.nranks * batch * steps / (ms * 1e-3),
+           "ms_per_step": ms / steps, "steps": steps, "warmup": warmup, "n_gpus": E.nranks, "higher_is_better": True, "scaling": "weak", "dtype": DTYPE,
            "config": {"workload": f"NiCorrectKeyProof verify, batch={batch} per GPU, {bits}-bit n, {batch} distinct moduli (device keygen), salt 'Zen Go X', 1/64 bad proofs",
                       "batch_per_gpu": batch, "n_bits": bits, "distinct_moduli": batch},
-           "e2e": {"value": E.world * batch * e2e_batches / e2e_s, "unit": "verifies/s", "h2d_bytes_per_step": int(work["n"].nbytes + work["sigma"].nbytes),
+           "e2e": {"value": E.nranks * batch * e2e_batches / e2e_s, "unit": "verifies/s", "h2d_bytes_per_step": int(work["n"].nbytes + work["sigma"].nbytes),
                    "d2h_bytes_per_step": batch, "steps": e2e_batches,
                    "how": "zkp_correct_key_ni_verify from pinned host buffers on two contexts / two host threads (double-buffered: one context's copies under "
                           "the other's kernels); host wall clock around synchronised calls"},
@@ -627,13 +642,13 @@ def measure_sigma(E, B=512, bits=4096, steps=5, warmup=3, want_cpu=True, jobs_sh
     best_s = min(seq_s, conc_s)
     bytes_in = sum(v.nbytes for v in w["mul"]) + sum(v.nbytes for v in w["verlin"])
     peak = E.imad_peak()
-    out = {"metric": f"MulProof+VerlinProof verifies/sec at {bits}-bit n", "unit": "verifies/s", "value": E.world * 2 * B * steps / (span_ms * 1e-3),
-           "ms_per_step": span_ms / steps, "steps": steps, "warmup": warmup, "n_gpus": E.world, "higher_is_better": True, "scaling": "weak", "dtype": DTYPE,
+    out = {"metric": f"MulProof+VerlinProof verifies/sec at {bits}-bit n", "unit": "verifies/s", "value": E.nranks * 2 * B * steps / (span_ms * 1e-3),
+           "ms_per_step": span_ms / steps, "steps": steps, "warmup": warmup, "n_gpus": E.nranks, "higher_is_better": True, "scaling": "weak", "dtype": DTYPE,
            "value_how": "device spans (CUDA events, first kernel to last kernel of each zkp_mul_verify / zkp_verlin_verify call; copies excluded), calls back to back on one context",
            "config": {"workload": f"MulProof verify x{B} + VerlinProof verify x{B} per GPU, {bits}-bit n ({2 * bits}-bit modulus), one key (the per-GPU share of BASELINE configs[4])",
                       "batch_per_gpu": 2 * B, "n_bits": bits},
-           "e2e": {"value": E.world * 2 * B * steps / best_s, "unit": "verifies/s", "h2d_bytes_per_step": int(bytes_in), "d2h_bytes_per_step": 3 * B, "steps": steps,
-                   "sequential": E.world * 2 * B * steps / seq_s, "two_contexts": E.world * 2 * B * steps / conc_s,
+           "e2e": {"value": E.nranks * 2 * B * steps / best_s, "unit": "verifies/s", "h2d_bytes_per_step": int(bytes_in), "d2h_bytes_per_step": 3 * B, "steps": steps,
+                   "sequential": E.nranks * 2 * B * steps / seq_s, "two_contexts": E.nranks * 2 * B * steps / conc_s,
                    "how": "one-shot calls from pinned host buffers, host wall clock around synchronised calls; `sequential` = both calls on one context, "
                           "`two_contexts` = the MulProof batch and the VerlinProof batch on two contexts / host threads at the same time; value = the faster"},
            "roofline": {"bound": "imad", "kernel": "modexp2m_jobs_kernel (K2h: every modexp of a call in one or two phased launches; gen_phi as one three-base simultaneous exponentiation)",
@@ -741,7 +756,7 @@ def run_b200(args):
         line = headline_line(E, args)
     elif args.config == "correct_key":
         line = measure_correct_key(E, batch=args.batch if args.batch != 1024 else 4096, steps=max(args.steps, 1), warmup=max(args.warmup, 3), want_cpu=not args.no_cpu)
-        line.update(vs_baseline=None, data="synthetic (device keygen, seeded)")
+        line.update(vs_baseline=None, data="synthetic (device keygen, seeded)")  # (collective timing: barrier + max over ranks inside)
     elif args.config == "sigma":
         line = measure_sigma(E, B=args.batch if args.batch != 1024 else 512, steps=max(args.steps, 1), warmup=max(args.warmup, 3), want_cpu=not args.no_cpu,
                              jobs_shape=args.jobs_shape)
@@ -758,21 +773,7 @@ def headline_line(E, args):
     r = measure_rangeproof(E, batch, args.steps, args.warmup, args.e2e_steps, args.cpu_seconds, want_cpu=not args.no_cpu)
     secondary = None
     if not args.no_secondary and N_BITS == 2048:
-        secondary = {}
-        secondary["correct_key_3072"] = measure_correct_key(E, want_cpu=not args.no_cpu)
-        secondary["mul_verlin_4096"] = measure_sigma(E, want_cpu=not args.no_cpu)
-        if E.world == 1:
-            secondary["latency_one_proof"] = measure_latency(E)
-            if not args.no_cpu:
-                z = measure_zero_cpu()
-                z["b200"] = measure_zero_gpu(E)
-                secondary["zero_1024_cpu"] = z
-        if E.world == 8 and batch != 8192:
-            # configs[3] as stated: 65 536 proofs over 8 GPUs = 8 192 per GPU; one timed step (22 s) after one untimed, kernels already warm
-            big = measure_rangeproof(E, 8192, 1, 1, 0, 0, want_cpu=False, want_gather=False)
-            secondary["rangeproof_65536_over_8"] = {"metric": METRIC, "unit": UNIT, "value": big["value"], "ms_per_step": big["ms"], "steps": 1, "warmup": 1,
-                                                   "n_gpus": E.world, "clocks": big["clocks"],
-                                                   "config": {"workload": workload_name(8192), "batch_per_gpu": 8192, "total_proofs": 8192 * E.world}}
+        secondary = run_secondary(E, args, batch)
     if E.rank != 0:
         return None
     return {
@@ -788,6 +789,62 @@ def headline_line(E, args):
                    "e2e_note": f"e2e is timed over {args.e2e_steps} steps (value over {args.steps}); a step is seconds long, so the host buffers' copies are <1 % of it"},
         "secondary": secondary,
     }
+
+
+def run_secondary(E, args, batch):
+    """The other BASELINE configs.  Every entry is measured by each rank ALONE (E.solo: no collectives inside, a failure is recorded
+    in the entry instead of taking the line - or the other ranks - down); one reduction at the end turns the per-rank rates of the
+    identical shards into whole-job rates (world x the slowest rank)."""
+    import traceback
+
+    sec = {}
+    E.solo = True
+
+    def guarded(name, fn):
+        try:
+            sec[name] = fn()
+        except BaseException as ex:  # SystemExit from a failed check included
+            sec[name] = {"error": f"{type(ex).__name__}: {ex}", "trace": traceback.format_exc(limit=3)}
+
+    guarded("correct_key_3072", lambda: measure_correct_key(E, want_cpu=not args.no_cpu))
+    guarded("mul_verlin_4096", lambda: measure_sigma(E, want_cpu=not args.no_cpu))
+    if E.world == 1:
+        guarded("latency_one_proof", lambda: measure_latency(E))
+        if not args.no_cpu:
+            def zero():
+                z = measure_zero_cpu()
+                z["b200"] = measure_zero_gpu(E)
+                return z
+            guarded("zero_1024_cpu", zero)
+    E.solo = False
+    if E.world > 1:
+        keys = [("correct_key_3072", "value"), ("correct_key_3072", "e2e"), ("mul_verlin_4096", "value"), ("mul_verlin_4096", "e2e")]
+
+        def local(name, what):
+            ent = sec.get(name, {})
+            if "error" in ent:
+                return None
+            return ent["value"] if what == "value" else ent["e2e"]["value"]
+
+        agg = E.combine_ranks([local(n, w) for n, w in keys])
+        for (name, what), v in zip(keys, agg):
+            ent = sec.get(name, {})
+            if "error" in ent:
+                continue
+            if v is None:
+                ent["error"] = "another rank failed this entry"
+            elif what == "value":
+                ent["value"], ent["n_gpus"] = v, E.world
+            else:
+                ent["e2e"]["value"] = v
+            ent["aggregation"] = f"{E.world} ranks, identical shards: whole-job rate = {E.world} x the slowest rank's rate"
+    if E.world == 8 and batch != 8192:
+        # configs[3] as stated: 65 536 proofs over 8 GPUs = 8 192 per GPU; one timed step (22 s) after one untimed, kernels already warm
+        big = measure_rangeproof(E, 8192, 1, 1, 0, 0, want_cpu=False, want_gather=False)
+        sec["rangeproof_65536_over_8"] = {"metric": METRIC, "unit": UNIT, "value": big["value"], "ms_per_step": big["ms"], "steps": 1, "warmup": 1,
+                                          "n_gpus": E.world, "clocks": big["clocks"],
+                                          "config": {"workload": workload_name(8192), "batch_per_gpu": 8192, "total_proofs": 8192 * E.world}}
+    return sec
 
 
 def run_reference(args):

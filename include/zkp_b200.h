@@ -258,9 +258,13 @@ int zkp_correct_message_verify(zkp_ctx* ctx, int batch, int M, int m_limbs, int 
  *                        (the parity tests run all three and compare)
  *   ZKP_TUNE_JOBS_SHAPE  lane layout of K2h, the one-launch heterogeneous modexp list of the sigma protocols:
  *                        0 = by job count (default), 1 = wide lanes (as K1m / K2m), 2 = narrow lanes (one job over
- *                        twice the lanes: fills the GPU at a few hundred proofs of 4096-bit n) */
+ *                        twice the lanes: fills the GPU at a few hundred proofs of 4096-bit n)
+ *   ZKP_TUNE_JOBS_ROWS   row form of K2h's narrow-lane and latency layouts: 0 = by layout (pair rows in the one-job-per-warp
+ *                        latency layout, single rows in the narrow-lane layout), 1 = single rows (one quotient digit per step,
+ *                        as K1m / K2m), 2 = pair rows (two multiplier limbs and a two-limb quotient per step) */
 #define ZKP_TUNE_ENC_KERNEL 0
 #define ZKP_TUNE_JOBS_SHAPE 1
+#define ZKP_TUNE_JOBS_ROWS 2
 int zkp_tune(zkp_ctx* ctx, int knob, int value);
 
 /* ---- measurement ----------------------------------------------------------

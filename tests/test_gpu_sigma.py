@@ -21,22 +21,27 @@ def verdict(fn):
         return 0
 
 
-# (key size, K2h lane layout: 0 = by job count - narrow lanes at these batch sizes -, 1 = wide lanes, 2 = narrow lanes,
-#  "k1" = the two-digit kernels switched off: every modexp by the single-purpose K1 / K2 launches, products by K3)
-@pytest.fixture(scope="module", params=[(1024, 0), (1024, 1), (1024, "k1"), (2048, 1), (2048, 2), (3072, 1), (3072, 2), (4096, 1), (4096, 2)],
-                ids=lambda p: f"{p[0]}-shape{p[1]}")
+# (key size, K2h lane layout, row form)
+#   layout: 0 = by job count (the one-job-per-warp latency layout at these batch sizes), 1 = wide lanes, 2 = narrow lanes,
+#           "k1" = the two-digit kernels switched off: every modexp by the single-purpose K1 / K2 launches, products by K3
+#   rows:   0 = the layout's default (pair rows in the narrow / latency layouts), 1 = single rows, 2 = pair rows
+@pytest.fixture(scope="module", params=[(1024, 0, 0), (1024, 1, 0), (1024, "k1", 0), (1024, 0, 1), (2048, 1, 0), (2048, 2, 0), (2048, 2, 1), (2048, 0, 0),
+                                        (3072, 1, 0), (3072, 2, 0), (3072, 2, 1), (4096, 1, 0), (4096, 2, 0), (4096, 2, 1)],
+                ids=lambda p: f"{p[0]}-shape{p[1]}-rows{p[2]}")
 def keyed(request, ctx):
     import zk_paillier_b200 as zk
 
-    bits, shape = request.param
+    bits, shape, rows = request.param
     p, q = keys(bits)[0]
     n = p * q
     nl = limbs_for(bits)
     ctx.tune(zk.native.TUNE_ENC_KERNEL, 1 if shape == "k1" else 0)
     ctx.set_key(to_limbs(n, nl))
     ctx.tune(zk.native.TUNE_JOBS_SHAPE, 0 if shape == "k1" else shape)
+    ctx.tune(zk.native.TUNE_JOBS_ROWS, rows)
     yield ctx, n, nl, random.Random(bits)
     ctx.tune(zk.native.TUNE_JOBS_SHAPE, 0)
+    ctx.tune(zk.native.TUNE_JOBS_ROWS, 0)
     ctx.tune(zk.native.TUNE_ENC_KERNEL, 0)
 
 

@@ -3,7 +3,9 @@ big-int arithmetic.  They were written BEFORE the kernels ran on a GPU and are k
   * the split-accumulator CIOS Montgomery step of mp_coop.cuh (cios_model.py),
   * the plain product on the same rows with the low half captured at lane 0 (mulwide_model.py),
   * Montgomery multiplication modulo n^2 in two-digit base-n form, the default encryption kernel (mont2d_model.py),
-  * the symmetric squaring (each pair of lane blocks once) + reduction-only rows of K1m variant 9 (sqr_sym_model.py)."""
+  * the symmetric squaring (each pair of lane blocks once) + reduction-only rows of K1m variant 9 (sqr_sym_model.py),
+  * the pair rows of K2h's narrow-lane and latency layouts: two multiplier limbs and a two-limb quotient per step
+    (cios_pair_model.py; every instantiated lane layout, initial accumulator, two-product form, the bounds of the hanging limbs)."""
 import os
 import runpy
 
@@ -12,7 +14,7 @@ import pytest
 HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "models")
 
 
-@pytest.mark.parametrize("name", ["cios_model.py", "mulwide_model.py", "mont2d_model.py", "sqr_sym_model.py"])
+@pytest.mark.parametrize("name", ["cios_model.py", "mulwide_model.py", "mont2d_model.py", "sqr_sym_model.py", "cios_pair_model.py"])
 def test_model(name, capsys):
     runpy.run_path(os.path.join(HERE, name), run_name="__main__")
     out = capsys.readouterr().out

@@ -120,6 +120,12 @@ static Enc2mKey enc2m_view(const zkp_ctx* c) {
   k.ops = c->enc2m_ops.as<uint32_t>();
   k.nops = c->enc2m_nops;
   k.n0inv = c->n.n0inv;
+  {  // -n^{-1} mod 2^64 by Newton iteration from the low 64 bits of n (odd)
+    const uint64_t n64 = (uint64_t)c->n.h_mod[0] | ((uint64_t)(c->n.S > 1 ? c->n.h_mod[1] : 0u) << 32);
+    uint64_t x = n64;  // correct to 3 bits
+    for (int i = 0; i < 6; ++i) x *= 2 - n64 * x;
+    k.n0inv_hi = (uint32_t)((0 - x) >> 32);
+  }
   k.S = c->n.S;
   return k;
 }
@@ -144,7 +150,7 @@ cudaError_t launch_pow_jobs(zkp_ctx* c, const PowJobs& jobs, const unsigned* job
   ++c->enc2m_launches;
   const size_t region = c->table_region_limbs ? c->table_off / c->table_region_limbs : 0;  // 0 = main stream, k + 1 = auxiliary stream k
   return launch_modexp2m_jobs(enc2m_view(c), jobs, c->nn.limbs, c->table.as<uint32_t>() + c->table_off, c->table_region_limbs,
-                              reinterpret_cast<unsigned*>(c->cursor.as<uint8_t>() + 256 * region), c->num_sms, c->stream, c->jobs_shape, jobs_dev);
+                              reinterpret_cast<unsigned*>(c->cursor.as<uint8_t>() + 256 * region), c->num_sms, c->stream, c->jobs_shape, jobs_dev, c->jobs_rows);
 }
 
 // A launch of so few encryptions that K1m's layout would leave sub-partitions with less than two warps (one proof: 256
@@ -565,6 +571,10 @@ int zkp_tune(zkp_ctx* c, int knob, int value) {
     case ZKP_TUNE_JOBS_SHAPE:
       if (value < 0 || value > 2) return fail(c, ZKP_E_ARG, "ZKP_TUNE_JOBS_SHAPE: 0 (by job count), 1 (wide lanes) or 2 (narrow lanes)");
       c->jobs_shape = value;
+      return ZKP_OK;
+    case ZKP_TUNE_JOBS_ROWS:
+      if (value < 0 || value > 2) return fail(c, ZKP_E_ARG, "ZKP_TUNE_JOBS_ROWS: 0 (default), 1 (single rows) or 2 (pair rows)");
+      c->jobs_rows = value;
       return ZKP_OK;
     default:
       return fail(c, ZKP_E_ARG, "unknown tuning knob");

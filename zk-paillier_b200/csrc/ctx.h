@@ -134,6 +134,7 @@ struct zkp_ctx {
   cudaEvent_t aux_ev[zkp::kAuxStreams] = {nullptr, nullptr, nullptr, nullptr}, fork_ev = nullptr;
   unsigned aux_used = 0;
   zkp::DevBuf cursor;                // K2h work-unit cursors, one 256-byte slot per stream (ensure_table)
+  int jobs_rows = 0;                 // K2h row form of the narrow / latency layouts: 0 = default, 1 = single rows, 2 = pair rows
   int jobs_shape = 0;                // K2h lane layout: 0 = by job count, 1 = wide lanes, 2 = narrow lanes (zkp_set_jobs_shape)
   zkp::DevBuf in0, in1, in2, in3, out0;  // generic staging for the one-shot calls
   bool profiling = false;

@@ -54,6 +54,7 @@ struct Enc2mKey {
   const uint32_t* ops;     // op list (enc2m_ops)
   int nops;
   uint32_t n0inv;          // -n^{-1} mod 2^32
+  uint32_t n0inv_hi;       // bits 32..63 of -n^{-1} mod 2^64 (pair rows: two quotient digits per step)
   int S;
 };
 bool enc2m_supported(const uint32_t* n_host, int S);
@@ -109,7 +110,8 @@ size_t jobs2m_scratch_limbs(int S, int num_sms, int total_jobs, int max_bases = 
 // shape 3 = one job per warp (the latency layout, chosen when a launch has at most one long job per SM sub-partition).
 // jobs_dev (optional, single-segment launches): device pointer to the actual job count (<= jobs.total).
 cudaError_t launch_modexp2m_jobs(const Enc2mKey& key, const PowJobs& jobs, int out_limbs, uint32_t* table, size_t table_limbs,
-                                 unsigned* cursor, int num_sms, cudaStream_t st, int shape = 0, const unsigned* jobs_dev = nullptr);
+                                 unsigned* cursor, int num_sms, cudaStream_t st, int shape = 0, const unsigned* jobs_dev = nullptr,
+                                 int rows = 0 /* narrow / latency layouts: 0 = default, 1 = single rows, 2 = pair rows */);
 
 // Montgomery setup for per-instance moduli: r2[i] = R^2 mod mods[i] ([count][S]), n0inv[i].
 // mods: [count][mod_limbs].

@@ -49,6 +49,8 @@ struct Enc2mParams {
 // MODE 1: both halves of a squaring run through one copy of the row loop (multiplier picked by SEL): smaller code.
 // MODE 2: multiplier limbs and quotient digits go through a per-group shared-memory scratch (kSg2m words), the row loop
 //         is rolled U pairs of steps deep: smallest code, no multiplier shuffles.
+// MODE 4: pair rows (Mp::cios_pair: two multiplier limbs and a two-limb quotient per step).  The serial quotient chain runs
+//         once per two rows: for launches with few warps per sub-partition (K2h's narrow-lane and latency layouts).
 template <int T, int L, int U, int MODE = 0>
 struct TwoDigit {
   using M = Mp<T, L>;
@@ -69,11 +71,17 @@ struct TwoDigit {
 
   // (x0, x1) <- (x0, x1)^2 / W
   static __device__ __forceinline__ void sqr(uint32_t (&x0)[L], uint32_t (&x1)[L], const uint32_t (&n)[L], uint32_t n0inv,
-                                             const uint32_t* s_klo, int lane, uint32_t zr, uint32_t* sg = nullptr) {
+                                             const uint32_t* s_klo, int lane, uint32_t zr, uint32_t* sg = nullptr, uint32_t n0hi = 0u) {
     uint32_t q[L], z0[L];
 #pragma unroll
     for (int j = 0; j < L; ++j) q[j] = 0;
-    if constexpr (MODE == 0 || MODE == 3) {
+    if constexpr (MODE == 4) {
+      const uint32_t delta = M::template mont_mul_p<false, true, 1, U>(z0, x0, x0, n, n0inv, n0hi, lane, z0, 0u, q, zr);
+      uint32_t top;
+      init_from_q(q, top, q, delta, s_klo, lane);
+      M::mod_double(x1, n, lane);
+      M::template mont_mul_p<true, false, 2, U>(x1, x0, x1, n, n0inv, n0hi, lane, q, top, q, zr);
+    } else if constexpr (MODE == 0 || MODE == 3) {
       uint32_t delta;
       if constexpr (MODE == 3) {  // symmetric squaring: every pair of lane blocks multiplied once, then S reduction-only rows
         uint32_t plo[L], phi[L];
@@ -124,11 +132,16 @@ struct TwoDigit {
   // (x0, x1) <- (x0, x1) (y0, y1) / W
   static __device__ __forceinline__ void mul(uint32_t (&x0)[L], uint32_t (&x1)[L], const uint32_t (&y0)[L], const uint32_t (&y1)[L],
                                              const uint32_t (&n)[L], uint32_t n0inv, const uint32_t* s_klo, int lane, uint32_t zr,
-                                             uint32_t* sg = nullptr) {
+                                             uint32_t* sg = nullptr, uint32_t n0hi = 0u) {
     uint32_t q[L], z0[L];
 #pragma unroll
     for (int j = 0; j < L; ++j) q[j] = 0;
-    if constexpr (MODE != 2) {
+    if constexpr (MODE == 4) {
+      const uint32_t delta = M::template mont_mul_p<false, true, 1, U>(z0, x0, y0, n, n0inv, n0hi, lane, z0, 0u, q, zr);
+      uint32_t top;
+      init_from_q(q, top, q, delta, s_klo, lane);
+      M::template mont_mul2_p<U>(x1, x0, y1, x1, y0, n, n0inv, n0hi, lane, q, top, zr);
+    } else if constexpr (MODE != 2) {
       const uint32_t delta = M::template mont_mul_x<false, true, 1, U>(z0, x0, y0, n, n0inv, lane, z0, 0u, q, zr);
       uint32_t top;
       init_from_q(q, top, q, delta, s_klo, lane);
@@ -193,7 +206,7 @@ struct TwoDigit {
   // need not be - a row of at most S limbs taken through the wide path has a zero high half.
   static __device__ __forceinline__ void entry_pair_u(uint32_t (&x0)[L], uint32_t (&x1)[L], const uint32_t* row, int limbs, bool wide,
                                                       const uint32_t* consts, const uint32_t (&n)[L], uint32_t n0inv,
-                                                      const uint32_t* s_klo, int lane, uint32_t zr, uint32_t* sg = nullptr) {
+                                                      const uint32_t* s_klo, int lane, uint32_t zr, uint32_t* sg = nullptr, uint32_t n0hi = 0u) {
     const int g = lane & (T - 1);
     if (!wide) {
       M::load_ext(x0, row, limbs, g);
@@ -211,7 +224,7 @@ struct TwoDigit {
       else M::load_ext(x0, row, limbs < S ? limbs : S, g);
 #pragma unroll
       for (int j = 0; j < L; ++j) x1[j] = 0;
-      mul(x0, x1, y0, y1, n, n0inv, s_klo, lane, zr, sg);
+      mul(x0, x1, y0, y1, n, n0inv, s_klo, lane, zr, sg, n0hi);
       if (half) {
 #pragma unroll
         for (int j = 0; j < L; ++j) {
@@ -512,10 +525,10 @@ __global__ void __launch_bounds__(kCtaThreads, MINB) modexp2m_var_kernel(const V
 // whichever warp is free next continues it.  done[unit] counts finished phases; the cursor hands phases out in
 // dependency order, so a warp that has to wait for the previous phase of its unit waits on a warp that is already
 // running (no deadlock), and with thousands of phase-units in flight it practically never waits.
-template <int T, int L, int MINB, int U>
+template <int T, int L, int MINB, int U, int MODE>
 __global__ void __launch_bounds__(kCtaThreads, MINB) modexp2m_jobs_kernel(const __grid_constant__ Jobs2mParams p) {
   using M = Mp<T, L>;
-  using TD = TwoDigit<T, L, U>;  // U: lane-owner iterations of a row loop unrolled together (L rows each)
+  using TD = TwoDigit<T, L, U, MODE>;  // U: lane-owner iterations of a row loop unrolled together; MODE 4: pair rows
   constexpr int S = T * L;
   constexpr int G = kCtaThreads / T;
   constexpr int GW = 32 / T;  // jobs per warp
@@ -523,7 +536,7 @@ __global__ void __launch_bounds__(kCtaThreads, MINB) modexp2m_jobs_kernel(const 
   const int lane = threadIdx.x & 31;
   const int g = lane & (T - 1);
   const int grp = threadIdx.x / T;
-  const uint32_t n0inv = p.key.n0inv;
+  const uint32_t n0inv = p.key.n0inv, n0hi = p.key.n0inv_hi;
   const uint32_t zr = p.zero;
   uint32_t n[L];
   M::load(n, p.key.mod + g * L);
@@ -580,10 +593,10 @@ __global__ void __launch_bounds__(kCtaThreads, MINB) modexp2m_jobs_kernel(const 
         const int base_limbs = sgm.base_limbs[kk];
         const bool wide_base = __any_sync(ZKP_FULL, base_limbs > S);
         uint32_t* tk = tab + (size_t)k * tab_base_stride;
-        TD::entry_pair_u(x0, x1, sgm.base[kk] + (size_t)rel * base_limbs, base_limbs, wide_base, p.key.consts, n, n0inv, s_klo, lane, zr);
+        TD::entry_pair_u(x0, x1, sgm.base[kk] + (size_t)rel * base_limbs, base_limbs, wide_base, p.key.consts, n, n0inv, s_klo, lane, zr, nullptr, n0hi);
         M::load(y0, p.key.consts + S + g * L);  // pair(W^2): into Montgomery form
         M::load(y1, p.key.consts + 2 * S + g * L);
-        TD::mul(x0, x1, y0, y1, n, n0inv, s_klo, lane, zr);
+        TD::mul(x0, x1, y0, y1, n, n0inv, s_klo, lane, zr, nullptr, n0hi);
         M::store(tk + 2 * S, x0);
         M::store(tk + 2 * S + S, x1);
 #pragma unroll
@@ -602,7 +615,7 @@ __global__ void __launch_bounds__(kCtaThreads, MINB) modexp2m_jobs_kernel(const 
         }
 #pragma unroll 1
         for (int t = 2; t < kTableVar; ++t) {
-          TD::mul(x0, x1, y0, y1, n, n0inv, s_klo, lane, zr);
+          TD::mul(x0, x1, y0, y1, n, n0inv, s_klo, lane, zr, nullptr, n0hi);
           M::store(tk + (size_t)t * 2 * S, x0);
           M::store(tk + (size_t)t * 2 * S + S, x1);
         }
@@ -618,7 +631,7 @@ __global__ void __launch_bounds__(kCtaThreads, MINB) modexp2m_jobs_kernel(const 
         const uint32_t* t0 = tab + (size_t)k * tab_base_stride + (size_t)exp_window2m(k == 1 ? e[1] : e[2], k == 1 ? el[1] : el[2], (hi - 1) * kWindowVar) * 2 * S;
         M::load(y0, t0);
         M::load(y1, t0 + S);
-        TD::mul(x0, x1, y0, y1, n, n0inv, s_klo, lane, zr);
+        TD::mul(x0, x1, y0, y1, n, n0inv, s_klo, lane, zr, nullptr, n0hi);
       }
     } else {
       if (lane == 0)
@@ -631,7 +644,7 @@ __global__ void __launch_bounds__(kCtaThreads, MINB) modexp2m_jobs_kernel(const 
 #pragma unroll 1
     for (int w = hi - 1 - (ph == 0 ? 1 : 0); w >= lo; --w) {  // one squaring chain for all bases (Straus)
 #pragma unroll 1
-      for (int q = 0; q < kWindowVar; ++q) TD::sqr(x0, x1, n, n0inv, s_klo, lane, zr);
+      for (int q = 0; q < kWindowVar; ++q) TD::sqr(x0, x1, n, n0inv, s_klo, lane, zr, nullptr, n0hi);
 #pragma unroll 1
       for (int k = 0; k < nb; ++k) {
         const uint32_t* ek = k == 0 ? e[0] : (k == 1 ? e[1] : e[2]);
@@ -639,7 +652,7 @@ __global__ void __launch_bounds__(kCtaThreads, MINB) modexp2m_jobs_kernel(const 
         const uint32_t* t0 = tab + (size_t)k * tab_base_stride + (size_t)exp_window2m(ek, elk, w * kWindowVar) * 2 * S;
         M::load(y0, t0);
         M::load(y1, t0 + S);
-        TD::mul(x0, x1, y0, y1, n, n0inv, s_klo, lane, zr);
+        TD::mul(x0, x1, y0, y1, n, n0inv, s_klo, lane, zr, nullptr, n0hi);
       }
     }
     if (lo > 0) {  // hand the job over to whoever takes its next phase
@@ -666,7 +679,7 @@ __global__ void __launch_bounds__(kCtaThreads, MINB) modexp2m_jobs_kernel(const 
       M::load_ext(y1, mrow, pl, g);
     }
     M::set_small(y0, 1u, g);
-    TD::mul(x0, x1, y0, y1, n, n0inv, s_klo, lane, zr);
+    TD::mul(x0, x1, y0, y1, n, n0inv, s_klo, lane, zr, nullptr, n0hi);
     TD::assemble_store(sgm.out + (size_t)rel * p.out_limbs, p.out_limbs, valid, x0, x1, n, lane);
   }
 }
@@ -989,7 +1002,7 @@ size_t jobs2m_scratch_limbs(int S, int num_sms, int total_jobs, int max_bases) {
   return resident > phased ? resident : phased;
 }
 
-template <int T, int L, int MINB, int U = 1>
+template <int T, int L, int MINB, int U = 1, int MODE = 0>
 static cudaError_t launch_jobs_one(Jobs2mParams& p, size_t table_limbs, int num_sms, cudaStream_t st) {
   constexpr int GW = 32 / T;
   constexpr int S = T * L;
@@ -1045,12 +1058,18 @@ static cudaError_t launch_jobs_one(Jobs2mParams& p, size_t table_limbs, int num_
   if (grid > need) grid = need;
   cudaError_t e = cudaMemsetAsync(p.cursor, 0, sizeof(unsigned), st);
   if (e != cudaSuccess) return e;
-  modexp2m_jobs_kernel<T, L, MINB, U><<<grid, kCtaThreads, 0, st>>>(p);
+  modexp2m_jobs_kernel<T, L, MINB, U, MODE><<<grid, kCtaThreads, 0, st>>>(p);
   return cudaGetLastError();
 }
 
+// Row form by layout, measured (profiles/r02_pair_rows.json): pair rows make ONE encryption 11 % faster in the latency layout
+// (13.3 -> 11.8 ms at 2048 bits) and the narrow throughput layout 10 % SLOWER (118 -> 133 ms, ZeroProof::verify x 1 536 at 4096
+// bits): the quotient chain is not what a lone warp waits for - it issues ~20 dependent instructions per row at ~4 cycles
+// each whatever their order - and with several warps per sub-partition the extra carry adds of the pair form cost issue slots.
+constexpr bool kPairRowsLatency = true, kPairRowsNarrow = false;
+
 cudaError_t launch_modexp2m_jobs(const Enc2mKey& key, const PowJobs& jobs, int out_limbs, uint32_t* table, size_t table_limbs,
-                                 unsigned* cursor, int num_sms, cudaStream_t st, int shape, const unsigned* jobs_dev) {
+                                 unsigned* cursor, int num_sms, cudaStream_t st, int shape, const unsigned* jobs_dev, int rows) {
   if (jobs_dev && jobs.nseg != 1) return cudaErrorInvalidValue;
   if (jobs.total <= 0) return cudaSuccess;
   if (jobs.nseg <= 0 || jobs.nseg > kMaxPowSegs || out_limbs % 2 || out_limbs > 2 * key.S) return cudaErrorInvalidValue;
@@ -1092,16 +1111,19 @@ cudaError_t launch_modexp2m_jobs(const Enc2mKey& key, const PowJobs& jobs, int o
     // whole warp (the latency of a single proof: RangeProofNi::prove alone is 256 encryptions)
     if (long_jobs <= (long long)num_sms * 4) shape = 3;
   }
+  // rows: 1 = single rows (as K1m / K2m), 2 = pair rows (two quotient digits per step); 0 = the default of the layout
+  bool pair = rows == 0 ? kPairRowsLatency : rows == 2;
   if (shape == 3) {
     switch (key.S) {
-      case 32: return launch_jobs_one<16, 2, kCtasPerSmNarrow, 2>(p, table_limbs, num_sms, st);
-      case 64: return launch_jobs_one<32, 2, kCtasPerSmNarrow, 2>(p, table_limbs, num_sms, st);
+      case 32: return pair ? launch_jobs_one<16, 2, kCtasPerSmNarrow, 2, 4>(p, table_limbs, num_sms, st) : launch_jobs_one<16, 2, kCtasPerSmNarrow, 2>(p, table_limbs, num_sms, st);
+      case 64: return pair ? launch_jobs_one<32, 2, kCtasPerSmNarrow, 2, 4>(p, table_limbs, num_sms, st) : launch_jobs_one<32, 2, kCtasPerSmNarrow, 2>(p, table_limbs, num_sms, st);
       default: shape = 2; break;  // 3072 / 4096-bit n: the narrow layouts are already one job per (half-)warp
     }
+  } else {
+    pair = rows == 0 ? kPairRowsNarrow : rows == 2;
   }
-  (void)jobs_shape_T;
 #ifdef ZKP_B200_LAB
-  if (shape == 2 && key.S == 128) {  // lab: row-loop unrolling of the narrow layout (ZKP_B200_K2H_UNROLL = 1 | 2 | 4)
+  if (shape == 2 && key.S == 128 && !pair) {  // lab: row-loop unrolling of the narrow layout (ZKP_B200_K2H_UNROLL = 1 | 2 | 4)
     static const int u = [] { const char* e = getenv("ZKP_B200_K2H_UNROLL"); return e ? atoi(e) : 2; }();
     if (u == 1) return launch_jobs_one<32, 4, kCtasPerSmNarrow, 1>(p, table_limbs, num_sms, st);
     if (u == 4) return launch_jobs_one<32, 4, kCtasPerSmNarrow, 4>(p, table_limbs, num_sms, st);
@@ -1109,10 +1131,10 @@ cudaError_t launch_modexp2m_jobs(const Enc2mKey& key, const PowJobs& jobs, int o
 #endif
   if (shape == 2) {
     switch (key.S) {
-      case 32: return launch_jobs_one<8, 4, kCtasPerSmNarrow, 2>(p, table_limbs, num_sms, st);
-      case 64: return launch_jobs_one<16, 4, kCtasPerSmNarrow, 2>(p, table_limbs, num_sms, st);
-      case 96: return launch_jobs_one<16, 6, kCtasPerSmNarrow, 2>(p, table_limbs, num_sms, st);
-      case 128: return launch_jobs_one<32, 4, kCtasPerSmNarrow, 2>(p, table_limbs, num_sms, st);
+      case 32: return pair ? launch_jobs_one<8, 4, kCtasPerSmNarrow, 2, 4>(p, table_limbs, num_sms, st) : launch_jobs_one<8, 4, kCtasPerSmNarrow, 2>(p, table_limbs, num_sms, st);
+      case 64: return pair ? launch_jobs_one<16, 4, kCtasPerSmNarrow, 2, 4>(p, table_limbs, num_sms, st) : launch_jobs_one<16, 4, kCtasPerSmNarrow, 2>(p, table_limbs, num_sms, st);
+      case 96: return pair ? launch_jobs_one<16, 6, kCtasPerSmNarrow, 2, 4>(p, table_limbs, num_sms, st) : launch_jobs_one<16, 6, kCtasPerSmNarrow, 2>(p, table_limbs, num_sms, st);
+      case 128: return pair ? launch_jobs_one<32, 4, kCtasPerSmNarrow, 2, 4>(p, table_limbs, num_sms, st) : launch_jobs_one<32, 4, kCtasPerSmNarrow, 2>(p, table_limbs, num_sms, st);
       default: return cudaErrorInvalidValue;
     }
   }

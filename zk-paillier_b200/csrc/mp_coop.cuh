@@ -73,6 +73,16 @@ __device__ __forceinline__ void madc_wide3_cc(uint32_t& d0, uint32_t& d1, uint32
                : "=&r"(d0), "=r"(d1) : "r"(a), "r"(b), "r"(c0), "r"(c1));
 }
 
+// (d1:d0) = a*b + (c1:c0), STARTING a carry chain, destination pair different from the addend pair
+__device__ __forceinline__ void mad_wide3_start_cc(uint32_t& d0, uint32_t& d1, uint32_t a, uint32_t b, uint32_t c0, uint32_t c1) {
+  asm volatile("mad.lo.cc.u32 %0, %2, %3, %4;\n\tmadc.hi.cc.u32 %1, %2, %3, %5;"
+               : "=&r"(d0), "=r"(d1) : "r"(a), "r"(b), "r"(c0), "r"(c1));
+}
+// r = a + b + carry, continuing a carry chain
+__device__ __forceinline__ void addc_cc3(uint32_t& r, uint32_t a, uint32_t b) {
+  asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+}
+
 template <int T, int L>
 struct Mp {
   static_assert(T == 2 || T == 4 || T == 8 || T == 16 || T == 32, "group width");
@@ -431,6 +441,178 @@ struct Mp {
     for (int j = 1; j <= L; ++j) addc_cc(E[j], O[j + 1]);
     addc(E[L + 1], 0);
     finish_x<3>(r, E, n, lane);
+  }
+
+  // ---- pair rows (model: tests/models/cios_pair_model.py) ------------------------------------------------------------
+  // Two multiplier limbs and a TWO-limb quotient per step: acc = (acc + a (b0 + b1 B) + (q0 + q1 B) n) / B^2, B = 2^32, with
+  // q0 + q1 B = (low 64 bits of acc + a (b0 + b1 B)) n' mod B^2 (n' = -n^-1 mod B^2): the same quotient digits as two single
+  // rows, but the serial chain through the quotient - broadcast, multiply, first products - runs once per TWO rows.  That is
+  // what a launch with few warps per sub-partition waits for (one proof's latency; the narrow-lane layouts of K2h); for the
+  // pipe-saturated wide rows of K1m it would only add multiplies.
+  // Arrays: E[w] at lane-local limb w (w <= L + 2), O[w] at limb w + 1 (w <= L + 1).  a[2m] b0 -> E pair m, a[2m+1] b0 -> O pair
+  // m, a[2m] b1 -> O pair m, a[2m+1] b1 -> E pair m + 1.  Dividing by B^2 shifts BOTH arrays by one aligned pair - done by the
+  // first chain of each array writing to the shifted destination - plus one bridge: O[1] (limb 2) lands on limb 0 and is added
+  // into E there with the carry of the vanishing limb 1, and the bridge's carry enters the first odd chain.  The two lowest
+  // limbs of every lane but lane 0 travel to the lane below.  The shift of a step is folded into the NEXT step; pair_finish
+  // does the last one.
+  //
+  // four in-place product chains of one (x, y0, y1): the n q products, and the second operand pair of the two-product form
+  static __device__ __forceinline__ void pair_mad(uint32_t (&E)[L + 3], uint32_t (&O)[L + 2], const uint32_t (&x)[L], uint32_t y0, uint32_t y1,
+                                                  uint32_t zr) {
+    mad_wide_cc(E[0], E[1], x[0], y0);  // even A
+#pragma unroll
+    for (int j = 2; j < L; j += 2) madc_wide_cc(E[j], E[j + 1], x[j], y0);
+    addc_cc(E[L], zr);
+    addc_cc(E[L + 1], zr);
+    addc(E[L + 2], zr);
+    mad_wide_cc(O[0], O[1], x[1], y0);  // odd A
+#pragma unroll
+    for (int j = 2; j < L; j += 2) madc_wide_cc(O[j], O[j + 1], x[j + 1], y0);
+    addc_cc(O[L], zr);
+    addc(O[L + 1], zr);
+    mad_wide_cc(O[0], O[1], x[0], y1);  // odd B
+#pragma unroll
+    for (int j = 2; j < L; j += 2) madc_wide_cc(O[j], O[j + 1], x[j], y1);
+    addc_cc(O[L], zr);
+    addc(O[L + 1], zr);
+    mad_wide_cc(E[2], E[3], x[1], y1);  // even B: one pair up
+#pragma unroll
+    for (int j = 2; j < L; j += 2) madc_wide_cc(E[j + 2], E[j + 3], x[j + 1], y1);
+    addc(E[L + 2], zr);
+  }
+  // One pair step.  TWO: a second product pair (a2, c0, c1) under the same reduction (mont_mul2_x).
+  template <bool TWO>
+  static __device__ __forceinline__ void cios_pair(uint32_t (&E)[L + 3], uint32_t (&O)[L + 2], const uint32_t (&a)[L], const uint32_t (&a2)[L],
+                                                   const uint32_t (&n)[L], uint32_t b0, uint32_t b1, uint32_t c0, uint32_t c1,
+                                                   uint32_t np0, uint32_t np1, int g, uint32_t& q0, uint32_t& q1, uint32_t zr) {
+    // the shift of the previous step: limb 1 vanishes (s1 goes to the lane below), the bridge, and its carry into odd chain A
+    uint32_t s1 = E[1];
+    add_cc(s1, O[0]);
+    addc_cc(E[2], O[1]);
+    uint32_t NO[L + 2], NE[L + 3];
+#pragma unroll
+    for (int j = 0; j < L; j += 2) madc_wide3_cc(NO[j], NO[j + 1], a[j + 1], b0, O[j + 2], O[j + 3]);  // odd A, shifted
+    NO[L] = addc_out();
+    NO[L + 1] = 0;
+    uint32_t r0 = __shfl_down_sync(ZKP_FULL, E[0], 1, T), r1 = __shfl_down_sync(ZKP_FULL, s1, 1, T);
+    if (g == T - 1) r0 = r1 = 0;
+    add_cc(E[L], r0);
+    addc_cc(E[L + 1], r1);
+    addc(E[L + 2], zr);
+    mad_wide3_start_cc(NE[0], NE[1], a[0], b0, E[2], E[3]);  // even A, shifted
+#pragma unroll
+    for (int j = 2; j < L; j += 2) madc_wide3_cc(NE[j], NE[j + 1], a[j], b0, E[j + 2], E[j + 3]);
+    addc_cc3(NE[L], E[L + 2], zr);
+    NE[L + 1] = addc_out();
+    NE[L + 2] = 0;
+    mad_wide_cc(NO[0], NO[1], a[0], b1);  // odd B
+#pragma unroll
+    for (int j = 2; j < L; j += 2) madc_wide_cc(NO[j], NO[j + 1], a[j], b1);
+    addc_cc(NO[L], zr);
+    addc(NO[L + 1], zr);
+    mad_wide_cc(NE[2], NE[3], a[1], b1);  // even B
+#pragma unroll
+    for (int j = 2; j < L; j += 2) madc_wide_cc(NE[j + 2], NE[j + 3], a[j + 1], b1);
+    addc(NE[L + 2], zr);
+    if (TWO) pair_mad(NE, NO, a2, c0, c1, zr);
+    // the two quotient digits from lane 0's low 64 bits
+    const uint32_t t0 = __shfl_sync(ZKP_FULL, NE[0], 0, T);
+    const uint32_t t1 = __shfl_sync(ZKP_FULL, NE[1] + NO[0], 0, T);
+    q0 = t0 * np0;
+    q1 = __umulhi(t0, np0) + t0 * np1 + t1 * np0;
+    pair_mad(NE, NO, n, q0, q1, zr);
+#pragma unroll
+    for (int j = 0; j < L + 3; ++j) E[j] = NE[j];
+#pragma unroll
+    for (int j = 0; j < L + 2; ++j) O[j] = NO[j];
+  }
+  // The shift of the last step, then the two arrays folded into the redundant accumulator finish_x takes (u[L] = the lane's overflow).
+  static __device__ __forceinline__ void pair_finish(uint32_t (&u)[L + 2], uint32_t (&E)[L + 3], uint32_t (&O)[L + 2], int g) {
+    uint32_t s1 = E[1];
+    add_cc(s1, O[0]);
+    addc_cc(E[2], O[1]);
+#pragma unroll
+    for (int j = 2; j < L + 1; ++j) addc_cc(O[j], 0);
+    addc(O[L + 1], 0);
+    uint32_t r0 = __shfl_down_sync(ZKP_FULL, E[0], 1, T), r1 = __shfl_down_sync(ZKP_FULL, s1, 1, T);
+    if (g == T - 1) r0 = r1 = 0;
+    add_cc(E[L], r0);
+    addc_cc(E[L + 1], r1);
+    addc(E[L + 2], 0);
+    u[0] = E[2];  // new limb w = old limb w + 2 = E[w + 2] + O[w + 1]
+    u[1] = E[3];
+    add_cc(u[1], O[2]);
+#pragma unroll
+    for (int j = 2; j <= L; ++j) {
+      u[j] = E[j + 2];
+      addc_cc(u[j], O[j + 1]);
+    }
+    u[L + 1] = addc_out();
+  }
+  // mont_mul_x by pair rows (same contract: INIT, CAPQ, NSUB; returns 1 iff the first subtraction was taken)
+  template <bool INIT, bool CAPQ, int NSUB, int U = 1>
+  static __device__ __forceinline__ uint32_t mont_mul_p(uint32_t (&r)[L], const uint32_t (&a)[L], const uint32_t (&b)[L], const uint32_t (&n)[L],
+                                                        uint32_t np0, uint32_t np1, int lane, const uint32_t (&init)[L], uint32_t init_top,
+                                                        uint32_t (&qcap)[L], uint32_t zr = 0u) {
+    const int g = lane & (T - 1);
+    uint32_t E[L + 3], O[L + 2];
+#pragma unroll
+    for (int j = 0; j < L + 3; ++j) E[j] = 0;
+#pragma unroll
+    for (int j = 0; j < L + 2; ++j) O[j] = 0;
+    // the first step shifts "the previous step": start two limbs up (E[w + 2] = limb w), as if a step had just ended
+    if (INIT) {
+#pragma unroll
+      for (int j = 0; j < L; ++j) E[j + 2] = init[j];
+      E[L + 2] = (g == T - 1) ? init_top : 0u;
+    }
+#pragma unroll U
+    for (int owner = 0; owner < T; ++owner) {
+      const bool mine = CAPQ && (g == owner);
+#pragma unroll
+      for (int j = 0; j < L; j += 2) {
+        const uint32_t b0 = __shfl_sync(ZKP_FULL, b[j], owner, T);
+        const uint32_t b1 = __shfl_sync(ZKP_FULL, b[j + 1], owner, T);
+        uint32_t q0, q1;
+        cios_pair<false>(E, O, a, a, n, b0, b1, 0u, 0u, np0, np1, g, q0, q1, zr);
+        if (CAPQ) {
+          qcap[j] = mine ? q0 : qcap[j];
+          qcap[j + 1] = mine ? q1 : qcap[j + 1];
+        }
+      }
+    }
+    uint32_t u[L + 2];
+    pair_finish(u, E, O, g);
+    return finish_x<NSUB>(r, u, n, lane);
+  }
+  // mont_mul2_x by pair rows
+  template <int U = 1>
+  static __device__ __forceinline__ void mont_mul2_p(uint32_t (&r)[L], const uint32_t (&a1)[L], const uint32_t (&b1)[L], const uint32_t (&a2)[L],
+                                                     const uint32_t (&b2)[L], const uint32_t (&n)[L], uint32_t np0, uint32_t np1, int lane,
+                                                     const uint32_t (&init)[L], uint32_t init_top, uint32_t zr = 0u) {
+    const int g = lane & (T - 1);
+    uint32_t E[L + 3], O[L + 2];
+    E[0] = E[1] = 0;
+#pragma unroll
+    for (int j = 0; j < L; ++j) E[j + 2] = init[j];
+    E[L + 2] = (g == T - 1) ? init_top : 0u;
+#pragma unroll
+    for (int j = 0; j < L + 2; ++j) O[j] = 0;
+#pragma unroll U
+    for (int owner = 0; owner < T; ++owner) {
+#pragma unroll
+      for (int j = 0; j < L; j += 2) {
+        const uint32_t p0 = __shfl_sync(ZKP_FULL, b1[j], owner, T);
+        const uint32_t p1 = __shfl_sync(ZKP_FULL, b1[j + 1], owner, T);
+        const uint32_t s0 = __shfl_sync(ZKP_FULL, b2[j], owner, T);
+        const uint32_t s1 = __shfl_sync(ZKP_FULL, b2[j + 1], owner, T);
+        uint32_t q0, q1;
+        cios_pair<true>(E, O, a1, a2, n, p0, p1, s0, s1, np0, np1, g, q0, q1, zr);
+      }
+    }
+    uint32_t u[L + 2];
+    pair_finish(u, E, O, g);
+    finish_x<3>(r, u, n, lane);
   }
 
   // ---- variants of the two-digit rows with a smaller code footprint (modexp2m.cu, TwoDigit MODE 1 / 2) -------------

@@ -102,8 +102,8 @@ __global__ void __launch_bounds__(kShaWarpThreads) sha256_transcript_warp_kernel
   const uint32_t nblocks = (total + 9 + 63) / 64;
   const unsigned long long bits = (unsigned long long)total * 8ull;
   uint32_t h[8] = {0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a, 0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19};
-  for (uint32_t blk0 = 0; blk0 < nblocks; blk0 += 2) {
-    // ---- this lane's word: word (lane & 15) of block blk0 + (lane >> 4)
+  // this lane's word of the block pair starting at blk0: word (lane & 15) of block blk0 + (lane >> 4)
+  auto assemble = [&](uint32_t blk0) -> uint32_t {
     const uint32_t blk = blk0 + (uint32_t)(lane >> 4);
     const uint32_t p0 = blk * 64u + 4u * (uint32_t)(lane & 15);
     uint32_t word = 0;
@@ -144,6 +144,13 @@ __global__ void __launch_bounds__(kShaWarpThreads) sha256_transcript_warp_kernel
         if ((lane & 15) == 15) word = (uint32_t)bits;
       }
     }
+    return word;
+  };
+  uint32_t word = assemble(0u);
+  for (uint32_t blk0 = 0; blk0 < nblocks; blk0 += 2) {
+    // the words of the NEXT block pair are fetched before this pair is compressed: independent work the scheduler can put
+    // under the serial round chain (the fetch is a binary search and four dependent global loads)
+    const uint32_t next = assemble(blk0 + 2u);
     // ---- compress the two blocks, one after the other; every lane runs the rounds on its own registers
 #pragma unroll 1
     for (int half = 0; half < 2; ++half) {
@@ -174,6 +181,7 @@ __global__ void __launch_bounds__(kShaWarpThreads) sha256_transcript_warp_kernel
       }
       h[0] += a; h[1] += bb; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
     }
+    word = next;
   }
   if (lane < 8) {
     const uint32_t v = h[lane];  // h is the same in every lane; lane i writes word i

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libzkp_b200.so")
 # measurement scripts may point at the lab build (make lab); the product path is always the in-tree library
 if os.environ.get("ZKP_B200_LIB"):
     LIB_PATH = os.path.abspath(os.environ["ZKP_B200_LIB"])
-TUNE_ENC_KERNEL, TUNE_JOBS_SHAPE = 0, 1
+TUNE_ENC_KERNEL, TUNE_JOBS_SHAPE, TUNE_JOBS_ROWS = 0, 1, 2
 
 ZKP_OK = 0
 RP_OPEN, RP_MASK1, RP_MASK2 = 0, 1, 2
