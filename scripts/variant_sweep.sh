@@ -1,5 +1,7 @@
 #!/bin/bash
 # K1m tuning sweep on one B200: every layout / loop-structure variant (modexp2m.cu: Enc2mConfig) at window 5, then window 6.
+# The variants exist only in the lab build: run `make lab` first.
+export ZKP_B200_LIB=zk-paillier_b200/libzkp_b200_lab.so
 mkdir -p gpurun_out
 rm -f gpurun_out/k1m_variants.jsonl
 for v in 0 1 2 3 4 5 6 7 8; do
