@@ -272,10 +272,11 @@ struct PowBatch {
         acc = dst;
       }
     }
-    // a plaintext without an encryption term would need a separate (1 + m n) factor: no caller builds one
-    bool has_enc = false;
-    for (int k = 0; k < it.nterm; ++k) has_enc = has_enc || !it.term[k].exp;
-    if (it.plain && !has_enc) s.bad = true;
+    // the plaintext factor rides on THE encryption term: a plaintext without one (a separate (1 + m n) factor) or with two
+    // (the factor applied twice) is not something a caller builds - refuse rather than compute something else than K2h would
+    int enc_terms = 0;
+    for (int k = 0; k < it.nterm; ++k) enc_terms += !it.term[k].exp;
+    if (it.plain ? enc_terms != 1 : false) s.bad = true;
   }
 };
 
