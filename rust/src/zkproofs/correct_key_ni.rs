@@ -41,7 +41,7 @@ impl NiCorrectKeyProof {
             eng.check(unsafe { ffi::zkp_correct_key_ni_rho(eng.h, b as i32, nl as i32, pack(n.iter(), nl).as_ptr(), salt.as_ptr(), salt.len() as i32, rho.as_mut_ptr()) });
             let rho = unpack(&rho, nl);
             // extract_nroot (kzen-paillier): sigma = rho^(N^-1 mod phi) by CRT - rho^(N^-1 mod p-1) mod p, the same mod q
-            let mut half = |prime: &dyn Fn(&DecryptionKey) -> &BigInt| -> Vec<BigInt> {
+            let half = |prime: &dyn Fn(&DecryptionKey) -> &BigInt| -> Vec<BigInt> {
                 let mods: Vec<BigInt> = dks.iter().map(|dk| prime(dk).clone()).collect();
                 let exps: Vec<BigInt> = dks
                     .iter()
@@ -72,7 +72,8 @@ impl NiCorrectKeyProof {
                             let (a, c) = (&sp[k * M2 + i], &sq[k * M2 + i]);
                             // a + p * ((c - a) * p^-1 mod q)
                             let h = BigInt::mod_mul(&BigInt::mod_sub(c, a, q), &pinv, q);
-                            a + p * h
+                            let ph = p * &h;
+                            a + &ph
                         })
                         .collect();
                     NiCorrectKeyProof { sigma_vec }

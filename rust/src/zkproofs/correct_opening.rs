@@ -7,12 +7,14 @@ use crate::engine::{fits, pack, Engine};
 use crate::ffi;
 
 pub trait CorrectOpening<R, CT> {
-    fn verify_opening(ek: &EncryptionKey, m: RawPlaintext, r: &R, c: CT) -> bool;
+    fn verify_opening(ek: &EncryptionKey, m: RawPlaintext, r: &R, c: &CT) -> bool;
 }
 
-impl<'c, 'm> CorrectOpening<Randomness, RawCiphertext<'c>> for Paillier {
-    fn verify_opening(ek: &EncryptionKey, m: RawPlaintext, r: &Randomness, c: RawCiphertext<'c>) -> bool {
-        verify_opening_batch(ek, &[m.0.into_owned()], &[r.0.clone()], &[c.0.into_owned()])[0]
+/// The reference implements the trait for every (R, CT) kzen-paillier can encrypt into; the engine has one ciphertext type,
+/// so the shim implements the instance the reference's own test uses (correct_opening.rs:47-56).
+impl<'c> CorrectOpening<Randomness, RawCiphertext<'c>> for Paillier {
+    fn verify_opening(ek: &EncryptionKey, m: RawPlaintext, r: &Randomness, c: &RawCiphertext<'c>) -> bool {
+        verify_opening_batch(ek, &[m.0.into_owned()], &[r.0.clone()], &[c.0.as_ref().clone()])[0]
     }
 }
 

@@ -99,8 +99,9 @@ impl MulProof {
                         fits(&s.e_a, nnl) && fits(&s.e_b, nnl) && fits(&s.e_c, nnl) && fits(&p.e_d, nnl) && fits(&p.e_db, nnl) && fits(&p.f, nl)
                     })
                     .collect();
-                let pick = |get: &dyn Fn(usize) -> &BigInt, limbs: usize| -> Vec<u32> {
-                    pack(idx.iter().zip(&ok).map(|(&i, &k)| if k { get(i) } else { &zero }), limbs)
+                // rows of the proofs that can be laid out; zero rows for the others (their verdict is already Reject)
+                let pick = |rows: Vec<&BigInt>, limbs: usize| -> Vec<u32> {
+                    pack(rows.into_iter().zip(&ok).map(|(x, &k)| if k { x } else { &zero }), limbs)
                 };
                 let z1: Vec<BigInt> = idx.iter().map(|&i| &proofs[i].z1 % &ek.nn).collect();
                 let z2: Vec<BigInt> = idx.iter().map(|&i| &proofs[i].z2 % &ek.nn).collect();
@@ -108,9 +109,9 @@ impl MulProof {
                 eng.check(unsafe {
                     ffi::zkp_mul_verify(
                         eng.h, idx.len() as i32,
-                        pick(&|i| &statement[i].e_a, nnl).as_ptr(), pick(&|i| &statement[i].e_b, nnl).as_ptr(), pick(&|i| &statement[i].e_c, nnl).as_ptr(),
-                        pick(&|i| &proofs[i].f, nl).as_ptr(), pack(z1.iter(), nnl).as_ptr(), pack(z2.iter(), nnl).as_ptr(),
-                        pick(&|i| &proofs[i].e_d, nnl).as_ptr(), pick(&|i| &proofs[i].e_db, nnl).as_ptr(), accept.as_mut_ptr(), fault.as_mut_ptr(),
+                        pick(idx.iter().map(|&i| &statement[i].e_a).collect(), nnl).as_ptr(), pick(idx.iter().map(|&i| &statement[i].e_b).collect(), nnl).as_ptr(), pick(idx.iter().map(|&i| &statement[i].e_c).collect(), nnl).as_ptr(),
+                        pick(idx.iter().map(|&i| &proofs[i].f).collect(), nl).as_ptr(), pack(z1.iter(), nnl).as_ptr(), pack(z2.iter(), nnl).as_ptr(),
+                        pick(idx.iter().map(|&i| &proofs[i].e_d).collect(), nnl).as_ptr(), pick(idx.iter().map(|&i| &proofs[i].e_db).collect(), nnl).as_ptr(), accept.as_mut_ptr(), fault.as_mut_ptr(),
                     )
                 });
                 for (k, &i) in idx.iter().enumerate() {

@@ -98,8 +98,9 @@ impl VerlinProof {
                         fits(&s.c, nnl) && fits(&s.c_prime, nnl) && fits(&s.phi_x, nnl) && fits(&p.phi_a, nnl) && fits(&p.z, zl) && fits(&p.z_prime, zl)
                     })
                     .collect();
-                let pick = |get: &dyn Fn(usize) -> &BigInt, limbs: usize| -> Vec<u32> {
-                    pack(idx.iter().zip(&ok).map(|(&i, &k)| if k { get(i) } else { &zero }), limbs)
+                // rows of the proofs that can be laid out; zero rows for the others (their verdict is already Reject)
+                let pick = |rows: Vec<&BigInt>, limbs: usize| -> Vec<u32> {
+                    pack(rows.into_iter().zip(&ok).map(|(x, &k)| if k { x } else { &zero }), limbs)
                 };
                 let zdp: Vec<BigInt> = idx
                     .iter()
@@ -110,8 +111,8 @@ impl VerlinProof {
                 eng.check(unsafe {
                     ffi::zkp_verlin_verify(
                         eng.h, idx.len() as i32, zl as i32,
-                        pick(&|i| &statement[i].c, nnl).as_ptr(), pick(&|i| &statement[i].c_prime, nnl).as_ptr(), pick(&|i| &statement[i].phi_x, nnl).as_ptr(),
-                        pick(&|i| &proofs[i].phi_a, nnl).as_ptr(), pick(&|i| &proofs[i].z, zl).as_ptr(), pick(&|i| &proofs[i].z_prime, zl).as_ptr(),
+                        pick(idx.iter().map(|&i| &statement[i].c).collect(), nnl).as_ptr(), pick(idx.iter().map(|&i| &statement[i].c_prime).collect(), nnl).as_ptr(), pick(idx.iter().map(|&i| &statement[i].phi_x).collect(), nnl).as_ptr(),
+                        pick(idx.iter().map(|&i| &proofs[i].phi_a).collect(), nnl).as_ptr(), pick(idx.iter().map(|&i| &proofs[i].z).collect(), zl).as_ptr(), pick(idx.iter().map(|&i| &proofs[i].z_prime).collect(), zl).as_ptr(),
                         pack(zdp.iter(), zl).as_ptr(), pack(r_z.iter(), nnl).as_ptr(), accept.as_mut_ptr(),
                     )
                 });
