@@ -9,7 +9,9 @@ NAMES = {0: "IMAD.WIDE.U32 independent (16 acc, 8 warps/SMSP)", 1: "IMAD.WIDE.U3
          7: "IMAD.HI.U32 independent", 8: "IMAD.WIDE.U32 zero addend (mul.wide)", 9: "IMAD.WIDE.U32 : IADD3 = 1:1",
          10: "IMAD.WIDE.U32 : LOP3 = 1:2", 11: "IMAD.WIDE.U32 32 accumulators", 12: "IMAD.WIDE.U32 loop-invariant multiplicands",
          13: "IMAD.WIDE.U32 : IMAD = 1:1 (rate counts the IMAD.WIDE only)", 14: "IMAD.WIDE.U32 independent, 1 warp/SMSP",
-         15: "IMAD.WIDE.U32 independent, 2 warps/SMSP", 16: "IMAD.WIDE.U32 independent, 4 warps/SMSP"}
+         15: "IMAD.WIDE.U32 independent, 2 warps/SMSP", 16: "IMAD.WIDE.U32 independent, 4 warps/SMSP",
+         17: "DFMA independent (16 acc)", 18: "exact 52x52 product: 2 DFMA + DADD + 2 64-bit adds (rate counts products)",
+         19: "DFMA : IMAD.WIDE.U32 = 1:1 (rate counts the DFMA only)"}
 ctx = zk.native.Context(0)
 sms = ctx.sm_count
 out = {}

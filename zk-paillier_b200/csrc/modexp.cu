@@ -624,6 +624,65 @@ __global__ void __launch_bounds__(256) imad_probe_kernel(int iters, uint32_t* si
   for (int j = 0; j < 16; ++j) x ^= v[j];
   if (x == 0x12345678u) sink[0] = x;
 }
+
+// Probes of the FP64 pipe ("what comes next": 52-bit limbs on DFMA, Emmart et al., ARITH 2018).
+//   17 DFMA, 16 independent accumulators
+//   18 one exact 52x52 -> 104-bit product per step: hi = fma_rz(a, b, 2^104), lo = fma_rz(a, b, (2^104 + 2^52) - hi), both words
+//      added into 64-bit integer accumulators (2 DFMA + 1 DADD + 2 IADD3 pairs); the rate counts PRODUCTS
+//   19 DFMA : IMAD.WIDE.U32 = 1 : 1 on independent registers (do the two pipes overlap?); the rate counts the DFMA
+template <int VARIANT>
+__global__ void __launch_bounds__(256) dfma_probe_kernel(int iters, uint32_t* sink) {
+  double a[16], u[16];
+  uint64_t lo[8], hi[8];
+  uint32_t w[16];
+  uint32_t seed = threadIdx.x * 2654435761u + blockIdx.x;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    seed = seed * 1664525u + 1013904223u;
+    a[j] = (double)(seed >> 6) * 67108864.0 + (double)(seed & 0x3ffffffu);  // an integer below 2^52
+    u[j] = (double)(seed >> 8);
+    w[j] = seed;
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) lo[j] = hi[j] = 0;
+  double b = (double)(seed | 1u) * 1048576.0;
+  const double c1 = 20282409603651670423947251286016.0;  // 2^104
+  const double c2 = 20282409603651674927546878656512.0;  // 2^104 + 2^52
+  for (int it = 0; it < iters; ++it) {
+    if (VARIANT == 17) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) asm volatile("fma.rz.f64 %0, %1, %2, %0;" : "+d"(u[j]) : "d"(a[j]), "d"(b));
+    } else if (VARIANT == 18) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        double h, l, sub;
+        asm volatile("fma.rz.f64 %0, %1, %2, %3;" : "=d"(h) : "d"(a[j]), "d"(b), "d"(c1));
+        asm volatile("sub.rz.f64 %0, %1, %2;" : "=d"(sub) : "d"(c2), "d"(h));
+        asm volatile("fma.rz.f64 %0, %1, %2, %3;" : "=d"(l) : "d"(a[j]), "d"(b), "d"(sub));
+        hi[j & 7] += (uint64_t)__double_as_longlong(h);
+        lo[j & 7] += (uint64_t)__double_as_longlong(l);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; j += 2) {
+        asm volatile("fma.rz.f64 %0, %1, %2, %0;" : "+d"(u[j]) : "d"(a[j]), "d"(b));
+        uint64_t acc = ((uint64_t)w[j + 1] << 32) | w[j];
+        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc) : "r"(w[(j + 2) & 15]), "r"(seed));
+        asm volatile("fma.rz.f64 %0, %1, %2, %0;" : "+d"(u[j + 1]) : "d"(a[j + 1]), "d"(b));
+        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc) : "r"(w[(j + 3) & 15]), "r"(seed));
+        w[j] = (uint32_t)acc;
+        w[j + 1] = (uint32_t)(acc >> 32);
+      }
+    }
+    b += (double)(it & 1);
+  }
+  uint64_t x = 0;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) x ^= (uint64_t)__double_as_longlong(u[j]) ^ w[j];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) x ^= lo[j] ^ hi[j];
+  if (x == 0x12345678u) sink[0] = (uint32_t)x;
+}
 #endif  // ZKP_B200_LAB
 
 #ifdef ZKP_B200_LAB
@@ -667,6 +726,13 @@ cudaError_t launch_imad_peak(int variant, int blocks, int iters, uint32_t* sink,
       default: imad_probe_kernel<13><<<blocks, 256, 0, st>>>(iters, sink); break;
     }
     *ops = (double)blocks * 256.0 * (double)iters * 16.0;  // multiply-adds of the probed kind (the filler instructions are not counted)
+    return cudaGetLastError();
+  }
+  if (variant >= 17 && variant <= 19) {
+    if (variant == 17) dfma_probe_kernel<17><<<blocks, 256, 0, st>>>(iters, sink);
+    if (variant == 18) dfma_probe_kernel<18><<<blocks, 256, 0, st>>>(iters, sink);
+    if (variant == 19) dfma_probe_kernel<19><<<blocks, 256, 0, st>>>(iters, sink);
+    *ops = (double)blocks * 256.0 * (double)iters * 16.0;  // DFMA (17, 19) or whole 52x52 products (18)
     return cudaGetLastError();
   }
   if (variant >= 14 && variant <= 16) {  // variant 0 at 1 / 2 / 4 warps per sub-partition (4 / 8 / 16 warps per SM)
