@@ -26,6 +26,38 @@ def test_library_exports_every_declared_symbol():
     assert lib.zkp_version() >= 100
 
 
+def test_ctypes_table_matches_the_header_parameter_by_parameter():
+    """A ctypes signature that drifts from the header corrupts memory silently: compare every parameter's kind."""
+    import ctypes as C
+
+    src = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "zkp_b200.h")).read(), flags=re.S)
+    want_ret = {"int": C.c_int, "void": None, "const char*": C.c_char_p, "long long": C.c_longlong}
+    pointee = {"uint32_t": C.c_uint32, "uint8_t": C.c_uint8, "double": C.c_double, "long long": C.c_longlong, "unsigned": C.c_uint}
+    checked, seen = 0, set()
+    for m in re.finditer(r"\b(const char\*|long long|int|void)\s+(zkp_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", src):
+        ret, name, args = m.group(1), m.group(2), " ".join(m.group(3).split())
+        res, argtypes = zk.native.SIGNATURES[name]
+        seen.add(name)
+        assert res is want_ret[ret] or res == want_ret[ret], (name, ret, res)
+        params = [] if args in ("", "void") else [a.strip() for a in args.split(",")]
+        assert len(params) == len(argtypes), f"{name}: header has {len(params)} parameters, native.SIGNATURES has {len(argtypes)}"
+        for i, (decl, ct) in enumerate(zip(params, argtypes)):
+            ctype = re.match(r"^(.*?[\s\*])[A-Za-z_][A-Za-z0-9_]*$", decl).group(1).replace("const ", "").strip()
+            where = f"{name} parameter {i} ({decl})"
+            if ctype.endswith("*"):
+                base = ctype.rstrip("*").strip()
+                if base in ("zkp_ctx", "void") or ctype.count("*") > 1:
+                    assert ct in (C.c_void_p,) or issubclass(ct, C._Pointer), where
+                elif base == "char":
+                    assert ct is C.c_char_p, where
+                else:
+                    assert issubclass(ct, C._Pointer) and ct._type_ is pointee[base], f"{where}: ctypes has {ct}"
+            else:
+                assert ct is {"int": C.c_int, "double": C.c_double, "long long": C.c_longlong, "size_t": C.c_size_t}[ctype], f"{where}: ctypes has {ct}"
+            checked += 1
+    assert checked > 300 and seen == set(zk.native.SIGNATURES)
+
+
 def test_library_contains_sm100a_code_only():
     out = subprocess.run(["cuobjdump", "-lelf", zk.native.LIB_PATH], capture_output=True, text=True).stdout
     archs = set(re.findall(r"sm_(\d+a?)", out))
