@@ -53,10 +53,9 @@ __global__ void __launch_bounds__(kShaThreads) sha256_transcript_kernel(const Sh
 // The same digest with ONE WARP per transcript, for batches too small to fill the GPU with one thread each (a batch of 1024
 // RangeProofNi transcripts is 32 warps of K4: 3 % of the SMs busy for 10 ms; one proof alone waits the same 10 ms twice).
 // The byte stream of a transcript is laid out first - every lane measures items (minimal big-endian length of to_bytes(),
-// zero -> 1 byte) and a warp scan turns the lengths into byte offsets in shared memory - after which any message word can
-// be fetched independently: lanes 0-15 assemble the 16 words of one block and lanes 16-31 those of the next (binary search
-// of the item, then its limbs), the words are broadcast by shuffle and every lane runs the 64 rounds on registers.  What is
-// left per block is the serial round chain itself.
+// zero -> 1 byte) and a warp scan turns the lengths into byte offsets in shared memory - after which any block can be
+// fetched independently (binary search of the item, then its limbs): each lane fetches ONE block of the next 32 and expands
+// its message schedule, and the 32 blocks are then compressed in order with the expanded words broadcast by shuffle.
 constexpr int kShaWarpThreads = 128;
 __device__ __forceinline__ const uint32_t* sha_item(const ShaSegs& segs, int b, int item, int& limbs) {
   int k = 0, first = 0;
@@ -102,78 +101,101 @@ __global__ void __launch_bounds__(kShaWarpThreads) sha256_transcript_warp_kernel
   const uint32_t nblocks = (total + 9 + 63) / 64;
   const unsigned long long bits = (unsigned long long)total * 8ull;
   uint32_t h[8] = {0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a, 0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19};
-  // this lane's word of the block pair starting at blk0: word (lane & 15) of block blk0 + (lane >> 4)
-  auto assemble = [&](uint32_t blk0) -> uint32_t {
-    const uint32_t blk = blk0 + (uint32_t)(lane >> 4);
-    const uint32_t p0 = blk * 64u + 4u * (uint32_t)(lane & 15);
-    uint32_t word = 0;
-    if (blk < nblocks) {
-      if (p0 < total) {
-        int lo = 0, hi = nitems - 1;  // the item that holds byte p0: largest i with off[i] <= p0
-        while (lo < hi) {
-          const int mid = (lo + hi + 1) >> 1;
-          if (off[mid] <= p0) lo = mid;
-          else hi = mid - 1;
-        }
-        int it = lo, limbs;
-        const uint32_t* ptr = sha_item(segs, b, it, limbs);
-        uint32_t start = off[it], end = off[it + 1];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint32_t pos = p0 + (uint32_t)k;
-          uint32_t byte;
-          if (pos < total) {
-            while (pos >= end) {  // next item (an item is at least one byte long)
-              ++it;
-              ptr = sha_item(segs, b, it, limbs);
-              start = end;
-              end = off[it + 1];
-            }
-            const uint32_t le = (end - start) - 1u - (pos - start);  // position from the least significant byte
-            byte = (__ldg(ptr + (le >> 2)) >> (8u * (le & 3u))) & 0xffu;
-          } else {
-            byte = pos == total ? 0x80u : 0u;
-          }
-          word = (word << 8) | byte;
-        }
-      } else if (p0 == total) {
-        word = 0x80000000u;
+  // the 16 message words of block blk (padding and length included), by the lane that owns the block
+  auto fetch = [&](uint32_t blk, uint32_t (&m)[16]) {
+    const uint32_t p0 = blk * 64u;
+    int it = 0, limbs = 0;
+    const uint32_t* ptr = nullptr;
+    uint32_t start = 0, end = 0;
+    if (blk < nblocks && p0 < total) {
+      int lo = 0, hi = nitems - 1;  // the item that holds byte p0: largest i with off[i] <= p0
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (off[mid] <= p0) lo = mid;
+        else hi = mid - 1;
       }
-      if (blk == nblocks - 1) {
-        if ((lane & 15) == 14) word = (uint32_t)(bits >> 32);
-        if ((lane & 15) == 15) word = (uint32_t)bits;
-      }
+      it = lo;
+      ptr = sha_item(segs, b, it, limbs);
+      start = off[it];
+      end = off[it + 1];
     }
-    return word;
-  };
-  uint32_t word = assemble(0u);
-  for (uint32_t blk0 = 0; blk0 < nblocks; blk0 += 2) {
-    // the words of the NEXT block pair are fetched before this pair is compressed: independent work the scheduler can put
-    // under the serial round chain (the fetch is a binary search and four dependent global loads)
-    const uint32_t next = assemble(blk0 + 2u);
-    // ---- compress the two blocks, one after the other; every lane runs the rounds on its own registers
-#pragma unroll 1
-    for (int half = 0; half < 2; ++half) {
-      if (blk0 + (uint32_t)half >= nblocks) break;
-      uint32_t m[16];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) m[i] = __shfl_sync(0xffffffffu, word, half * 16 + i);
+    for (int k = 0; k < 16; ++k) {
+      const uint32_t pos = p0 + 4u * (uint32_t)k;
+      uint32_t word = 0;
+      if (blk < nblocks) {
+        if (pos < total) {
+          while (pos >= end) {  // next item (an item is at least one byte long)
+            ++it;
+            ptr = sha_item(segs, b, it, limbs);
+            start = end;
+            end = off[it + 1];
+          }
+          if (pos + 4u <= end) {
+            // four bytes of one item: bits [sh, sh + 32) of its little-endian limbs, sh = 8 (bytes below the word)
+            const uint32_t sh = 8u * (end - pos - 4u);
+            const uint32_t lo32 = __ldg(ptr + (sh >> 5));
+            const uint32_t hi32 = (sh & 31u) ? __ldg(ptr + (sh >> 5) + 1) : 0u;
+            word = __funnelshift_r(lo32, hi32, sh & 31u);
+          } else {
+#pragma unroll
+            for (int bq = 0; bq < 4; ++bq) {  // the word straddles items or the end of the message
+              const uint32_t pb = pos + (uint32_t)bq;
+              uint32_t byte;
+              if (pb < total) {
+                while (pb >= end) {
+                  ++it;
+                  ptr = sha_item(segs, b, it, limbs);
+                  start = end;
+                  end = off[it + 1];
+                }
+                const uint32_t le = end - 1u - pb;  // position from the least significant byte
+                byte = (__ldg(ptr + (le >> 2)) >> (8u * (le & 3u))) & 0xffu;
+              } else {
+                byte = pb == total ? 0x80u : 0u;
+              }
+              word = (word << 8) | byte;
+            }
+          }
+        } else if (pos == total) {
+          word = 0x80000000u;
+        }
+      }
+      m[k] = word;
+    }
+    if (blk == nblocks - 1) {
+      m[14] = (uint32_t)(bits >> 32);
+      m[15] = (uint32_t)bits;
+    }
+  };
+  // 32 blocks per pass: lane j fetches block base + j and expands its message schedule (W_i + K_i, 64 registers) - the part
+  // of SHA-256 that is parallel across blocks - then the blocks are compressed in order, every lane running the rounds on its
+  // own copy of the state with the expanded words broadcast from the owning lane.  What is left per block is the serial
+  // round chain and one shuffle per round.
+  for (uint32_t base = 0; base < nblocks; base += 32u) {
+    uint32_t m[16], kw[64];
+    fetch(base + (uint32_t)lane, m);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) kw[i] = m[i] + kSha256K[i];
+#pragma unroll
+    for (int i = 16; i < 64; ++i) {
+      const uint32_t w15 = m[(i + 1) & 15], w2 = m[(i + 14) & 15];
+      const uint32_t s0 = rotr32(w15, 7) ^ rotr32(w15, 18) ^ (w15 >> 3);
+      const uint32_t s1 = rotr32(w2, 17) ^ rotr32(w2, 19) ^ (w2 >> 10);
+      const uint32_t wi = m[i & 15] + s0 + m[(i + 9) & 15] + s1;
+      m[i & 15] = wi;
+      kw[i] = wi + kSha256K[i];
+    }
+    const int nb = (int)min(32u, nblocks - base);
+#pragma unroll 1
+    for (int j = 0; j < nb; ++j) {
       uint32_t a = h[0], bb = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7];
 #pragma unroll
       for (int i = 0; i < 64; ++i) {
-        uint32_t wi;
-        if (i < 16) {
-          wi = m[i];
-        } else {
-          const uint32_t w15 = m[(i + 1) & 15], w2 = m[(i + 14) & 15];
-          const uint32_t s0 = rotr32(w15, 7) ^ rotr32(w15, 18) ^ (w15 >> 3);
-          const uint32_t s1 = rotr32(w2, 17) ^ rotr32(w2, 19) ^ (w2 >> 10);
-          wi = m[i & 15] + s0 + m[(i + 9) & 15] + s1;
-          m[i & 15] = wi;
-        }
+        const uint32_t x = __shfl_sync(0xffffffffu, kw[i], j);
         const uint32_t S1 = rotr32(e, 6) ^ rotr32(e, 11) ^ rotr32(e, 25);
         const uint32_t ch = (e & f) ^ (~e & g);
-        const uint32_t t1 = hh + S1 + ch + kSha256K[i] + wi;
+        const uint32_t t1 = (hh + x) + S1 + ch;
         const uint32_t S0 = rotr32(a, 2) ^ rotr32(a, 13) ^ rotr32(a, 22);
         const uint32_t mj = (a & bb) ^ (a & c) ^ (bb & c);
         const uint32_t t2 = S0 + mj;
@@ -181,7 +203,6 @@ __global__ void __launch_bounds__(kShaWarpThreads) sha256_transcript_warp_kernel
       }
       h[0] += a; h[1] += bb; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
     }
-    word = next;
   }
   if (lane < 8) {
     const uint32_t v = h[lane];  // h is the same in every lane; lane i writes word i
