@@ -56,7 +56,8 @@ impl CorrectMessageProof {
             eng.use_key(ek);
             let (nl, nnl) = (eng.nl(), eng.nnl());
             let ml = nl; // message rows: reduced mod n (only m mod n enters (m n + 1) % nn)
-            let valid: Vec<BigInt> = (0..b).flat_map(|_| valid_messages.iter().map(|v| v % &ek.n)).collect();
+            let reduced: Vec<BigInt> = valid_messages.iter().map(|v| v % &ek.n).collect();
+            let valid: Vec<BigInt> = (0..b).flat_map(|_| reduced.iter().cloned()).collect();
             let msgs: Vec<BigInt> = messages.iter().map(|v| v % &ek.n).collect();
             let (mut c, mut e, mut z, mut a, mut fault) = (vec![0u32; b * nnl], vec![0u32; b * m * E_LIMBS], vec![0u32; b * m * nl], vec![0u32; b * m * nnl], vec![0u8; b]);
             eng.check(unsafe {

@@ -90,15 +90,13 @@ impl CompositeDLogProof {
     }
 }
 
-/// wi_dlog_proof.rs:94-107 (host-side helper of the reference's tests; not on the device path)
+/// wi_dlog_proof.rs:94-107 (host-side helper of the reference's tests; not on the device path): a^((p-1)/2) mod p with the
+/// exponent taken as (p - 1) * 2^-1 mod p, and every outcome but 1 - a multiple of p included - reported as -1, as there.
 pub fn legendre_symbol(a: &BigInt, p: &BigInt) -> i32 {
-    let exp = (p - BigInt::one()).div_floor(&BigInt::from(2));
-    let ls = BigInt::mod_pow(a, &exp, p);
-    if ls == p - BigInt::one() {
-        -1
-    } else if ls.is_zero() {
-        0
-    } else {
+    let half = BigInt::mod_mul(&(p - BigInt::one()), &BigInt::mod_inv(&BigInt::from(2), p).unwrap(), p);
+    if BigInt::mod_pow(a, &half, p) == BigInt::one() {
         1
+    } else {
+        -1
     }
 }
