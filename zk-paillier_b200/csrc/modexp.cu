@@ -271,7 +271,6 @@ struct MulParams {
 template <int T, int L>
 __global__ void __launch_bounds__(kCtaThreads) modmul_shared_kernel(const MulParams p) {
   using M = Mp<T, L>;
-  constexpr int S = T * L;
   constexpr int G = kCtaThreads / T;
   const int lane = threadIdx.x & 31;
   const int g = lane & (T - 1);

@@ -978,11 +978,6 @@ constexpr int kPhasedUnitsPerSmsp = 12;   // phased scheduling while the launch 
 constexpr int kPhaseTargetPerSmsp = 24;   // ... cut so that every sub-partition sees about this many phase-units
 constexpr int kMinWinPerPhase = 8;
 
-static int jobs_shape_T(int S, int shape) {
-  int T, L;
-  if (!pick_shape(S, T, L)) return 0;
-  return shape == 2 ? 2 * T : T;
-}
 static int scan_windows(int exp_bits) { return (exp_bits + kWindowVar - 1) / kWindowVar; }
 
 // limbs of scratch one launch needs: the window tables (by job when phased, else by resident group), the accumulators

@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(kShaWarpThreads) sha256_transcript_warp_kernel
     const uint32_t p0 = blk * 64u;
     int it = 0, limbs = 0;
     const uint32_t* ptr = nullptr;
-    uint32_t start = 0, end = 0;
+    uint32_t end = 0;
     if (blk < nblocks && p0 < total) {
       int lo = 0, hi = nitems - 1;  // the item that holds byte p0: largest i with off[i] <= p0
       while (lo < hi) {
@@ -116,7 +116,6 @@ __global__ void __launch_bounds__(kShaWarpThreads) sha256_transcript_warp_kernel
       }
       it = lo;
       ptr = sha_item(segs, b, it, limbs);
-      start = off[it];
       end = off[it + 1];
     }
 #pragma unroll
@@ -128,7 +127,6 @@ __global__ void __launch_bounds__(kShaWarpThreads) sha256_transcript_warp_kernel
           while (pos >= end) {  // next item (an item is at least one byte long)
             ++it;
             ptr = sha_item(segs, b, it, limbs);
-            start = end;
             end = off[it + 1];
           }
           if (pos + 4u <= end) {
@@ -146,8 +144,7 @@ __global__ void __launch_bounds__(kShaWarpThreads) sha256_transcript_warp_kernel
                 while (pb >= end) {
                   ++it;
                   ptr = sha_item(segs, b, it, limbs);
-                  start = end;
-                  end = off[it + 1];
+                        end = off[it + 1];
                 }
                 const uint32_t le = end - 1u - pb;  // position from the least significant byte
                 byte = (__ldg(ptr + (le >> 2)) >> (8u * (le & 3u))) & 0xffu;
