@@ -166,7 +166,9 @@ int zkp_rp_verify_run(zkp_ctx* ctx);
 /* RangeProof::verifier_output against the verifier's own ChallengeBits (interactive proof, range_proof.rs:254-355). */
 int zkp_rp_verify_run_with_challenge(zkp_ctx* ctx, const uint8_t* challenge, int chal_bytes);
 int zkp_rp_verify_fetch(zkp_ctx* ctx, uint8_t* accept, uint8_t* fault, uint8_t* digest);
-/* Number of Paillier encryptions the last verify_run performed (ef + #Open per proof). */
+/* Number of Paillier encryptions the last verify_run performed (ef + #Open per proof: the plan follows the variant of each
+ * response, so that the encryptions run beside the transcript hash; a response whose variant contradicts its challenge bit is
+ * encrypted too - the reference skips it, the verdict is the same). */
 long long zkp_rp_verify_enc_count(zkp_ctx* ctx);
 
 /* ---- NiCorrectKeyProof::verify (correct_key_ni.rs:73-100) -------------------

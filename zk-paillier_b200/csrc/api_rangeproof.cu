@@ -302,9 +302,13 @@ int zkp_rp_verify_run_with_challenge(zkp_ctx* c, const uint8_t* challenge, int c
   const int be = batch * ef;
   ZKP_CU(c, cudaMemsetAsync(s.v_fault.p, 0, (size_t)batch, st));
   ZKP_CU(c, cudaMemsetAsync(s.v_count.p, 0, 16, st));
-  {  // e = H(n, c1.., c2..)  (range_proof_ni.rs:89-92)
-    ProfScope ps(c, KID_SHA, batch);
-    ZKP_CU(c, launch_sha256_transcript(rp_transcript(c, s.pv_c, batch, ef), batch, s.v_digest.as<uint8_t>(), st));
+  if (!challenge) {  // e = H(n, c1.., c2..)  (range_proof_ni.rs:89-92) on an auxiliary stream, beside the encryptions below
+    ZKP_CU(c, fork_stream(c, 0));
+    {
+      ProfScope ps(c, KID_SHA, batch);
+      ZKP_CU(c, launch_sha256_transcript(rp_transcript(c, s.pv_c, batch, ef), batch, s.v_digest.as<uint8_t>(), c->stream));
+    }
+    ZKP_CU(c, main_stream(c));
   }
   RpVerifyArgs a;
   a.batch = batch; a.ef = ef; a.wl = wl; a.nl = nl;
@@ -331,8 +335,10 @@ int zkp_rp_verify_run_with_challenge(zkp_ctx* c, const uint8_t* challenge, int c
     ZKP_CU(c, launch_modmul_select(c->nn.view(), a.sel, s.pv_c, s.pv_c + (size_t)be * nnl, nnl, s.v_cx.as<uint32_t>(), nnl,
                                    ef, s.v_cmul.as<uint32_t>(), nnl, be, st));
   }
+  ZKP_CU(c, join_streams(c));  // the digest is needed from here on
   {
     ProfScope ps(c, KID_OTHER, be);
+    ZKP_CU(c, launch_rp_bits(a, st));
     ZKP_CU(c, launch_rp_check(a, st));
     ZKP_CU(c, launch_rp_accept(a.ok, a.fault, batch, ef, s.v_accept.as<uint8_t>(), st));
   }

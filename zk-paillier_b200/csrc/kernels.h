@@ -194,6 +194,7 @@ cudaError_t launch_rp_prep(const uint32_t* range, const uint32_t* w1in, uint32_t
                            int ef, int wl, uint8_t* fault, cudaStream_t st);
 cudaError_t launch_rp_respond(const RpProveArgs& a, cudaStream_t st);
 cudaError_t launch_rp_plan(const RpVerifyArgs& a, cudaStream_t st);
+cudaError_t launch_rp_bits(const RpVerifyArgs& a, cudaStream_t st);
 cudaError_t launch_rp_check(const RpVerifyArgs& a, cudaStream_t st);
 cudaError_t launch_rp_accept(const uint8_t* ok, const uint8_t* fault, int batch, int ef, uint8_t* accept,
                              cudaStream_t st);

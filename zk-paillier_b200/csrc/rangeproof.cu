@@ -365,26 +365,21 @@ cudaError_t launch_rp_respond(const RpProveArgs& a, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------ verify: plan
-// For each (proof, i): the challenge bit, the (bit, variant) match of
-// range_proof.rs:276/314/345, the interval predicates (:300-309, :338-340), and
-// the Paillier encryptions to run, appended to a compact job list
-// (2 for Open, 1 for Mask).  sel[t] tells K3 which ciphertext to multiply by
-// cipher_x (0 none, 1 c1, 2 c2).
+// For each (proof, i): the interval predicates (range_proof.rs:300-309, :338-340) and the Paillier encryptions to run,
+// appended to a compact job list (2 for Open, 1 for Mask).  sel[t] tells K3 which ciphertext to multiply by cipher_x
+// (0 none, 1 c1, 2 c2).  The plan follows the VARIANT of each response, not the challenge bit: what the verifier has
+// to encrypt is written in the proof, so the encryptions can start while the transcript is still being hashed on another
+// stream; rp_bits_kernel applies the (bit, variant) match of :276/314/345 afterwards.  A response whose variant
+// contradicts its bit is therefore encrypted although the reference would skip it - the verdict is the same `false`.
 __global__ void rp_plan_kernel(RpVerifyArgs a) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= a.batch * a.ef) return;
-  const int b = t / a.ef, i = t % a.ef;
+  const int b = t / a.ef;
   const int wl = a.wl, nl = a.nl;
-  const uint32_t e = a.chal ? challenge_bit_raw(a.chal + (size_t)b * a.chal_bytes, a.chal_bytes, i)
-                            : challenge_bit(a.digest + (size_t)b * 32, i);
   const uint8_t k = a.kind[t];
   a.sel[t] = 0;
-  if (e == 2u || k > ZKP_RP_MASK2_) {  // the reference panics (index out of range) / has no such variant
+  if (k > ZKP_RP_MASK2_) {  // the reference has no such variant
     a.fault[b] = 1;
-    a.ok[t] = 0;
-    return;
-  }
-  if ((e == 0u) != (k == ZKP_RP_OPEN_)) {  // `_ => false`
     a.ok[t] = 0;
     return;
   }
@@ -416,6 +411,24 @@ __global__ void rp_plan_kernel(RpVerifyArgs a) {
     uint32_t* jp = a.jobs_plain + (size_t)(slot + j) * wl;
     for (int q = 0; q < nl; ++q) jb[q] = rr[(size_t)j * nl + q];
     for (int q = 0; q < wl; ++q) jp[q] = rw[(size_t)j * wl + q];
+  }
+}
+
+// ------------------------------------------------------------ verify: bits
+// The challenge bit of every (proof, i) against the variant of its response (range_proof.rs:276/314/345: `_ => false`);
+// a bit index past the digest (leading zero bytes stripped) is where the reference panics (:273-274).
+__global__ void rp_bits_kernel(RpVerifyArgs a) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= a.batch * a.ef) return;
+  const int b = t / a.ef, i = t % a.ef;
+  const uint32_t e = a.chal ? challenge_bit_raw(a.chal + (size_t)b * a.chal_bytes, a.chal_bytes, i)
+                            : challenge_bit(a.digest + (size_t)b * 32, i);
+  const uint8_t k = a.kind[t];
+  if (e == 2u) {
+    a.fault[b] = 1;
+    a.ok[t] = 0;
+  } else if (k <= ZKP_RP_MASK2_ && (e == 0u) != (k == ZKP_RP_OPEN_)) {
+    a.ok[t] = 0;
   }
 }
 
@@ -458,6 +471,12 @@ cudaError_t launch_rp_plan(const RpVerifyArgs& a, cudaStream_t st) {
   const int total = a.batch * a.ef;
   if (total <= 0) return cudaSuccess;
   rp_plan_kernel<<<(total + 127) / 128, 128, 0, st>>>(a);
+  return cudaGetLastError();
+}
+cudaError_t launch_rp_bits(const RpVerifyArgs& a, cudaStream_t st) {
+  const int total = a.batch * a.ef;
+  if (total <= 0) return cudaSuccess;
+  rp_bits_kernel<<<(total + 127) / 128, 128, 0, st>>>(a);
   return cudaGetLastError();
 }
 cudaError_t launch_rp_check(const RpVerifyArgs& a, cudaStream_t st) {
