@@ -53,3 +53,41 @@ def test_errors_are_reported_not_thrown():
     assert r["ok"] is False and r["kind"] == "error"
     r = call("nope")
     assert r["ok"] is False
+
+
+def test_bigint_on_adversarial_limb_patterns():
+    """Operands built from the limbs that break multiword arithmetic - 0, 1, 2^31, 2^32 - 1, 2^32 - 2 and a random one -
+    at every length up to 9 limbs: carries that ripple across the whole number, borrows out of zero limbs, the
+    over-estimated quotient digits of algorithm D (divisor top limb 2^31 or 2^32 - 1, dividend top limbs equal to it)."""
+    import math
+
+    rng = random.Random(7)
+    pat = [0, 1, 2**31, 2**32 - 1, 2**32 - 2]
+
+    def build(nl):
+        v = 0
+        for _ in range(nl):
+            v = (v << 32) | (rng.choice(pat) if rng.random() < 0.8 else rng.getrandbits(32))
+        return v
+
+    checked = 0
+    for la in range(1, 10):
+        for lb in range(1, 7):
+            for _ in range(12):
+                a, b = build(la), build(lb)
+                if b == 0:
+                    b = 1
+                r = call("bigint.selftest", a=str(a), b=str(b))
+                assert r["ok"], (a, b, r)
+                assert int(r["sum"]) == a + b and int(r["prod"]) == a * b, (a, b)
+                assert int(r["quot"]) == a // b and int(r["rem"]) == a % b, (a, b)
+                if a >= b:
+                    assert int(r["diff"]) == a - b, (a, b)
+                g = math.gcd(a, b)
+                assert int(r["gcd"]) == g, (a, b)
+                if g == 1 and b > 1:
+                    assert int(r["inv"]) == pow(a, -1, b), (a, b)
+                assert r["hex"] == po.serde_bigint_native(a) and r["bits"] == a.bit_length() and r["roundtrip"] is True
+                assert int(r["or"]) == a | b and int(r["shl"]) == a << 37 and int(r["shr"]) == a >> 37 and r["mod_small"] == a % 4093
+                checked += 1
+    assert checked == 9 * 6 * 12
