@@ -91,3 +91,38 @@ def test_bigint_on_adversarial_limb_patterns():
                 assert int(r["or"]) == a | b and int(r["shl"]) == a << 37 and int(r["shr"]) == a >> 37 and r["mod_small"] == a % 4093
                 checked += 1
     assert checked == 9 * 6 * 12
+
+
+def test_request_json_is_untrusted_input():
+    """The request text is parsed by the mirror's own JSON reader (host/json.hpp): malformed, truncated, deeply nested or
+    oddly escaped input is an error reply, never a crash or an exception across the C boundary."""
+    import ctypes as C
+    import json
+    import os
+
+    from util import ROOT
+
+    call("bigint.selftest", a="1", b="1")  # loads the library
+    import hostlib
+
+    lib = hostlib._lib
+
+    def raw(op, text):
+        p = lib.zkh_call(op.encode(), text)
+        try:
+            return json.loads(C.string_at(p).decode())
+        finally:
+            lib.zkh_free(p)
+
+    good = raw("bigint.selftest", b'{"a": "6", "b": "4", "extra": [1, -7, true, false, null, {"k": "\\u00e9\\n\\t\\"\\\\"}]}')
+    assert good["ok"] and good["sum"] == "10"
+    for bad in (b"", b"{", b'{"a": "6", "b": "4"', b'{"a": "6" "b": "4"}', b'{"a": "6", "b": "4"} trailing', b'{"a": "\\uZZZZ", "b": "1"}',
+                b'{"a": "6", "b": "4", "x": ' + b"[" * 100000 + b"}", b'{"a": "6", "b": "4", "x": ' + b'{"y":' * 5000 + b"1" + b"}" * 5000 + b"}",
+                b"\xff\xfe\x00garbage", b'{"a": 6, "b": 4}', b'["a", "b"]', b"null",
+                b'{"a": "6", "b": "4", "x": 2.5e3}'):  # the wire format has integers only (u8 / usize): a fraction or exponent is refused
+        r = raw("bigint.selftest", bad)
+        assert r["ok"] is False and r.get("kind") == "error", (bad[:40], r)
+    # a very long decimal string is data, not a parser problem
+    big = "9" * 4000
+    r = raw("bigint.selftest", json.dumps({"a": big, "b": "7"}).encode())
+    assert r["ok"] and int(r["rem"]) == int(big) % 7
